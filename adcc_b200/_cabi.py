@@ -1,0 +1,74 @@
+"""ctypes binding of include/adccb.h (the C ABI of libadccb.so).
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is no CPU
+fallback: a missing library or a failing call raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libadccb.so")
+
+_lib = None
+
+c_i64 = ctypes.c_int64
+c_dbl = ctypes.c_double
+c_ptr = ctypes.c_void_p
+
+
+def _declare(lib):
+    lib.adccb_version.restype = ctypes.c_int
+    lib.adccb_last_error.restype = ctypes.c_char_p
+    lib.adccb_launch_count.restype = ctypes.c_longlong
+    lib.adccb_device_info.argtypes = [ctypes.POINTER(ctypes.c_int)] * 3
+    lib.adccb_dgemm.argtypes = [c_ptr, c_i64, c_i64, c_i64, c_dbl, c_ptr, c_i64, c_i64, c_ptr,
+                                c_i64, c_i64, c_dbl, c_ptr, c_i64, c_ptr, c_i64, ctypes.c_int]
+    lib.adccb_strided_gather.argtypes = [c_ptr, ctypes.c_int, ctypes.POINTER(c_i64),
+                                         ctypes.POINTER(c_i64), c_dbl, c_ptr, c_dbl, c_ptr, c_dbl,
+                                         c_ptr]
+    lib.adccb_elementwise.argtypes = [c_ptr, ctypes.c_int, c_i64, c_dbl, c_ptr, c_ptr, c_dbl,
+                                      c_dbl, c_ptr]
+    lib.adccb_direct_sum.argtypes = [c_ptr, c_i64, c_i64, c_dbl, c_ptr, c_dbl, c_ptr, c_ptr]
+    lib.adccb_lincomb.argtypes = [c_ptr, ctypes.c_int, ctypes.POINTER(c_dbl),
+                                  ctypes.POINTER(c_ptr), c_i64, c_dbl, c_ptr]
+    lib.adccb_dot_many.argtypes = [c_ptr, ctypes.c_int, c_ptr, ctypes.POINTER(c_ptr), c_i64,
+                                   c_dbl, c_dbl, c_ptr, c_ptr, c_i64]
+    lib.adccb_spin_project.argtypes = [c_ptr, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                       ctypes.POINTER(ctypes.c_int), c_dbl, c_ptr, c_ptr]
+    lib.adccb_spin_singlet.argtypes = [c_ptr, ctypes.POINTER(ctypes.c_int),
+                                       ctypes.POINTER(ctypes.c_int), c_ptr]
+    for name in EXPORTS:
+        if name not in ("adccb_last_error", "adccb_launch_count"):
+            getattr(lib, name).restype = ctypes.c_int
+
+
+EXPORTS = [
+    "adccb_version", "adccb_last_error", "adccb_launch_count", "adccb_device_info",
+    "adccb_dgemm", "adccb_strided_gather", "adccb_elementwise", "adccb_direct_sum",
+    "adccb_lincomb", "adccb_dot_many", "adccb_spin_project", "adccb_spin_singlet",
+]
+
+
+def lib():
+    """Load libadccb.so (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: the CUDA backend has not been built "
+                "(run `python -c 'import __graft_entry__ as g; g.build()'`). "
+                "adcc_b200 has no CPU fallback.")
+        loaded = ctypes.CDLL(LIB_PATH)
+        _declare(loaded)
+        _lib = loaded
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        msg = lib().adccb_last_error().decode()
+        raise RuntimeError(f"adccb: {msg}")
+
+
+def launch_count():
+    return int(lib().adccb_launch_count())

@@ -1,0 +1,221 @@
+"""Device-side primitives: thin Python wrappers around the C ABI (include/adccb.h).
+
+torch is used for device memory and streams only; every arithmetic operation below is one of
+the hand-written sm_100a kernels in adcc_b200/csrc.  No CPU fallback exists.
+"""
+import ctypes
+import numpy as np
+import torch
+
+from . import _cabi
+
+F64 = torch.float64
+EW_AXPBY, EW_MUL, EW_DIV, EW_FILL, EW_DIV_SHIFT, EW_ADD_SCALAR = range(6)
+
+_ws = {}
+
+
+def device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("adcc_b200 needs a CUDA device (B200, sm_100a); no CPU fallback.")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def workspace(nbytes=None):
+    """Per-device scratch (split-K partials, reduction partials)."""
+    dev = torch.cuda.current_device()
+    want = max(nbytes or 0, 64 << 20)
+    ws = _ws.get(dev)
+    if ws is None or ws.numel() * 8 < want:
+        ws = torch.empty(want // 8, dtype=F64, device=device())
+        _ws[dev] = ws
+    return ws
+
+
+def empty(shape):
+    return torch.empty(tuple(int(s) for s in shape), dtype=F64, device=device())
+
+
+def zeros(shape):
+    t = empty(shape)
+    fill(t, 0.0)
+    return t
+
+
+def from_numpy(arr):
+    arr = np.ascontiguousarray(arr, dtype=np.float64)
+    return torch.from_numpy(arr).to(device())
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _check_dev(*ts):
+    for t in ts:
+        if t is not None and (not t.is_cuda or t.dtype != F64):
+            raise ValueError("expected CUDA float64 tensors")
+
+
+# --------------------------------------------------------------------------------- GEMM
+def gemm(A, B, out=None, alpha=1.0, beta=0.0, tile_hint=0):
+    """out[m,n] = alpha * sum_k A[m,k] B[n,k] + beta*out.  A, B: 2-D views (any strides)."""
+    _check_dev(A, B, out)
+    M, K = A.shape
+    N, K2 = B.shape
+    if K != K2:
+        raise ValueError("gemm: inner extents differ")
+    if out is None:
+        out = empty((M, N))
+        beta = 0.0
+    if out.stride(1) != 1 and out.numel() > 0:
+        raise ValueError("gemm: output must be row-major")
+    ldc = out.stride(0) if M > 1 else max(N, 1)
+    ws = workspace()
+    _cabi.check(_cabi.lib().adccb_dgemm(
+        _stream(), M, N, K, float(alpha), _ptr(A), A.stride(0), A.stride(1), _ptr(B),
+        B.stride(0), B.stride(1), float(beta), _ptr(out), ldc, _ptr(ws), ws.numel() * 8,
+        int(tile_hint)))
+    return out
+
+
+# --------------------------------------------------------------------------------- gather
+def gather(inp, shape, in_strides, alpha=1.0, add=None, gamma=0.0, out=None, beta=0.0):
+    """out[o] = alpha*inp.flat[sum o_d*in_strides[d]] + gamma*add[o] + beta*out[o]."""
+    _check_dev(inp, add, out)
+    shape = [int(s) for s in shape]
+    if out is None:
+        out = empty(shape)
+        beta = 0.0
+    elif not out.is_contiguous():
+        raise ValueError("gather: out must be contiguous")
+    if add is not None and not add.is_contiguous():
+        raise ValueError("gather: add must be contiguous")
+    nd = len(shape)
+    sh = (ctypes.c_int64 * max(nd, 1))(*shape)
+    st = (ctypes.c_int64 * max(nd, 1))(*[int(s) for s in in_strides])
+    _cabi.check(_cabi.lib().adccb_strided_gather(
+        _stream(), nd, sh, st, float(alpha), _ptr(inp), float(gamma), _ptr(add), float(beta),
+        _ptr(out)))
+    return out
+
+
+def permute(t, perm, alpha=1.0, add=None, gamma=0.0, out=None, beta=0.0):
+    """Contiguous alpha * t.permute(perm) (+ gamma*add + beta*out)."""
+    shape = [t.shape[p] for p in perm]
+    strides = [t.stride(p) for p in perm]
+    return gather(t, shape, strides, alpha=alpha, add=add, gamma=gamma, out=out, beta=beta)
+
+
+def contiguous(t):
+    if t.is_contiguous():
+        return t
+    return gather(t, list(t.shape), list(t.stride()))
+
+
+# --------------------------------------------------------------------------------- elementwise
+def _ew(op, n, alpha, x, y, c, beta, out):
+    _cabi.check(_cabi.lib().adccb_elementwise(_stream(), op, n, float(alpha), _ptr(x), _ptr(y),
+                                              float(c), float(beta), _ptr(out)))
+    return out
+
+
+def fill(t, value):
+    return _ew(EW_FILL, t.numel(), 1.0, None, None, value, 0.0, t)
+
+
+def axpby(alpha, x, beta, y):
+    """y = alpha*x + beta*y (contiguous, same numel)."""
+    return _ew(EW_AXPBY, x.numel(), alpha, x, None, 0.0, beta, y)
+
+
+def scaled_copy(x, alpha=1.0):
+    x = contiguous(x)
+    return _ew(EW_AXPBY, x.numel(), alpha, x, None, 0.0, 0.0, torch.empty_like(x))
+
+
+def mul(x, y, alpha=1.0):
+    return _ew(EW_MUL, x.numel(), alpha, x, y, 0.0, 0.0, torch.empty_like(x))
+
+
+def div(x, y, alpha=1.0):
+    return _ew(EW_DIV, x.numel(), alpha, x, y, 0.0, 0.0, torch.empty_like(x))
+
+
+def div_shift(x, d, shift):
+    """x / (d - shift): Jacobi preconditioner."""
+    return _ew(EW_DIV_SHIFT, x.numel(), 1.0, x, d, shift, 0.0, torch.empty_like(x))
+
+
+def add_scalar(x, c):
+    return _ew(EW_ADD_SCALAR, x.numel(), 1.0, x, None, c, 0.0, torch.empty_like(x))
+
+
+def direct_sum(a, b, sa=1.0, sb=1.0):
+    """out[p..., q...] = sa*a[p...] + sb*b[q...]"""
+    a, b = contiguous(a), contiguous(b)
+    out = empty(tuple(a.shape) + tuple(b.shape))
+    _cabi.check(_cabi.lib().adccb_direct_sum(_stream(), a.numel(), b.numel(), float(sa), _ptr(a),
+                                             float(sb), _ptr(b), _ptr(out)))
+    return out
+
+
+# --------------------------------------------------------------------------------- vectors
+def lincomb(coeffs, tensors, out=None, beta=0.0):
+    n = tensors[0].numel()
+    for t in tensors:
+        if not t.is_contiguous() or t.numel() != n:
+            raise ValueError("lincomb: tensors must be contiguous and equally sized")
+    if out is None:
+        out = torch.empty_like(tensors[0])
+        beta = 0.0
+    k = len(tensors)
+    cs = (ctypes.c_double * k)(*[float(c) for c in coeffs])
+    ps = (ctypes.c_void_p * k)(*[t.data_ptr() for t in tensors])
+    _cabi.check(_cabi.lib().adccb_lincomb(_stream(), k, cs, ps, n, float(beta), _ptr(out)))
+    return out
+
+
+def dot_many(x, ys, scale=1.0):
+    """numpy array of <x, y_j>; one pass over x and all y_j; one D2H copy."""
+    n = x.numel()
+    k = len(ys)
+    if k == 0:
+        return np.zeros(0)
+    for t in [x] + list(ys):
+        if not t.is_contiguous() or t.numel() != n:
+            raise ValueError("dot_many: tensors must be contiguous and equally sized")
+    out = torch.empty(k, dtype=F64, device=x.device)
+    ws = workspace()
+    ps = (ctypes.c_void_p * k)(*[t.data_ptr() for t in ys])
+    _cabi.check(_cabi.lib().adccb_dot_many(_stream(), k, _ptr(x), ps, n, float(scale), 0.0,
+                                           _ptr(out), _ptr(ws), ws.numel() * 8))
+    return out.cpu().numpy()
+
+
+def dot(x, y):
+    return float(dot_many(x, [y])[0])
+
+
+# --------------------------------------------------------------------------------- spin
+def spin_project(t, n_alpha, fac):
+    t = contiguous(t)
+    nd = t.dim()
+    out = torch.empty_like(t)
+    sh = (ctypes.c_int * nd)(*[int(s) for s in t.shape])
+    na = (ctypes.c_int * nd)(*[int(s) for s in n_alpha])
+    _cabi.check(_cabi.lib().adccb_spin_project(_stream(), nd, sh, na, float(fac), _ptr(t), _ptr(out)))
+    return out
+
+
+def spin_singlet_(t, n_alpha):
+    if not t.is_contiguous() or t.dim() != 4:
+        raise ValueError("spin_singlet_: contiguous rank-4 tensor expected")
+    sh = (ctypes.c_int * 4)(*[int(s) for s in t.shape])
+    na = (ctypes.c_int * 4)(*[int(s) for s in n_alpha])
+    _cabi.check(_cabi.lib().adccb_spin_singlet(_stream(), sh, na, _ptr(t)))
+    return t

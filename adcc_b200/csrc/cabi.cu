@@ -1,0 +1,111 @@
+// extern "C" surface of libadccb.so (see include/adccb.h for the contract).
+#include "common.cuh"
+#include "../../include/adccb.h"
+#include <atomic>
+
+namespace adccb {
+
+static thread_local std::string g_error;
+static std::atomic<long long> g_launches{0};
+
+void set_error(const std::string& msg) { g_error = msg; }
+int fail(const std::string& msg) {
+  g_error = msg;
+  return 1;
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int dgemm_strided(cudaStream_t st, long long M, long long N, long long K, double alpha,
+                  const double* A, long long ars, long long acs, const double* B, long long brs,
+                  long long bcs, double beta, double* C, long long ldc, double* ws,
+                  long long ws_bytes, int tile_hint);
+int strided_gather(cudaStream_t st, int nd, const long long* shape, const long long* istride,
+                   double alpha, const double* in, double gamma, const double* add, double beta,
+                   double* out);
+int elementwise(cudaStream_t st, int op, long long n, double alpha, const double* x,
+                const double* y, double c, double beta, double* out);
+int direct_sum(cudaStream_t st, long long na, long long nb, double sa, const double* a, double sb,
+               const double* b, double* out);
+int lincomb(cudaStream_t st, int nvec, const double* coeff, const double* const* ptrs, long long n,
+            double beta, double* out);
+int dot_many(cudaStream_t st, int nvec, const double* x, const double* const* ys, long long n,
+             double scale, double beta, double* out_dev, double* ws, long long ws_bytes);
+int spin_project(cudaStream_t st, int nd, const int* shape, const int* nalpha, double fac,
+                 const double* in, double* out);
+int spin_singlet(cudaStream_t st, const int* shape, const int* nalpha, double* T);
+
+}  // namespace adccb
+
+using namespace adccb;
+static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+
+extern "C" {
+
+int adccb_version(void) { return 100; }
+const char* adccb_last_error(void) { return g_error.c_str(); }
+long long adccb_launch_count(void) { return g_launches.load(); }
+
+int adccb_device_info(int* sm, int* major, int* minor) {
+  int dev = 0;
+  ADCCB_CUDA_OK(cudaGetDevice(&dev));
+  ADCCB_CUDA_OK(cudaDeviceGetAttribute(sm, cudaDevAttrMultiProcessorCount, dev));
+  ADCCB_CUDA_OK(cudaDeviceGetAttribute(major, cudaDevAttrComputeCapabilityMajor, dev));
+  ADCCB_CUDA_OK(cudaDeviceGetAttribute(minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return 0;
+}
+
+int adccb_dgemm(void* stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A,
+                int64_t a_rs, int64_t a_cs, const double* B, int64_t b_rs, int64_t b_cs,
+                double beta, double* C, int64_t ldc, double* ws, int64_t ws_bytes, int tile_hint) {
+  return dgemm_strided((cudaStream_t)stream, M, N, K, alpha, A, a_rs, a_cs, B, b_rs, b_cs, beta, C,
+                       ldc, ws, ws_bytes, tile_hint);
+}
+
+int adccb_strided_gather(void* stream, int ndim, const int64_t* shape, const int64_t* in_stride,
+                         double alpha, const double* in, double gamma, const double* add,
+                         double beta, double* out) {
+  return strided_gather((cudaStream_t)stream, ndim, (const long long*)shape,
+                        (const long long*)in_stride, alpha, in, gamma, add, beta, out);
+}
+
+int adccb_elementwise(void* stream, int op, int64_t n, double alpha, const double* x,
+                      const double* y, double c, double beta, double* out) {
+  return elementwise((cudaStream_t)stream, op, n, alpha, x, y, c, beta, out);
+}
+
+int adccb_direct_sum(void* stream, int64_t na, int64_t nb, double sa, const double* a, double sb,
+                     const double* b, double* out) {
+  return direct_sum((cudaStream_t)stream, na, nb, sa, a, sb, b, out);
+}
+
+int adccb_lincomb(void* stream, int nvec, const double* host_coeff, const double* const* host_ptrs,
+                  int64_t n, double beta, double* out) {
+  return lincomb((cudaStream_t)stream, nvec, host_coeff, host_ptrs, n, beta, out);
+}
+
+int adccb_dot_many(void* stream, int nvec, const double* x, const double* const* host_ys, int64_t n,
+                   double scale, double beta, double* out_dev, double* ws, int64_t ws_bytes) {
+  return dot_many((cudaStream_t)stream, nvec, x, host_ys, n, scale, beta, out_dev, ws, ws_bytes);
+}
+
+int adccb_spin_project(void* stream, int ndim, const int* shape, const int* n_alpha, double fac,
+                       const double* in, double* out) {
+  return spin_project((cudaStream_t)stream, ndim, shape, n_alpha, fac, in, out);
+}
+
+int adccb_spin_singlet(void* stream, const int* shape, const int* n_alpha, double* T) {
+  return spin_singlet((cudaStream_t)stream, shape, n_alpha, T);
+}
+
+}  // extern "C"

@@ -1,0 +1,408 @@
+// FP64 contraction core:  C[m,n] = alpha * sum_k A[m,k] * B[n,k] + beta * C[m,n]
+//
+// Replaces libtensor's block-wise DGEMM evaluation reached from
+// libadcc_src/TensorImpl.cc:856-876,901-1117 (tensordot -> lt::contract).
+//
+// Fast path (dgemm_tn_tma_kernel): both operands K-contiguous, 16-byte aligned rows.
+//   * one producer warp streams 16-wide K slabs of A and B into a STAGES-deep shared-memory
+//     ring with TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B, zero fill out of bounds),
+//     completion tracked by mbarrier transaction counts;
+//   * consumer warps read DMMA fragments with conflict-free LDS.128 (row permutation inside
+//     each 8-row block + the 128B swizzle) and issue DMMA.8x8x4 (the only FP64 tensor shape
+//     sm_100a has natively; every larger mma.sync f64 shape lowers to it);
+//   * accumulators stay in registers; the epilogue applies alpha/beta or writes split-K
+//     partials that a second kernel reduces in a fixed order (deterministic).
+// Fallback path (dgemm_generic_kernel): arbitrary element strides, used when the TMA
+// alignment rules do not hold (odd leading dimension) - same DMMA core, plain loads.
+#include "common.cuh"
+#include <vector>
+#include <mutex>
+
+namespace adccb {
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + TMA
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      " selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// TMA + DMMA kernel
+// ---------------------------------------------------------------------------------------
+constexpr int kBK = 16;  // doubles per K slab = one 128-byte swizzle row
+
+template <int WARPS_M, int WARPS_N, int MB, int NB, int STAGES>
+struct TileCfg {
+  static constexpr int kConsumerWarps = WARPS_M * WARPS_N;
+  static constexpr int kThreads = (kConsumerWarps + 1) * 32;
+  static constexpr int BM = WARPS_M * MB * 8;
+  static constexpr int BN = WARPS_N * NB * 8;
+  static constexpr int A_BYTES = BM * kBK * 8;
+  static constexpr int B_BYTES = BN * kBK * 8;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;
+};
+
+template <int WARPS_M, int WARPS_N, int MB, int NB, int STAGES>
+__global__ void __launch_bounds__((WARPS_M * WARPS_N + 1) * 32, 1)
+dgemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA,
+                    const __grid_constant__ CUtensorMap tmB, double* __restrict__ C,
+                    long long ldc, int M, int N, int K, int k_per_split, double alpha,
+                    double beta, double* __restrict__ partial) {
+  using Cfg = TileCfg<WARPS_M, WARPS_N, MB, NB, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  // full[s] at bar_base + 8*s, empty[s] at bar_base + 8*(STAGES+s)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.x, tile_n = blockIdx.y, split = blockIdx.z;
+  const int k_begin = split * k_per_split;
+  const int k_end = min(K, k_begin + k_per_split);
+  const int n_iters = (k_end - k_begin + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_base + 8 * s, 1);
+      mbar_init(bar_base + 8 * (STAGES + s), Cfg::kConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == Cfg::kConsumerWarps) {
+    // ===== TMA producer (one elected lane) =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(bar_base + 8 * (STAGES + s), ph ^ 1);
+        const uint32_t full = bar_base + 8 * s;
+        mbar_expect_tx(full, Cfg::STAGE_BYTES);
+        const uint32_t dst = smem_base + s * Cfg::STAGE_BYTES;
+        const int k0 = k_begin + it * kBK;
+        tma_load_2d(dst, &tmA, full, k0, tile_m * Cfg::BM);
+        tma_load_2d(dst + Cfg::A_BYTES, &tmB, full, k0, tile_n * Cfg::BN);
+      }
+    }
+    return;
+  }
+
+  // ===== DMMA consumers =====
+  const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+  const int g = lane >> 2, t = lane & 3;
+  // fragment row g of every 8-row block lives in tile row pg: lanes of one quarter warp then
+  // hit rows r and r^4, whose swizzled 16B chunks fall into disjoint bank groups
+  const int pg = (g >> 1) | ((g & 1) << 2);
+  const uint32_t a_off = (uint32_t)((wm * MB * 8 + pg) * 128 + ((t ^ pg) << 4));
+  const uint32_t b_off = (uint32_t)(Cfg::A_BYTES + (wn * NB * 8 + pg) * 128 + ((t ^ pg) << 4));
+
+  double acc[MB][NB][2];
+#pragma unroll
+  for (int i = 0; i < MB; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  for (int it = 0; it < n_iters; ++it) {
+    const int s = it % STAGES;
+    const uint32_t ph = (it / STAGES) & 1;
+    mbar_wait(bar_base + 8 * s, ph);
+    const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES + a_off;
+    const uint32_t sb = smem_base + s * Cfg::STAGE_BYTES + b_off;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      // logical 16B chunk t + 4h of the row: doubles k = 8h + 2t, 8h + 2t + 1.  The same
+      // k <-> (h, t, slot) relabelling is used for A and B, which leaves the dot product intact.
+      double2 af[MB], bf[NB];
+#pragma unroll
+      for (int i = 0; i < MB; ++i) af[i] = lds128((sa + i * 1024) ^ (h << 6));
+#pragma unroll
+      for (int j = 0; j < NB; ++j) bf[j] = lds128((sb + j * 1024) ^ (h << 6));
+#pragma unroll
+      for (int i = 0; i < MB; ++i)
+#pragma unroll
+        for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x);
+#pragma unroll
+      for (int i = 0; i < MB; ++i)
+#pragma unroll
+        for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i].y, bf[j].y);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + s));
+  }
+
+  // ===== epilogue: thread holds C[row pg][cols t, t+4] of each 8x8 block =====
+  const int row0 = tile_m * Cfg::BM + wm * MB * 8 + pg;
+  const int col0 = tile_n * Cfg::BN + wn * NB * 8 + t;
+  if (partial != nullptr) {
+    double* P = partial + (size_t)split * (size_t)M * (size_t)N;
+#pragma unroll
+    for (int i = 0; i < MB; ++i) {
+      const int r = row0 + i * 8;
+      if (r >= M) continue;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int c = col0 + j * 8;
+        if (c < N) P[(size_t)r * N + c] = acc[i][j][0];
+        if (c + 4 < N) P[(size_t)r * N + c + 4] = acc[i][j][1];
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < MB; ++i) {
+    const int r = row0 + i * 8;
+    if (r >= M) continue;
+    double* Crow = C + (size_t)r * ldc;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int c = col0 + j * 8;
+      if (c < N) Crow[c] = (beta == 0.0) ? alpha * acc[i][j][0] : alpha * acc[i][j][0] + beta * Crow[c];
+      if (c + 4 < N)
+        Crow[c + 4] = (beta == 0.0) ? alpha * acc[i][j][1] : alpha * acc[i][j][1] + beta * Crow[c + 4];
+    }
+  }
+}
+
+// fixed-order reduction of split-K partials
+__global__ void splitk_reduce_kernel(const double* __restrict__ partial, int splits, long long MN,
+                                     int N, double* __restrict__ C, long long ldc, double alpha,
+                                     double beta) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < MN;
+       idx += (long long)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < splits; ++k) s += partial[(size_t)k * MN + idx];
+    const long long r = idx / N, c = idx % N;
+    double* dst = C + r * ldc + c;
+    *dst = (beta == 0.0) ? alpha * s : alpha * s + beta * (*dst);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// generic fallback: arbitrary element strides (A(m,k) = A[m*ars + k*acs], same for B)
+// 64x64 tile, 4 warps (2x2), each warp 32x32, BK = 16, plain loads -> padded smem -> DMMA
+// ---------------------------------------------------------------------------------------
+constexpr int GB = 64;        // tile edge
+constexpr int GPITCH = 18;    // doubles per smem row (16 + 2 pad; keeps 16B alignment)
+
+__global__ void __launch_bounds__(128)
+dgemm_generic_kernel(int M, int N, int K, double alpha, const double* __restrict__ A,
+                     long long ars, long long acs, const double* __restrict__ B, long long brs,
+                     long long bcs, double beta, double* __restrict__ C, long long ldc) {
+  __shared__ __align__(16) double sA[GB * GPITCH];
+  __shared__ __align__(16) double sB[GB * GPITCH];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = blockIdx.x * GB, n0 = blockIdx.y * GB;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  for (int k0 = 0; k0 < K; k0 += kBK) {
+    for (int e = threadIdx.x; e < GB * kBK; e += 128) {
+      int r, k;
+      // pick the traversal order that makes the contiguous operand dimension fastest
+      if (acs == 1) { r = e / kBK; k = e % kBK; } else { k = e / GB; r = e % GB; }
+      double v = 0.0;
+      if (m0 + r < M && k0 + k < K) v = A[(long long)(m0 + r) * ars + (long long)(k0 + k) * acs];
+      sA[r * GPITCH + k] = v;
+      if (bcs == 1) { r = e / kBK; k = e % kBK; } else { k = e / GB; r = e % GB; }
+      v = 0.0;
+      if (n0 + r < N && k0 + k < K) v = B[(long long)(n0 + r) * brs + (long long)(k0 + k) * bcs];
+      sB[r * GPITCH + k] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kBK; kk += 4) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = sA[(wm * 32 + i * 8 + g) * GPITCH + kk + t];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = sB[(wn * 32 + j * 8 + g) * GPITCH + kk + t];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + wm * 32 + i * 8 + g;
+    if (r >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = n0 + wn * 32 + j * 8 + 2 * t + q;
+        if (c >= N) continue;
+        double* dst = C + (long long)r * ldc + c;
+        *dst = (beta == 0.0) ? alpha * acc[i][j][q] : alpha * acc[i][j][q] + beta * (*dst);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static bool make_map_2d(CUtensorMap* tm, const double* base, long long rows, long long cols,
+                        long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 8};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int WARPS_M, int WARPS_N, int MB, int NB, int STAGES>
+static int launch_tma(cudaStream_t st, int M, int N, int K, double alpha, const double* A,
+                      long long lda, const double* B, long long ldb, double beta, double* C,
+                      long long ldc, double* ws, long long ws_bytes) {
+  using Cfg = TileCfg<WARPS_M, WARPS_N, MB, NB, STAGES>;
+  auto kern = dgemm_tn_tma_kernel<WARPS_M, WARPS_N, MB, NB, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADCCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  if (!make_map_2d(&tmA, A, M, K, lda, Cfg::BM) || !make_map_2d(&tmB, B, N, K, ldb, Cfg::BN))
+    return fail("cuTensorMapEncodeTiled failed");
+  const int tm = (M + Cfg::BM - 1) / Cfg::BM, tn = (N + Cfg::BN - 1) / Cfg::BN;
+  const long long tiles = (long long)tm * tn;
+  // split K when the output has too few tiles to fill the machine
+  int splits = 1;
+  const int nsm = sm_count();
+  const int k_slabs = (K + kBK - 1) / kBK;
+  if (tiles < nsm && k_slabs >= 64 && ws != nullptr) {
+    splits = (int)((2LL * nsm + tiles - 1) / tiles);
+    if (splits > k_slabs / 16) splits = k_slabs / 16;
+    const long long per = (long long)M * N * 8;
+    if (per > 0 && (long long)splits * per > ws_bytes) splits = (int)(ws_bytes / per);
+    if (splits < 1) splits = 1;
+  }
+  int k_per_split = ((k_slabs + splits - 1) / splits) * kBK;
+  splits = (K + k_per_split - 1) / k_per_split;
+  dim3 grid(tm, tn, splits);
+  if (tn > 65535) return fail("dgemm: too many N tiles");
+  double* partial = splits > 1 ? ws : nullptr;
+  kern<<<grid, Cfg::kThreads, Cfg::SMEM_BYTES, st>>>(tmA, tmB, C, ldc, M, N, K, k_per_split, alpha,
+                                                    beta, partial);
+  ADCCB_LAUNCH_OK();
+  count_launch();
+  if (splits > 1) {
+    const long long MN = (long long)M * N;
+    int blocks = (int)std::min<long long>((MN + 255) / 256, 4LL * nsm);
+    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(partial, splits, MN, N, C, ldc, alpha, beta);
+    ADCCB_LAUNCH_OK();
+    count_launch();
+  }
+  return 0;
+}
+
+int dgemm_strided(cudaStream_t st, long long M, long long N, long long K, double alpha,
+                  const double* A, long long ars, long long acs, const double* B, long long brs,
+                  long long bcs, double beta, double* C, long long ldc, double* ws,
+                  long long ws_bytes, int tile_hint) {
+  if (M <= 0 || N <= 0) return 0;
+  if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff) return fail("dgemm: extent exceeds int32");
+  if (K <= 0) {
+    // C = beta * C
+    dim3 grid((unsigned)((M + GB - 1) / GB), (unsigned)((N + GB - 1) / GB));
+    dgemm_generic_kernel<<<grid, 128, 0, st>>>((int)M, (int)N, 0, alpha, A, ars, acs, B, brs, bcs, beta, C, ldc);
+    ADCCB_LAUNCH_OK();
+    count_launch();
+    return 0;
+  }
+  const bool tma_ok = acs == 1 && bcs == 1 && (ars % 2 == 0) && (brs % 2 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && get_encode_fn() != nullptr &&
+                      ((long long)M * N * K >= 32LL * 32 * 32);
+  if (tma_ok) {
+    // tile choice: 112-row tiles waste less when M is just above a multiple of 112
+    // (e.g. 780 occupied pairs -> 7 x 112 = 784 instead of 7 x 128 = 896)
+    auto waste = [](long long m, int bm) { return ((m + bm - 1) / bm) * bm - m; };
+    bool use112 = tile_hint == 112 || (tile_hint == 0 && waste(M, 112) * 1.0 / 112 < waste(M, 128) * 1.0 / 128 &&
+                                       (M + 111) / 112 * 112 < (M + 127) / 128 * 128);
+    if (use112)
+      return launch_tma<1, 8, 14, 2, 6>(st, (int)M, (int)N, (int)K, alpha, A, ars, B, brs, beta, C, ldc, ws, ws_bytes);
+    return launch_tma<2, 4, 8, 4, 6>(st, (int)M, (int)N, (int)K, alpha, A, ars, B, brs, beta, C, ldc, ws, ws_bytes);
+  }
+  dim3 grid((unsigned)((M + GB - 1) / GB), (unsigned)((N + GB - 1) / GB));
+  if (grid.y > 65535) return fail("dgemm(generic): too many N tiles");
+  dgemm_generic_kernel<<<grid, 128, 0, st>>>((int)M, (int)N, (int)K, alpha, A, ars, acs, B, brs, bcs, beta, C, ldc);
+  ADCCB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+}  // namespace adccb

@@ -1,0 +1,87 @@
+/* adccb.h - C ABI of the B200 (sm_100a) tensor backend that replaces adcc's libtensor
+ * TensorImpl path for the ADC matvec + Davidson hot path.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, non-zero on failure; the message of the last
+ *     failure on the calling thread is returned by adccb_last_error() (the Python shim turns
+ *     it into ValueError / RuntimeError as libadcc_src/pyiface/ExportAdcc.cc:63-71 does);
+ *   - all pointers are DEVICE pointers to FP64 data unless a parameter is named host_*;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are
+ *     asynchronous with respect to the host; nothing is owned or freed by the library;
+ *   - tensors are dense, row-major; extents/strides are counted in elements (int64).
+ *
+ * Each function cites the reference interface it replaces (paths relative to the adcc
+ * source tree, v0.18.0).
+ */
+#ifndef ADCCB_H
+#define ADCCB_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int adccb_version(void);
+const char* adccb_last_error(void);
+/* number of kernels launched by this library in the current process (bench: gpu_launches) */
+long long adccb_launch_count(void);
+/* SM count and compute capability of the current device */
+int adccb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* K1 contraction core.  C[m,n] = alpha * sum_k A(m,k) * B(n,k) + beta * C[m,n],
+ * A(m,k) = A[m*a_rs + k*a_cs], B(n,k) = B[n*b_rs + k*b_cs], C row-major with leading dim ldc.
+ * K-contiguous, 16-byte aligned operands take the TMA + DMMA path, everything else the
+ * generic DMMA path.  `ws` is scratch for split-K partials (may be NULL: no split-K).
+ * tile_hint: 0 = automatic, 112 / 128 = force the row-tile height.
+ * Replaces libadcc::TensorImpl<N>::tensordot -> libtensor::expr::contract + eval
+ * (libadcc_src/TensorImpl.cc:856-876, 901-1117; libadcc_src/Tensor.hh:189-196). */
+int adccb_dgemm(void* stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A,
+                int64_t a_rs, int64_t a_cs, const double* B, int64_t b_rs, int64_t b_cs,
+                double beta, double* C, int64_t ldc, double* ws, int64_t ws_bytes, int tile_hint);
+
+/* out[o] = alpha * in[sum_d o_d * in_stride[d]] + gamma * add[o] + beta * out[o] for a
+ * contiguous `out` of the given shape (rank <= 8); `add` may be NULL.
+ * Covers transpose / copy / diagonal extraction / (anti)symmetrisation:
+ * libadcc_src/TensorImpl.cc:681-717 (transpose), :667-678 (copy), :489-565 (diagonal),
+ * :1147-1264 (symmetrise / antisymmetrise; libadcc_src/Tensor.hh:218-244). */
+int adccb_strided_gather(void* stream, int ndim, const int64_t* shape, const int64_t* in_stride,
+                         double alpha, const double* in, double gamma, const double* add,
+                         double beta, double* out);
+
+/* out = alpha * f(x, y) + beta * out over n elements; op: 0 x, 1 x*y, 2 x/y, 3 c (fill),
+ * 4 x/(y - c) (Jacobi preconditioner, adcc/solver/preconditioner.py:65-82), 5 x + c.
+ * Replaces scale/add/multiply/divide/set_mask: libadcc_src/TensorImpl.cc:568-664, :431-462. */
+int adccb_elementwise(void* stream, int op, int64_t n, double alpha, const double* x,
+                      const double* y, double c, double beta, double* out);
+
+/* out[p*nb + q] = sa * a[p] + sb * b[q].  libadcc_src/TensorImpl.cc:741-789 (direct_sum). */
+int adccb_direct_sum(void* stream, int64_t na, int64_t nb, double sa, const double* a, double sb,
+                     const double* b, double* out);
+
+/* out = beta * out + sum_k host_coeff[k] * host_ptrs[k][:] (one pass over all inputs).
+ * libadcc_src/TensorImpl.cc:604-624 (add_linear_combination) reached from
+ * libadcc_src/pyiface/export_Tensor.cc:260-277 (linear_combination_strict). */
+int adccb_lincomb(void* stream, int nvec, const double* host_coeff, const double* const* host_ptrs,
+                  int64_t n, double beta, double* out);
+
+/* out_dev[j] = beta * out_dev[j] + scale * <x, y_j>, j < nvec, in one pass over x and every
+ * y_j with a fixed-order two-stage reduction.  ws: >= 32*592*8 bytes of device scratch.
+ * libadcc_src/TensorImpl.cc:1120-1144 (dot with a list), libadcc_src/Tensor.hh:198-206. */
+int adccb_dot_many(void* stream, int nvec, const double* x, const double* const* host_ys, int64_t n,
+                   double scale, double beta, double* out_dev, double* ws, int64_t ws_bytes);
+
+/* Spin-block symmetry of restricted singlet (fac=+1) / triplet (fac=-1) vectors on dense
+ * [alpha|beta]^rank tensors (rank 2 or 4): out = (T + fac * flip(T)) / 2, spin-changing blocks
+ * zeroed.  Dense counterpart of the spin-block maps adcc/guess/guess_zero.py:121-161 that
+ * libtensor keeps structurally (libadcc_src/TensorImpl/as_lt_symmetry.cc:100-172). */
+int adccb_spin_project(void* stream, int ndim, const int* shape, const int* n_alpha, double fac,
+                       const double* in, double* out);
+
+/* In-place singlet purification of a doubles tensor T[i,j,a,b]:
+ * T[aaaa] = T[abab] + T[abba], T[bbbb] = T[aaaa].
+ * libadcc_src/amplitude_vector_enforce_spin_kind.cc:33-170. */
+int adccb_spin_singlet(void* stream, const int* shape, const int* n_alpha, double* T);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADCCB_H */

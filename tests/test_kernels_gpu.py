@@ -1,0 +1,132 @@
+"""Kernel-level parity: every C-ABI entry point against NumPy on the same seeded inputs."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def be():
+    import torch
+    from adcc_b200 import backend
+    torch.cuda.set_device(0)
+    return backend
+
+
+def _rel(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (780, 1000, 2048), (100, 36, 10), (1, 7, 50),
+                                   (257, 130, 4098), (40, 400, 40000), (16, 16, 2)])
+def test_gemm_tn_tma(be, M, N, K):
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((M, K))
+    B = rng.standard_normal((N, K))
+    C = be.gemm(be.from_numpy(A), be.from_numpy(B)).cpu().numpy()
+    ref = A @ B.T
+    assert _rel(C, ref) < 1e-13
+    # alpha / beta
+    C0 = rng.standard_normal((M, N))
+    out = be.from_numpy(C0)
+    be.gemm(be.from_numpy(A), be.from_numpy(B), out=out, alpha=-0.5, beta=2.0)
+    assert _rel(out.cpu().numpy(), -0.5 * ref + 2.0 * C0) < 1e-13
+
+
+@pytest.mark.parametrize("hint", [112, 128])
+def test_gemm_tile_variants(be, hint):
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((300, 514))
+    B = rng.standard_normal((333, 514))
+    C = be.gemm(be.from_numpy(A), be.from_numpy(B), tile_hint=hint).cpu().numpy()
+    assert _rel(C, A @ B.T) < 1e-13
+
+
+def test_gemm_generic_strides(be):
+    rng = np.random.default_rng(7)
+    # odd leading dimension -> generic path; transposed operands
+    A = rng.standard_normal((37, 51))
+    B = rng.standard_normal((29, 51))
+    C = be.gemm(be.from_numpy(A), be.from_numpy(B)).cpu().numpy()
+    assert _rel(C, A @ B.T) < 1e-13
+    At = be.from_numpy(A.T.copy()).t()      # (37,51) view with strides (1,37)
+    Bt = be.from_numpy(B.T.copy()).t()
+    C = be.gemm(At, Bt).cpu().numpy()
+    assert _rel(C, A @ B.T) < 1e-13
+    # empty K
+    out = be.from_numpy(np.ones((4, 5)))
+    be.gemm(be.empty((4, 0)), be.empty((5, 0)), out=out, beta=3.0)
+    assert np.allclose(out.cpu().numpy(), 3.0)
+
+
+@pytest.mark.parametrize("shape,perm", [((6, 5, 4, 3), (1, 0, 3, 2)), ((10, 10, 38, 38), (2, 3, 0, 1)),
+                                        ((33, 65), (1, 0)), ((4, 9, 7), (2, 0, 1)), ((5,), (0,)),
+                                        ((3, 4, 5, 6, 7), (4, 2, 0, 3, 1)), ((40, 40, 64, 64), (0, 2, 1, 3))])
+def test_permute(be, shape, perm):
+    rng = np.random.default_rng(3)
+    T = rng.standard_normal(shape)
+    out = be.permute(be.from_numpy(T), perm).cpu().numpy()
+    assert np.array_equal(out, T.transpose(perm))
+
+
+def test_gather_symmetrise_and_diagonal(be):
+    rng = np.random.default_rng(11)
+    T = rng.standard_normal((6, 6, 8, 8))
+    t = be.from_numpy(T)
+    # antisymmetrise(0,1) = 0.5*(T - T.swap) in one pass
+    out = be.permute(t, (1, 0, 2, 3), alpha=-0.5, add=t, gamma=0.5).cpu().numpy()
+    assert np.allclose(out, 0.5 * (T - T.transpose(1, 0, 2, 3)), atol=1e-15)
+    # diagonal "iaia->ia"
+    X = rng.standard_normal((5, 7, 5, 7))
+    x = be.from_numpy(X)
+    d = be.gather(x, (5, 7), (x.stride(0) + x.stride(2), x.stride(1) + x.stride(3))).cpu().numpy()
+    assert np.array_equal(d, np.einsum("iaia->ia", X))
+
+
+def test_elementwise_family(be):
+    rng = np.random.default_rng(2)
+    x, y = rng.standard_normal(10007), rng.standard_normal(10007) + 3.0
+    dx, dy = be.from_numpy(x), be.from_numpy(y)
+    assert np.array_equal(be.mul(dx, dy).cpu().numpy(), x * y)
+    assert np.array_equal(be.div(dx, dy).cpu().numpy(), x / y)
+    assert np.array_equal(be.div_shift(dx, dy, 0.25).cpu().numpy(), x / (y - 0.25))
+    assert np.array_equal(be.add_scalar(dx, 1.5).cpu().numpy(), x + 1.5)
+    z = be.from_numpy(y)
+    be.axpby(2.0, dx, -1.0, z)
+    assert np.allclose(z.cpu().numpy(), 2.0 * x - y, rtol=1e-15)
+    a, b = rng.standard_normal((4, 5)), rng.standard_normal((3,))
+    ds = be.direct_sum(be.from_numpy(a), be.from_numpy(b), 1.0, -1.0).cpu().numpy()
+    assert np.array_equal(ds, a[:, :, None] - b[None, None, :])
+
+
+def test_lincomb_and_dots(be):
+    rng = np.random.default_rng(4)
+    n, k = 123457, 37
+    X = rng.standard_normal((k, n))
+    c = rng.standard_normal(k)
+    ts = [be.from_numpy(X[i]) for i in range(k)]
+    out = be.lincomb(c, ts).cpu().numpy()
+    assert _rel(out, c @ X) < 1e-14
+    d = be.dot_many(ts[0], ts)
+    assert _rel(d, X @ X[0]) < 1e-13
+    # deterministic
+    assert np.array_equal(d, be.dot_many(ts[0], ts))
+    # empty / tiny
+    e = be.from_numpy(np.array([2.0]))
+    assert be.dot(e, e) == 4.0
+
+
+def test_spin_kernels(be):
+    from oracle.davidson import enforce_spin_maps, enforce_spin_kind
+    rng = np.random.default_rng(9)
+    na = [3, 3, 4, 4]
+    T = rng.standard_normal((6, 6, 8, 8))
+    S = rng.standard_normal((6, 8))
+    for fac in (1.0, -1.0):
+        ref = enforce_spin_maps({"ph": S.copy(), "pphh": T.copy()}, na, fac)
+        assert np.allclose(be.spin_project(be.from_numpy(T), na, fac).cpu().numpy(), ref["pphh"], atol=1e-15)
+        assert np.allclose(be.spin_project(be.from_numpy(S), [3, 4], fac).cpu().numpy(), ref["ph"], atol=1e-15)
+    ref = enforce_spin_kind(T.copy(), na, "singlet")
+    t = be.from_numpy(T)
+    be.spin_singlet_(t, na)
+    assert np.array_equal(t.cpu().numpy(), ref)
