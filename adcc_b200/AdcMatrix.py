@@ -1,0 +1,292 @@
+"""ADC secular matrix: block table interpreter, diagonal, matvec.
+
+API of adcc/AdcMatrix.py:205-472 (``AdcMatrix(method, hf_or_mp, block_orders, intermediates,
+diagonal_precomputed)``, ``matvec`` / ``@`` / ``rmatvec``, ``block_apply``, ``diagonal``,
+``blocks``, ``axis_blocks``/``axis_spaces``/``axis_lengths``/``shape``,
+``construct_symmetrisation_for_blocks``, ``block_view``) and the block-order rules of
+:74-130.  The blocks are the contraction tables of adcc_b200/adc_pp.py; ``matvec`` evaluates
+all terms of all blocks and merges the terms of each output block in one fused lincomb launch.
+"""
+import numpy as np
+
+from . import adc_pp
+from .AdcMethod import AdcMethod
+from .AmplitudeVector import AmplitudeVector
+from .functions import einsum, linear_combination_strict
+from .Intermediates import Intermediates
+from .LazyMp import LazyMp
+from .ReferenceState import ReferenceState
+from .Tensor import Tensor
+from .timings import Timer
+
+_SPECIAL_ORDERS = {"adc2x": {"ph_ph": 2, "ph_pphh": 1, "pphh_ph": 1, "pphh_pphh": 1}}
+
+
+class AdcMatrixlike:
+    """Marker base class for objects that behave like an ADC matrix."""
+
+
+def default_block_orders(method):
+    base = method.base_method.name
+    if base in _SPECIAL_ORDERS:
+        return dict(_SPECIAL_ORDERS[base])
+    level = method.level
+    spaces = ["ph", "pphh"][:level // 2 + 1]
+    ret = {}
+    for i1, bra in enumerate(spaces):
+        for i2, ket in enumerate(spaces):
+            order = level - i1 - i2
+            ret[f"{bra}_{ket}"] = None if order < 0 else order
+    return ret
+
+
+class AdcMatrix(AdcMatrixlike):
+    def __init__(self, method, hf_or_mp, block_orders=None, intermediates=None,
+                 diagonal_precomputed=None):
+        if isinstance(hf_or_mp, ReferenceState):
+            hf_or_mp = LazyMp(hf_or_mp)
+        elif not isinstance(hf_or_mp, LazyMp):
+            try:
+                hf_or_mp = LazyMp(ReferenceState(hf_or_mp))
+            except Exception:
+                raise TypeError("hf_or_mp is not a valid object. It needs to be either a LazyMp, "
+                                "a ReferenceState or SCF data.")
+        if not isinstance(method, AdcMethod):
+            method = AdcMethod(method)
+        if diagonal_precomputed is not None and not isinstance(diagonal_precomputed, AmplitudeVector):
+            raise TypeError("diagonal_precomputed needs to be an AmplitudeVector.")
+
+        self.timer = Timer()
+        self.method = method
+        self.ground_state = hf_or_mp
+        self.reference_state = hf_or_mp.reference_state
+        self.mospaces = self.reference_state.mospaces
+        self.is_core_valence_separated = method.is_core_valence_separated
+        self.ndim = 2
+        self.extra_terms = []
+        self.intermediates = intermediates if intermediates is not None else Intermediates(hf_or_mp)
+
+        hf = self.reference_state
+        if hf.has_core_occupied_space and not self.is_core_valence_separated:
+            raise ValueError("Cannot run a general (non-core-valence approximated) ADC method on "
+                             "top of a ground state with a core-valence separation.")
+        if not hf.has_core_occupied_space and self.is_core_valence_separated:
+            raise ValueError("Cannot run a core-valence approximated ADC method on top of a "
+                             "ground state without a core-valence separation.")
+
+        self.block_orders = default_block_orders(method)
+        if block_orders is not None:
+            self.block_orders.update(block_orders)
+        self._validate_block_orders()
+        self._variant = "cvs" if self.is_core_valence_separated else ""
+        self._const = {}
+
+        with self.timer.record("build"):
+            self._tables = {}
+            for blk, order in self.block_orders.items():
+                if order is None:
+                    continue
+                key = (self._variant, blk, order)
+                if key not in adc_pp.BLOCKS:
+                    raise ValueError(f"Could not dispatch: spaces={blk.split('_')} order={order} "
+                                     f"variant={self._variant}. Probably the secular matrix is not "
+                                     "implemented for the requested method.")
+                self._tables[blk] = adc_pp.BLOCKS[key]
+            self.blocks = {blk: self._make_apply(blk) for blk in self._tables}
+            # resolve constant operands now: triggers ERI staging and intermediate builds
+            for blk in self._tables:
+                for _, expr in self._tables[blk][2]:
+                    self._resolve_constants(expr)
+            if diagonal_precomputed is not None:
+                self._diagonal = diagonal_precomputed
+            else:
+                diag = 0
+                for blk, order in self.block_orders.items():
+                    if order is None:
+                        continue
+                    d = adc_pp.diagonal(self._variant, blk, order, hf, self.ground_state,
+                                        self.intermediates)
+                    if isinstance(d, AmplitudeVector):
+                        diag = d if isinstance(diag, int) else diag + d
+                self._diagonal = diag.evaluate()
+                for t in self._diagonal.values():
+                    t._contig()
+            self._init_space_data(self._diagonal)
+
+    # ------------------------------------------------------------------ bookkeeping
+    def _validate_block_orders(self):
+        for block, order in self.block_orders.items():
+            if order is None:
+                continue
+            if order < 0:
+                raise ValueError("block orders need to be non-negative")
+            bra, ket = block.split("_")
+            for sp in (bra, ket):
+                n_p, n_h = sp.count("p"), sp.count("h")
+                if "p" * n_p + "h" * n_h != sp or n_p != n_h:
+                    raise ValueError(f"Invalid block {block} for a pp ADC matrix.")
+            if bra == ket:
+                continue
+            inv = self.block_orders.get(f"{ket}_{bra}")
+            if inv is None or inv != order:
+                raise ValueError(f"{block} and {ket}_{bra} should always have the same order.")
+            if self.block_orders.get(f"{bra}_{bra}") is None or self.block_orders.get(f"{ket}_{ket}") is None:
+                raise ValueError(f"Can only have a coupling block {block} if both diagonal blocks "
+                                 "are in the matrix too.")
+
+    def _init_space_data(self, diagonal):
+        self.axis_spaces = {}
+        self.axis_lengths = {}
+        for block in diagonal.blocks:
+            self.axis_spaces[block] = list(diagonal[block].subspaces)
+            self.axis_lengths[block] = int(np.prod([self.mospaces.n_orbs(sp)
+                                                    for sp in self.axis_spaces[block]]))
+        n = sum(self.axis_lengths.values())
+        self.shape = (n, n)
+
+    def __repr__(self):
+        ret = f"AdcMatrix({self.method.name}, "
+        for blk, o in self.block_orders.items():
+            ret += f"{blk}={o}, "
+        return ret + ")"
+
+    def __len__(self):
+        return self.shape[0]
+
+    @property
+    def axis_blocks(self):
+        return sorted(self.axis_spaces, key=len)
+
+    def diagonal(self):
+        return self._diagonal
+
+    # ------------------------------------------------------------------ interpreter
+    def _operand(self, name, ampl):
+        if name == "u1":
+            return ampl["ph"]
+        if name == "u2":
+            return ampl["pphh"]
+        if name not in self._const:
+            if name == "t2":
+                t = self.ground_state.t2oo
+            elif name in adc_pp.INTERMEDIATES or name in Intermediates.generators:
+                t = getattr(self.intermediates, name)
+            else:
+                t = getattr(self.reference_state, name)
+            self._const[name] = t
+        return self._const[name]
+
+    def _resolve_constants(self, expr):
+        if expr[0] == "einsum":
+            for op in expr[2]:
+                if isinstance(op, tuple):
+                    self._resolve_constants(op)
+                elif op not in ("u1", "u2"):
+                    self._operand(op, None)
+        else:
+            self._resolve_constants(expr[1])
+
+    def _eval(self, expr, ampl):
+        kind = expr[0]
+        if kind == "einsum":
+            ops = [self._eval(o, ampl) if isinstance(o, tuple) else self._operand(o, ampl)
+                   for o in expr[2]]
+            return einsum(expr[1], *ops)
+        t = self._eval(expr[1], ampl)
+        if kind == "asym":
+            for pair in expr[2]:
+                t = t.antisymmetrise(*pair)
+            return t
+        if kind == "sym":
+            return t.symmetrise(*expr[2])
+        raise ValueError(kind)
+
+    def _terms(self, blk, ampl):
+        inb, outb, terms = self._tables[blk]
+        if inb is None or inb not in ampl:
+            return None, []
+        return outb, [(c, self._eval(e, ampl)) for c, e in terms]
+
+    def _make_apply(self, blk):
+        def apply(ampl):
+            outb, terms = self._terms(blk, ampl)
+            if not terms:
+                return 0
+            res = linear_combination_strict([c for c, _ in terms], [t for _, t in terms])
+            return AmplitudeVector(**{outb: res})
+        return apply
+
+    def block_apply(self, block, tensor):
+        if not isinstance(tensor, Tensor):
+            raise TypeError("tensor should be an adcc.Tensor")
+        with self.timer.record(f"apply/{block}"):
+            outblock, inblock = block.split("_")
+            ret = self.blocks[block](AmplitudeVector(**{inblock: tensor}))
+            return getattr(ret, outblock)
+
+    def matvec(self, v):
+        """sigma = M v  (adcc/AdcMatrix.py:390-396)."""
+        with self.timer.record("matvec"):
+            if self.extra_terms:
+                return sum(block(v) for block in self.blocks.values())
+            collected = {}
+            for blk in self._tables:
+                outb, terms = self._terms(blk, v)
+                if terms:
+                    collected.setdefault(outb, []).extend(terms)
+            return AmplitudeVector(**{
+                outb: linear_combination_strict([c for c, _ in terms], [t for _, t in terms])
+                for outb, terms in collected.items()})
+
+    def rmatvec(self, v):
+        return self.matvec(v)
+
+    def __matmul__(self, other):
+        if isinstance(other, AmplitudeVector):
+            return self.matvec(other)
+        if isinstance(other, list) and all(isinstance(e, AmplitudeVector) for e in other):
+            return [self.matvec(ov) for ov in other]
+        return NotImplemented
+
+    def block_view(self, block):
+        b1, b2 = block.split("_")
+        if b1 != b2:
+            raise NotImplementedError("Off-diagonal block views not yet implemented.")
+        block_orders = {bl: None for bl in self.block_orders}
+        block_orders[block] = self.block_orders[block]
+        return AdcMatrix(self.method, self.ground_state, block_orders=block_orders,
+                         intermediates=self.intermediates)
+
+    def construct_symmetrisation_for_blocks(self):
+        """adcc/AdcMatrix.py:431-472."""
+        ret = {}
+        if self.is_core_valence_separated:
+            ret["pphh"] = lambda v: v.antisymmetrise([(2, 3)])
+        else:
+            def symmetrise_generic_adc_doubles(invec):
+                scratch = invec.antisymmetrise([(0, 1)]).antisymmetrise([(2, 3)])
+                return scratch.symmetrise([(0, 1), (2, 3)])
+            ret["pphh"] = symmetrise_generic_adc_doubles
+        return ret
+
+    def to_ndarray(self, out=None):
+        """Dense matrix in the plain (non-orthonormalised) product basis; tests only."""
+        n = self.shape[0]
+        mat = np.zeros((n, n))
+        diag = self._diagonal
+        offs, off = {}, 0
+        for blk in self.axis_blocks:
+            offs[blk] = off
+            off += self.axis_lengths[blk]
+        for col in range(n):
+            vec = diag.zeros_like()
+            for blk in self.axis_blocks:
+                if offs[blk] <= col < offs[blk] + self.axis_lengths[blk]:
+                    arr = np.zeros(self.axis_lengths[blk])
+                    arr[col - offs[blk]] = 1.0
+                    vec[blk] = Tensor.from_ndarray(self.mospaces, self.axis_spaces[blk],
+                                                   arr.reshape(diag[blk].shape))
+            res = self.matvec(vec)
+            for blk in res.blocks:
+                mat[offs[blk]:offs[blk] + self.axis_lengths[blk], col] = res[blk].to_ndarray().ravel()
+        return mat

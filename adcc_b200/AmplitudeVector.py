@@ -1,0 +1,105 @@
+"""Block vector of the ADC eigenproblem: {"ph": Tensor, "pphh": Tensor}.
+
+Same behaviour as adcc/AmplitudeVector.py:25-165: attribute access to blocks, blockwise
+arithmetic with scalars or other vectors, ``__add__`` tolerating missing blocks and dropping
+blocks that sum to the integer 0, ``dot`` with one vector (float) or a list (ndarray), ``@``.
+"""
+import numpy as np
+
+
+class AmplitudeVector(dict):
+    def __init__(self, **blocks):
+        super().__init__(**blocks)
+
+    def __getattr__(self, key):
+        try:
+            return self[key]
+        except KeyError:
+            raise AttributeError(key)
+
+    def __setattr__(self, key, item):
+        if key in self:
+            self[key] = item
+        else:
+            raise AttributeError(key)
+
+    @property
+    def blocks(self):
+        return sorted(self.keys())
+
+    @property
+    def needs_evaluation(self):
+        return any(t.needs_evaluation for t in self.values())
+
+    def evaluate(self):
+        for t in self.values():
+            t.evaluate()
+        return self
+
+    def _map(self, fn):
+        return AmplitudeVector(**{k: fn(t) for k, t in self.items()})
+
+    def copy(self): return self._map(lambda t: t.copy())
+    def ones_like(self): return self._map(lambda t: t.ones_like())
+    def empty_like(self): return self._map(lambda t: t.empty_like())
+    def nosym_like(self): return self._map(lambda t: t.nosym_like())
+    def zeros_like(self): return self._map(lambda t: t.zeros_like())
+
+    def set_random(self):
+        for t in self.values():
+            t.set_random()
+        return self
+
+    def dot(self, other):
+        if isinstance(other, list):
+            return sum(np.asarray(self[b].dot([av[b] for av in other])) for b in self.keys())
+        return sum(self[b].dot(other[b]) for b in self.keys())
+
+    def __matmul__(self, other):
+        if isinstance(other, AmplitudeVector):
+            return self.dot(other)
+        if isinstance(other, list) and all(isinstance(e, AmplitudeVector) for e in other):
+            return self.dot(other)
+        return NotImplemented
+
+    def _blockwise(self, fname, other):
+        if isinstance(other, AmplitudeVector):
+            if sorted(other.blocks) != sorted(self.blocks):
+                raise ValueError(f"Blocks of both AmplitudeVector objects need to agree to perform {fname}")
+            ret = {k: getattr(t, fname)(other[k]) for k, t in self.items()}
+        else:
+            ret = {k: getattr(t, fname)(other) for k, t in self.items()}
+        if any(r is NotImplemented for r in ret.values()):
+            return NotImplemented
+        return AmplitudeVector(**ret)
+
+    def __mul__(self, o): return self._blockwise("__mul__", o)
+    def __rmul__(self, o): return self._blockwise("__rmul__", o)
+    def __sub__(self, o): return self._blockwise("__sub__", o)
+    def __rsub__(self, o): return self._blockwise("__rsub__", o)
+    def __truediv__(self, o): return self._blockwise("__truediv__", o)
+    def __imul__(self, o): return self._blockwise("__imul__", o)
+    def __iadd__(self, o): return self._blockwise("__iadd__", o)
+    def __isub__(self, o): return self._blockwise("__isub__", o)
+    def __itruediv__(self, o): return self._blockwise("__itruediv__", o)
+
+    def __add__(self, other):
+        if isinstance(other, AmplitudeVector):
+            ret = {}
+            for k in sorted(set(self.blocks) | set(other.blocks)):
+                a, b = self.get(k, 0), other.get(k, 0)
+                v = b if isinstance(a, int) and a == 0 else (a if isinstance(b, int) and b == 0 else a + b)
+                if not (isinstance(v, int) and v == 0):
+                    ret[k] = v
+            return AmplitudeVector(**ret)
+        return AmplitudeVector(**{k: t + other for k, t in self.items()})
+
+    def __radd__(self, other):
+        if isinstance(other, AmplitudeVector):
+            return other.__add__(self)
+        if isinstance(other, int) and other == 0:   # sum() start value
+            return self
+        return AmplitudeVector(**{k: other + t for k, t in self.items()})
+
+    def __repr__(self):
+        return "AmplitudeVector(" + "=..., ".join(self.blocks) + "=...)"

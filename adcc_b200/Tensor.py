@@ -1,0 +1,419 @@
+"""Device-resident FP64 tensor with the adcc.Tensor / libadcc.Tensor interface.
+
+Contract mirrored: libadcc_src/Tensor.hh:45-417 (method semantics), the Python-visible
+surface libadcc.pyi:633-793 / libadcc_src/pyiface/export_Tensor.cc:424-544 (operators,
+overloads, argument forms) and adcc/Tensor.py:28-112.  The libtensor backend
+(libadcc_src/TensorImpl.cc) is replaced by dense spin-orbital storage in HBM (a torch CUDA
+buffer used as memory only) operated on by the sm_100a kernels behind include/adccb.h.
+Evaluation is eager: ``needs_evaluation`` is always False and ``evaluate()`` returns self;
+``transpose`` is a zero-copy stride view like the reference's deferred permutation
+(TensorImpl.cc:681-717).
+"""
+import numbers
+import numpy as np
+import torch
+
+from . import backend as be
+from .Symmetry import Symmetry
+from .MoSpaces import split_spaces
+
+
+def _parse_perm_args(args):
+    """Accept (0,1) | [(0,1),(2,3)] | ((0,1),(2,3)) | (0,1),(2,3)  (export_Tensor.cc:33-59)."""
+    if len(args) == 1 and isinstance(args[0], (list, tuple)) and len(args[0]) > 0 \
+            and isinstance(args[0][0], (list, tuple)):
+        args = tuple(args[0])
+    if len(args) > 0 and all(isinstance(a, numbers.Integral) for a in args):
+        args = (tuple(args),)
+    perms = [tuple(int(x) for x in a) for a in args]
+    return perms
+
+
+class Tensor:
+    def __init__(self, sym_or_mo, space=None, permutations=None, spin_block_maps=None,
+                 spin_blocks_forbidden=None):
+        if isinstance(sym_or_mo, Symmetry):
+            sym = sym_or_mo
+        else:
+            if space is None:
+                raise ValueError("space needs to be given if a MoSpaces object is passed")
+            sym = Symmetry(sym_or_mo, space, permutations, spin_block_maps, spin_blocks_forbidden)
+        self.mospaces = sym.mospaces
+        self.subspaces = list(sym.subspaces)
+        self.symmetry = sym
+        self._data = be.zeros(sym.shape)
+        self._mutable = True
+        self._layouts = {}
+
+    # ------------------------------------------------------------------ construction helpers
+    @classmethod
+    def _wrap(cls, mospaces, subspaces, data, symmetry=None):
+        self = cls.__new__(cls)
+        self.mospaces = mospaces
+        self.subspaces = list(subspaces)
+        self.symmetry = symmetry
+        self._data = data
+        self._mutable = True
+        self._layouts = {}
+        return self
+
+    def _like(self, data, keep_symmetry=True):
+        return Tensor._wrap(self.mospaces, self.subspaces, data,
+                            self.symmetry if keep_symmetry else None)
+
+    @classmethod
+    def from_ndarray(cls, mospaces, space, array, symmetry=None):
+        subspaces = split_spaces(space) if isinstance(space, str) else list(space)
+        return cls._wrap(mospaces, subspaces, be.from_numpy(array), symmetry)
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def shape(self): return tuple(self._data.shape)
+    @property
+    def ndim(self): return self._data.dim()
+    @property
+    def size(self): return self._data.numel()
+    @property
+    def space(self): return "".join(self.subspaces)
+    @property
+    def mutable(self): return self._mutable
+    @property
+    def needs_evaluation(self): return False
+    @property
+    def T(self): return self.transpose()
+    @property
+    def flags(self): return None
+
+    def __len__(self): return self.shape[0]
+    def evaluate(self): return self
+    def set_immutable(self): self._mutable = False
+
+    def _contig(self):
+        if not self._data.is_contiguous():
+            self._data = be.contiguous(self._data)
+        return self._data
+
+    def _require_mutable(self):
+        if not self._mutable:
+            raise RuntimeError("Tensor is immutable")
+
+    def describe_symmetry(self):
+        return self.symmetry.describe() if self.symmetry is not None else "Symmetry(none)"
+
+    def describe_expression(self, stage="unoptimised"):
+        return f"evaluated dense tensor {self.space} {self.shape}"
+
+    def __repr__(self):
+        return f"Tensor({self.space}, shape={self.shape}, device={self._data.device})"
+
+    # ------------------------------------------------------------------ *_like / fill
+    def copy(self):
+        return self._like(be.scaled_copy(self._data, 1.0))
+
+    def zeros_like(self):
+        return self._like(be.zeros(self.shape))
+
+    empty_like = zeros_like      # export_Tensor.cc:451
+
+    def ones_like(self):
+        t = be.empty(self.shape)
+        be.fill(t, 1.0)
+        return self._like(t)
+
+    def nosym_like(self):
+        return self._like(be.zeros(self.shape), keep_symmetry=False)
+
+    def fill(self, value):
+        self._require_mutable()
+        be.fill(self._contig(), float(value))
+        return self
+
+    def set_random(self):
+        """Random values honouring the permutational symmetry (TensorImpl.cc:465-468)."""
+        self._require_mutable()
+        rng = np.random.default_rng(np.random.randint(0, 2**31 - 1))
+        arr = rng.uniform(-1.0, 1.0, size=self.shape)
+        sym = self.symmetry
+        if sym is not None and sym.has_permutations:
+            acc = np.zeros_like(arr)
+            for axes, sign in sym._perms:
+                acc += sign * arr.transpose(axes)
+            arr = acc / len(sym._perms)
+        self._data = be.from_numpy(arr)
+        return self
+
+    def set_mask(self, mask, value):
+        """Set all elements whose indices agree where the mask letters agree
+        (TensorImpl.cc:406-462), e.g. ``set_mask("ii", 1.0)`` writes the diagonal."""
+        self._require_mutable()
+        if len(mask) != self.ndim:
+            raise ValueError("mask length must equal the tensor rank")
+        letters = sorted(set(mask), key=mask.index)
+        t = self._contig()
+        if len(letters) == self.ndim:
+            be.fill(t, float(value))
+            return
+        # strided view over the generalised diagonal
+        shape, strides = [], []
+        for c in letters:
+            axes = [k for k, m in enumerate(mask) if m == c]
+            ext = {t.shape[a] for a in axes}
+            if len(ext) != 1:
+                raise ValueError("set_mask: axes sharing a letter need equal extents")
+            shape.append(ext.pop())
+            strides.append(sum(t.stride(a) for a in axes))
+        view = torch.as_strided(t, shape, strides)
+        view.fill_(float(value))       # tiny (delta tensors); plain device memset-style write
+
+    # ------------------------------------------------------------------ host transfer
+    def to_ndarray(self):
+        return self._data.detach().cpu().numpy().copy() if self._data.is_contiguous() \
+            else be.contiguous(self._data).cpu().numpy()
+
+    def set_from_ndarray(self, array, symmetry_tolerance=None):
+        self._require_mutable()
+        array = np.asarray(array, dtype=float)
+        if array.shape != self.shape:
+            raise ValueError(f"Shape mismatch: tensor {self.shape} vs array {array.shape}")
+        if symmetry_tolerance is not None and self.symmetry is not None:
+            for axes, sign in self.symmetry._perms[1:]:
+                if np.max(np.abs(array - sign * array.transpose(axes))) > symmetry_tolerance:
+                    raise ValueError("The array does not have the symmetry of the tensor")
+        self._data = be.from_numpy(array)
+        return self
+
+    # ------------------------------------------------------------------ element access
+    def _norm_index(self, index):
+        if not isinstance(index, tuple):
+            index = (index,)
+        if len(index) != self.ndim:
+            raise ValueError("Number of indices does not match the tensor rank")
+        out = []
+        for i, n in zip(index, self.shape):
+            i = int(i)
+            if i < 0:
+                i += n
+            if not 0 <= i < n:
+                raise IndexError("index out of range")
+            out.append(i)
+        return tuple(out)
+
+    def is_allowed(self, index):
+        index = self._norm_index(tuple(index))
+        return True if self.symmetry is None else self.symmetry.is_allowed(index)
+
+    def __getitem__(self, index):
+        index = self._norm_index(index)
+        return float(self._data[index].item())
+
+    def __setitem__(self, index, value):
+        self._require_mutable()
+        index = self._norm_index(index)
+        t = self._contig()
+        if self.symmetry is None or self.symmetry.empty:
+            t[index] = float(value)
+            return
+        orb = self.symmetry.orbit(index, float(value))
+        if orb is None:
+            raise RuntimeError(f"Setting tensor index {index} is not allowed by symmetry "
+                               "(TensorImpl.cc:1268-1271)")
+        idx = torch.tensor([list(k) for k in orb], device=t.device, dtype=torch.long)
+        vals = torch.tensor(list(orb.values()), device=t.device, dtype=t.dtype)
+        t[tuple(idx[:, k] for k in range(self.ndim))] = vals
+
+    def _select(self, n, key, reverse):
+        arr = self.to_ndarray()
+        order = np.argsort(key(arr), axis=None, kind="stable")
+        if reverse:
+            order = order[::-1]
+        out = []
+        sym = self.symmetry if (self.symmetry is not None and not self.symmetry.empty) else None
+        for flat in order:
+            idx = tuple(int(x) for x in np.unravel_index(flat, arr.shape))
+            if sym is not None and not sym.is_canonical(idx):
+                continue
+            out.append((idx, float(arr[idx])))
+            if len(out) >= n:
+                break
+        return out
+
+    def select_n_min(self, n): return self._select(n, lambda a: a, False)
+    def select_n_max(self, n): return self._select(n, lambda a: a, True)
+    def select_n_absmin(self, n): return self._select(n, np.abs, False)
+    def select_n_absmax(self, n): return self._select(n, np.abs, True)
+
+    # ------------------------------------------------------------------ arithmetic
+    def _check_same(self, other):
+        if self.shape != other.shape:
+            raise ValueError(f"Shape mismatch: {self.shape} vs {other.shape}")
+        if self.subspaces != other.subspaces:
+            raise ValueError(f"Subspace mismatch: {self.space} vs {other.space}")
+
+    def __pos__(self): return self
+    def __neg__(self): return self._like(be.scaled_copy(self._data, -1.0))
+
+    def __add__(self, other):
+        if isinstance(other, numbers.Number):
+            if other == 0:
+                return self
+            return self._like(be.add_scalar(self._contig(), float(other)))
+        if isinstance(other, Tensor):
+            self._check_same(other)
+            return self._like(be.lincomb([1.0, 1.0], [self._contig(), other._contig()]))
+        return NotImplemented
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        if isinstance(other, numbers.Number):
+            return self.__add__(-other)
+        if isinstance(other, Tensor):
+            self._check_same(other)
+            return self._like(be.lincomb([1.0, -1.0], [self._contig(), other._contig()]))
+        return NotImplemented
+
+    def __rsub__(self, other):
+        if isinstance(other, numbers.Number):
+            t = be.scaled_copy(self._data, -1.0)
+            return self._like(t if other == 0 else be.add_scalar(t, float(other)))
+        return NotImplemented
+
+    def __mul__(self, other):
+        if isinstance(other, numbers.Number):
+            return self._like(be.scaled_copy(self._data, float(other)))
+        if isinstance(other, Tensor):
+            self._check_same(other)
+            return self._like(be.mul(self._contig(), other._contig()))
+        return NotImplemented
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, other):
+        if isinstance(other, numbers.Number):
+            return self._like(be.scaled_copy(self._data, 1.0 / float(other)))
+        if isinstance(other, Tensor):
+            self._check_same(other)
+            return self._like(be.div(self._contig(), other._contig()))
+        return NotImplemented
+
+    def __iadd__(self, other):
+        self._require_mutable()
+        if isinstance(other, Tensor):
+            self._check_same(other)
+            be.axpby(1.0, other._contig(), 1.0, self._contig())
+            return self
+        return NotImplemented
+
+    def __isub__(self, other):
+        self._require_mutable()
+        if isinstance(other, Tensor):
+            self._check_same(other)
+            be.axpby(-1.0, other._contig(), 1.0, self._contig())
+            return self
+        return NotImplemented
+
+    def __imul__(self, other):
+        self._require_mutable()
+        if isinstance(other, numbers.Number):
+            t = self._contig()
+            be.axpby(float(other), t, 0.0, t)
+            return self
+        return NotImplemented
+
+    def __itruediv__(self, other):
+        if isinstance(other, numbers.Number):
+            return self.__imul__(1.0 / float(other))
+        return NotImplemented
+
+    def div_shifted(self, diagonal, shift):
+        """self / (diagonal - shift) in one kernel (Jacobi preconditioner; the reference
+        materialises ``diagonal - shift`` first, export_Tensor.cc:380-391)."""
+        self._check_same(diagonal)
+        return self._like(be.div_shift(self._contig(), diagonal._contig(), float(shift)))
+
+    def dot(self, other):
+        if isinstance(other, Tensor):
+            self._check_same(other)
+            return be.dot(self._contig(), other._contig())
+        if isinstance(other, (list, tuple)):
+            for o in other:
+                self._check_same(o)
+            return be.dot_many(self._contig(), [o._contig() for o in other])
+        raise TypeError("dot expects a Tensor or a list of Tensors")
+
+    # ------------------------------------------------------------------ index manipulation
+    def transpose(self, axes=None):
+        if axes is None:
+            axes = tuple(reversed(range(self.ndim)))
+        axes = tuple(int(a) for a in axes)
+        if sorted(axes) != list(range(self.ndim)):
+            raise ValueError("axes is not a permutation of the tensor axes")
+        return Tensor._wrap(self.mospaces, [self.subspaces[a] for a in axes],
+                            self._data.permute(axes))
+
+    def diagonal(self, *axes):
+        """Diagonal over the given axes (default: 0 and 1); the diagonal axis is appended last
+        (libadcc_src/Tensor.hh:147-153)."""
+        if len(axes) == 0:
+            axes = (0, 1)
+        if len(axes) == 1 and isinstance(axes[0], (list, tuple)):
+            axes = tuple(axes[0])
+        axes = [int(a) for a in axes]
+        if len(axes) < 2 or len(set(axes)) != len(axes):
+            raise ValueError("diagonal needs at least two distinct axes")
+        if len({self.subspaces[a] for a in axes}) != 1:
+            raise ValueError("diagonal axes need to belong to the same subspace")
+        t = self._data
+        rest = [k for k in range(self.ndim) if k not in axes]
+        shape = [t.shape[k] for k in rest] + [t.shape[axes[0]]]
+        strides = [t.stride(k) for k in rest] + [sum(t.stride(a) for a in axes)]
+        out = be.gather(t, shape, strides)
+        return Tensor._wrap(self.mospaces, [self.subspaces[k] for k in rest] + [self.subspaces[axes[0]]], out)
+
+    def _symm(self, perms, sign):
+        perms = _parse_perm_args(perms)
+        if not perms:
+            if self.ndim != 2:
+                raise ValueError("symmetrise without arguments is only valid for matrices")
+            perms = [(0, 1)]
+        if any(len(p) != 2 for p in perms):
+            raise NotImplementedError("only pair (anti)symmetrisation is implemented")
+        flat = [a for p in perms for a in p]
+        if len(set(flat)) != len(flat):
+            raise ValueError("index pairs need to be disjoint")
+        axes = list(range(self.ndim))
+        for a, b in perms:
+            if self.subspaces[a] != self.subspaces[b]:
+                raise ValueError("(anti)symmetrisation needs axes of the same subspace")
+            axes[a], axes[b] = axes[b], axes[a]
+        base = self._contig()
+        out = be.permute(base, axes, alpha=0.5 * sign, add=base, gamma=0.5)
+        return Tensor._wrap(self.mospaces, self.subspaces, out)
+
+    def symmetrise(self, *perms):
+        """1/2 (T + P T) with all given transpositions applied simultaneously (Tensor.hh:218-231)."""
+        return self._symm(perms, +1.0)
+
+    def antisymmetrise(self, *perms):
+        """1/2 (T - P T)  (Tensor.hh:233-244)."""
+        return self._symm(perms, -1.0)
+
+    def __matmul__(self, other):
+        if isinstance(other, Tensor):
+            from .functions import tensordot
+            return tensordot(self, other, axes=([1], [0]))
+        return NotImplemented
+
+    # ------------------------------------------------------------------ cached layouts
+    def layout(self, axes):
+        """Contiguous copy with permuted axes; cached for immutable tensors (ERI blocks,
+        amplitudes, intermediates) so each constant operand is re-laid out for its GEMM once."""
+        axes = tuple(axes)
+        if axes == tuple(range(self.ndim)) and self._data.is_contiguous():
+            return self._data
+        if not self._mutable and axes in self._layouts:
+            return self._layouts[axes]
+        out = be.permute(self._data, axes)
+        if not self._mutable:
+            self._layouts[axes] = out
+        return out

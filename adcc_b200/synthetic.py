@@ -1,0 +1,50 @@
+"""Synthetic SCF inputs (pure NumPy; inputs only, no arithmetic of the hot path).
+
+``restricted_scf_dict`` builds a restricted closed-shell data dict with the key layout of
+adcc/DataHfProvider.py:84-141 (ERI kept spatial under ``eri_ffff_spatial``) with the shapes of
+BASELINE.json's molecular configs: canonical orbitals (diagonal Fock), a
+random 8-fold-symmetric chemists' ERI scaled so that the ADC matrix stays diagonally dominant,
+identity MO coefficients and random symmetric dipole integrals.
+"""
+import numpy as np
+
+# (n_orb spatial, n_occ spatial, core orbitals for CVS, seed): shapes of SURVEY.md 8.0
+SHAPES = {
+    "h2o_ccpvdz": (24, 5, 0, 1001),      # C1: o=10, v=38 spin orbitals
+    "h2o_ccpvtz": (58, 5, 0, 1002),      # C2: o=10, v=106
+    "methyloxirane_ccpvdz": (86, 16, 0, 1003),   # C3: o=32, v=140
+    "h2o_ccpvtz_cvs": (58, 5, 1, 1002),  # C4: c=2, o=8, v=106
+    "ne_ccpvtz_cvs": (30, 5, 1, 1004),   # C4': c=2, o=8, v=50
+}
+
+
+def restricted_scf_dict(n_orb, n_occ, seed=1001, scale=0.05, conv_tol=1e-12):
+    rng = np.random.default_rng(seed)
+    occ_e = np.concatenate(([-20.0], np.linspace(-1.6, -0.4, n_occ - 1))) if n_occ > 1 else np.array([-0.5])
+    virt_e = np.linspace(0.15, 4.0, n_orb - n_occ)
+    orben = np.concatenate((occ_e, virt_e))
+    g = rng.standard_normal((n_orb,) * 4)
+    # 8-fold symmetry of real chemists' integrals (pq|rs)
+    g = g + g.transpose(1, 0, 2, 3)
+    g = g + g.transpose(0, 1, 3, 2)
+    g = g + g.transpose(2, 3, 0, 1)
+    g *= scale / 8.0
+    dip = rng.standard_normal((3, n_orb, n_orb))
+    dip = 0.5 * (dip + dip.transpose(0, 2, 1))
+    occ = np.array([1.0] * n_occ + [0.0] * (n_orb - n_occ))
+    eye = np.eye(n_orb)
+    return {
+        "restricted": True, "conv_tol": conv_tol, "energy_scf": 0.0, "spin_multiplicity": 1,
+        "orbcoeff_fb": np.vstack([eye, eye]),
+        "occupation_f": np.concatenate([occ, occ]),
+        "orben_f": np.concatenate([orben, orben]),
+        "fock_ff": np.diag(np.concatenate([orben, orben])),
+        "eri_ffff_spatial": g,
+        "multipoles": {"elec_1": dip, "nuclear_0": 2.0 * n_occ, "nuclear_1": np.zeros(3)},
+        "backend": f"synthetic(n_orb={n_orb},n_occ={n_occ},seed={seed})",
+    }
+
+
+def named_case(name):
+    n_orb, n_occ, core, seed = SHAPES[name]
+    return restricted_scf_dict(n_orb, n_occ, seed), core

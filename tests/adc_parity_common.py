@@ -1,0 +1,84 @@
+"""Shared parity checks: product path (whatever backend is active) versus the oracle."""
+import numpy as np
+
+import oracle
+
+METHODS = ["adc0", "adc1", "adc2", "adc2x", "adc3",
+           "cvs-adc0", "cvs-adc1", "cvs-adc2", "cvs-adc2x", "cvs-adc3"]
+SINGLETS = {
+    "adc0": [0.99048446, 1.04450741, 1.15356339], "adc1": [0.48343609, 0.57420044, 0.60213699],
+    "adc2": [0.47051314, 0.57255495, 0.59367339], "adc2x": [0.44511182, 0.55139508, 0.57146893],
+    "adc3": [0.45197068, 0.55572706, 0.57861241],
+    "cvs-adc0": [20.83623681, 20.99931574], "cvs-adc1": [20.10577515, 20.16512502],
+    "cvs-adc2": [20.0045422, 20.08771799], "cvs-adc2x": [19.90528006, 19.9990468],
+    "cvs-adc3": [19.93138526, 20.02055267],
+}
+SIGMA_RTOL = 1e-11      # north star: sigma vectors within 1e-11 relative
+ENERGY_ATOL = 1e-8      # north star: excitation energies within 1e-8 Hartree
+
+
+def build_pair(data, method, core):
+    import adcc_b200 as adcc
+    ref = adcc.ReferenceState(data, core_orbitals=core)
+    matrix = adcc.AdcMatrix(method, ref)
+    oref = oracle.OracleRefState(oracle.OracleHf(data), core_orbitals=core)
+    omatrix = oracle.OracleAdcMatrix(method, oref)
+    return matrix, omatrix
+
+
+def random_vector(matrix, omatrix, seed):
+    import adcc_b200 as adcc
+    rng = np.random.default_rng(seed)
+    ov = {k: rng.standard_normal(s) for k, s in omatrix.shapes.items()}
+    if "pphh" in ov:
+        ov["pphh"] = omatrix.symmetrise_doubles(ov["pphh"])
+    v = adcc.AmplitudeVector(**{
+        k: adcc.Tensor.from_ndarray(matrix.mospaces, matrix.axis_spaces[k], arr) for k, arr in ov.items()})
+    return v, ov
+
+
+def rel_err(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def check_matvec_parity(data, method, core, seed=42):
+    matrix, omatrix = build_pair(data, method, core)
+    # diagonal
+    for k, d in omatrix.diagonal().items():
+        assert rel_err(matrix.diagonal()[k].to_ndarray(), d) < SIGMA_RTOL, f"diagonal {k}"
+    v, ov = random_vector(matrix, omatrix, seed)
+    sig = matrix.matvec(v)
+    osig = omatrix.matvec(ov)
+    assert sorted(sig.blocks) == sorted(osig)
+    for k in osig:
+        assert rel_err(sig[k].to_ndarray(), osig[k]) < SIGMA_RTOL, f"sigma {k}"
+    # per-block applies (AdcMatrix.block_apply, adcc/tests/AdcMatrix_test.py:256-285)
+    for blk in omatrix.blocks:
+        outb, inb = blk.split("_")
+        if inb not in ov or matrix.block_orders[blk] in (None, 0) and outb != inb:
+            continue
+        ores = omatrix.blocks[blk]({inb: ov[inb]})
+        if ores is None:
+            continue
+        res = matrix.block_apply(blk, v[inb])
+        assert rel_err(res.to_ndarray(), ores[outb]) < SIGMA_RTOL, f"block {blk}"
+    # hermiticity <u|Mw> = <Mu|w>
+    w, _ = random_vector(matrix, omatrix, seed + 1)
+    lhs, rhs = v @ matrix.matvec(w), sig @ w
+    assert abs(lhs - rhs) < 1e-11 * max(1.0, abs(lhs))
+    return matrix, omatrix
+
+
+def check_run_parity(data, method, kind, core, n=None):
+    import adcc_b200 as adcc
+    if n is None:
+        n = len(SINGLETS[method]) if method in SINGLETS else 3
+    kw = {"singlet": {"n_singlets": n}, "triplet": {"n_triplets": n}, "any": {"n_states": n}}[kind]
+    state = adcc.run_adc(data, method=method, conv_tol=1e-9, core_orbitals=core, output=None, **kw)
+    okw = dict(kw)
+    ostate = oracle.run_adc(data, method, conv_tol=1e-9, core_orbitals=core,
+                            kind="any" if kind == "any" else kind, **okw)
+    assert state.converged and ostate.converged
+    np.testing.assert_allclose(state.excitation_energy, ostate.eigenvalues, atol=ENERGY_ATOL, rtol=0)
+    assert state.n_iter == ostate.n_iter
+    return state, ostate

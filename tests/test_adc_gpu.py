@@ -1,0 +1,66 @@
+"""Parity of the CUDA product path (through the C ABI) against the CPU oracle.
+
+sigma vectors: max|delta| / max|sigma| <= 1e-11; excitation energies <= 1e-8 Ha (north star).
+"""
+import numpy as np
+import pytest
+
+from oracle.hfdata import load_h2o_sto3g
+from adc_parity_common import (METHODS, SINGLETS, check_matvec_parity, check_run_parity)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def h2o():
+    return load_h2o_sto3g()
+
+
+@pytest.fixture(autouse=True)
+def _native_loaded():
+    from adcc_b200 import _cabi
+    assert _cabi.lib().adccb_version() >= 100      # the CUDA library is the thing under test
+    before = _cabi.launch_count()
+    yield
+    assert _cabi.launch_count() > before           # kernels of libadccb.so really ran
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_matvec_vs_oracle_h2o(h2o, method):
+    check_matvec_parity(h2o, method, 1 if method.startswith("cvs") else None)
+
+
+@pytest.mark.parametrize("method", METHODS)
+@pytest.mark.parametrize("kind", ["singlet", "triplet"])
+def test_run_adc_vs_oracle_and_smoke_table(h2o, method, kind):
+    state, _ = check_run_parity(h2o, method, kind, 1 if method.startswith("cvs") else None)
+    if kind == "singlet":
+        # reference known answers, adcc/tests/smoke_test.py:32-58
+        np.testing.assert_allclose(state.excitation_energy, SINGLETS[method], atol=1e-6)
+    assert state.n_iter <= 40          # adcc/tests/functionality_test.py:135
+
+
+@pytest.mark.parametrize("method", ["adc2", "adc2x", "adc3"])
+def test_matvec_synthetic_c1_shape(method):
+    # BASELINE configs[0] shape: o=10, v=38 spin orbitals
+    from adcc_b200.synthetic import named_case
+    data, core = named_case("h2o_ccpvdz")
+    check_matvec_parity(data, method, None)
+
+
+@pytest.mark.parametrize("method", ["cvs-adc2", "cvs-adc2x", "cvs-adc3"])
+def test_matvec_synthetic_cvs_shape(method):
+    from adcc_b200.synthetic import restricted_scf_dict
+    data = restricted_scf_dict(20, 5, seed=1004)
+    check_matvec_parity(data, method, 1)
+
+
+def test_davidson_synthetic_c1_adc2_3_singlets():
+    # BASELINE configs[0]: ADC(2), 3 singlets
+    from adcc_b200.synthetic import named_case
+    data, _ = named_case("h2o_ccpvdz")
+    check_run_parity(data, "adc2", "singlet", None, n=3)
+
+
+def test_any_kind_unrestricted_style(h2o):
+    check_run_parity(h2o, "adc2", "any", None, n=4)

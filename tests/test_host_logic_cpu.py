@@ -1,0 +1,119 @@
+"""Host logic (einsum planner, block tables, Davidson, guesses, workflow) against the oracle,
+on CPU tensors through the TEST-ONLY shim tests/cpu_shim.py (the build container has no GPU).
+The same checks run through the real CUDA backend in tests/test_adc_gpu.py."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle.hfdata import load_h2o_sto3g
+
+import cpu_shim
+from adc_parity_common import (METHODS, check_matvec_parity, check_run_parity, SINGLETS)
+
+
+@pytest.fixture(autouse=True)
+def shim(monkeypatch):
+    cpu_shim.install(monkeypatch)
+
+
+@pytest.fixture(scope="module")
+def h2o():
+    return load_h2o_sto3g()
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_matvec_vs_oracle(h2o, method):
+    check_matvec_parity(h2o, method, 1 if method.startswith("cvs") else None)
+
+
+@pytest.mark.parametrize("method", METHODS)
+@pytest.mark.parametrize("kind", ["singlet", "triplet", "any"])
+def test_run_adc_vs_oracle(h2o, method, kind):
+    check_run_parity(h2o, method, kind, 1 if method.startswith("cvs") else None)
+
+
+def test_synthetic_restricted_small():
+    from adcc_b200.synthetic import restricted_scf_dict
+    data = restricted_scf_dict(9, 3, seed=7)
+    for method in ("adc2", "adc2x", "adc3"):
+        check_matvec_parity(data, method, None)
+    data = restricted_scf_dict(9, 4, seed=8)
+    check_matvec_parity(data, "cvs-adc2x", 1)
+    check_run_parity(data, "cvs-adc2", "singlet", 1, n=2)
+
+
+def test_api_surface_and_errors(h2o):
+    import adcc_b200 as adcc
+    with pytest.raises(adcc.InputError):
+        adcc.run_adc(h2o, method="adc2")                       # no states requested
+    with pytest.raises(adcc.InputError):
+        adcc.run_adc(h2o, method="cvs-adc2", n_singlets=1)      # core_orbitals missing
+    with pytest.raises(adcc.InputError):
+        adcc.run_adc(h2o, method="adc7", n_singlets=1)
+    with pytest.raises(adcc.InputError):
+        adcc.run_adc(h2o, method="adc2", n_singlets=1, n_triplets=1)
+    refstate = adcc.ReferenceState(h2o)
+    with pytest.raises(ValueError):
+        adcc.AdcMatrix("cvs-adc2", refstate)
+    matrix = adcc.AdcMatrix("adc2", refstate)
+    assert matrix.axis_blocks == ["ph", "pphh"]
+    assert matrix.shape == (40 + 1600, 40 + 1600)
+    assert matrix.block_orders == {"ph_ph": 2, "ph_pphh": 1, "pphh_ph": 1, "pphh_pphh": 0}
+    guesses = adcc.guesses_singlet(matrix, 3)
+    with pytest.raises(ValueError):
+        adcc.jacobi_davidson(matrix, guesses, n_ep=5)
+    with pytest.raises(TypeError):
+        adcc.jacobi_davidson("nomatrix", guesses)
+    # n_applies bookkeeping (adcc/tests/solver/davidson_test.py:60-62)
+    state = adcc.jacobi_davidson(matrix, guesses, n_ep=2, conv_tol=1e-6)
+    assert state.n_applies >= len(guesses)
+    assert state.converged
+
+
+def test_tensor_algebra_semantics(h2o):
+    """Closed-form expectations in the style of libadcc_src/tests/TensorTest.cc:99-970 and
+    adcc/tests/einsum_test.py (numpy.einsum as the reference, rtol 1e-10 / atol 1e-14)."""
+    import adcc_b200 as adcc
+    from adcc_b200.functions import einsum, direct_sum, tensordot
+    ref = adcc.ReferenceState(h2o)
+    rng = np.random.default_rng(0)
+    oovv = ref.oovv
+    ovov = ref.ovov
+    a = oovv.to_ndarray()
+    bnd = ovov.to_ndarray()
+    np.testing.assert_allclose(einsum("ijab,kbjc->ikac", oovv, ovov).to_ndarray(),
+                               np.einsum("ijab,kbjc->ikac", a, bnd), rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(einsum("ijab,ijab->", oovv, oovv), np.einsum("ijab,ijab->", a, a))
+    np.testing.assert_allclose(einsum("iaia->ia", ovov).to_ndarray(), np.einsum("iaia->ia", bnd))
+    np.testing.assert_allclose(einsum("ijab->baji", oovv).to_ndarray(), a.transpose(3, 2, 1, 0))
+    np.testing.assert_allclose(tensordot(oovv, ovov, axes=([2, 3], [1, 3])).to_ndarray(),
+                               np.tensordot(a, bnd, axes=([2, 3], [1, 3])), rtol=1e-10, atol=1e-14)
+    # symmetrise / antisymmetrise include the 1/2 (Tensor.hh:229-244)
+    np.testing.assert_allclose(oovv.antisymmetrise(0, 1).to_ndarray(), 0.5 * (a - a.transpose(1, 0, 2, 3)))
+    np.testing.assert_allclose(oovv.symmetrise((0, 1), (2, 3)).to_ndarray(),
+                               0.5 * (a + a.transpose(1, 0, 3, 2)))
+    with pytest.raises(ValueError):
+        ovov.symmetrise(0, 1)                      # different subspaces
+    # direct_sum and diagonal conventions (Appendix A.5)
+    fo, fv = ref.foo.diagonal(), ref.fvv.diagonal()
+    ds = direct_sum("a-i->ia", fv, fo).to_ndarray()
+    np.testing.assert_allclose(ds, -fo.to_ndarray()[:, None] + fv.to_ndarray()[None, :])
+    assert ovov.diagonal(0, 2).shape == (4, 4, 10)
+    # scalar +/- 0 returns self, arithmetic
+    assert (oovv + 0) is oovv
+    np.testing.assert_allclose((2.0 * oovv - oovv / 2.0).to_ndarray(), 1.5 * a)
+    np.testing.assert_allclose((oovv * oovv).to_ndarray(), a * a)
+    assert abs(oovv.dot(oovv) - np.vdot(a, a)) < 1e-12
+    np.testing.assert_allclose(oovv.dot([oovv, oovv]), [np.vdot(a, a)] * 2)
+    # element access honours symmetry
+    sym = adcc.Symmetry(ref.mospaces, "o1o1v1v1", permutations=["ijab", "-jiab", "-ijba"])
+    t = adcc.Tensor(sym)
+    t[0, 1, 2, 3] = 1.0
+    assert t[1, 0, 2, 3] == -1.0 and t[1, 0, 3, 2] == 1.0
+    assert not t.is_allowed((1, 1, 2, 3))
+    with pytest.raises(RuntimeError):
+        t[1, 1, 2, 3] = 1.0
+    assert t.select_n_max(1)[0][0] == (0, 1, 2, 3)
+    # immutability of imported tensors (ReferenceState.cc:471,507)
+    with pytest.raises(RuntimeError):
+        oovv.fill(1.0)
