@@ -42,7 +42,7 @@ def default_block_orders(method):
 
 class AdcMatrix(AdcMatrixlike):
     def __init__(self, method, hf_or_mp, block_orders=None, intermediates=None,
-                 diagonal_precomputed=None):
+                 diagonal_precomputed=None, doubles_storage="auto"):
         if isinstance(hf_or_mp, ReferenceState):
             hf_or_mp = LazyMp(hf_or_mp)
         elif not isinstance(hf_or_mp, LazyMp):
@@ -80,6 +80,8 @@ class AdcMatrix(AdcMatrixlike):
         self._validate_block_orders()
         self._variant = "cvs" if self.is_core_valence_separated else ""
         self._const = {}
+        self.doubles_storage = self._select_storage(doubles_storage)
+        self._engine = None
 
         with self.timer.record("build"):
             self._tables = {}
@@ -93,12 +95,24 @@ class AdcMatrix(AdcMatrixlike):
                                      "implemented for the requested method.")
                 self._tables[blk] = adc_pp.BLOCKS[key]
             self.blocks = {blk: self._make_apply(blk) for blk in self._tables}
-            # resolve constant operands now: triggers ERI staging and intermediate builds
-            for blk in self._tables:
-                for _, expr in self._tables[blk][2]:
-                    self._resolve_constants(expr)
+            if self.doubles_storage == "packed":
+                from .packed import PackedAdcEngine
+                self._engine = PackedAdcEngine(self)
+                self.blocks = {blk: self._make_engine_apply(blk) for blk in self._tables
+                               if self._tables[blk][0] is not None}
+                dph = adc_pp.diagonal(self._variant, "ph_ph", self.block_orders["ph_ph"], hf,
+                                      self.ground_state, self.intermediates)
+                dph.ph._contig()
+                self._diagonal = AmplitudeVector(ph=dph.ph, pphh=self._engine.diagonal_pphh)
+            else:
+                # resolve constant operands now: triggers ERI staging and intermediate builds
+                for blk in self._tables:
+                    for _, expr in self._tables[blk][2]:
+                        self._resolve_constants(expr)
             if diagonal_precomputed is not None:
                 self._diagonal = diagonal_precomputed
+            elif self.doubles_storage == "packed":
+                pass
             else:
                 diag = 0
                 for blk, order in self.block_orders.items():
@@ -114,6 +128,20 @@ class AdcMatrix(AdcMatrixlike):
             self._init_space_data(self._diagonal)
 
     # ------------------------------------------------------------------ bookkeeping
+    def _select_storage(self, requested):
+        """'dense' (generic table interpreter) or 'packed' (antisymmetry-packed doubles,
+        adcc_b200/packed.py).  'auto' packs when the dense doubles vector would exceed 1 GiB."""
+        if requested not in ("auto", "dense", "packed"):
+            raise ValueError("doubles_storage needs to be 'auto', 'dense' or 'packed'")
+        packable = (not self.is_core_valence_separated and self.method.level == 2
+                    and self.block_orders.get("pphh_pphh") in (0, 1))
+        if requested == "packed" and not packable:
+            raise NotImplementedError("packed doubles storage is implemented for ADC(2) and ADC(2)-x")
+        if requested == "auto":
+            no, nv = self.mospaces.n_orbs("o1"), self.mospaces.n_orbs("v1")
+            return "packed" if (packable and no * no * nv * nv * 8 >= (1 << 30)) else "dense"
+        return requested
+
     def _validate_block_orders(self):
         for block, order in self.block_orders.items():
             if order is None:
@@ -216,6 +244,15 @@ class AdcMatrix(AdcMatrixlike):
             return AmplitudeVector(**{outb: res})
         return apply
 
+    def _make_engine_apply(self, blk):
+        outb, inb = blk.split("_")
+
+        def apply(ampl):
+            if inb not in ampl:
+                return 0
+            return AmplitudeVector(**{outb: self._engine.block_apply(blk, ampl[inb])})
+        return apply
+
     def block_apply(self, block, tensor):
         if not isinstance(tensor, Tensor):
             raise TypeError("tensor should be an adcc.Tensor")
@@ -227,6 +264,8 @@ class AdcMatrix(AdcMatrixlike):
     def matvec(self, v):
         """sigma = M v  (adcc/AdcMatrix.py:390-396)."""
         with self.timer.record("matvec"):
+            if self._engine is not None:
+                return self._engine.matvec(v)
             if self.extra_terms:
                 return sum(block(v) for block in self.blocks.values())
             collected = {}
@@ -255,7 +294,7 @@ class AdcMatrix(AdcMatrixlike):
         block_orders = {bl: None for bl in self.block_orders}
         block_orders[block] = self.block_orders[block]
         return AdcMatrix(self.method, self.ground_state, block_orders=block_orders,
-                         intermediates=self.intermediates)
+                         intermediates=self.intermediates, doubles_storage="dense")
 
     def construct_symmetrisation_for_blocks(self):
         """adcc/AdcMatrix.py:431-472."""

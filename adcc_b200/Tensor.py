@@ -58,8 +58,8 @@ class Tensor:
         return self
 
     def _like(self, data, keep_symmetry=True):
-        return Tensor._wrap(self.mospaces, self.subspaces, data,
-                            self.symmetry if keep_symmetry else None)
+        return type(self)._wrap(self.mospaces, self.subspaces, data,
+                                self.symmetry if keep_symmetry else None)
 
     @classmethod
     def from_ndarray(cls, mospaces, space, array, symmetry=None):
@@ -111,17 +111,17 @@ class Tensor:
         return self._like(be.scaled_copy(self._data, 1.0))
 
     def zeros_like(self):
-        return self._like(be.zeros(self.shape))
+        return self._like(be.zeros(self._data.shape))
 
     empty_like = zeros_like      # export_Tensor.cc:451
 
     def ones_like(self):
-        t = be.empty(self.shape)
+        t = be.empty(self._data.shape)
         be.fill(t, 1.0)
         return self._like(t)
 
     def nosym_like(self):
-        return self._like(be.zeros(self.shape), keep_symmetry=False)
+        return self._like(be.zeros(self._data.shape), keep_symmetry=False)
 
     def fill(self, value):
         self._require_mutable()
@@ -244,6 +244,9 @@ class Tensor:
 
     # ------------------------------------------------------------------ arithmetic
     def _check_same(self, other):
+        if type(self) is not type(other):
+            raise ValueError("Cannot combine tensors with different storage "
+                             f"({type(self).__name__} vs {type(other).__name__})")
         if self.shape != other.shape:
             raise ValueError(f"Shape mismatch: {self.shape} vs {other.shape}")
         if self.subspaces != other.subspaces:

@@ -37,6 +37,17 @@ def _declare(lib):
                                        ctypes.POINTER(ctypes.c_int), c_dbl, c_ptr, c_ptr]
     lib.adccb_spin_singlet.argtypes = [c_ptr, ctypes.POINTER(ctypes.c_int),
                                        ctypes.POINTER(ctypes.c_int), c_ptr]
+    c_int = ctypes.c_int
+    lib.adccb_packed_unpack.argtypes = [c_ptr, c_int, c_int, c_ptr, c_ptr]
+    lib.adccb_packed_pack.argtypes = [c_ptr, c_int, c_int, c_ptr, c_ptr]
+    lib.adccb_packed_expand.argtypes = [c_ptr, c_int, c_int, c_int, c_ptr, c_ptr]
+    lib.adccb_packed_fold_virt.argtypes = [c_ptr, c_i64, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr,
+                                           c_dbl, c_ptr]
+    lib.adccb_packed_fold_occ.argtypes = [c_ptr, c_int, c_int, c_ptr, c_dbl, c_ptr]
+    lib.adccb_packed_diagonal.argtypes = [c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]
+    lib.adccb_pair_select.argtypes = [c_ptr, c_i64, c_int, c_i64, c_ptr, c_ptr]
+    lib.adccb_synth_fill.argtypes = [c_ptr, c_int, c_int, c_int, c_int, ctypes.c_uint64, c_dbl,
+                                     c_i64, c_i64, c_ptr]
     for name in EXPORTS:
         if name not in ("adccb_last_error", "adccb_launch_count"):
             getattr(lib, name).restype = ctypes.c_int
@@ -46,6 +57,8 @@ EXPORTS = [
     "adccb_version", "adccb_last_error", "adccb_launch_count", "adccb_device_info",
     "adccb_dgemm", "adccb_strided_gather", "adccb_elementwise", "adccb_direct_sum",
     "adccb_lincomb", "adccb_dot_many", "adccb_spin_project", "adccb_spin_singlet",
+    "adccb_packed_unpack", "adccb_packed_pack", "adccb_packed_expand", "adccb_packed_fold_virt",
+    "adccb_packed_fold_occ", "adccb_packed_diagonal", "adccb_pair_select", "adccb_synth_fill",
 ]
 
 

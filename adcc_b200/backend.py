@@ -138,8 +138,11 @@ def scaled_copy(x, alpha=1.0):
     return _ew(EW_AXPBY, x.numel(), alpha, x, None, 0.0, 0.0, torch.empty_like(x))
 
 
-def mul(x, y, alpha=1.0):
-    return _ew(EW_MUL, x.numel(), alpha, x, y, 0.0, 0.0, torch.empty_like(x))
+def mul(x, y, alpha=1.0, out=None, beta=0.0):
+    """out = alpha * x * y + beta * out (new tensor if out is None)."""
+    if out is None:
+        out, beta = torch.empty_like(x), 0.0
+    return _ew(EW_MUL, x.numel(), alpha, x, y, 0.0, beta, out)
 
 
 def div(x, y, alpha=1.0):
@@ -219,3 +222,79 @@ def spin_singlet_(t, n_alpha):
     na = (ctypes.c_int * 4)(*[int(s) for s in n_alpha])
     _cabi.check(_cabi.lib().adccb_spin_singlet(_stream(), sh, na, _ptr(t)))
     return t
+
+
+# --------------------------------------------------------------------------------- packed doubles
+def n_pairs(n):
+    return n * (n - 1) // 2
+
+
+def packed_unpack(U, no, nv):
+    out = empty((no, no, nv, nv))
+    _cabi.check(_cabi.lib().adccb_packed_unpack(_stream(), no, nv, _ptr(U), _ptr(out)))
+    return out
+
+
+def packed_pack(T, no, nv):
+    T = contiguous(T)
+    U = empty((n_pairs(no), n_pairs(nv)))
+    _cabi.check(_cabi.lib().adccb_packed_pack(_stream(), no, nv, _ptr(T), _ptr(U)))
+    return U
+
+
+def packed_expand(which, U, no, nv, out=None):
+    """which: 0 X[i,a,k,c]; 1 Ue[i,j,AB]; 2 Uh[a,JK,b]."""
+    shape = {0: (no * nv, no * nv), 1: (no, no * n_pairs(nv)), 2: (nv, n_pairs(no) * nv)}[which]
+    if out is None:
+        out = empty(shape)
+    _cabi.check(_cabi.lib().adccb_packed_expand(_stream(), which, no, nv, _ptr(U), _ptr(out)))
+    return out
+
+
+def packed_fold_virt(S, nv, sa, P1, off1, P2=None, off2=None, alpha=1.0):
+    """S[r,AB] += alpha (F_r[a,b] - F_r[b,a]); off1/off2: int64 device tensors (len = rows of S)."""
+    nrows = S.shape[0]
+    _cabi.check(_cabi.lib().adccb_packed_fold_virt(
+        _stream(), nrows, nv, int(sa), _ptr(P1), ctypes.c_void_p(off1.data_ptr()), _ptr(P2),
+        ctypes.c_void_p(off2.data_ptr()) if off2 is not None else ctypes.c_void_p(0),
+        float(alpha), _ptr(S)))
+    return S
+
+
+def packed_fold_occ(S, C, no, nv, alpha=1.0):
+    _cabi.check(_cabi.lib().adccb_packed_fold_occ(_stream(), no, nv, _ptr(C), float(alpha), _ptr(S)))
+    return S
+
+
+def packed_diagonal(no, nv, dov, doo=None, dvv=None):
+    D = empty((n_pairs(no), n_pairs(nv)))
+    _cabi.check(_cabi.lib().adccb_packed_diagonal(_stream(), no, nv, _ptr(dov), _ptr(doo), _ptr(dvv),
+                                                  _ptr(D)))
+    return D
+
+
+def pair_select(t, axis):
+    """Keep p<q of the adjacent equal-extent axes (axis, axis+1) of a contiguous tensor."""
+    t = contiguous(t)
+    n = t.shape[axis]
+    assert t.shape[axis + 1] == n
+    L = int(np.prod(t.shape[:axis], dtype=np.int64)) if axis > 0 else 1
+    R = int(np.prod(t.shape[axis + 2:], dtype=np.int64)) if axis + 2 < t.dim() else 1
+    out = empty(tuple(t.shape[:axis]) + (n_pairs(n),) + tuple(t.shape[axis + 2:]))
+    _cabi.check(_cabi.lib().adccb_pair_select(_stream(), L, n, R, _ptr(t), _ptr(out)))
+    return out
+
+
+def int64_tensor(values):
+    return torch.tensor([int(v) for v in values], dtype=torch.int64, device=device())
+
+
+SYNTH_LAYOUTS = {"vvvv_packed": 0, "oooo_packed": 1, "ovov_jbkc": 2, "ovvv_jabc": 3, "ovvv_ajbc": 4,
+                 "ooov_ijkb": 5, "ooov_ijak": 6, "dense": 7}
+SYNTH_BLOCKS = {"oooo": 0, "ooov": 1, "oovv": 2, "ovov": 3, "ovvv": 4, "vvvv": 5}
+
+
+def synth_fill(out, layout, no, nv, seed, scale, block="vvvv", row_begin=0):
+    _cabi.check(_cabi.lib().adccb_synth_fill(_stream(), SYNTH_LAYOUTS[layout], SYNTH_BLOCKS[block], no, nv,
+                                             int(seed), float(scale), out.numel(), int(row_begin), _ptr(out)))
+    return out

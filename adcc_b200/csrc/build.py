@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(os.path.dirname(HERE), "libadccb.so")
-SOURCES = ["cabi.cu", "dgemm.cu", "tensor_ops.cu"]
+SOURCES = ["cabi.cu", "dgemm.cu", "tensor_ops.cu", "packed_ops.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "adccb.h")]
 
 

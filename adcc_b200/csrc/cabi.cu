@@ -45,6 +45,19 @@ int spin_project(cudaStream_t st, int nd, const int* shape, const int* nalpha, d
                  const double* in, double* out);
 int spin_singlet(cudaStream_t st, const int* shape, const int* nalpha, double* T);
 
+int packed_unpack(cudaStream_t st, int no, int nv, const double* U, double* out);
+int packed_pack(cudaStream_t st, int no, int nv, const double* T, double* U);
+int packed_expand(cudaStream_t st, int which, int no, int nv, const double* U, double* out);
+int packed_fold_virt(cudaStream_t st, long long nrows, int nv, long long sa, const double* P1,
+                     const long long* off1, const double* P2, const long long* off2, double alpha,
+                     double* S);
+int packed_fold_occ(cudaStream_t st, int no, int nv, const double* C, double alpha, double* S);
+int packed_diagonal(cudaStream_t st, int no, int nv, const double* dov, const double* doo,
+                    const double* dvv, double* D);
+int pair_select(cudaStream_t st, long long L, int n, long long R, const double* in, double* out);
+int synth_fill(cudaStream_t st, int layout, int blk, int no, int nv, unsigned long long seed,
+               double scale, long long n, long long row_begin, double* out);
+
 }  // namespace adccb
 
 using namespace adccb;
@@ -106,6 +119,36 @@ int adccb_spin_project(void* stream, int ndim, const int* shape, const int* n_al
 
 int adccb_spin_singlet(void* stream, const int* shape, const int* n_alpha, double* T) {
   return spin_singlet((cudaStream_t)stream, shape, n_alpha, T);
+}
+
+int adccb_packed_unpack(void* stream, int no, int nv, const double* U, double* out) {
+  return packed_unpack((cudaStream_t)stream, no, nv, U, out);
+}
+int adccb_packed_pack(void* stream, int no, int nv, const double* T, double* U) {
+  return packed_pack((cudaStream_t)stream, no, nv, T, U);
+}
+int adccb_packed_expand(void* stream, int which, int no, int nv, const double* U, double* out) {
+  return packed_expand((cudaStream_t)stream, which, no, nv, U, out);
+}
+int adccb_packed_fold_virt(void* stream, int64_t nrows, int nv, int64_t sa, const double* P1,
+                           const int64_t* off1, const double* P2, const int64_t* off2,
+                           double alpha, double* S) {
+  return packed_fold_virt((cudaStream_t)stream, nrows, nv, sa, P1, (const long long*)off1, P2,
+                          (const long long*)off2, alpha, S);
+}
+int adccb_packed_fold_occ(void* stream, int no, int nv, const double* C, double alpha, double* S) {
+  return packed_fold_occ((cudaStream_t)stream, no, nv, C, alpha, S);
+}
+int adccb_packed_diagonal(void* stream, int no, int nv, const double* dov, const double* doo,
+                          const double* dvv, double* D) {
+  return packed_diagonal((cudaStream_t)stream, no, nv, dov, doo, dvv, D);
+}
+int adccb_pair_select(void* stream, int64_t L, int n, int64_t R, const double* in, double* out) {
+  return pair_select((cudaStream_t)stream, L, n, R, in, out);
+}
+int adccb_synth_fill(void* stream, int layout, int blk, int no, int nv, uint64_t seed, double scale,
+                     int64_t n, int64_t row_begin, double* out) {
+  return synth_fill((cudaStream_t)stream, layout, blk, no, nv, seed, scale, n, row_begin, out);
 }
 
 }  // extern "C"

@@ -1,0 +1,409 @@
+// Antisymmetry-packed doubles store: kernels that move between the packed layout
+//   U[IJ, AB],  IJ = pair(i<j) = j(j-1)/2 + i,  AB = pair(a<b) = b(b-1)/2 + a
+// and the GEMM-ready dense layouts the ADC(2)/ADC(2)-x matvec needs, plus the counter-based
+// generator of the synthetic nocc=40/nvirt=400 workload.
+//
+// The doubles part of an ADC vector is antisymmetric in (i,j) and in (a,b)
+// (adcc/guess/guess_zero.py:163-171, adcc/AdcMatrix.py:445-455); libtensor stores only the
+// canonical blocks, here only the canonical ELEMENTS are stored (1/4 of the dense size), so the
+// explicit doubles symmetrisation (AdcMatrix.py:449-455) is the identity on this store and
+// every Davidson vector operation moves 4x fewer bytes.  All kernels are HBM-bound.
+#include "common.cuh"
+#include <algorithm>
+
+namespace adccb {
+
+__device__ __forceinline__ long long pair_index(int p, int q) {  // p < q
+  return (long long)q * (q - 1) / 2 + p;
+}
+// inverse of pair_index: largest q with q(q-1)/2 <= P
+__device__ __forceinline__ void pair_decode(long long P, int& p, int& q) {
+  long long qq = (long long)((1.0 + sqrt(1.0 + 8.0 * (double)P)) * 0.5);
+  while (qq * (qq - 1) / 2 > P) --qq;
+  while ((qq + 1) * qq / 2 <= P) ++qq;
+  q = (int)qq;
+  p = (int)(P - qq * (qq - 1) / 2);
+}
+
+// ---------------------------------------------------------------------------------------
+// dense <-> packed
+// ---------------------------------------------------------------------------------------
+// out[i,j,a,b] = s_ij s_ab U[pair(ij), pair(ab)]
+__global__ void unpack_dense_kernel(int no, int nv, const double* __restrict__ U,
+                                    double* __restrict__ out) {
+  const long long npv = (long long)nv * (nv - 1) / 2;
+  const long long n = (long long)no * no * nv * nv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(idx % nv), a = (int)((idx / nv) % nv);
+    const int j = (int)((idx / ((long long)nv * nv)) % no), i = (int)(idx / ((long long)nv * nv * no));
+    double v = 0.0;
+    if (i != j && a != b) {
+      const double s = ((i < j) == (a < b)) ? 1.0 : -1.0;
+      v = s * U[pair_index(min(i, j), max(i, j)) * npv + pair_index(min(a, b), max(a, b))];
+    }
+    out[idx] = v;
+  }
+}
+
+// U[IJ,AB] = 1/4 (T[ijab] - T[jiab] - T[ijba] + T[jiba])   (= doubles symmetrisation + pack)
+__global__ void pack_dense_kernel(int no, int nv, const double* __restrict__ T,
+                                  double* __restrict__ U) {
+  const long long npv = (long long)nv * (nv - 1) / 2, npo = (long long)no * (no - 1) / 2;
+  const long long n = npo * npv;
+  const long long s0 = (long long)no * nv * nv, s1 = (long long)nv * nv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int i, j, a, b;
+    pair_decode(idx / npv, i, j);
+    pair_decode(idx % npv, a, b);
+    U[idx] = 0.25 * (T[i * s0 + j * s1 + (long long)a * nv + b] - T[j * s0 + i * s1 + (long long)a * nv + b] -
+                     T[i * s0 + j * s1 + (long long)b * nv + a] + T[j * s0 + i * s1 + (long long)b * nv + a]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// GEMM-ready expansions of the packed trial vector
+// ---------------------------------------------------------------------------------------
+// X[i,a,k,c] = u[i,k,a,c]   (ovov-term operand, o*v x o*v); one CTA per (i,k)
+__global__ void expand_iakc_kernel(int no, int nv, const double* __restrict__ U,
+                                   double* __restrict__ X) {
+  const long long npv = (long long)nv * (nv - 1) / 2;
+  const int i = blockIdx.x / no, k = blockIdx.x % no;
+  double* dst = X + ((long long)i * nv * no + k) * nv;     // + a*(no*nv) + c
+  const long long astride = (long long)no * nv;
+  if (i == k) {
+    for (int e = threadIdx.x; e < nv * nv; e += blockDim.x) dst[(e / nv) * astride + (e % nv)] = 0.0;
+    return;
+  }
+  const double sik = (i < k) ? 1.0 : -1.0;
+  const double* row = U + pair_index(min(i, k), max(i, k)) * npv;
+  for (int e = threadIdx.x; e < nv * nv; e += blockDim.x) {
+    const int a = e / nv, c = e % nv;
+    double v = 0.0;
+    if (a != c) v = ((a < c) ? sik : -sik) * row[pair_index(min(a, c), max(a, c))];
+    dst[a * astride + c] = v;
+  }
+}
+
+// Ue[i,j,AB] = s_ij U[pair(ij),AB]; one CTA per (i,j)
+__global__ void expand_occ_kernel(int no, long long npv, const double* __restrict__ U,
+                                  double* __restrict__ Ue) {
+  const int i = blockIdx.x / no, j = blockIdx.x % no;
+  double* dst = Ue + (long long)blockIdx.x * npv;
+  if (i == j) {
+    for (long long e = threadIdx.x; e < npv; e += blockDim.x) dst[e] = 0.0;
+    return;
+  }
+  const double s = (i < j) ? 1.0 : -1.0;
+  const double* row = U + pair_index(min(i, j), max(i, j)) * npv;
+  for (long long e = threadIdx.x; e < npv; e += blockDim.x) dst[e] = s * row[e];
+}
+
+// Uh[a,JK,b] = u[JK,a,b] = s_ab U[JK,pair(ab)]; grid (npo, a-chunks)
+__global__ void expand_virt_t_kernel(long long npo, int nv, const double* __restrict__ U,
+                                     double* __restrict__ Uh) {
+  const long long npv = (long long)nv * (nv - 1) / 2;
+  const long long JK = blockIdx.x;
+  const double* row = U + JK * npv;
+  for (int a = blockIdx.y; a < nv; a += gridDim.y) {
+    double* dst = Uh + ((long long)a * npo + JK) * nv;
+    for (int b = threadIdx.x; b < nv; b += blockDim.x) {
+      double v = 0.0;
+      if (a != b) v = ((a < b) ? 1.0 : -1.0) * row[pair_index(min(a, b), max(a, b))];
+      dst[b] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// epilogues that fold GEMM results back into the packed sigma vector
+// ---------------------------------------------------------------------------------------
+// S[r, pair(a,b)] += alpha * (F_r[a,b] - F_r[b,a]),  F_r[a,b] = P1[off1[r] + a*sa + b]
+//                                                            - (P2 ? P2[off2[r] + a*sa + b] : 0)
+// 32x32 tiles over (a,b) with a shared-memory transpose so that every global access is coalesced.
+__global__ void pack_antisym_virt_kernel(int nv, long long sa, const double* __restrict__ P1,
+                                         const long long* __restrict__ off1,
+                                         const double* __restrict__ P2,
+                                         const long long* __restrict__ off2, double alpha,
+                                         double* __restrict__ S) {
+  __shared__ double tile[32][33];
+  const long long npv = (long long)nv * (nv - 1) / 2;
+  const long long r = blockIdx.z;
+  const int a0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  if (a0 > b0 + 31) return;   // tile entirely below the diagonal (a > b everywhere)
+  const double* F1 = P1 + off1[r];
+  const double* F2 = P2 ? P2 + off2[r] : nullptr;
+  // tile[bb][aa] = F[a0+aa, b0+bb] read coalesced along b
+  for (int aa = threadIdx.y; aa < 32; aa += blockDim.y) {
+    const int a = a0 + aa, b = b0 + threadIdx.x;
+    double v = 0.0;
+    if (a < nv && b < nv) {
+      v = F1[(long long)a * sa + b];
+      if (F2) v -= F2[(long long)a * sa + b];
+    }
+    tile[threadIdx.x][aa] = v;
+  }
+  __syncthreads();
+  double* Srow = S + r * npv;
+  for (int bb = threadIdx.y; bb < 32; bb += blockDim.y) {
+    const int b = b0 + bb, a = a0 + threadIdx.x;
+    if (a < b && b < nv) {
+      double fba = F1[(long long)b * sa + a];
+      if (F2) fba -= F2[(long long)b * sa + a];
+      Srow[pair_index(a, b)] += alpha * (tile[bb][threadIdx.x] - fba);
+    }
+  }
+}
+
+// S[pair(ij), AB] += alpha * (C[i,j,AB] - C[j,i,AB]); one CTA per pair
+__global__ void pack_antisym_occ_kernel(int no, long long npv, const double* __restrict__ C,
+                                        double alpha, double* __restrict__ S) {
+  int i, j;
+  pair_decode(blockIdx.x, i, j);
+  const double* c1 = C + ((long long)i * no + j) * npv;
+  const double* c2 = C + ((long long)j * no + i) * npv;
+  double* dst = S + (long long)blockIdx.x * npv;
+  for (long long e = threadIdx.x; e < npv; e += blockDim.x) dst[e] += alpha * (c1[e] - c2[e]);
+}
+
+// D[IJ,AB] = 1/2 (dov[i,a] + dov[j,b] + dov[i,b] + dov[j,a]) + doo[i,j] + dvv[a,b]
+// (packed form of adcc/adc_pp/matrix.py:109-124 (doo = dvv = 0, dov = e_a - e_i) and :212-231)
+__global__ void packed_diagonal_kernel(int no, int nv, const double* __restrict__ dov,
+                                       const double* __restrict__ doo, const double* __restrict__ dvv,
+                                       double* __restrict__ D) {
+  const long long npv = (long long)nv * (nv - 1) / 2, npo = (long long)no * (no - 1) / 2;
+  const long long n = npo * npv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int i, j, a, b;
+    pair_decode(idx / npv, i, j);
+    pair_decode(idx % npv, a, b);
+    double v = 0.5 * (dov[i * nv + a] + dov[j * nv + b] + dov[i * nv + b] + dov[j * nv + a]);
+    if (doo) v += doo[i * no + j];
+    if (dvv) v += dvv[(long long)a * nv + b];
+    D[idx] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// synthetic antisymmetrised integrals from a counter-based hash
+//   <pq||rs> = sign * phi(seed, block, canonical(p,q,r,s)),  phi uniform in sqrt(3)*scale*[-1,1)
+// layout codes select which tensor/layout is written (the value definition is shared with
+// adcc_b200/synthetic.py::synthetic_eri_value, which the CPU oracle uses).
+// ---------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  unsigned long long z = x;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+
+enum EriBlock { BLK_OOOO = 0, BLK_OOOV = 1, BLK_OOVV = 2, BLK_OVOV = 3, BLK_OVVV = 4, BLK_VVVV = 5 };
+
+__host__ __device__ __forceinline__ double synthetic_eri(unsigned long long seed, int blk, int p,
+                                                         int q, int r, int s, double scale) {
+  double sign = 1.0;
+  const bool bra_same = (blk == BLK_OOOO || blk == BLK_OOOV || blk == BLK_OOVV || blk == BLK_VVVV);
+  const bool ket_same = (blk == BLK_OOOO || blk == BLK_OOVV || blk == BLK_OVVV || blk == BLK_VVVV);
+  if (bra_same) {
+    if (p == q) return 0.0;
+    if (p > q) { int t = p; p = q; q = t; sign = -sign; }
+  }
+  if (ket_same) {
+    if (r == s) return 0.0;
+    if (r > s) { int t = r; r = s; s = t; sign = -sign; }
+  }
+  if (blk == BLK_OOOO || blk == BLK_VVVV || blk == BLK_OVOV) {
+    if (p > r || (p == r && q > s)) { int t = p; p = r; r = t; t = q; q = s; s = t; }
+  }
+  const unsigned long long key = ((((unsigned long long)p * 1024ULL + q) * 1024ULL + r) * 1024ULL + s);
+  const unsigned long long h = splitmix64(seed ^ splitmix64(key * 8ULL + (unsigned long long)blk));
+  const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
+  return sign * (2.0 * u - 1.0) * 1.7320508075688772 * scale;
+}
+
+enum EriLayout {
+  LAY_VVVV_PACKED = 0,   // W[AB,CD]
+  LAY_OOOO_PACKED = 1,   // O[IJ,KL]
+  LAY_OVOV_JBKC = 2,     // Y[(j,b),(k,c)] = <kb||jc>
+  LAY_OVVV_JABC = 3,     // V1[(j,AB),c]  = <jc||ab>
+  LAY_OVVV_AJBC = 4,     // V2[a,(j,BC)]  = <ja||bc>
+  LAY_OOOV_IJKB = 5,     // G1[i,(JK,b)]  = <jk||ib>
+  LAY_OOOV_IJAK = 6,     // G2[(IJ,a),k]  = <ij||ka>
+  LAY_DENSE = 7          // dense [p,q,r,s] of block `blk`
+};
+
+__global__ void synth_fill_kernel(int layout, int blk, int no, int nv, unsigned long long seed,
+                                  double scale, long long n, long long row_begin,
+                                  double* __restrict__ out) {
+  const long long npv = (long long)nv * (nv - 1) / 2, npo = (long long)no * (no - 1) / 2;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    int a, b, c, d, i, j, k, l;
+    switch (layout) {
+      case LAY_VVVV_PACKED: {
+        pair_decode(row_begin + idx / npv, a, b);
+        pair_decode(idx % npv, c, d);
+        v = synthetic_eri(seed, BLK_VVVV, a, b, c, d, scale);
+      } break;
+      case LAY_OOOO_PACKED: {
+        pair_decode(idx / npo, i, j);
+        pair_decode(idx % npo, k, l);
+        v = synthetic_eri(seed, BLK_OOOO, i, j, k, l, scale);
+      } break;
+      case LAY_OVOV_JBKC: {
+        c = (int)(idx % nv); k = (int)((idx / nv) % no);
+        b = (int)((idx / ((long long)nv * no)) % nv); j = (int)(idx / ((long long)nv * no * nv));
+        v = synthetic_eri(seed, BLK_OVOV, k, b, j, c, scale);
+      } break;
+      case LAY_OVVV_JABC: {
+        c = (int)(idx % nv);
+        pair_decode((idx / nv) % npv, a, b);
+        j = (int)(idx / ((long long)nv * npv));
+        v = synthetic_eri(seed, BLK_OVVV, j, c, a, b, scale);
+      } break;
+      case LAY_OVVV_AJBC: {
+        pair_decode(idx % npv, b, c);
+        j = (int)((idx / npv) % no);
+        a = (int)(idx / (npv * no));
+        v = synthetic_eri(seed, BLK_OVVV, j, a, b, c, scale);
+      } break;
+      case LAY_OOOV_IJKB: {
+        b = (int)(idx % nv);
+        pair_decode((idx / nv) % npo, j, k);
+        i = (int)(idx / ((long long)nv * npo));
+        v = synthetic_eri(seed, BLK_OOOV, j, k, i, b, scale);
+      } break;
+      case LAY_OOOV_IJAK: {
+        k = (int)(idx % no); a = (int)((idx / no) % nv);
+        pair_decode(idx / ((long long)no * nv), i, j);
+        v = synthetic_eri(seed, BLK_OOOV, i, j, k, a, scale);
+      } break;
+      default: {
+        const int e3 = (blk == BLK_OOOO) ? no : nv;
+        const int e2 = (blk == BLK_OOOO || blk == BLK_OOOV || blk == BLK_OVOV) ? no : nv;
+        const int e1 = (blk == BLK_OVOV || blk == BLK_OVVV || blk == BLK_VVVV) ? nv : no;
+        const int s = (int)(idx % e3), r = (int)((idx / e3) % e2);
+        const int q = (int)((idx / ((long long)e3 * e2)) % e1), p = (int)(idx / ((long long)e3 * e2 * e1));
+        v = synthetic_eri(seed, blk, p, q, r, s, scale);
+      }
+    }
+    out[idx] = v;
+  }
+}
+
+
+// out[l, pair(p,q), r] = in[l, p, q, r] for p < q  (staging of ERI blocks whose antisymmetric
+// index pair is stored packed: ooov first pair, ovvv last pair)
+__global__ void pair_select_kernel(long long L, int n, long long R, const double* __restrict__ in,
+                                   double* __restrict__ out) {
+  const long long np = (long long)n * (n - 1) / 2;
+  const long long total = L * np * R;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx % R, P = (idx / R) % np, l = idx / (R * np);
+    int p, q;
+    pair_decode(P, p, q);
+    out[idx] = in[((l * n + p) * n + q) * R + r];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host entry points
+// ---------------------------------------------------------------------------------------
+static inline int blocks_for(long long n, int threads) {
+  long long b = (n + threads - 1) / threads;
+  return (int)std::max<long long>(1, std::min<long long>(b, 64LL * sm_count()));
+}
+
+int packed_unpack(cudaStream_t st, int no, int nv, const double* U, double* out) {
+  const long long n = (long long)no * no * nv * nv;
+  if (n == 0) return 0;
+  unpack_dense_kernel<<<blocks_for(n, 256), 256, 0, st>>>(no, nv, U, out);
+  ADCCB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+int packed_pack(cudaStream_t st, int no, int nv, const double* T, double* U) {
+  const long long n = (long long)no * (no - 1) / 2 * ((long long)nv * (nv - 1) / 2);
+  if (n == 0) return 0;
+  pack_dense_kernel<<<blocks_for(n, 256), 256, 0, st>>>(no, nv, T, U);
+  ADCCB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+int packed_expand(cudaStream_t st, int which, int no, int nv, const double* U, double* out) {
+  const long long npv = (long long)nv * (nv - 1) / 2, npo = (long long)no * (no - 1) / 2;
+  if (npv == 0 || npo == 0) return 0;
+  if (which == 0) {
+    expand_iakc_kernel<<<no * no, 256, 0, st>>>(no, nv, U, out);
+  } else if (which == 1) {
+    expand_occ_kernel<<<no * no, 256, 0, st>>>(no, npv, U, out);
+  } else if (which == 2) {
+    dim3 grid((unsigned)npo, (unsigned)std::min(nv, 8));
+    expand_virt_t_kernel<<<grid, 128, 0, st>>>(npo, nv, U, out);
+  } else {
+    return fail("packed_expand: unknown layout");
+  }
+  ADCCB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+int packed_fold_virt(cudaStream_t st, long long nrows, int nv, long long sa, const double* P1,
+                     const long long* off1, const double* P2, const long long* off2, double alpha,
+                     double* S) {
+  if (nrows == 0 || nv < 2) return 0;
+  if (nrows > 65535) return fail("packed_fold_virt: too many rows");
+  const int t = (nv + 31) / 32;
+  dim3 grid(t, t, (unsigned)nrows);
+  pack_antisym_virt_kernel<<<grid, dim3(32, 8), 0, st>>>(nv, sa, P1, off1, P2, off2, alpha, S);
+  ADCCB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+int packed_fold_occ(cudaStream_t st, int no, int nv, const double* C, double alpha, double* S) {
+  const long long npv = (long long)nv * (nv - 1) / 2, npo = (long long)no * (no - 1) / 2;
+  if (npv == 0 || npo == 0) return 0;
+  pack_antisym_occ_kernel<<<(unsigned)npo, 256, 0, st>>>(no, npv, C, alpha, S);
+  ADCCB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+int packed_diagonal(cudaStream_t st, int no, int nv, const double* dov, const double* doo,
+                    const double* dvv, double* D) {
+  const long long n = (long long)no * (no - 1) / 2 * ((long long)nv * (nv - 1) / 2);
+  if (n == 0) return 0;
+  packed_diagonal_kernel<<<blocks_for(n, 256), 256, 0, st>>>(no, nv, dov, doo, dvv, D);
+  ADCCB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+int synth_fill(cudaStream_t st, int layout, int blk, int no, int nv, unsigned long long seed,
+               double scale, long long n, long long row_begin, double* out) {
+  if (n <= 0) return 0;
+  if (no >= 1024 || nv >= 1024) return fail("synth_fill: extents must be < 1024");
+  synth_fill_kernel<<<blocks_for(n, 256), 256, 0, st>>>(layout, blk, no, nv, seed, scale, n, row_begin, out);
+  ADCCB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+int pair_select(cudaStream_t st, long long L, int n, long long R, const double* in, double* out) {
+  const long long total = L * ((long long)n * (n - 1) / 2) * R;
+  if (total <= 0) return 0;
+  pair_select_kernel<<<blocks_for(total, 256), 256, 0, st>>>(L, n, R, in, out);
+  ADCCB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+}  // namespace adccb

@@ -9,8 +9,15 @@ _FORBIDDEN_D = ["aabb", "bbaa", "aaab", "aaba", "abaa", "baaa", "abbb", "babb", 
 
 
 def guess_zero(matrix, spin_change=0, spin_block_symmetrisation="none"):
+    packed = getattr(matrix, "doubles_storage", "dense") == "packed"
+
+    def make(block, sym):
+        if packed and block == "pphh":
+            from ..packed import PackedDoubles
+            return PackedDoubles.zeros(sym.mospaces, sym.subspaces, sym)
+        return Tensor(sym)
     return AmplitudeVector(**{
-        block: Tensor(sym) for block, sym in guess_symmetries(
+        block: make(block, sym) for block, sym in guess_symmetries(
             matrix, spin_change=spin_change,
             spin_block_symmetrisation=spin_block_symmetrisation).items()})
 

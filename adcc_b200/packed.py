@@ -1,0 +1,425 @@
+"""Antisymmetry-packed doubles store and the hand-scheduled ADC(2) / ADC(2)-x matvec on it.
+
+Why: the doubles part of every ADC vector is antisymmetric in (i,j) and (a,b)
+(adcc/guess/guess_zero.py:163-171) and so are <ab||cd> and <ij||kl>.  Keeping only i<j, a<b
+(and c<d of the vvvv block) turns the dominant term  1/2 u[ijcd] <ab||cd>
+(adcc/adc_pp/matrix.py:244) into ONE GEMM  S[IJ,AB] = sum_CD U[IJ,CD] W[AB,CD]  with 8x fewer
+flops and 4x less memory: the BASELINE config-5 vvvv block (204.8 GB dense) becomes 50.9 GB
+and fits a single B200 next to the other operands.  Every Davidson vector shrinks 4x, and
+the explicit doubles symmetrisation (adcc/AdcMatrix.py:449-455) is the identity.
+
+``PackedDoubles`` is a Tensor whose storage is U[IJ,AB]; ``PackedAdcEngine`` evaluates the
+blocks of adcc/adc_pp/matrix.py:127-133 (pphh_pphh_0), :234-246 (pphh_pphh_1), :270-276
+(ph_pphh_1), :288-294 (pphh_ph_1) and :353-375 (ph_ph_2) on that store.  Requires canonical
+orbitals (diagonal Fock), which every SCF reference adcc accepts provides.
+"""
+import numpy as np
+
+from . import backend as be
+from .AmplitudeVector import AmplitudeVector
+from .Tensor import Tensor
+
+
+class PackedDoubles(Tensor):
+    """pphh tensor, antisymmetric in (0,1) and (2,3), stored as U[pair(i<j), pair(a<b)]."""
+
+    @classmethod
+    def zeros(cls, mospaces, subspaces, symmetry=None):
+        no, nv = mospaces.n_orbs(subspaces[0]), mospaces.n_orbs(subspaces[2])
+        if subspaces[0] != subspaces[1] or subspaces[2] != subspaces[3]:
+            raise ValueError("PackedDoubles needs equal occupied and equal virtual subspaces")
+        return cls._wrap(mospaces, subspaces, be.zeros((be.n_pairs(no), be.n_pairs(nv))), symmetry)
+
+    @classmethod
+    def from_dense(cls, tensor):
+        """Antisymmetrise + pack a dense pphh Tensor in one kernel."""
+        no, nv = tensor.shape[0], tensor.shape[2]
+        return cls._wrap(tensor.mospaces, tensor.subspaces,
+                         be.packed_pack(tensor._contig(), no, nv), tensor.symmetry)
+
+    @property
+    def _no(self): return self.mospaces.n_orbs(self.subspaces[0])
+    @property
+    def _nv(self): return self.mospaces.n_orbs(self.subspaces[2])
+    @property
+    def shape(self): return (self._no, self._no, self._nv, self._nv)
+    @property
+    def ndim(self): return 4
+    @property
+    def size(self): return self._no ** 2 * self._nv ** 2
+    @property
+    def packed_shape(self): return tuple(self._data.shape)
+
+    def __repr__(self):
+        return f"PackedDoubles({self.space}, packed={self.packed_shape})"
+
+    #: +1 for tensors that are SYMMETRIC under i<->j and a<->b (the matrix diagonal); -1 otherwise
+    parity = -1
+
+    def to_dense(self):
+        dense = be.packed_unpack(self._contig(), self._no, self._nv)
+        if self.parity > 0:
+            ones = torch_like_ones(self._contig())
+            dense = be.mul(dense, be.packed_unpack(ones, self._no, self._nv))   # sign^2 = 1
+        return Tensor._wrap(self.mospaces, self.subspaces, dense, self.symmetry)
+
+    def to_ndarray(self):
+        return self.to_dense().to_ndarray()
+
+    def set_from_ndarray(self, array, symmetry_tolerance=None):
+        self._require_mutable()
+        array = np.asarray(array, dtype=float)
+        if array.shape != self.shape:
+            raise ValueError(f"Shape mismatch: tensor {self.shape} vs array {array.shape}")
+        tol = 1e-12 if symmetry_tolerance is None else symmetry_tolerance
+        if (np.max(np.abs(array + array.transpose(1, 0, 2, 3))) > tol
+                or np.max(np.abs(array + array.transpose(0, 1, 3, 2))) > tol):
+            raise ValueError("array is not antisymmetric in (0,1) and (2,3)")
+        self._data = be.packed_pack(be.from_numpy(array), self._no, self._nv)
+        return self
+
+    def set_random(self):
+        self._require_mutable()
+        rng = np.random.default_rng(np.random.randint(0, 2**31 - 1))
+        self._data = be.from_numpy(rng.uniform(-1.0, 1.0, size=self._data.shape))
+        return self
+
+    def dot(self, other):
+        # Frobenius product of the DENSE tensors: every stored element occurs 4x
+        # (adcc/AmplitudeVector.py:85-95)
+        if isinstance(other, Tensor):
+            self._check_same(other)
+            return 4.0 * be.dot(self._contig(), other._contig())
+        for o in other:
+            self._check_same(o)
+        return be.dot_many(self._contig(), [o._contig() for o in other], scale=4.0)
+
+    def _locate(self, index):
+        i, j, a, b = self._norm_index(index)
+        if i == j or a == b:
+            return None, 0.0
+        sign = 1.0 if ((i < j) == (a < b)) else -1.0
+        i, j = min(i, j), max(i, j)
+        a, b = min(a, b), max(a, b)
+        return (j * (j - 1) // 2 + i, b * (b - 1) // 2 + a), sign
+
+    def is_allowed(self, index):
+        loc, _ = self._locate(tuple(index))
+        if loc is None:
+            return False
+        return True if self.symmetry is None else self.symmetry.is_allowed(self._norm_index(tuple(index)))
+
+    def __getitem__(self, index):
+        loc, sign = self._locate(index)
+        return 0.0 if loc is None else sign * float(self._data[loc].item())
+
+    def __setitem__(self, index, value):
+        self._require_mutable()
+        index = self._norm_index(index)
+        orb = {index: float(value)}
+        if self.symmetry is not None and not self.symmetry.empty:
+            orb = self.symmetry.orbit(index, float(value))
+        if orb is None or self._locate(index)[0] is None:
+            raise RuntimeError(f"Setting tensor index {index} is not allowed by symmetry")
+        t = self._contig()
+        for ix, val in orb.items():
+            loc, sign = self._locate(ix)
+            t[loc] = sign * val
+
+    def _select(self, n, key, reverse):
+        raise NotImplementedError("select_n_* is not available on the packed doubles store")
+
+    def transpose(self, axes=None):
+        return self.to_dense().transpose(axes)
+
+    def diagonal(self, *axes):
+        return self.to_dense().diagonal(*axes)
+
+    def _symm(self, perms, sign):
+        from .Tensor import _parse_perm_args
+        perms = sorted(tuple(sorted(p)) for p in _parse_perm_args(perms))
+        if sign < 0 and perms in ([(0, 1)], [(2, 3)]):
+            return self            # 1/2 (T - P T) = T for an antisymmetric pair
+        if sign > 0 and perms == [(0, 1), (2, 3)]:
+            return self            # simultaneous swap of two antisymmetric pairs
+        return self.to_dense()._symm(perms, sign)
+
+
+def torch_like_ones(t):
+    ones = be.empty(tuple(t.shape))
+    be.fill(ones, 1.0)
+    return ones
+
+
+class DenseSource:
+    """Stages the packed / GEMM-ready operands from a ReferenceState's dense device blocks."""
+
+    def __init__(self, hf, mp):
+        self.hf, self.mp = hf, mp
+        self.no, self.nv = hf.mospaces.n_orbs("o1"), hf.mospaces.n_orbs("v1")
+
+    def vvvv_packed(self):
+        return be.packed_pack(self.hf.vvvv._contig(), self.nv, self.nv)
+
+    def oooo_packed(self):
+        return be.packed_pack(self.hf.oooo._contig(), self.no, self.no)
+
+    def ovov_jbkc(self):     # Y[(j,b),(k,c)] = <kb||jc>
+        return be.permute(self.hf.ovov._data, (2, 1, 0, 3)).reshape(self.no * self.nv, self.no * self.nv)
+
+    def ovvv_jabc(self):     # V1[(j,AB),c] = <jc||ab>
+        sel = be.pair_select(self.hf.ovvv._contig(), 2)              # [j,c,AB]
+        return be.permute(sel, (0, 2, 1)).reshape(-1, self.nv)
+
+    def ovvv_ajbc(self):     # V2[a,(j,BC)] = <ja||bc>
+        sel = be.pair_select(self.hf.ovvv._contig(), 2)              # [j,a,BC]
+        return be.permute(sel, (1, 0, 2)).reshape(self.nv, -1)
+
+    def ooov_ijkb(self):     # G1[i,(JK,b)] = <jk||ib>
+        sel = be.pair_select(self.hf.ooov._contig(), 0)              # [JK,i,b]
+        return be.permute(sel, (1, 0, 2)).reshape(self.no, -1)
+
+    def ooov_ijak(self):     # G2[(IJ,a),k] = <ij||ka>
+        sel = be.pair_select(self.hf.ooov._contig(), 0)              # [IJ,k,a]
+        return be.permute(sel, (0, 2, 1)).reshape(-1, self.no)
+
+    def diag_vv(self):
+        from .functions import einsum
+        return einsum("abab->ab", self.hf.vvvv).symmetrise()._contig()
+
+
+class PackedAdcEngine:
+    """ADC(2) / ADC(2)-x matvec on the packed doubles store (see module docstring)."""
+
+    def __init__(self, matrix, source=None):
+        from .functions import einsum, direct_sum
+        hf, mp, im = matrix.reference_state, matrix.ground_state, matrix.intermediates
+        self.matrix = matrix
+        self.mospaces = hf.mospaces
+        self.no, self.nv = hf.mospaces.n_orbs("o1"), hf.mospaces.n_orbs("v1")
+        no, nv = self.no, self.nv
+        self.npo, self.npv = be.n_pairs(no), be.n_pairs(nv)
+        self.order_dd = matrix.block_orders["pphh_pphh"]
+        if matrix.block_orders["ph_ph"] != 2 or matrix.block_orders["ph_pphh"] != 1:
+            raise NotImplementedError("packed engine: ADC(2) and ADC(2)-x only")
+        foo, fvv = hf.foo.to_ndarray(), hf.fvv.to_ndarray()
+        offdiag = max(np.max(np.abs(foo - np.diag(np.diag(foo)))), np.max(np.abs(fvv - np.diag(np.diag(fvv)))))
+        if offdiag > 1e-12:
+            raise NotImplementedError("packed engine needs canonical orbitals (diagonal Fock)")
+        src = source if source is not None else getattr(hf, "packed_source", None)
+        if src is None:
+            src = DenseSource(hf, mp)
+        self.flops = {}
+
+        # ---- singles-singles block folded into one (ov x ov) matrix  (matrix.py:353-375)
+        i1, i2 = im.adc2_i1, im.adc2_i2
+        m1 = einsum("ij,ab->iajb", _delta_like(hf.foo), i1) - einsum("ij,ab->iajb", i2, _delta_like(hf.fvv))
+        m1 = m1 - hf.ovov.transpose((2, 1, 0, 3))               # - <ja||ib>
+        m1 = m1 - 0.5 * im.term_t2_eri.transpose((0, 2, 1, 3))  # - 1/2 term[ikac] -> [i,a,k,c]
+        self.M1 = m1._contig().reshape(no * nv, no * nv)
+
+        # ---- couplings (matrix.py:270-276, 288-294)
+        self.V1 = src.ovvv_jabc()
+        self.V2 = src.ovvv_ajbc()
+        self.G1 = src.ooov_ijkb()
+        self.G2 = src.ooov_ijak()
+
+        # ---- doubles-doubles (matrix.py:127-133, 234-246)
+        eo = be.from_numpy(np.diag(foo))
+        ev = be.from_numpy(np.diag(fvv))
+        d0_ov = be.direct_sum(eo, ev, -1.0, 1.0)                 # e_a - e_i
+        self.D0 = be.packed_diagonal(no, nv, d0_ov)              # e_a + e_b - e_i - e_j
+        if self.order_dd == 1:
+            self.W = src.vvvv_packed()
+            self.O = src.oooo_packed()
+            self.Y = src.ovov_jbkc()
+            d_ov = (direct_sum("a-i->ia", hf.fvv.diagonal(), hf.foo.diagonal())
+                    - 2.0 * einsum("iaia->ia", hf.ovov))._contig()
+            d_oo = einsum("ijij->ij", hf.oooo).symmetrise()._contig()
+            diag = be.packed_diagonal(no, nv, d_ov, d_oo, src.diag_vv())
+        else:
+            diag = self.D0
+        self.diagonal_pphh = PackedDoubles._wrap(self.mospaces, ["o1", "o1", "v1", "v1"], diag)
+        self.diagonal_pphh.parity = +1
+        self.diagonal_pphh.set_immutable()
+        # row offsets for the virtual-pair folds
+        pairs = [(i, j) for j in range(no) for i in range(j)]
+        self._off_ovov_1 = be.int64_tensor([(i * nv * no + j) * nv for i, j in pairs])
+        self._off_ovov_2 = be.int64_tensor([(j * nv * no + i) * nv for i, j in pairs])
+        self._off_rows = be.int64_tensor([r * nv * nv for r in range(self.npo)])
+        self._count_flops()
+
+    def _count_flops(self):
+        no, nv, npo, npv = self.no, self.nv, self.npo, self.npv
+        f = {"ph_ph": 2.0 * (no * nv) ** 2,
+             "ph_pphh": 2.0 * no * nv * (no * npv) + 2.0 * no * nv * (npo * nv),
+             "pphh_ph": 2.0 * no * (no * npv) * nv + 2.0 * (npo * nv) * nv * no}
+        if self.order_dd == 1:
+            f["pphh_pphh/vvvv"] = 2.0 * npo * npv * npv
+            f["pphh_pphh/oooo"] = 2.0 * npo * npo * npv
+            f["pphh_pphh/ovov"] = 2.0 * (no * nv) ** 3
+        self.flops = f
+        self.flops_per_matvec = sum(f.values())
+
+    # ------------------------------------------------------------------ block applies
+    def apply_ph_ph(self, u1):
+        x = u1._contig().reshape(1, self.no * self.nv)
+        return be.gemm(x, self.M1).reshape(self.no, self.nv)          # sum_jb M1[(ia),(jb)] u[jb]
+
+    def apply_ph_pphh(self, U):
+        no, nv = self.no, self.nv
+        Ue = be.packed_expand(1, U, no, nv)                 # [i,(j,BC)]
+        s1 = be.gemm(Ue, self.V2, alpha=2.0)                 # sum_{j,b<c} 2 u[ij,bc] <ja||bc>
+        Uh = be.packed_expand(2, U, no, nv)                 # [a,(JK,b)]
+        be.gemm(self.G1, Uh, out=s1, alpha=2.0, beta=1.0)    # sum_{j<k,b} 2 <jk||ib> u[jk,ab]
+        return s1
+
+    def apply_pphh_ph(self, u1, S):
+        no, nv = self.no, self.nv
+        x = u1._contig()
+        c1 = be.gemm(x, self.V1)                             # [i,(j,AB)] = sum_c u[ic] <jc||ab>
+        be.packed_fold_occ(S, c1, no, nv, alpha=0.5)         # antisymmetrise(0,1)
+        xt = be.permute(x, (1, 0))                           # [b,k]
+        c2 = be.gemm(self.G2, xt)                            # [(IJ,a),b] = sum_k <ij||ka> u[kb]
+        be.packed_fold_virt(S, nv, nv, c2, self._off_rows, alpha=-0.5)   # - antisymmetrise(2,3)
+        return S
+
+    def apply_pphh_pphh(self, U, S, beta):
+        """S = beta*S + (pphh_pphh block) U."""
+        no, nv = self.no, self.nv
+        # 0th order: 2 A_ab(u f_vv) - 2 A_ij(f_oo u) = (e_a + e_b - e_i - e_j) u for canonical orbitals
+        be.mul(U, self.D0, out=S, beta=beta)
+        if self.order_dd == 0:
+            return S
+        be.gemm(U, self.W, out=S, alpha=1.0, beta=1.0)       # 1/2 u[ijcd] <ab||cd> = sum_{c<d}
+        Ut = be.permute(U, (1, 0))                           # [AB,KL]
+        be.gemm(self.O, Ut, out=S, alpha=1.0, beta=1.0)      # 1/2 <ij||kl> u[klab] = sum_{k<l}
+        X = be.packed_expand(0, U, no, nv)                  # [(i,a),(k,c)] = u[ikac]
+        T = be.gemm(X, self.Y)                               # [(i,a),(j,b)] = sum_kc u[ikac] <kb||jc>
+        del X
+        # -4 A_ij A_ab T = -(T[ia,jb] - T[ja,ib] - T[ib,ja] + T[jb,ia])
+        be.packed_fold_virt(S, nv, no * nv, T, self._off_ovov_1, T, self._off_ovov_2, alpha=-1.0)
+        return S
+
+    # ------------------------------------------------------------------ matvec
+    def _wrap_ph(self, data):
+        return Tensor._wrap(self.mospaces, ["o1", "v1"], data)
+
+    def _wrap_pphh(self, data):
+        return PackedDoubles._wrap(self.mospaces, ["o1", "o1", "v1", "v1"], data)
+
+    def matvec(self, v):
+        u1, u2 = v["ph"], v["pphh"]
+        if not isinstance(u2, PackedDoubles):
+            u2 = PackedDoubles.from_dense(u2)
+        U = u2._contig()
+        s1 = self.apply_ph_ph(u1)
+        s1c = self.apply_ph_pphh(U)
+        be.axpby(1.0, s1c, 1.0, s1)
+        S = be.empty((self.npo, self.npv))
+        self.apply_pphh_pphh(U, S, 0.0)
+        self.apply_pphh_ph(u1, S)
+        return AmplitudeVector(ph=self._wrap_ph(s1), pphh=self._wrap_pphh(S))
+
+    def block_apply(self, block, tensor):
+        if block == "ph_ph":
+            return self._wrap_ph(self.apply_ph_ph(tensor))
+        if block == "ph_pphh":
+            t = tensor if isinstance(tensor, PackedDoubles) else PackedDoubles.from_dense(tensor)
+            return self._wrap_ph(self.apply_ph_pphh(t._contig()))
+        S = be.zeros((self.npo, self.npv))
+        if block == "pphh_ph":
+            return self._wrap_pphh(self.apply_pphh_ph(tensor, S))
+        if block == "pphh_pphh":
+            t = tensor if isinstance(tensor, PackedDoubles) else PackedDoubles.from_dense(tensor)
+            return self._wrap_pphh(self.apply_pphh_pphh(t._contig(), S, 0.0))
+        raise ValueError(block)
+
+
+def _delta_like(t):
+    d = t.zeros_like()
+    d._mutable = True
+    d.set_mask("ii", 1.0)
+    return d
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 5: synthetic ADC(2)-x workload generated on the device
+# ------------------------------------------------------------------------------------------------
+class SyntheticSource:
+    """Writes every ERI operand of the packed engine directly in its GEMM layout from the
+    counter-based hash (adccb_synth_fill): nothing is staged through the host, and the
+    204.8 GB dense vvvv block never exists."""
+
+    def __init__(self, no, nv, seed, scale):
+        self.no, self.nv, self.seed, self.scale = no, nv, seed, scale
+        self.npo, self.npv = be.n_pairs(no), be.n_pairs(nv)
+
+    def _fill(self, shape, layout, **kw):
+        out = be.empty(shape)
+        return be.synth_fill(out, layout, self.no, self.nv, self.seed, self.scale, **kw)
+
+    def vvvv_packed(self, row_begin=0, n_rows=None):
+        n_rows = self.npv - row_begin if n_rows is None else n_rows
+        return self._fill((n_rows, self.npv), "vvvv_packed", row_begin=row_begin)
+
+    def oooo_packed(self): return self._fill((self.npo, self.npo), "oooo_packed")
+    def ovov_jbkc(self): return self._fill((self.no * self.nv, self.no * self.nv), "ovov_jbkc")
+    def ovvv_jabc(self): return self._fill((self.no * self.npv, self.nv), "ovvv_jabc")
+    def ovvv_ajbc(self): return self._fill((self.nv, self.no * self.npv), "ovvv_ajbc")
+    def ooov_ijkb(self): return self._fill((self.no, self.npo * self.nv), "ooov_ijkb")
+    def ooov_ijak(self): return self._fill((self.npo * self.nv, self.no), "ooov_ijak")
+
+    def diag_vv(self):
+        from .synthetic import synthetic_eri_value
+        a, b = np.meshgrid(np.arange(self.nv), np.arange(self.nv), indexing="ij")
+        return be.from_numpy(synthetic_eri_value(self.seed, "vvvv", a, b, a, b, self.scale))
+
+    def dense(self, block):
+        shape = [self.no if c == "o" else self.nv for c in block]
+        return self._fill(shape, "dense", block=block)
+
+
+def synthetic_reference_state(no, nv, seed=20261019, scale=0.02):
+    """ReferenceState of the synthetic workload: unrestricted-style (no spin-block maps, no spin
+    zeros), canonical orbitals with e_occ = linspace(-2.0,-0.3,no), e_virt = linspace(0.2,4.0,nv),
+    <pq||rs> from the counter-based hash.  Dense oooo/ooov/oovv/ovov blocks are generated on
+    demand; ovvv and vvvv exist only in the packed GEMM layouts of ``packed_source``."""
+    from .DataHfProvider import HartreeFockProvider
+    from .ReferenceState import ReferenceState
+    from .synthetic import synthetic_orbital_energies, synthetic_eri_value
+    if no % 2 or nv % 2:
+        raise ValueError("no and nv must be even (equal alpha and beta counts)")
+    e_o, e_v = synthetic_orbital_energies(no, nv)
+    na = (no + nv) // 2
+    orben = np.concatenate((e_o[0::2], e_v[0::2], e_o[1::2], e_v[1::2]))
+    occ = np.concatenate((np.ones(no // 2), np.zeros(nv // 2), np.ones(no // 2), np.zeros(nv // 2)))
+
+    class SyntheticHfProvider(HartreeFockProvider):
+        def get_restricted(self): return False
+        def get_conv_tol(self): return 1e-12
+        def get_n_orbs_alpha(self): return na
+        def get_n_bas(self): return na
+        def fill_occupation_f(self, out): out[:] = occ
+        def fill_orben_f(self, out): out[:] = orben
+        def fill_orbcoeff_fb(self, out): out[:] = np.vstack((np.eye(na), np.eye(na)))
+        def fill_fock_ff(self, slices, out): out[:] = np.diag(orben)[slices]
+        def get_backend(self): return f"synthetic(no={no},nv={nv},seed={seed})"
+        def get_spin_multiplicity(self): return 0
+
+    class SyntheticReferenceState(ReferenceState):
+        def _stage_eri(self, sp):
+            letters = "".join("o" if s == "o1" else "v" for s in sp)
+            if letters not in ("oooo", "ooov", "oovv", "ovov", "ovvv", "vvvv"):
+                raise NotImplementedError(f"synthetic block {letters} is not defined")
+            n = int(np.prod([self.mospaces.n_orbs(s) for s in sp], dtype=np.int64))
+            if n * 8 > (8 << 30):
+                raise MemoryError(f"dense {letters} block of the synthetic workload is not "
+                                  "materialised; use the packed operands")
+            return self.packed_source.dense(letters)
+
+    ref = SyntheticReferenceState.__new__(SyntheticReferenceState)
+    ref.packed_source = SyntheticSource(no, nv, seed, scale)
+    ReferenceState.__init__(ref, SyntheticHfProvider(), import_all_below_n_orbs=None)
+    ref.synthetic = dict(no=no, nv=nv, seed=seed, scale=scale)
+    return ref

@@ -48,3 +48,62 @@ def restricted_scf_dict(n_orb, n_occ, seed=1001, scale=0.05, conv_tol=1e-12):
 def named_case(name):
     n_orb, n_occ, core, seed = SHAPES[name]
     return restricted_scf_dict(n_orb, n_occ, seed), core
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE config 5: counter-based synthetic antisymmetrised ERIs.
+# This is the DEFINITION of the inputs; the CUDA generator (csrc/packed_ops.cu::synthetic_eri)
+# implements the same integer hash, so the CPU oracle can evaluate any <pq||rs> entry.
+# ----------------------------------------------------------------------------------------------
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+ERI_BLOCKS = {"oooo": 0, "ooov": 1, "oovv": 2, "ovov": 3, "ovvv": 4, "vvvv": 5}
+
+
+def _splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+    z = x
+    z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+    z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+    return z ^ (z >> np.uint64(31))
+
+
+def synthetic_eri_value(seed, block, p, q, r, s, scale):
+    """<pq||rs> of the synthetic workload for integer index arrays (broadcastable)."""
+    blk = ERI_BLOCKS[block]
+    p, q, r, s = (np.asarray(x, dtype=np.int64) for x in np.broadcast_arrays(p, q, r, s))
+    p, q, r, s = p.copy(), q.copy(), r.copy(), s.copy()
+    sign = np.ones(p.shape)
+    zero = np.zeros(p.shape, dtype=bool)
+    if block in ("oooo", "ooov", "oovv", "vvvv"):
+        zero |= p == q
+        sw = p > q
+        p, q = np.where(sw, q, p), np.where(sw, p, q)
+        sign = np.where(sw, -sign, sign)
+    if block in ("oooo", "oovv", "ovvv", "vvvv"):
+        zero |= r == s
+        sw = r > s
+        r, s = np.where(sw, s, r), np.where(sw, r, s)
+        sign = np.where(sw, -sign, sign)
+    if block in ("oooo", "vvvv", "ovov"):
+        sw = (p > r) | ((p == r) & (q > s))
+        p, r = np.where(sw, r, p), np.where(sw, p, r)
+        q, s = np.where(sw, s, q), np.where(sw, q, s)
+    with np.errstate(over="ignore"):
+        key = ((p.astype(np.uint64) * np.uint64(1024) + q.astype(np.uint64)) * np.uint64(1024)
+               + r.astype(np.uint64)) * np.uint64(1024) + s.astype(np.uint64)
+        h = _splitmix64(np.uint64(seed) ^ _splitmix64(key * np.uint64(8) + np.uint64(blk)))
+    u = (h >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    val = sign * (2.0 * u - 1.0) * 1.7320508075688772 * scale
+    return np.where(zero, 0.0, val)
+
+
+def synthetic_eri_block(seed, block, no, nv, scale):
+    """Dense spin-orbital block (small sizes only; used by the oracle in parity tests)."""
+    ext = [no if c == "o" else nv for c in block]
+    idx = np.meshgrid(*[np.arange(e) for e in ext], indexing="ij")
+    return synthetic_eri_value(seed, block, *idx, scale)
+
+
+def synthetic_orbital_energies(no, nv):
+    """e_occ = linspace(-2.0, -0.3, no), e_virt = linspace(0.2, 4.0, nv)."""
+    return np.linspace(-2.0, -0.3, no), np.linspace(0.2, 4.0, nv)

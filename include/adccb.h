@@ -81,6 +81,45 @@ int adccb_spin_project(void* stream, int ndim, const int* shape, const int* n_al
  * libadcc_src/amplitude_vector_enforce_spin_kind.cc:33-170. */
 int adccb_spin_singlet(void* stream, const int* shape, const int* n_alpha, double* T);
 
+/* ---- antisymmetry-packed doubles store: U[IJ,AB], IJ = j(j-1)/2+i (i<j), AB = b(b-1)/2+a (a<b).
+ * The doubles part of every ADC vector is antisymmetric in (i,j) and (a,b)
+ * (adcc/guess/guess_zero.py:163-171); libtensor stores canonical blocks only, this store keeps
+ * canonical elements only.  no / nv = number of occupied / virtual spin orbitals. */
+
+/* out[i,j,a,b] (dense) from packed U, with signs and zero diagonals (Tensor::export_to,
+ * libadcc_src/TensorImpl.cc:1369-1376). */
+int adccb_packed_unpack(void* stream, int no, int nv, const double* U, double* out);
+/* U[IJ,AB] = 1/4 (T[ijab] - T[jiab] - T[ijba] + T[jiba]) from dense T: import + the doubles
+ * symmetrisation of adcc/AdcMatrix.py:449-455 in one pass. */
+int adccb_packed_pack(void* stream, int no, int nv, const double* T, double* U);
+/* GEMM-ready expansions of packed U: which = 0: X[i,a,k,c] = u[ikac]; 1: Ue[i,j,AB] = u[ij,AB];
+ * 2: Uh[a,JK,b] = u[JK,ab]. */
+int adccb_packed_expand(void* stream, int which, int no, int nv, const double* U, double* out);
+/* S[r, AB] += alpha * (F_r[a,b] - F_r[b,a]), F_r[a,b] = P1[off1[r] + a*sa + b] - P2[off2[r] + a*sa + b]
+ * (P2/off2 may be NULL); off1/off2: device int64 arrays of length nrows.  Folds the ovov-type
+ * and ooov-type GEMM results into packed sigma (the antisymmetrise(2,3) of
+ * adcc/adc_pp/matrix.py:241-243, 291-292). */
+int adccb_packed_fold_virt(void* stream, int64_t nrows, int nv, int64_t sa, const double* P1,
+                           const int64_t* off1, const double* P2, const int64_t* off2,
+                           double alpha, double* S);
+/* S[pair(i,j), AB] += alpha * (C[i,j,AB] - C[j,i,AB])  (antisymmetrise(0,1), matrix.py:291). */
+int adccb_packed_fold_occ(void* stream, int no, int nv, const double* C, double alpha, double* S);
+/* D[IJ,AB] = 1/2 (dov[i,a]+dov[j,b]+dov[i,b]+dov[j,a]) + doo[i,j] + dvv[a,b] (doo, dvv may be
+ * NULL): packed diagonal of the pphh-pphh block, adcc/adc_pp/matrix.py:109-124, 212-231. */
+int adccb_packed_diagonal(void* stream, int no, int nv, const double* dov, const double* doo,
+                          const double* dvv, double* D);
+/* out[l, pair(p<q), r] = in[l, p, q, r]: keeps the canonical half of an antisymmetric index pair
+ * while staging ERI blocks (ooov first pair, ovvv last pair) into their GEMM layout. */
+int adccb_pair_select(void* stream, int64_t L, int n, int64_t R, const double* in, double* out);
+/* Synthetic antisymmetrised ERIs of BASELINE config 5 generated in place from a counter-based
+ * hash (no host data): layout 0 W[AB,CD] (vvvv, rows row_begin..), 1 O[IJ,KL] (oooo),
+ * 2 Y[(j,b),(k,c)] = <kb||jc>, 3 V1[(j,AB),c] = <jc||ab>, 4 V2[a,(j,BC)] = <ja||bc>,
+ * 5 G1[i,(JK,b)] = <jk||ib>, 6 G2[(IJ,a),k] = <ij||ka>, 7 dense block blk
+ * (0 oooo, 1 ooov, 2 oovv, 3 ovov, 4 ovvv, 5 vvvv).  n = number of elements written.
+ * Stands in for ReferenceState::eri -> import_eri_* (libadcc_src/ReferenceState.cc:478-509). */
+int adccb_synth_fill(void* stream, int layout, int blk, int no, int nv, uint64_t seed, double scale,
+                     int64_t n, int64_t row_begin, double* out);
+
 #ifdef __cplusplus
 }
 #endif

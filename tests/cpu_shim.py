@@ -88,11 +88,138 @@ def install(monkeypatch):
         t[ni:, nj:, na:, nb:] = new
         return t
 
+
+    # ---- packed doubles primitives (numpy restatements of csrc/packed_ops.cu)
+    def _pairs(n):
+        return [(p, q) for q in range(n) for p in range(q)]
+
+    def packed_unpack(U, no, nv):
+        out = torch.zeros((no, no, nv, nv), dtype=F64)
+        po, pv = _pairs(no), _pairs(nv)
+        Un = U.numpy()
+        o = out.numpy()
+        for I, (i, j) in enumerate(po):
+            for A, (a, b) in enumerate(pv):
+                x = Un[I, A]
+                o[i, j, a, b] = x; o[j, i, a, b] = -x; o[i, j, b, a] = -x; o[j, i, b, a] = x
+        return out
+
+    def packed_pack(T, no, nv):
+        t = T.contiguous().numpy().reshape(no, no, nv, nv)
+        t = 0.25 * (t - t.transpose(1, 0, 2, 3) - t.transpose(0, 1, 3, 2) + t.transpose(1, 0, 3, 2))
+        po, pv = _pairs(no), _pairs(nv)
+        ii = np.array([p[0] for p in po], dtype=int); jj = np.array([p[1] for p in po], dtype=int)
+        aa = np.array([p[0] for p in pv], dtype=int); bb = np.array([p[1] for p in pv], dtype=int)
+        if len(po) == 0 or len(pv) == 0:
+            return torch.zeros((len(po), len(pv)), dtype=F64)
+        return from_numpy(t[ii[:, None], jj[:, None], aa[None, :], bb[None, :]])
+
+    def packed_expand(which, U, no, nv, out=None):
+        d = packed_unpack(U, no, nv)
+        if which == 0:
+            return d.permute(0, 2, 1, 3).contiguous().reshape(no * nv, no * nv)
+        if which == 1:
+            pv = _pairs(nv)
+            aa = torch.tensor([p[0] for p in pv], dtype=torch.long); bb = torch.tensor([p[1] for p in pv], dtype=torch.long)
+            return d[:, :, aa, bb].contiguous().reshape(no, -1)
+        po = _pairs(no)
+        ii = torch.tensor([p[0] for p in po], dtype=torch.long); jj = torch.tensor([p[1] for p in po], dtype=torch.long)
+        return d[ii, jj].permute(1, 0, 2).contiguous().reshape(nv, -1)
+
+    def packed_fold_virt(S, nv, sa, P1, off1, P2=None, off2=None, alpha=1.0):
+        pv = _pairs(nv)
+        aa = np.array([p[0] for p in pv], dtype=int); bb = np.array([p[1] for p in pv], dtype=int)
+        p1 = P1.contiguous().reshape(-1).numpy()
+        p2 = P2.contiguous().reshape(-1).numpy() if P2 is not None else None
+        Sn = S.numpy()
+        for r in range(S.shape[0]):
+            def F(a, b):
+                v = p1[int(off1[r]) + a * sa + b]
+                if p2 is not None:
+                    v = v - p2[int(off2[r]) + a * sa + b]
+                return v
+            Sn[r] += alpha * (F(aa, bb) - F(bb, aa))
+        return S
+
+    def packed_fold_occ(S, C, no, nv, alpha=1.0):
+        c = C.contiguous().reshape(no, no, -1)
+        for I, (i, j) in enumerate(_pairs(no)):
+            S[I] += alpha * (c[i, j] - c[j, i])
+        return S
+
+    def packed_diagonal(no, nv, dov, doo=None, dvv=None):
+        po, pv = _pairs(no), _pairs(nv)
+        D = torch.zeros((len(po), len(pv)), dtype=F64)
+        dov = dov.reshape(no, nv)
+        for I, (i, j) in enumerate(po):
+            for A, (a, b) in enumerate(pv):
+                v = 0.5 * (dov[i, a] + dov[j, b] + dov[i, b] + dov[j, a])
+                if doo is not None:
+                    v = v + doo.reshape(no, no)[i, j]
+                if dvv is not None:
+                    v = v + dvv.reshape(nv, nv)[a, b]
+                D[I, A] = v
+        return D
+
+    def pair_select(t, axis):
+        n = t.shape[axis]
+        pp = _pairs(n)
+        ii = torch.tensor([p[0] for p in pp], dtype=torch.long); jj = torch.tensor([p[1] for p in pp], dtype=torch.long)
+        idx = [slice(None)] * t.dim()
+        idx[axis] = ii
+        idx[axis + 1] = jj
+        res = t.contiguous()[tuple(idx)]
+        # advanced indices adjacent -> result axis stays in place
+        return res.contiguous()
+
+    def int64_tensor(values):
+        return torch.tensor([int(v) for v in values], dtype=torch.int64)
+
+    def synth_fill(out, layout, no, nv, seed, scale, block="vvvv", row_begin=0):
+        from adcc_b200.synthetic import synthetic_eri_value as val
+        po, pv = np.array(_pairs(no), dtype=int).reshape(-1, 2), np.array(_pairs(nv), dtype=int).reshape(-1, 2)
+        o, v = np.arange(no), np.arange(nv)
+        if layout == "vvvv_packed":
+            rows = pv[row_begin:row_begin + out.shape[0]]
+            arr = val(seed, "vvvv", rows[:, 0][:, None], rows[:, 1][:, None], pv[:, 0][None, :], pv[:, 1][None, :], scale)
+        elif layout == "oooo_packed":
+            arr = val(seed, "oooo", po[:, 0][:, None], po[:, 1][:, None], po[:, 0][None, :], po[:, 1][None, :], scale)
+        elif layout == "ovov_jbkc":
+            j, b, k, c = np.meshgrid(o, v, o, v, indexing="ij")
+            arr = val(seed, "ovov", k, b, j, c, scale)
+        elif layout == "ovvv_jabc":
+            j, AB, c = np.meshgrid(o, np.arange(len(pv)), v, indexing="ij")
+            arr = val(seed, "ovvv", j, c, pv[AB, 0], pv[AB, 1], scale)
+        elif layout == "ovvv_ajbc":
+            a, j, BC = np.meshgrid(v, o, np.arange(len(pv)), indexing="ij")
+            arr = val(seed, "ovvv", j, a, pv[BC, 0], pv[BC, 1], scale)
+        elif layout == "ooov_ijkb":
+            i, JK, b = np.meshgrid(o, np.arange(len(po)), v, indexing="ij")
+            arr = val(seed, "ooov", po[JK, 0], po[JK, 1], i, b, scale)
+        elif layout == "ooov_ijak":
+            IJ, a, k = np.meshgrid(np.arange(len(po)), v, o, indexing="ij")
+            arr = val(seed, "ooov", po[IJ, 0], po[IJ, 1], k, a, scale)
+        else:
+            from adcc_b200.synthetic import synthetic_eri_block
+            arr = synthetic_eri_block(seed, block, no, nv, scale)
+        out.copy_(torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).reshape(out.shape))
+        return out
+
+    def mul(x, y, alpha=1.0, out=None, beta=0.0):
+        res = alpha * x * y
+        if out is None:
+            return res.contiguous()
+        out.copy_(res + beta * out if beta != 0.0 else res)
+        return out
+
     for name, fn in dict(empty=empty, zeros=zeros, from_numpy=from_numpy, gemm=gemm, gather=gather,
                          permute=permute, contiguous=contiguous, fill=fill, axpby=axpby,
                          scaled_copy=scaled_copy, mul=mul, div=div, div_shift=div_shift,
                          add_scalar=add_scalar, direct_sum=direct_sum, lincomb=lincomb,
                          dot_many=dot_many, dot=dot, spin_project=spin_project,
-                         spin_singlet_=spin_singlet_).items():
+                         spin_singlet_=spin_singlet_, packed_unpack=packed_unpack, packed_pack=packed_pack,
+                         packed_expand=packed_expand, packed_fold_virt=packed_fold_virt,
+                         packed_fold_occ=packed_fold_occ, packed_diagonal=packed_diagonal,
+                         pair_select=pair_select, int64_tensor=int64_tensor, synth_fill=synth_fill).items():
         monkeypatch.setattr(be, name, fn)
     monkeypatch.setattr(be, "device", lambda: cpu)

@@ -1,0 +1,71 @@
+"""Shared checks for the packed engine (run through the CPU shim here and through CUDA on the GPU box)."""
+import numpy as np
+
+import oracle
+from oracle.hfdata import load_h2o_sto3g
+from oracle.synthetic import OracleSyntheticRef
+from adc_parity_common import random_vector, rel_err, SIGMA_RTOL, ENERGY_ATOL
+
+
+def _packed_vector(adcc, v):
+    from adcc_b200.packed import PackedDoubles
+    return adcc.AmplitudeVector(ph=v.ph, pphh=PackedDoubles.from_dense(v.pphh))
+
+
+def _compare(adcc, m, om, seed=3):
+    v, ov = random_vector(m, om, seed)
+    vp = _packed_vector(adcc, v)
+    sig, osig = m.matvec(vp), om.matvec(ov)
+    assert rel_err(sig.ph.to_ndarray(), osig["ph"]) < SIGMA_RTOL
+    assert rel_err(sig.pphh.to_ndarray(), osig["pphh"]) < SIGMA_RTOL
+    for blk in ("ph_ph", "ph_pphh", "pphh_ph", "pphh_pphh"):
+        outb, inb = blk.split("_")
+        res = m.block_apply(blk, vp[inb])
+        ores = om.blocks[blk]({inb: ov[inb]})[outb]
+        assert rel_err(res.to_ndarray(), ores) < SIGMA_RTOL, blk
+    assert rel_err(m.diagonal().ph.to_ndarray(), om.diagonal()["ph"]) < SIGMA_RTOL
+    dd, od = m.diagonal().pphh.to_ndarray(), om.diagonal()["pphh"]
+    mask = np.ones_like(od, dtype=bool)
+    n_o, n_v = od.shape[0], od.shape[2]
+    mask[np.arange(n_o), np.arange(n_o)] = False
+    mask[:, :, np.arange(n_v), np.arange(n_v)] = False
+    assert rel_err(dd[mask], od[mask]) < SIGMA_RTOL
+    # hermiticity on the packed store
+    w, _ = random_vector(m, om, seed + 1)
+    wp = _packed_vector(adcc, w)
+    lhs, rhs = vp @ m.matvec(wp), sig @ wp
+    assert abs(lhs - rhs) < 1e-11 * max(1.0, abs(lhs))
+    return sig, osig
+
+
+def check_packed_matrix(method, data=None):
+    import adcc_b200 as adcc
+    data = data if data is not None else load_h2o_sto3g()
+    m = adcc.AdcMatrix(method, adcc.ReferenceState(data), doubles_storage="packed")
+    om = oracle.OracleAdcMatrix(method, oracle.OracleRefState(oracle.OracleHf(data)))
+    return _compare(adcc, m, om)
+
+
+def check_packed_run(method, n=4):
+    import adcc_b200 as adcc
+    data = load_h2o_sto3g()
+    m = adcc.AdcMatrix(method, adcc.ReferenceState(data), doubles_storage="packed")
+    st = adcc.run_adc(m, n_states=n, conv_tol=1e-9, output=None)
+    ost = oracle.run_adc(data, method, n_states=n, conv_tol=1e-9)
+    assert st.converged
+    np.testing.assert_allclose(st.excitation_energy, ost.eigenvalues, atol=ENERGY_ATOL, rtol=0)
+    assert st.n_iter == ost.n_iter
+
+
+def check_synthetic(no, nv, seed=5, run=True):
+    import adcc_b200 as adcc
+    from adcc_b200.packed import synthetic_reference_state
+    ref = synthetic_reference_state(no, nv, seed=seed, scale=0.02)
+    om = oracle.OracleAdcMatrix("adc2x", OracleSyntheticRef(no, nv, seed=seed, scale=0.02))
+    m = adcc.AdcMatrix("adc2x", ref, doubles_storage="packed")
+    _compare(adcc, m, om)
+    if run:
+        st = adcc.run_adc(m, n_states=3, conv_tol=1e-8, output=None)
+        ost = oracle.run_adc(om, "adc2x", n_states=3, conv_tol=1e-8)
+        assert st.converged
+        np.testing.assert_allclose(st.excitation_energy, ost.eigenvalues, atol=ENERGY_ATOL, rtol=0)

@@ -1,0 +1,67 @@
+"""Packed doubles store + ADC(2)/ADC(2)-x engine + synthetic workload: host logic against the
+oracle through the TEST-ONLY CPU shim (see tests/cpu_shim.py)."""
+import numpy as np
+import pytest
+
+import cpu_shim
+from packed_parity_common import check_packed_matrix, check_packed_run, check_synthetic
+
+
+@pytest.fixture(autouse=True)
+def shim(monkeypatch):
+    cpu_shim.install(monkeypatch)
+
+
+@pytest.mark.parametrize("method", ["adc2", "adc2x"])
+def test_packed_matvec_h2o(method):
+    check_packed_matrix(method)
+
+
+@pytest.mark.parametrize("method", ["adc2", "adc2x"])
+def test_packed_davidson_h2o(method):
+    check_packed_run(method)
+
+
+def test_synthetic_workload_small():
+    check_synthetic(6, 10, seed=5)
+
+
+def test_packed_tensor_semantics():
+    import adcc_b200 as adcc
+    from adcc_b200.packed import PackedDoubles
+    from oracle.hfdata import load_h2o_sto3g
+    ref = adcc.ReferenceState(load_h2o_sto3g())
+    rng = np.random.default_rng(0)
+    d = rng.standard_normal((10, 10, 4, 4))
+    d = d - d.transpose(1, 0, 2, 3)
+    d = d - d.transpose(0, 1, 3, 2)
+    t = adcc.Tensor.from_ndarray(ref.mospaces, "o1o1v1v1", d)
+    p = PackedDoubles.from_dense(t)
+    assert p.shape == (10, 10, 4, 4) and p.packed_shape == (45, 6)
+    np.testing.assert_allclose(p.to_ndarray(), d, atol=1e-15)
+    assert abs(p.dot(p) - np.vdot(d, d)) < 1e-11          # dense Frobenius weight (4x)
+    np.testing.assert_allclose((2.0 * p - p / 4.0).to_ndarray(), 1.75 * d, atol=1e-14)
+    assert p.antisymmetrise(0, 1) is p and p.symmetrise([(0, 1), (2, 3)]) is p
+    assert p[1, 0, 2, 3] == -p[0, 1, 2, 3] and p[0, 0, 1, 2] == 0.0
+    with pytest.raises(ValueError):
+        p + t                                              # mixed storage
+    q = p.zeros_like()
+    q[0, 1, 2, 3] = 2.0
+    assert q[1, 0, 3, 2] == 2.0 and q[0, 1, 3, 2] == -2.0
+    with pytest.raises(ValueError):
+        PackedDoubles.zeros(ref.mospaces, ["o1", "o1", "v1", "v1"]).set_from_ndarray(np.ones((10, 10, 4, 4)))
+
+
+def test_synthetic_definition_symmetries():
+    from adcc_b200.synthetic import synthetic_eri_block
+    for blk, bra, ket, swap in (("vvvv", True, True, True), ("oooo", True, True, True),
+                                ("oovv", True, True, False), ("ooov", True, False, False),
+                                ("ovvv", False, True, False), ("ovov", False, False, True)):
+        v = synthetic_eri_block(11, blk, 4, 6, 0.02)
+        if bra:
+            assert np.array_equal(v, -v.transpose(1, 0, 2, 3))
+        if ket:
+            assert np.array_equal(v, -v.transpose(0, 1, 3, 2))
+        if swap:
+            assert np.array_equal(v, v.transpose(2, 3, 0, 1))
+        assert 0.015 < v[v != 0].std() < 0.025

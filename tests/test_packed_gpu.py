@@ -1,0 +1,98 @@
+"""Packed doubles kernels + engine + device-side synthetic generator on the B200 (C ABI path)."""
+import numpy as np
+import pytest
+
+from packed_parity_common import check_packed_matrix, check_packed_run, check_synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def be():
+    import torch
+    from adcc_b200 import backend
+    torch.cuda.set_device(0)
+    return backend
+
+
+@pytest.mark.parametrize("no,nv", [(4, 6), (6, 34), (10, 38), (2, 2)])
+def test_pack_unpack_expand_fold(be, no, nv):
+    rng = np.random.default_rng(no * nv)
+    d = rng.standard_normal((no, no, nv, nv))
+    d = d - d.transpose(1, 0, 2, 3)
+    d = d - d.transpose(0, 1, 3, 2)
+    U = be.packed_pack(be.from_numpy(d), no, nv)
+    npo, npv = no * (no - 1) // 2, nv * (nv - 1) // 2
+    assert tuple(U.shape) == (npo, npv)
+    assert np.allclose(be.packed_unpack(U, no, nv).cpu().numpy(), d, atol=1e-15)
+    X = be.packed_expand(0, U, no, nv).cpu().numpy().reshape(no, nv, no, nv)
+    assert np.array_equal(X, d.transpose(0, 2, 1, 3))
+    po = [(i, j) for j in range(no) for i in range(j)]
+    pv = [(a, b) for b in range(nv) for a in range(b)]
+    Ue = be.packed_expand(1, U, no, nv).cpu().numpy().reshape(no, no, npv)
+    assert np.array_equal(Ue, np.stack([d[:, :, a, b] for a, b in pv], axis=-1))
+    Uh = be.packed_expand(2, U, no, nv).cpu().numpy().reshape(nv, npo, nv)
+    assert np.array_equal(Uh, np.stack([d[i, j] for i, j in po], axis=1))
+    # folds
+    C = rng.standard_normal((no, no, npv))
+    S0 = rng.standard_normal((npo, npv))
+    S = be.from_numpy(S0)
+    be.packed_fold_occ(S, be.from_numpy(C), no, nv, alpha=0.5)
+    ref = S0 + 0.5 * np.stack([C[i, j] - C[j, i] for i, j in po])
+    assert np.allclose(S.cpu().numpy(), ref, atol=1e-14)
+    C2 = rng.standard_normal((npo, nv, nv))
+    S = be.from_numpy(S0)
+    be.packed_fold_virt(S, nv, nv, be.from_numpy(C2), be.int64_tensor([r * nv * nv for r in range(npo)]), alpha=-0.5)
+    ref = S0 - 0.5 * np.stack([C2[:, a, b] - C2[:, b, a] for a, b in pv], axis=1)
+    assert np.allclose(S.cpu().numpy(), ref, atol=1e-14)
+    # pair_select
+    T = rng.standard_normal((3, nv, nv, 5))
+    sel = be.pair_select(be.from_numpy(T), 1).cpu().numpy()
+    assert np.array_equal(sel, np.stack([T[:, a, b, :] for a, b in pv], axis=1))
+
+
+def test_synth_fill_matches_definition(be):
+    """The CUDA hash generator is bit-identical to the NumPy definition of the inputs."""
+    import cpu_shim
+
+    class MP:                      # collect the numpy reference implementation without patching
+        def __init__(self): self.fns = {}
+        def setattr(self, obj, name, val): self.fns[name] = val
+    mp = MP()
+    cpu_shim.install(mp)
+    import torch
+    no, nv, seed, scale = 6, 10, 20261019, 0.02
+    npo, npv = 15, 45
+    shapes = {"vvvv_packed": (npv, npv), "oooo_packed": (npo, npo), "ovov_jbkc": (no * nv, no * nv),
+              "ovvv_jabc": (no * npv, nv), "ovvv_ajbc": (nv, no * npv), "ooov_ijkb": (no, npo * nv),
+              "ooov_ijak": (npo * nv, no)}
+    for layout, shape in shapes.items():
+        dev = be.synth_fill(be.empty(shape), layout, no, nv, seed, scale).cpu().numpy()
+        ref = mp.fns["synth_fill"](torch.empty(shape, dtype=torch.float64), layout, no, nv, seed, scale).numpy()
+        assert np.array_equal(dev, ref), layout
+    from adcc_b200.synthetic import synthetic_eri_block
+    for blk in ("oooo", "ooov", "oovv", "ovov", "ovvv", "vvvv"):
+        shape = [no if c == "o" else nv for c in blk]
+        dev = be.synth_fill(be.empty(shape), "dense", no, nv, seed, scale, block=blk).cpu().numpy()
+        assert np.array_equal(dev, synthetic_eri_block(seed, blk, no, nv, scale)), blk
+    # row_begin chunking of the big operand
+    part = be.synth_fill(be.empty((10, npv)), "vvvv_packed", no, nv, seed, scale, row_begin=7).cpu().numpy()
+    full = be.synth_fill(be.empty((npv, npv)), "vvvv_packed", no, nv, seed, scale).cpu().numpy()
+    assert np.array_equal(part, full[7:17])
+
+
+@pytest.mark.parametrize("method", ["adc2", "adc2x"])
+def test_packed_engine_h2o(method):
+    check_packed_matrix(method)
+    check_packed_run(method)
+
+
+def test_packed_engine_c1_shape():
+    from adcc_b200.synthetic import named_case
+    data, _ = named_case("h2o_ccpvdz")
+    check_packed_matrix("adc2x", data)
+
+
+@pytest.mark.parametrize("no,nv", [(6, 10), (10, 38), (16, 48)])
+def test_synthetic_workload_vs_oracle(no, nv):
+    check_synthetic(no, nv, seed=5, run=(nv <= 38))
