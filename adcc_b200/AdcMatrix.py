@@ -42,7 +42,7 @@ def default_block_orders(method):
 
 class AdcMatrix(AdcMatrixlike):
     def __init__(self, method, hf_or_mp, block_orders=None, intermediates=None,
-                 diagonal_precomputed=None, doubles_storage="auto"):
+                 diagonal_precomputed=None, doubles_storage="auto", shard=None):
         if isinstance(hf_or_mp, ReferenceState):
             hf_or_mp = LazyMp(hf_or_mp)
         elif not isinstance(hf_or_mp, LazyMp):
@@ -81,6 +81,8 @@ class AdcMatrix(AdcMatrixlike):
         self._variant = "cvs" if self.is_core_valence_separated else ""
         self._const = {}
         self.doubles_storage = self._select_storage(doubles_storage)
+        if shard is not None and (shard[1] > 1) and self.doubles_storage != "packed":
+            raise NotImplementedError("multi-GPU sharding is implemented for the packed doubles store")
         self._engine = None
 
         with self.timer.record("build"):
@@ -97,7 +99,7 @@ class AdcMatrix(AdcMatrixlike):
             self.blocks = {blk: self._make_apply(blk) for blk in self._tables}
             if self.doubles_storage == "packed":
                 from .packed import PackedAdcEngine
-                self._engine = PackedAdcEngine(self)
+                self._engine = PackedAdcEngine(self, shard=shard)
                 self.blocks = {blk: self._make_engine_apply(blk) for blk in self._tables
                                if self._tables[blk][0] is not None}
                 dph = adc_pp.diagonal(self._variant, "ph_ph", self.block_orders["ph_ph"], hf,

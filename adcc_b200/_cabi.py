@@ -42,12 +42,12 @@ def _declare(lib):
     lib.adccb_packed_pack.argtypes = [c_ptr, c_int, c_int, c_ptr, c_ptr]
     lib.adccb_packed_expand.argtypes = [c_ptr, c_int, c_int, c_int, c_ptr, c_ptr]
     lib.adccb_packed_fold_virt.argtypes = [c_ptr, c_i64, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr,
-                                           c_dbl, c_ptr]
-    lib.adccb_packed_fold_occ.argtypes = [c_ptr, c_int, c_int, c_ptr, c_dbl, c_ptr]
+                                           c_ptr, c_dbl, c_ptr]
+    lib.adccb_packed_fold_occ.argtypes = [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_dbl, c_ptr]
     lib.adccb_packed_diagonal.argtypes = [c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]
     lib.adccb_pair_select.argtypes = [c_ptr, c_i64, c_int, c_i64, c_ptr, c_ptr]
     lib.adccb_synth_fill.argtypes = [c_ptr, c_int, c_int, c_int, c_int, ctypes.c_uint64, c_dbl,
-                                     c_i64, c_i64, c_ptr]
+                                     c_i64, c_i64, c_int, c_int, c_ptr]
     for name in EXPORTS:
         if name not in ("adccb_last_error", "adccb_launch_count"):
             getattr(lib, name).restype = ctypes.c_int

@@ -251,18 +251,23 @@ def packed_expand(which, U, no, nv, out=None):
     return out
 
 
-def packed_fold_virt(S, nv, sa, P1, off1, P2=None, off2=None, alpha=1.0):
-    """S[r,AB] += alpha (F_r[a,b] - F_r[b,a]); off1/off2: int64 device tensors (len = rows of S)."""
-    nrows = S.shape[0]
+def packed_fold_virt(S, nv, sa, P1, off1, P2=None, off2=None, alpha=1.0, rows=None):
+    """S[rows[r],AB] += alpha (F_r[a,b] - F_r[b,a]); off1/off2/rows: int64 device tensors."""
+    nrows = off1.numel()
+    if nrows == 0:
+        return S
     _cabi.check(_cabi.lib().adccb_packed_fold_virt(
         _stream(), nrows, nv, int(sa), _ptr(P1), ctypes.c_void_p(off1.data_ptr()), _ptr(P2),
         ctypes.c_void_p(off2.data_ptr()) if off2 is not None else ctypes.c_void_p(0),
+        ctypes.c_void_p(rows.data_ptr()) if rows is not None else ctypes.c_void_p(0),
         float(alpha), _ptr(S)))
     return S
 
 
-def packed_fold_occ(S, C, no, nv, alpha=1.0):
-    _cabi.check(_cabi.lib().adccb_packed_fold_occ(_stream(), no, nv, _ptr(C), float(alpha), _ptr(S)))
+def packed_fold_occ(S, C, no, nv, alpha=1.0, j_begin=0, nj=None):
+    nj = no if nj is None else nj
+    _cabi.check(_cabi.lib().adccb_packed_fold_occ(_stream(), no, nv, int(j_begin), int(nj), _ptr(C),
+                                                  float(alpha), _ptr(S)))
     return S
 
 
@@ -294,7 +299,8 @@ SYNTH_LAYOUTS = {"vvvv_packed": 0, "oooo_packed": 1, "ovov_jbkc": 2, "ovvv_jabc"
 SYNTH_BLOCKS = {"oooo": 0, "ooov": 1, "oovv": 2, "ovov": 3, "ovvv": 4, "vvvv": 5}
 
 
-def synth_fill(out, layout, no, nv, seed, scale, block="vvvv", row_begin=0):
+def synth_fill(out, layout, no, nv, seed, scale, block="vvvv", row_begin=0, j_begin=0, nj=0):
     _cabi.check(_cabi.lib().adccb_synth_fill(_stream(), SYNTH_LAYOUTS[layout], SYNTH_BLOCKS[block], no, nv,
-                                             int(seed), float(scale), out.numel(), int(row_begin), _ptr(out)))
+                                             int(seed), float(scale), out.numel(), int(row_begin),
+                                             int(j_begin), int(nj), _ptr(out)))
     return out

@@ -49,14 +49,15 @@ int packed_unpack(cudaStream_t st, int no, int nv, const double* U, double* out)
 int packed_pack(cudaStream_t st, int no, int nv, const double* T, double* U);
 int packed_expand(cudaStream_t st, int which, int no, int nv, const double* U, double* out);
 int packed_fold_virt(cudaStream_t st, long long nrows, int nv, long long sa, const double* P1,
-                     const long long* off1, const double* P2, const long long* off2, double alpha,
-                     double* S);
-int packed_fold_occ(cudaStream_t st, int no, int nv, const double* C, double alpha, double* S);
+                     const long long* off1, const double* P2, const long long* off2,
+                     const long long* rows, double alpha, double* S);
+int packed_fold_occ(cudaStream_t st, int no, int nv, int j_begin, int nj, const double* C,
+                    double alpha, double* S);
 int packed_diagonal(cudaStream_t st, int no, int nv, const double* dov, const double* doo,
                     const double* dvv, double* D);
 int pair_select(cudaStream_t st, long long L, int n, long long R, const double* in, double* out);
 int synth_fill(cudaStream_t st, int layout, int blk, int no, int nv, unsigned long long seed,
-               double scale, long long n, long long row_begin, double* out);
+               double scale, long long n, long long row_begin, int j_begin, int nj, double* out);
 
 }  // namespace adccb
 
@@ -132,12 +133,13 @@ int adccb_packed_expand(void* stream, int which, int no, int nv, const double* U
 }
 int adccb_packed_fold_virt(void* stream, int64_t nrows, int nv, int64_t sa, const double* P1,
                            const int64_t* off1, const double* P2, const int64_t* off2,
-                           double alpha, double* S) {
+                           const int64_t* rows, double alpha, double* S) {
   return packed_fold_virt((cudaStream_t)stream, nrows, nv, sa, P1, (const long long*)off1, P2,
-                          (const long long*)off2, alpha, S);
+                          (const long long*)off2, (const long long*)rows, alpha, S);
 }
-int adccb_packed_fold_occ(void* stream, int no, int nv, const double* C, double alpha, double* S) {
-  return packed_fold_occ((cudaStream_t)stream, no, nv, C, alpha, S);
+int adccb_packed_fold_occ(void* stream, int no, int nv, int j_begin, int nj, const double* C,
+                          double alpha, double* S) {
+  return packed_fold_occ((cudaStream_t)stream, no, nv, j_begin, nj, C, alpha, S);
 }
 int adccb_packed_diagonal(void* stream, int no, int nv, const double* dov, const double* doo,
                           const double* dvv, double* D) {
@@ -147,8 +149,8 @@ int adccb_pair_select(void* stream, int64_t L, int n, int64_t R, const double* i
   return pair_select((cudaStream_t)stream, L, n, R, in, out);
 }
 int adccb_synth_fill(void* stream, int layout, int blk, int no, int nv, uint64_t seed, double scale,
-                     int64_t n, int64_t row_begin, double* out) {
-  return synth_fill((cudaStream_t)stream, layout, blk, no, nv, seed, scale, n, row_begin, out);
+                     int64_t n, int64_t row_begin, int j_begin, int nj, double* out) {
+  return synth_fill((cudaStream_t)stream, layout, blk, no, nv, seed, scale, n, row_begin, j_begin, nj, out);
 }
 
 }  // extern "C"

@@ -388,14 +388,21 @@ int dgemm_strided(cudaStream_t st, long long M, long long N, long long K, double
                       ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && get_encode_fn() != nullptr &&
                       ((long long)M * N * K >= 32LL * 32 * 32);
   if (tma_ok) {
-    // tile choice: 112-row tiles waste less when M is just above a multiple of 112
+    // row-tile height: the smallest tile that covers M for skinny outputs (these are HBM-bound
+    // streams over the big operand, so DMMA rows spent on zero padding would make them
+    // tensor-bound instead), else whichever of 112 / 128 pads M less
     // (e.g. 780 occupied pairs -> 7 x 112 = 784 instead of 7 x 128 = 896)
-    auto waste = [](long long m, int bm) { return ((m + bm - 1) / bm) * bm - m; };
-    bool use112 = tile_hint == 112 || (tile_hint == 0 && waste(M, 112) * 1.0 / 112 < waste(M, 128) * 1.0 / 128 &&
-                                       (M + 111) / 112 * 112 < (M + 127) / 128 * 128);
-    if (use112)
-      return launch_tma<1, 8, 14, 2, 6>(st, (int)M, (int)N, (int)K, alpha, A, ars, B, brs, beta, C, ldc, ws, ws_bytes);
-    return launch_tma<2, 4, 8, 4, 6>(st, (int)M, (int)N, (int)K, alpha, A, ars, B, brs, beta, C, ldc, ws, ws_bytes);
+#define ADCCB_TMA(WM, WN, MB, NB) \
+  return launch_tma<WM, WN, MB, NB, 6>(st, (int)M, (int)N, (int)K, alpha, A, ars, B, brs, beta, C, ldc, ws, ws_bytes)
+    if (tile_hint == 0 || tile_hint == 16 || tile_hint == 40 || tile_hint == 64) {
+      if (tile_hint == 16 || (tile_hint == 0 && M <= 16)) ADCCB_TMA(1, 8, 2, 2);
+      if (tile_hint == 40 || (tile_hint == 0 && M <= 40)) ADCCB_TMA(1, 8, 5, 2);
+      if (tile_hint == 64 || (tile_hint == 0 && M <= 64)) ADCCB_TMA(1, 8, 8, 2);
+    }
+    const long long pad112 = (M + 111) / 112 * 112, pad128 = (M + 127) / 128 * 128;
+    if (tile_hint == 112 || (tile_hint == 0 && pad112 < pad128)) ADCCB_TMA(1, 8, 14, 2);
+    ADCCB_TMA(2, 4, 8, 4);
+#undef ADCCB_TMA
   }
   dim3 grid((unsigned)((M + GB - 1) / GB), (unsigned)((N + GB - 1) / GB));
   if (grid.y > 65535) return fail("dgemm(generic): too many N tiles");

@@ -125,7 +125,8 @@ __global__ void expand_virt_t_kernel(long long npo, int nv, const double* __rest
 __global__ void pack_antisym_virt_kernel(int nv, long long sa, const double* __restrict__ P1,
                                          const long long* __restrict__ off1,
                                          const double* __restrict__ P2,
-                                         const long long* __restrict__ off2, double alpha,
+                                         const long long* __restrict__ off2,
+                                         const long long* __restrict__ rows, double alpha,
                                          double* __restrict__ S) {
   __shared__ double tile[32][33];
   const long long npv = (long long)nv * (nv - 1) / 2;
@@ -145,7 +146,7 @@ __global__ void pack_antisym_virt_kernel(int nv, long long sa, const double* __r
     tile[threadIdx.x][aa] = v;
   }
   __syncthreads();
-  double* Srow = S + r * npv;
+  double* Srow = S + (rows ? rows[r] : r) * npv;
   for (int bb = threadIdx.y; bb < 32; bb += blockDim.y) {
     const int b = b0 + bb, a = a0 + threadIdx.x;
     if (a < b && b < nv) {
@@ -165,6 +166,20 @@ __global__ void pack_antisym_occ_kernel(int no, long long npv, const double* __r
   const double* c2 = C + ((long long)j * no + i) * npv;
   double* dst = S + (long long)blockIdx.x * npv;
   for (long long e = threadIdx.x; e < npv; e += blockDim.x) dst[e] += alpha * (c1[e] - c2[e]);
+}
+
+// slab form: C[i, jl, AB] holds occupied index j = j_begin + jl only.  pass 0 adds +alpha C[i,jl]
+// to S[pair(i,j)] for i < j, pass 1 adds -alpha C[i,jl] to S[pair(j,i)] for i > j; inside one pass
+// every S row is touched by one CTA only.
+__global__ void pack_antisym_occ_slab_kernel(int no, int j_begin, int nj, long long npv, int pass,
+                                             const double* __restrict__ C, double alpha,
+                                             double* __restrict__ S) {
+  const int i = blockIdx.x / nj, jl = blockIdx.x % nj, j = j_begin + jl;
+  if (i == j || (pass == 0) != (i < j)) return;
+  const double* c = C + (long long)blockIdx.x * npv;
+  double* dst = S + pair_index(min(i, j), max(i, j)) * npv;
+  const double a = (pass == 0) ? alpha : -alpha;
+  for (long long e = threadIdx.x; e < npv; e += blockDim.x) dst[e] += a * c[e];
 }
 
 // D[IJ,AB] = 1/2 (dov[i,a] + dov[j,b] + dov[i,b] + dov[j,a]) + doo[i,j] + dvv[a,b]
@@ -236,8 +251,8 @@ enum EriLayout {
 };
 
 __global__ void synth_fill_kernel(int layout, int blk, int no, int nv, unsigned long long seed,
-                                  double scale, long long n, long long row_begin,
-                                  double* __restrict__ out) {
+                                  double scale, long long n, long long row_begin, int j_begin,
+                                  int nj, double* __restrict__ out) {
   const long long npv = (long long)nv * (nv - 1) / 2, npo = (long long)no * (no - 1) / 2;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -256,19 +271,19 @@ __global__ void synth_fill_kernel(int layout, int blk, int no, int nv, unsigned 
       } break;
       case LAY_OVOV_JBKC: {
         c = (int)(idx % nv); k = (int)((idx / nv) % no);
-        b = (int)((idx / ((long long)nv * no)) % nv); j = (int)(idx / ((long long)nv * no * nv));
+        b = (int)((idx / ((long long)nv * no)) % nv); j = j_begin + (int)(idx / ((long long)nv * no * nv));
         v = synthetic_eri(seed, BLK_OVOV, k, b, j, c, scale);
       } break;
       case LAY_OVVV_JABC: {
         c = (int)(idx % nv);
         pair_decode((idx / nv) % npv, a, b);
-        j = (int)(idx / ((long long)nv * npv));
+        j = j_begin + (int)(idx / ((long long)nv * npv));
         v = synthetic_eri(seed, BLK_OVVV, j, c, a, b, scale);
       } break;
       case LAY_OVVV_AJBC: {
         pair_decode(idx % npv, b, c);
-        j = (int)((idx / npv) % no);
-        a = (int)(idx / (npv * no));
+        j = j_begin + (int)((idx / npv) % nj);
+        a = (int)(idx / (npv * nj));
         v = synthetic_eri(seed, BLK_OVVV, j, a, b, c, scale);
       } break;
       case LAY_OOOV_IJKB: {
@@ -356,24 +371,34 @@ int packed_expand(cudaStream_t st, int which, int no, int nv, const double* U, d
 }
 
 int packed_fold_virt(cudaStream_t st, long long nrows, int nv, long long sa, const double* P1,
-                     const long long* off1, const double* P2, const long long* off2, double alpha,
-                     double* S) {
+                     const long long* off1, const double* P2, const long long* off2,
+                     const long long* rows, double alpha, double* S) {
   if (nrows == 0 || nv < 2) return 0;
   if (nrows > 65535) return fail("packed_fold_virt: too many rows");
   const int t = (nv + 31) / 32;
   dim3 grid(t, t, (unsigned)nrows);
-  pack_antisym_virt_kernel<<<grid, dim3(32, 8), 0, st>>>(nv, sa, P1, off1, P2, off2, alpha, S);
+  pack_antisym_virt_kernel<<<grid, dim3(32, 8), 0, st>>>(nv, sa, P1, off1, P2, off2, rows, alpha, S);
   ADCCB_LAUNCH_OK();
   count_launch();
   return 0;
 }
 
-int packed_fold_occ(cudaStream_t st, int no, int nv, const double* C, double alpha, double* S) {
+int packed_fold_occ(cudaStream_t st, int no, int nv, int j_begin, int nj, const double* C,
+                    double alpha, double* S) {
   const long long npv = (long long)nv * (nv - 1) / 2, npo = (long long)no * (no - 1) / 2;
   if (npv == 0 || npo == 0) return 0;
-  pack_antisym_occ_kernel<<<(unsigned)npo, 256, 0, st>>>(no, npv, C, alpha, S);
-  ADCCB_LAUNCH_OK();
-  count_launch();
+  if (j_begin == 0 && (nj <= 0 || nj == no)) {
+    pack_antisym_occ_kernel<<<(unsigned)npo, 256, 0, st>>>(no, npv, C, alpha, S);
+    ADCCB_LAUNCH_OK();
+    count_launch();
+    return 0;
+  }
+  if (j_begin < 0 || j_begin + nj > no) return fail("packed_fold_occ: slab out of range");
+  for (int pass = 0; pass < 2; ++pass) {
+    pack_antisym_occ_slab_kernel<<<(unsigned)(no * nj), 256, 0, st>>>(no, j_begin, nj, npv, pass, C, alpha, S);
+    ADCCB_LAUNCH_OK();
+  }
+  count_launch(2);
   return 0;
 }
 
@@ -388,10 +413,12 @@ int packed_diagonal(cudaStream_t st, int no, int nv, const double* dov, const do
 }
 
 int synth_fill(cudaStream_t st, int layout, int blk, int no, int nv, unsigned long long seed,
-               double scale, long long n, long long row_begin, double* out) {
+               double scale, long long n, long long row_begin, int j_begin, int nj, double* out) {
   if (n <= 0) return 0;
   if (no >= 1024 || nv >= 1024) return fail("synth_fill: extents must be < 1024");
-  synth_fill_kernel<<<blocks_for(n, 256), 256, 0, st>>>(layout, blk, no, nv, seed, scale, n, row_begin, out);
+  if (nj <= 0) nj = no;
+  synth_fill_kernel<<<blocks_for(n, 256), 256, 0, st>>>(layout, blk, no, nv, seed, scale, n, row_begin,
+                                                        j_begin, nj, out);
   ADCCB_LAUNCH_OK();
   count_launch();
   return 0;

@@ -158,22 +158,29 @@ class DenseSource:
         self.hf, self.mp = hf, mp
         self.no, self.nv = hf.mospaces.n_orbs("o1"), hf.mospaces.n_orbs("v1")
 
-    def vvvv_packed(self):
-        return be.packed_pack(self.hf.vvvv._contig(), self.nv, self.nv)
+    def vvvv_packed(self, row_begin=0, n_rows=None):
+        full = be.packed_pack(self.hf.vvvv._contig(), self.nv, self.nv)
+        if row_begin == 0 and n_rows is None:
+            return full
+        return be.contiguous(full[row_begin:row_begin + n_rows])
 
     def oooo_packed(self):
         return be.packed_pack(self.hf.oooo._contig(), self.no, self.no)
 
-    def ovov_jbkc(self):     # Y[(j,b),(k,c)] = <kb||jc>
-        return be.permute(self.hf.ovov._data, (2, 1, 0, 3)).reshape(self.no * self.nv, self.no * self.nv)
+    def _jslice(self, j_begin, nj):
+        return slice(j_begin, self.no if nj is None else j_begin + nj)
 
-    def ovvv_jabc(self):     # V1[(j,AB),c] = <jc||ab>
+    def ovov_jbkc(self, j_begin=0, nj=None):     # Y[(j,b),(k,c)] = <kb||jc>
+        full = be.permute(self.hf.ovov._data, (2, 1, 0, 3))
+        return be.contiguous(full[self._jslice(j_begin, nj)]).reshape(-1, self.no * self.nv)
+
+    def ovvv_jabc(self, j_begin=0, nj=None):     # V1[(j,AB),c] = <jc||ab>
         sel = be.pair_select(self.hf.ovvv._contig(), 2)              # [j,c,AB]
-        return be.permute(sel, (0, 2, 1)).reshape(-1, self.nv)
+        return be.permute(sel[self._jslice(j_begin, nj)], (0, 2, 1)).reshape(-1, self.nv)
 
-    def ovvv_ajbc(self):     # V2[a,(j,BC)] = <ja||bc>
+    def ovvv_ajbc(self, j_begin=0, nj=None):     # V2[a,(j,BC)] = <ja||bc>
         sel = be.pair_select(self.hf.ovvv._contig(), 2)              # [j,a,BC]
-        return be.permute(sel, (1, 0, 2)).reshape(self.nv, -1)
+        return be.permute(sel[self._jslice(j_begin, nj)], (1, 0, 2)).reshape(self.nv, -1)
 
     def ooov_ijkb(self):     # G1[i,(JK,b)] = <jk||ib>
         sel = be.pair_select(self.hf.ooov._contig(), 0)              # [JK,i,b]
@@ -191,8 +198,9 @@ class DenseSource:
 class PackedAdcEngine:
     """ADC(2) / ADC(2)-x matvec on the packed doubles store (see module docstring)."""
 
-    def __init__(self, matrix, source=None):
+    def __init__(self, matrix, source=None, shard=None):
         from .functions import einsum, direct_sum
+        self.rank, self.world = shard if shard is not None else (0, 1)
         hf, mp, im = matrix.reference_state, matrix.ground_state, matrix.intermediates
         self.matrix = matrix
         self.mospaces = hf.mospaces
@@ -219,10 +227,18 @@ class PackedAdcEngine:
         self.M1 = m1._contig().reshape(no * nv, no * nv)
 
         # ---- couplings (matrix.py:270-276, 288-294)
-        self.V1 = src.ovvv_jabc()
-        self.V2 = src.ovvv_ajbc()
-        self.G1 = src.ooov_ijkb()
-        self.G2 = src.ooov_ijak()
+        # slabs owned by this rank (world == 1: everything)
+        r, w = self.rank, self.world
+        self.j0, j1 = (r * no) // w, ((r + 1) * no) // w
+        self.nj = j1 - self.j0
+        cut = [min(self.npv, ((k * self.npv // w + 127) // 128) * 128) for k in range(w)] + [self.npv]
+        self.ab0, self.ab1 = cut[r], cut[r + 1]
+        cut_o = [min(self.npo, ((k * self.npo // w + 1) // 2) * 2) for k in range(w)] + [self.npo]
+        self.ij0, self.ij1 = cut_o[r], cut_o[r + 1]
+        self.V1 = src.ovvv_jabc(self.j0, self.nj)
+        self.V2 = src.ovvv_ajbc(self.j0, self.nj)
+        self.G1 = src.ooov_ijkb() if r == 0 else None
+        self.G2 = src.ooov_ijak() if r == 0 else None
 
         # ---- doubles-doubles (matrix.py:127-133, 234-246)
         eo = be.from_numpy(np.diag(foo))
@@ -230,9 +246,9 @@ class PackedAdcEngine:
         d0_ov = be.direct_sum(eo, ev, -1.0, 1.0)                 # e_a - e_i
         self.D0 = be.packed_diagonal(no, nv, d0_ov)              # e_a + e_b - e_i - e_j
         if self.order_dd == 1:
-            self.W = src.vvvv_packed()
+            self.W = src.vvvv_packed(self.ab0, self.ab1 - self.ab0)
             self.O = src.oooo_packed()
-            self.Y = src.ovov_jbkc()
+            self.Y = src.ovov_jbkc(self.j0, self.nj)
             d_ov = (direct_sum("a-i->ia", hf.fvv.diagonal(), hf.foo.diagonal())
                     - 2.0 * einsum("iaia->ia", hf.ovov))._contig()
             d_oo = einsum("ijij->ij", hf.oooo).symmetrise()._contig()
@@ -247,6 +263,17 @@ class PackedAdcEngine:
         self._off_ovov_1 = be.int64_tensor([(i * nv * no + j) * nv for i, j in pairs])
         self._off_ovov_2 = be.int64_tensor([(j * nv * no + i) * nv for i, j in pairs])
         self._off_rows = be.int64_tensor([r * nv * nv for r in range(self.npo)])
+        if self.world > 1:
+            # ovov fold of a j-slab: T_r[(i,a),(jl,b)], offset (i*nv + a)*(nj*nv) + jl*nv + b
+            njv = self.nj * nv
+            own = range(self.j0, self.j0 + self.nj)
+            p_hi = [(i, j) for (i, j) in pairs if j in own]       # -(T[ia,jb] - T[ib,ja])
+            p_lo = [(i, j) for (i, j) in pairs if i in own]       # +(T[ja,ib] - T[jb,ia])
+            row = {p: k for k, p in enumerate(pairs)}
+            self._sl_hi = (be.int64_tensor([i * nv * njv + (j - self.j0) * nv for i, j in p_hi]),
+                           be.int64_tensor([row[p] for p in p_hi]))
+            self._sl_lo = (be.int64_tensor([j * nv * njv + (i - self.j0) * nv for i, j in p_lo]),
+                           be.int64_tensor([row[p] for p in p_lo]))
         self._count_flops()
 
     def _count_flops(self):
@@ -260,6 +287,27 @@ class PackedAdcEngine:
             f["pphh_pphh/ovov"] = 2.0 * (no * nv) ** 3
         self.flops = f
         self.flops_per_matvec = sum(f.values())
+
+    # ------------------------------------------------------------------ kernel timing hooks
+    def enable_kernel_timing(self, on=True):
+        """Record CUDA events around the two dominant GEMM launches (bench.py roofline)."""
+        self._events = {} if on else None
+
+    def _mark(self, name, which):
+        ev = getattr(self, "_events", None)
+        if ev is None:
+            return
+        import torch
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream())
+        ev.setdefault(name, []).append(e)
+
+    def kernel_times_ms(self):
+        """{name: [ms per launch]} from the recorded events (call after a synchronize)."""
+        out = {}
+        for name, evs in (getattr(self, "_events", None) or {}).items():
+            out[name] = [evs[k].elapsed_time(evs[k + 1]) for k in range(0, len(evs) - 1, 2)]
+        return out
 
     # ------------------------------------------------------------------ block applies
     def apply_ph_ph(self, u1):
@@ -291,11 +339,15 @@ class PackedAdcEngine:
         be.mul(U, self.D0, out=S, beta=beta)
         if self.order_dd == 0:
             return S
+        self._mark("vvvv", 0)
         be.gemm(U, self.W, out=S, alpha=1.0, beta=1.0)       # 1/2 u[ijcd] <ab||cd> = sum_{c<d}
+        self._mark("vvvv", 1)
         Ut = be.permute(U, (1, 0))                           # [AB,KL]
         be.gemm(self.O, Ut, out=S, alpha=1.0, beta=1.0)      # 1/2 <ij||kl> u[klab] = sum_{k<l}
         X = be.packed_expand(0, U, no, nv)                  # [(i,a),(k,c)] = u[ikac]
+        self._mark("ovov", 0)
         T = be.gemm(X, self.Y)                               # [(i,a),(j,b)] = sum_kc u[ikac] <kb||jc>
+        self._mark("ovov", 1)
         del X
         # -4 A_ij A_ab T = -(T[ia,jb] - T[ja,ib] - T[ib,ja] + T[jb,ia])
         be.packed_fold_virt(S, nv, no * nv, T, self._off_ovov_1, T, self._off_ovov_2, alpha=-1.0)
@@ -308,11 +360,76 @@ class PackedAdcEngine:
     def _wrap_pphh(self, data):
         return PackedDoubles._wrap(self.mospaces, ["o1", "o1", "v1", "v1"], data)
 
+    def _matvec_sharded(self, u1, U):
+        """Partial sigma from this rank's slabs, then ONE all-reduce of the packed (ph + pphh)
+        buffer (NCCL over NVLink on the GPU box).  vvvv: AB-row slab of W; ovov, ovvv: occupied
+        j-slab; oooo: KL slab of the contraction index; D0 and M1: row slabs."""
+        import torch.distributed as dist
+        no, nv, npo, npv = self.no, self.nv, self.npo, self.npv
+        buf = be.zeros((npo * npv + no * nv,))
+        S = buf[:npo * npv].view(npo, npv)
+        s1 = buf[npo * npv:].view(1, no * nv)
+        x = u1._contig()
+        r0, r1 = self.j0 * nv, (self.j0 + self.nj) * nv
+        # ph_ph: rows (i in slab, a) of the folded singles matrix
+        if r1 > r0:
+            be.gemm(x.reshape(1, -1), self.M1[r0:r1], out=s1[:, r0:r1])
+        s1m = s1.view(no, nv)
+        if self.nj > 0:
+            # ph_pphh: contraction index (j,BC) restricted to the slab
+            Ue = be.packed_expand(1, U, no, nv)
+            k0, k1 = self.j0 * npv, (self.j0 + self.nj) * npv
+            be.gemm(Ue[:, k0:k1], self.V2, out=s1m, alpha=2.0, beta=1.0)
+            del Ue
+        if self.rank == 0:
+            Uh = be.packed_expand(2, U, no, nv)
+            be.gemm(self.G1, Uh, out=s1m, alpha=2.0, beta=1.0)
+            del Uh
+        # pphh_pphh
+        if self.ij1 > self.ij0:
+            be.mul(U[self.ij0:self.ij1], self.D0[self.ij0:self.ij1], out=S[self.ij0:self.ij1])
+        if self.order_dd == 1:
+            if self.ab1 > self.ab0:
+                self._mark("vvvv", 0)
+                be.gemm(U, self.W, out=S[:, self.ab0:self.ab1], alpha=1.0, beta=1.0)
+                self._mark("vvvv", 1)
+            if self.ij1 > self.ij0:
+                Ut = be.permute(U[self.ij0:self.ij1], (1, 0))            # [AB, KL slab]
+                be.gemm(self.O[:, self.ij0:self.ij1], Ut, out=S, alpha=1.0, beta=1.0)
+                del Ut
+            if self.nj > 0:
+                X = be.packed_expand(0, U, no, nv)
+                self._mark("ovov", 0)
+                T = be.gemm(X, self.Y)                                   # [(i,a),(jl,b)]
+                self._mark("ovov", 1)
+                del X
+                njv = self.nj * nv
+                off, rows = self._sl_hi
+                be.packed_fold_virt(S, nv, njv, T, off, alpha=-1.0, rows=rows)
+                off, rows = self._sl_lo
+                be.packed_fold_virt(S, nv, njv, T, off, alpha=+1.0, rows=rows)
+                del T
+        # pphh_ph
+        if self.nj > 0:
+            c1 = be.gemm(x, self.V1)                                     # [i,(jl,AB)]
+            be.packed_fold_occ(S, c1, no, nv, alpha=0.5, j_begin=self.j0, nj=self.nj)
+            del c1
+        if self.rank == 0:
+            c2 = be.gemm(self.G2, be.permute(x, (1, 0)))
+            be.packed_fold_virt(S, nv, nv, c2, self._off_rows, alpha=-0.5)
+            del c2
+        self._mark("allreduce", 0)
+        dist.all_reduce(buf)
+        self._mark("allreduce", 1)
+        return AmplitudeVector(ph=self._wrap_ph(s1.view(no, nv)), pphh=self._wrap_pphh(S))
+
     def matvec(self, v):
         u1, u2 = v["ph"], v["pphh"]
         if not isinstance(u2, PackedDoubles):
             u2 = PackedDoubles.from_dense(u2)
         U = u2._contig()
+        if self.world > 1:
+            return self._matvec_sharded(u1, U)
         s1 = self.apply_ph_ph(u1)
         s1c = self.apply_ph_pphh(U)
         be.axpby(1.0, s1c, 1.0, s1)
@@ -364,9 +481,19 @@ class SyntheticSource:
         return self._fill((n_rows, self.npv), "vvvv_packed", row_begin=row_begin)
 
     def oooo_packed(self): return self._fill((self.npo, self.npo), "oooo_packed")
-    def ovov_jbkc(self): return self._fill((self.no * self.nv, self.no * self.nv), "ovov_jbkc")
-    def ovvv_jabc(self): return self._fill((self.no * self.npv, self.nv), "ovvv_jabc")
-    def ovvv_ajbc(self): return self._fill((self.nv, self.no * self.npv), "ovvv_ajbc")
+
+    def ovov_jbkc(self, j_begin=0, nj=None):
+        nj = self.no - j_begin if nj is None else nj
+        return self._fill((nj * self.nv, self.no * self.nv), "ovov_jbkc", j_begin=j_begin, nj=nj)
+
+    def ovvv_jabc(self, j_begin=0, nj=None):
+        nj = self.no - j_begin if nj is None else nj
+        return self._fill((nj * self.npv, self.nv), "ovvv_jabc", j_begin=j_begin, nj=nj)
+
+    def ovvv_ajbc(self, j_begin=0, nj=None):
+        nj = self.no - j_begin if nj is None else nj
+        return self._fill((self.nv, nj * self.npv), "ovvv_ajbc", j_begin=j_begin, nj=nj)
+
     def ooov_ijkb(self): return self._fill((self.no, self.npo * self.nv), "ooov_ijkb")
     def ooov_ijak(self): return self._fill((self.npo * self.nv, self.no), "ooov_ijak")
 

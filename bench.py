@@ -1,0 +1,347 @@
+#!/usr/bin/env python3
+"""Headline benchmark: ADC(2)-x matrix-vector products per second on the synthetic
+nocc=40 / nvirt=400 workload (BASELINE.json configs[4]; fits ONE B200 because the doubles
+vectors and the vvvv block are stored antisymmetry-packed, 50.9 GB instead of 204.8 GB).
+
+    python bench.py --gpus N --steps K --warmup W          # this framework (CUDA, sm_100a)
+    python bench.py --impl reference ...                   # CPU arm: NumPy restatement (oracle)
+
+One "step" = one sigma = M u through the public API (AdcMatrix.matvec).  Prints ONE JSON line.
+  value      matvecs/s with the trial vector resident in HBM
+  e2e        same through AdcMatrix.matvec with HOST (pinned) buffers: H2D of (u1, packed u2) and
+             D2H of sigma inside the timed region
+  roofline   dominant kernel (packed vvvv DMMA GEMM): executed flops / CUDA-event time against the
+             DMMA.8x8x4 issue peak measured on this pool (profiles/r01_fp64_peak_microbench.txt;
+             MEASURED_PEAKS.json carries no FP64 figure)
+  cpu_baseline  oracle timed on the host cores on a bounded reduced-size sample, extrapolated by
+             the dense flop count (labelled as such)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NO, NV = 40, 400
+SEED, SCALE = 20261019, 0.02
+FP64_DMMA_PEAK_TFLOPS = 37.17          # tools/microbench/fp64_peak.cu on this pool's B200
+METRIC = "adc2x_matvecs_per_second"
+UNIT = "matvec/s"
+
+
+def dense_flops(no, nv):
+    """As-written dense flops of one ADC(2)-x matvec (9.16e13 at 40/400)."""
+    o, v = no, nv
+    return (2.0 * o**2 * v**4 + 2.0 * o**3 * v**3 + 2.0 * o**4 * v**2     # vvvv, ovov, oooo terms
+            + 3 * 2.0 * o**2 * v**3 + 3 * 2.0 * o**3 * v**2               # fvv/ovvv and foo/ooov terms
+            + 2 * 2.0 * (o * v)**2)                                       # ph_ph GEMVs
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.samples:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for nme, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (NumPy restatement of the reference equations) on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(no_s=16, nv_s=96, n_matvec=3):
+    import oracle
+    from oracle.synthetic import OracleSyntheticRef
+    t0 = time.perf_counter()
+    om = oracle.OracleAdcMatrix("adc2x", OracleSyntheticRef(no_s, nv_s, seed=SEED, scale=SCALE))
+    t_build = time.perf_counter() - t0
+    rng = np.random.default_rng(1)
+    v = {k: rng.standard_normal(s) for k, s in om.shapes.items()}
+    v["pphh"] = om.symmetrise_doubles(v["pphh"])
+    om.matvec(v)                                  # warm-up (einsum path caches, BLAS threads)
+    times = []
+    for _ in range(n_matvec):
+        t0 = time.perf_counter()
+        om.matvec(v)
+        times.append(time.perf_counter() - t0)
+    t = float(np.median(times))
+    ratio = dense_flops(no_s, nv_s) / dense_flops(NO, NV)
+    return {
+        "value": ratio / t,                        # matvec/s extrapolated to nocc=40 / nvirt=400
+        "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+        "sample": (f"oracle (NumPy/OpenBLAS dense spin-orbital restatement) ADC(2)-x matvec at "
+                   f"nocc={no_s}, nvirt={nv_s}: {t:.3f} s/matvec over {n_matvec} reps "
+                   f"(build {t_build:.1f} s); EXTRAPOLATED to nocc={NO}, nvirt={NV} by the dense "
+                   f"flop ratio {1 / ratio:.0f}x (the dense vvvv block, 204.8 GB, cannot exist on "
+                   f"this host); libtensor itself is not installable offline"),
+        "seconds_per_matvec_sample": t,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    res = cpu_sample(n_matvec=max(1, args.steps))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 / res["value"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic ADC(2)-x matvec nocc={NO} nvirt={NV} (BASELINE configs[4])",
+                   "note": "CPU arm = NumPy restatement on a reduced-size sample, extrapolated"},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import adcc_b200 as adcc
+    from adcc_b200 import _cabi, backend as be
+    from adcc_b200.packed import PackedDoubles, synthetic_reference_state
+
+    no, nv = args.nocc, args.nvirt
+    t0 = time.perf_counter()
+    ref = synthetic_reference_state(no, nv, seed=SEED, scale=SCALE)
+    matrix = adcc.AdcMatrix("adc2x", ref, doubles_storage="packed",
+                            **({"shard": (rank, world)} if world > 1 else {}))
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0
+    eng = matrix._engine
+    npo, npv = eng.npo, eng.npv
+
+    # trial vector: seeded, normalised, antisymmetric by construction of the packed store
+    g = torch.Generator(device="cpu").manual_seed(SEED + 1)
+    u1_host = torch.randn(no, nv, generator=g, dtype=torch.float64).pin_memory()
+    u2_host = torch.randn(npo, npv, generator=g, dtype=torch.float64).pin_memory()
+    nrm = float(torch.sqrt((u1_host**2).sum() + 4.0 * (u2_host**2).sum()))
+    u1_host /= nrm
+    u2_host /= nrm
+    sig1_host = torch.empty_like(u1_host).pin_memory()
+    sig2_host = torch.empty_like(u2_host).pin_memory()
+
+    def to_vec(h1, h2):
+        d1 = h1.to("cuda", non_blocking=True)
+        d2 = h2.to("cuda", non_blocking=True)
+        return adcc.AmplitudeVector(
+            ph=adcc.Tensor._wrap(ref.mospaces, ["o1", "v1"], d1),
+            pphh=PackedDoubles._wrap(ref.mospaces, ["o1", "o1", "v1", "v1"], d2))
+
+    v = to_vec(u1_host, u2_host)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-input timing -----------------------------------------------------------------
+    for _ in range(args.warmup):
+        sig = matrix.matvec(v)
+    eng.enable_kernel_timing(True)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _cabi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sig = matrix.matvec(v)
+    e1.record()
+    barrier()
+    launches = _cabi.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    ktimes = eng.kernel_times_ms()
+    eng.enable_kernel_timing(False)
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+
+    # ---- end to end: host buffers in, host buffers out -------------------------------------------
+    for _ in range(1):
+        s = matrix.matvec(to_vec(u1_host, u2_host))
+        sig1_host.copy_(s.ph._data, non_blocking=True)
+        sig2_host.copy_(s.pphh._data, non_blocking=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        s = matrix.matvec(to_vec(u1_host, u2_host))
+        sig1_host.copy_(s.ph._data, non_blocking=True)
+        sig2_host.copy_(s.pphh._data, non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    ms_e2e /= args.steps
+    h2d = 8 * (u1_host.numel() + u2_host.numel())
+    d2h = 8 * (sig1_host.numel() + sig2_host.numel())
+
+    # ---- invariants at full size (size-independent parity properties) ---------------------------
+    checks = {}
+    if rank == 0 or world > 1:
+        g2 = torch.Generator(device="cpu").manual_seed(SEED + 2)
+        w = to_vec(torch.randn(no, nv, generator=g2, dtype=torch.float64).pin_memory(),
+                   torch.randn(npo, npv, generator=g2, dtype=torch.float64).pin_memory())
+        mw = matrix.matvec(w)
+        lhs, rhs = v @ mw, sig @ w
+        checks["hermiticity_rel"] = abs(lhs - rhs) / max(abs(lhs), 1e-300)
+
+    # ---- time to converged states ----------------------------------------------------------------
+    davidson = None
+    if args.davidson and world == 1:
+        td0 = time.perf_counter()
+        state = adcc.run_adc(matrix, n_states=args.n_states, kind="any", n_guesses=2 * args.n_states,
+                             conv_tol=1e-6, output=None)
+        torch.cuda.synchronize()
+        davidson = {"n_states": args.n_states, "conv_tol": 1e-6, "converged": bool(state.converged),
+                    "n_iter": int(state.n_iter), "n_applies": int(state.n_applies),
+                    "time_to_converged_s": time.perf_counter() - td0,
+                    "excitation_energies": [float(e) for e in state.excitation_energy]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------
+    f_vvvv = eng.flops["pphh_pphh/vvvv"] / world
+    t_vvvv = float(np.mean(ktimes["vvvv"])) if ktimes.get("vvvv") else None
+    t_ovov = float(np.mean(ktimes["ovov"])) if ktimes.get("ovov") else None
+    achieved = f_vvvv / (t_vvvv * 1e-3) * 1e-12 if t_vvvv else None
+    roofline = {
+        "bound": "tensor", "kernel": "dgemm_tn_tma_kernel (packed vvvv term, DMMA.8x8x4)",
+        "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+        "frac": achieved / FP64_DMMA_PEAK_TFLOPS if achieved else None,
+        "peak_source": "measured DMMA.8x8x4 issue peak on this pool (profiles/r01_fp64_peak_microbench.txt); "
+                       "MEASURED_PEAKS.json has no FP64 entry; cuBLAS DGEMM reaches 36.2-36.5 here",
+        "flops_per_launch": f_vvvv, "ms_per_launch": t_vvvv,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture
+        # profiles/r01_vvvv_gemm.ncu-rep (1 GPU, nocc=40/nvirt=400): 80.31 GB + 0.51 GB per launch;
+        # algorithmic: W 50.9 GB once + U 0.5 GB per wave of N tiles (29.5 waves) + sigma RMW 1 GB
+        "traffic": 8.082e10 if (world == 1 and no == NO and nv == NV) else None,
+        "second_kernel": {"name": "dgemm_tn_tma_kernel (ovov term)", "flops_per_launch": eng.flops["pphh_pphh/ovov"],
+                          "ms_per_launch": t_ovov,
+                          "achieved": eng.flops["pphh_pphh/ovov"] / (t_ovov * 1e-3) * 1e-12 if t_ovov else None},
+        "share_of_step": (t_vvvv / ms_step) if t_vvvv else None,
+    }
+    cpu = cpu_sample() if (world == 1 and not args.no_cpu_baseline) else None
+    line = {
+        "metric": METRIC, "value": 1000.0 / ms_step, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"synthetic ADC(2)-x matvec nocc={no} nvirt={nv} (BASELINE configs[4]), "
+                               "random antisymmetrised FP64 ERIs from a counter-based hash",
+                   "storage": "antisymmetry-packed doubles + vvvv (50.9 GB instead of 204.8 GB dense)",
+                   "l2": "inputs (vvvv 50.9 GB, ovvv 2x10.2 GB) exceed the 126 MB L2 every step",
+                   "seed": SEED, "parallelism": f"virtual-pair slabs x{world}" if world > 1 else "single GPU"},
+        "executed_tflop_per_step": eng.flops_per_matvec * 1e-12,
+        "dense_tflop_per_step": dense_flops(no, nv) * 1e-12,
+        "achieved_tflops_executed": eng.flops_per_matvec / (ms_step * 1e-3) * 1e-12,
+        "e2e": {"value": 1000.0 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "clocks": clocks,
+        "checks": checks,
+        "build_s": t_build,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if davidson is not None:
+        line["davidson"] = davidson
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="adcc_b200", choices=["adcc_b200", "reference"])
+    ap.add_argument("--nocc", type=int, default=NO)
+    ap.add_argument("--nvirt", type=int, default=NV)
+    ap.add_argument("--n-states", type=int, default=5)
+    ap.add_argument("--no-davidson", dest="davidson", action="store_false")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        import __graft_entry__
+        __graft_entry__.build()
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -95,15 +95,19 @@ int adccb_packed_pack(void* stream, int no, int nv, const double* T, double* U);
 /* GEMM-ready expansions of packed U: which = 0: X[i,a,k,c] = u[ikac]; 1: Ue[i,j,AB] = u[ij,AB];
  * 2: Uh[a,JK,b] = u[JK,ab]. */
 int adccb_packed_expand(void* stream, int which, int no, int nv, const double* U, double* out);
-/* S[r, AB] += alpha * (F_r[a,b] - F_r[b,a]), F_r[a,b] = P1[off1[r] + a*sa + b] - P2[off2[r] + a*sa + b]
- * (P2/off2 may be NULL); off1/off2: device int64 arrays of length nrows.  Folds the ovov-type
+/* S[rows[r], AB] += alpha * (F_r[a,b] - F_r[b,a]), F_r[a,b] = P1[off1[r] + a*sa + b] - P2[off2[r] + a*sa + b]
+ * (P2/off2 may be NULL; rows NULL = identity); off1/off2/rows: device int64 arrays of length nrows.  Folds the ovov-type
  * and ooov-type GEMM results into packed sigma (the antisymmetrise(2,3) of
  * adcc/adc_pp/matrix.py:241-243, 291-292). */
 int adccb_packed_fold_virt(void* stream, int64_t nrows, int nv, int64_t sa, const double* P1,
                            const int64_t* off1, const double* P2, const int64_t* off2,
-                           double alpha, double* S);
-/* S[pair(i,j), AB] += alpha * (C[i,j,AB] - C[j,i,AB])  (antisymmetrise(0,1), matrix.py:291). */
-int adccb_packed_fold_occ(void* stream, int no, int nv, const double* C, double alpha, double* S);
+                           const int64_t* rows, double alpha, double* S);
+/* S[pair(i,j), AB] += alpha * (C[i,j,AB] - C[j,i,AB])  (antisymmetrise(0,1), matrix.py:291).
+ * C is [no, nj, npv] and holds the slab j = j_begin .. j_begin+nj-1 of the second occupied index
+ * (nj = no, j_begin = 0: the full tensor); a slab contributes only the terms it owns, so that the
+ * per-rank partial sigma vectors of a sharded matvec add up. */
+int adccb_packed_fold_occ(void* stream, int no, int nv, int j_begin, int nj, const double* C,
+                          double alpha, double* S);
 /* D[IJ,AB] = 1/2 (dov[i,a]+dov[j,b]+dov[i,b]+dov[j,a]) + doo[i,j] + dvv[a,b] (doo, dvv may be
  * NULL): packed diagonal of the pphh-pphh block, adcc/adc_pp/matrix.py:109-124, 212-231. */
 int adccb_packed_diagonal(void* stream, int no, int nv, const double* dov, const double* doo,
@@ -116,9 +120,11 @@ int adccb_pair_select(void* stream, int64_t L, int n, int64_t R, const double* i
  * 2 Y[(j,b),(k,c)] = <kb||jc>, 3 V1[(j,AB),c] = <jc||ab>, 4 V2[a,(j,BC)] = <ja||bc>,
  * 5 G1[i,(JK,b)] = <jk||ib>, 6 G2[(IJ,a),k] = <ij||ka>, 7 dense block blk
  * (0 oooo, 1 ooov, 2 oovv, 3 ovov, 4 ovvv, 5 vvvv).  n = number of elements written.
- * Stands in for ReferenceState::eri -> import_eri_* (libadcc_src/ReferenceState.cc:478-509). */
+ * Stands in for ReferenceState::eri -> import_eri_* (libadcc_src/ReferenceState.cc:478-509).
+ * Slabs for sharding: row_begin = first AB row of layout 0; layouts 2, 3, 4 generate the occupied
+ * slab j = j_begin .. j_begin+nj-1 (nj <= 0: all). */
 int adccb_synth_fill(void* stream, int layout, int blk, int no, int nv, uint64_t seed, double scale,
-                     int64_t n, int64_t row_begin, double* out);
+                     int64_t n, int64_t row_begin, int j_begin, int nj, double* out);
 
 #ifdef __cplusplus
 }

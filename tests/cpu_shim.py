@@ -126,25 +126,31 @@ def install(monkeypatch):
         ii = torch.tensor([p[0] for p in po], dtype=torch.long); jj = torch.tensor([p[1] for p in po], dtype=torch.long)
         return d[ii, jj].permute(1, 0, 2).contiguous().reshape(nv, -1)
 
-    def packed_fold_virt(S, nv, sa, P1, off1, P2=None, off2=None, alpha=1.0):
+    def packed_fold_virt(S, nv, sa, P1, off1, P2=None, off2=None, alpha=1.0, rows=None):
         pv = _pairs(nv)
         aa = np.array([p[0] for p in pv], dtype=int); bb = np.array([p[1] for p in pv], dtype=int)
         p1 = P1.contiguous().reshape(-1).numpy()
         p2 = P2.contiguous().reshape(-1).numpy() if P2 is not None else None
         Sn = S.numpy()
-        for r in range(S.shape[0]):
+        for r in range(len(off1)):
             def F(a, b):
                 v = p1[int(off1[r]) + a * sa + b]
                 if p2 is not None:
                     v = v - p2[int(off2[r]) + a * sa + b]
                 return v
-            Sn[r] += alpha * (F(aa, bb) - F(bb, aa))
+            Sn[int(rows[r]) if rows is not None else r] += alpha * (F(aa, bb) - F(bb, aa))
         return S
 
-    def packed_fold_occ(S, C, no, nv, alpha=1.0):
-        c = C.contiguous().reshape(no, no, -1)
-        for I, (i, j) in enumerate(_pairs(no)):
-            S[I] += alpha * (c[i, j] - c[j, i])
+    def packed_fold_occ(S, C, no, nv, alpha=1.0, j_begin=0, nj=None):
+        nj = no if nj is None else nj
+        c = C.contiguous().reshape(no, nj, -1)
+        for i in range(no):
+            for jl in range(nj):
+                j = j_begin + jl
+                if i == j:
+                    continue
+                row = max(i, j) * (max(i, j) - 1) // 2 + min(i, j)
+                S[row] += (alpha if i < j else -alpha) * c[i, jl]
         return S
 
     def packed_diagonal(no, nv, dov, doo=None, dvv=None):
@@ -175,7 +181,9 @@ def install(monkeypatch):
     def int64_tensor(values):
         return torch.tensor([int(v) for v in values], dtype=torch.int64)
 
-    def synth_fill(out, layout, no, nv, seed, scale, block="vvvv", row_begin=0):
+    def synth_fill(out, layout, no, nv, seed, scale, block="vvvv", row_begin=0, j_begin=0, nj=0):
+        nj = no if nj <= 0 else nj
+        osl = np.arange(j_begin, j_begin + nj)
         from adcc_b200.synthetic import synthetic_eri_value as val
         po, pv = np.array(_pairs(no), dtype=int).reshape(-1, 2), np.array(_pairs(nv), dtype=int).reshape(-1, 2)
         o, v = np.arange(no), np.arange(nv)
@@ -185,13 +193,13 @@ def install(monkeypatch):
         elif layout == "oooo_packed":
             arr = val(seed, "oooo", po[:, 0][:, None], po[:, 1][:, None], po[:, 0][None, :], po[:, 1][None, :], scale)
         elif layout == "ovov_jbkc":
-            j, b, k, c = np.meshgrid(o, v, o, v, indexing="ij")
+            j, b, k, c = np.meshgrid(osl, v, o, v, indexing="ij")
             arr = val(seed, "ovov", k, b, j, c, scale)
         elif layout == "ovvv_jabc":
-            j, AB, c = np.meshgrid(o, np.arange(len(pv)), v, indexing="ij")
+            j, AB, c = np.meshgrid(osl, np.arange(len(pv)), v, indexing="ij")
             arr = val(seed, "ovvv", j, c, pv[AB, 0], pv[AB, 1], scale)
         elif layout == "ovvv_ajbc":
-            a, j, BC = np.meshgrid(v, o, np.arange(len(pv)), indexing="ij")
+            a, j, BC = np.meshgrid(v, osl, np.arange(len(pv)), indexing="ij")
             arr = val(seed, "ovvv", j, a, pv[BC, 0], pv[BC, 1], scale)
         elif layout == "ooov_ijkb":
             i, JK, b = np.meshgrid(o, np.arange(len(po)), v, indexing="ij")

@@ -18,7 +18,8 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (780, 1000, 2048), (100, 36, 10), (1, 7, 50),
-                                   (257, 130, 4098), (40, 400, 40000), (16, 16, 2)])
+                                   (257, 130, 4098), (40, 400, 40000), (16, 16, 2), (33, 70, 96),
+                                   (64, 1000, 512), (12, 300, 100000)])
 def test_gemm_tn_tma(be, M, N, K):
     rng = np.random.default_rng(M + N + K)
     A = rng.standard_normal((M, K))
@@ -33,7 +34,7 @@ def test_gemm_tn_tma(be, M, N, K):
     assert _rel(out.cpu().numpy(), -0.5 * ref + 2.0 * C0) < 1e-13
 
 
-@pytest.mark.parametrize("hint", [112, 128])
+@pytest.mark.parametrize("hint", [16, 40, 64, 112, 128])
 def test_gemm_tile_variants(be, hint):
     rng = np.random.default_rng(5)
     A = rng.standard_normal((300, 514))
