@@ -82,3 +82,19 @@ def check_run_parity(data, method, kind, core, n=None):
     np.testing.assert_allclose(state.excitation_energy, ostate.eigenvalues, atol=ENERGY_ATOL, rtol=0)
     assert state.n_iter == ostate.n_iter
     return state, ostate
+
+
+def check_oscillator_strengths(data, method, core, n=3):
+    """transition dipoles / oscillator strengths, product vs oracle (<= 1e-6 rel)."""
+    import adcc_b200 as adcc
+    from oracle.properties import oscillator_strengths
+    n = 2 if method.startswith("cvs") else n
+    state = adcc.run_adc(data, method=method, n_singlets=n, conv_tol=1e-9, core_orbitals=core, output=None)
+    ostate = oracle.run_adc(data, method, n_singlets=n, conv_tol=1e-9, core_orbitals=core)
+    oref = oracle.OracleRefState(oracle.OracleHf(data), core_orbitals=core)
+    of, omu = oscillator_strengths(oracle.OracleAdcMatrix(method, oref), ostate)
+    f = state.oscillator_strength
+    assert f.shape == of.shape
+    np.testing.assert_allclose(f, of, rtol=1e-6, atol=1e-10)
+    assert np.all(f >= 0)
+    return f

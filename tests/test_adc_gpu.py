@@ -64,3 +64,9 @@ def test_davidson_synthetic_c1_adc2_3_singlets():
 
 def test_any_kind_unrestricted_style(h2o):
     check_run_parity(h2o, "adc2", "any", None, n=4)
+
+
+@pytest.mark.parametrize("method", ["adc1", "adc2", "adc2x", "adc3", "cvs-adc2"])
+def test_oscillator_strengths_vs_oracle(h2o, method):
+    from adc_parity_common import check_oscillator_strengths
+    check_oscillator_strengths(h2o, method, 1 if method.startswith("cvs") else None)

@@ -117,3 +117,9 @@ def test_tensor_algebra_semantics(h2o):
     # immutability of imported tensors (ReferenceState.cc:471,507)
     with pytest.raises(RuntimeError):
         oovv.fill(1.0)
+
+
+@pytest.mark.parametrize("method", ["adc1", "adc2", "adc2x", "adc3", "cvs-adc2"])
+def test_oscillator_strengths_vs_oracle(h2o, method):
+    from adc_parity_common import check_oscillator_strengths
+    check_oscillator_strengths(h2o, method, 1 if method.startswith("cvs") else None)
