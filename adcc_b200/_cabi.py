@@ -29,6 +29,7 @@ def _declare(lib):
     lib.adccb_elementwise.argtypes = [c_ptr, ctypes.c_int, c_i64, c_dbl, c_ptr, c_ptr, c_dbl,
                                       c_dbl, c_ptr]
     lib.adccb_direct_sum.argtypes = [c_ptr, c_i64, c_i64, c_dbl, c_ptr, c_dbl, c_ptr, c_ptr]
+    lib.adccb_add_columns.argtypes = [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64]
     lib.adccb_lincomb.argtypes = [c_ptr, ctypes.c_int, ctypes.POINTER(c_dbl),
                                   ctypes.POINTER(c_ptr), c_i64, c_dbl, c_ptr]
     lib.adccb_dot_many.argtypes = [c_ptr, ctypes.c_int, c_ptr, ctypes.POINTER(c_ptr), c_i64,
@@ -56,7 +57,7 @@ def _declare(lib):
 EXPORTS = [
     "adccb_version", "adccb_last_error", "adccb_launch_count", "adccb_device_info",
     "adccb_dgemm", "adccb_strided_gather", "adccb_elementwise", "adccb_direct_sum",
-    "adccb_lincomb", "adccb_dot_many", "adccb_spin_project", "adccb_spin_singlet",
+    "adccb_add_columns", "adccb_lincomb", "adccb_dot_many", "adccb_spin_project", "adccb_spin_singlet",
     "adccb_packed_unpack", "adccb_packed_pack", "adccb_packed_expand", "adccb_packed_fold_virt",
     "adccb_packed_fold_occ", "adccb_packed_diagonal", "adccb_pair_select", "adccb_synth_fill",
 ]

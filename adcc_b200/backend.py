@@ -168,6 +168,13 @@ def direct_sum(a, b, sa=1.0, sb=1.0):
 
 
 # --------------------------------------------------------------------------------- vectors
+def add_columns(S, col0, G, ncols):
+    """S[:, col0:col0+ncols] += G[:, :ncols] (2-D row-major, unit column stride)."""
+    _cabi.check(_cabi.lib().adccb_add_columns(_stream(), S.shape[0], int(ncols), _ptr(S), S.stride(0),
+                                              int(col0), _ptr(G), G.stride(0)))
+    return S
+
+
 def lincomb(coeffs, tensors, out=None, beta=0.0):
     n = tensors[0].numel()
     for t in tensors:
@@ -242,12 +249,15 @@ def packed_pack(T, no, nv):
     return U
 
 
-def packed_expand(which, U, no, nv, out=None):
-    """which: 0 X[i,a,k,c]; 1 Ue[i,j,AB]; 2 Uh[a,JK,b]."""
-    shape = {0: (no * nv, no * nv), 1: (no, no * n_pairs(nv)), 2: (nv, n_pairs(no) * nv)}[which]
+def packed_expand(which, U, no, nv, out=None, n_pairs_o=None):
+    """which: 0 X[i,a,k,c]; 1 Ue[i,j,AB]; 2 Uh[a,JK,b] (n_pairs_o: number of JK rows in U when a row
+    slab of the packed vector is expanded)."""
+    npo = n_pairs(no) if n_pairs_o is None else n_pairs_o
+    shape = {0: (no * nv, no * nv), 1: (no, no * n_pairs(nv)), 2: (nv, npo * nv)}[which]
     if out is None:
         out = empty(shape)
-    _cabi.check(_cabi.lib().adccb_packed_expand(_stream(), which, no, nv, _ptr(U), _ptr(out)))
+    _cabi.check(_cabi.lib().adccb_packed_expand(_stream(), which, no if n_pairs_o is None else -npo, nv,
+                                                _ptr(U), _ptr(out)))
     return out
 
 

@@ -37,6 +37,8 @@ int elementwise(cudaStream_t st, int op, long long n, double alpha, const double
                 const double* y, double c, double beta, double* out);
 int direct_sum(cudaStream_t st, long long na, long long nb, double sa, const double* a, double sb,
                const double* b, double* out);
+int add_columns(cudaStream_t st, long long nrows, long long ncols, double* S, long long lds,
+                long long col0, const double* G, long long ldg);
 int lincomb(cudaStream_t st, int nvec, const double* coeff, const double* const* ptrs, long long n,
             double beta, double* out);
 int dot_many(cudaStream_t st, int nvec, const double* x, const double* const* ys, long long n,
@@ -101,6 +103,11 @@ int adccb_elementwise(void* stream, int op, int64_t n, double alpha, const doubl
 int adccb_direct_sum(void* stream, int64_t na, int64_t nb, double sa, const double* a, double sb,
                      const double* b, double* out) {
   return direct_sum((cudaStream_t)stream, na, nb, sa, a, sb, b, out);
+}
+
+int adccb_add_columns(void* stream, int64_t nrows, int64_t ncols, double* S, int64_t lds, int64_t col0,
+                      const double* G, int64_t ldg) {
+  return add_columns((cudaStream_t)stream, nrows, ncols, S, lds, col0, G, ldg);
 }
 
 int adccb_lincomb(void* stream, int nvec, const double* host_coeff, const double* const* host_ptrs,

@@ -353,7 +353,10 @@ int packed_pack(cudaStream_t st, int no, int nv, const double* T, double* U) {
 }
 
 int packed_expand(cudaStream_t st, int which, int no, int nv, const double* U, double* out) {
-  const long long npv = (long long)nv * (nv - 1) / 2, npo = (long long)no * (no - 1) / 2;
+  // no < 0 (which == 2 only): U is a slab of -no rows of the packed vector
+  const long long npv = (long long)nv * (nv - 1) / 2;
+  const long long npo = (no < 0) ? -(long long)no : (long long)no * (no - 1) / 2;
+  if (no < 0 && which != 2) return fail("packed_expand: row slabs are supported for layout 2 only");
   if (npv == 0 || npo == 0) return 0;
   if (which == 0) {
     expand_iakc_kernel<<<no * no, 256, 0, st>>>(no, nv, U, out);

@@ -213,6 +213,27 @@ int direct_sum(cudaStream_t st, long long na, long long nb, double sa, const dou
   return 0;
 }
 
+// S[i, col0 + c] += G[i, c]  (adds a gathered column slab into the packed sigma vector)
+__global__ void add_columns_kernel(long long nrows, long long ncols, double* __restrict__ S,
+                                   long long lds, long long col0, const double* __restrict__ G,
+                                   long long ldg) {
+  const long long n = nrows * ncols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx / ncols, c = idx - i * ncols;
+    S[i * lds + col0 + c] += G[i * ldg + c];
+  }
+}
+
+int add_columns(cudaStream_t st, long long nrows, long long ncols, double* S, long long lds,
+                long long col0, const double* G, long long ldg) {
+  if (nrows * ncols <= 0) return 0;
+  add_columns_kernel<<<grid_for(nrows * ncols, 256, 4), 256, 0, st>>>(nrows, ncols, S, lds, col0, G, ldg);
+  ADCCB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // lincomb:  out = sum_k c[k] * x[k]   (k <= kMaxVec per launch, one pass, one write)
 // ---------------------------------------------------------------------------------------

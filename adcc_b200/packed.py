@@ -233,12 +233,14 @@ class PackedAdcEngine:
         self.nj = j1 - self.j0
         cut = [min(self.npv, ((k * self.npv // w + 127) // 128) * 128) for k in range(w)] + [self.npv]
         self.ab0, self.ab1 = cut[r], cut[r + 1]
+        self._cuts = cut
+        self._wmax = max(cut[k + 1] - cut[k] for k in range(w))
         cut_o = [min(self.npo, ((k * self.npo // w + 1) // 2) * 2) for k in range(w)] + [self.npo]
         self.ij0, self.ij1 = cut_o[r], cut_o[r + 1]
         self.V1 = src.ovvv_jabc(self.j0, self.nj)
         self.V2 = src.ovvv_ajbc(self.j0, self.nj)
-        self.G1 = src.ooov_ijkb() if r == 0 else None
-        self.G2 = src.ooov_ijak() if r == 0 else None
+        self.G1 = src.ooov_ijkb()
+        self.G2 = src.ooov_ijak()
 
         # ---- doubles-doubles (matrix.py:127-133, 234-246)
         eo = be.from_numpy(np.diag(foo))
@@ -263,6 +265,7 @@ class PackedAdcEngine:
         self._off_ovov_1 = be.int64_tensor([(i * nv * no + j) * nv for i, j in pairs])
         self._off_ovov_2 = be.int64_tensor([(j * nv * no + i) * nv for i, j in pairs])
         self._off_rows = be.int64_tensor([r * nv * nv for r in range(self.npo)])
+        self._rows_ij = be.int64_tensor(list(range(self.ij0, self.ij1)))
         if self.world > 1:
             # ovov fold of a j-slab: T_r[(i,a),(jl,b)], offset (i*nv + a)*(nj*nv) + jl*nv + b
             njv = self.nj * nv
@@ -361,46 +364,50 @@ class PackedAdcEngine:
         return PackedDoubles._wrap(self.mospaces, ["o1", "o1", "v1", "v1"], data)
 
     def _matvec_sharded(self, u1, U):
-        """Partial sigma from this rank's slabs, then ONE all-reduce of the packed (ph + pphh)
-        buffer (NCCL over NVLink on the GPU box).  vvvv: AB-row slab of W; ovov, ovvv: occupied
-        j-slab; oooo: KL slab of the contraction index; D0 and M1: row slabs."""
+        """Per-rank partial sigma from this rank's operand slabs.
+
+        Everything except the vvvv term is accumulated into one packed (pphh + ph) buffer whose
+        all-reduce runs on a high-priority side stream WHILE the vvvv GEMM (disjoint AB-column
+        slab per rank, the longest kernel) computes; the column slabs are then all-gathered and
+        added.  Slabs: vvvv: AB rows of W; ovov / ovvv: occupied j; oooo, D0, ooov terms: IJ
+        pairs; ph_ph: rows of M1.  All ranks end with the identical, complete sigma."""
+        import torch
         import torch.distributed as dist
         no, nv, npo, npv = self.no, self.nv, self.npo, self.npv
+        world = self.world
         buf = be.zeros((npo * npv + no * nv,))
         S = buf[:npo * npv].view(npo, npv)
         s1 = buf[npo * npv:].view(1, no * nv)
+        s1m = s1.view(no, nv)
         x = u1._contig()
+        ij0, ij1 = self.ij0, self.ij1
+        nij = ij1 - ij0
+        # ---- ph_ph: rows (i in slab, a) of the folded singles matrix
         r0, r1 = self.j0 * nv, (self.j0 + self.nj) * nv
-        # ph_ph: rows (i in slab, a) of the folded singles matrix
         if r1 > r0:
             be.gemm(x.reshape(1, -1), self.M1[r0:r1], out=s1[:, r0:r1])
-        s1m = s1.view(no, nv)
+        # ---- ph_pphh
         if self.nj > 0:
-            # ph_pphh: contraction index (j,BC) restricted to the slab
             Ue = be.packed_expand(1, U, no, nv)
             k0, k1 = self.j0 * npv, (self.j0 + self.nj) * npv
             be.gemm(Ue[:, k0:k1], self.V2, out=s1m, alpha=2.0, beta=1.0)
             del Ue
-        if self.rank == 0:
-            Uh = be.packed_expand(2, U, no, nv)
-            be.gemm(self.G1, Uh, out=s1m, alpha=2.0, beta=1.0)
+        if nij > 0:
+            Uh = be.packed_expand(2, U[ij0:ij1], nij, nv, n_pairs_o=nij)        # [a,(JK slab,b)]
+            be.gemm(self.G1[:, ij0 * nv:ij1 * nv], Uh, out=s1m, alpha=2.0, beta=1.0)
             del Uh
-        # pphh_pphh
-        if self.ij1 > self.ij0:
-            be.mul(U[self.ij0:self.ij1], self.D0[self.ij0:self.ij1], out=S[self.ij0:self.ij1])
+        # ---- pphh_pphh without the vvvv term
+        if nij > 0:
+            be.mul(U[ij0:ij1], self.D0[ij0:ij1], out=S[ij0:ij1])
         if self.order_dd == 1:
-            if self.ab1 > self.ab0:
-                self._mark("vvvv", 0)
-                be.gemm(U, self.W, out=S[:, self.ab0:self.ab1], alpha=1.0, beta=1.0)
-                self._mark("vvvv", 1)
-            if self.ij1 > self.ij0:
-                Ut = be.permute(U[self.ij0:self.ij1], (1, 0))            # [AB, KL slab]
-                be.gemm(self.O[:, self.ij0:self.ij1], Ut, out=S, alpha=1.0, beta=1.0)
+            if nij > 0:
+                Ut = be.permute(U[ij0:ij1], (1, 0))                               # [AB, KL slab]
+                be.gemm(self.O[:, ij0:ij1], Ut, out=S, alpha=1.0, beta=1.0)
                 del Ut
             if self.nj > 0:
                 X = be.packed_expand(0, U, no, nv)
                 self._mark("ovov", 0)
-                T = be.gemm(X, self.Y)                                   # [(i,a),(jl,b)]
+                T = be.gemm(X, self.Y)                                           # [(i,a),(jl,b)]
                 self._mark("ovov", 1)
                 del X
                 njv = self.nj * nv
@@ -409,18 +416,51 @@ class PackedAdcEngine:
                 off, rows = self._sl_lo
                 be.packed_fold_virt(S, nv, njv, T, off, alpha=+1.0, rows=rows)
                 del T
-        # pphh_ph
+        # ---- pphh_ph
         if self.nj > 0:
-            c1 = be.gemm(x, self.V1)                                     # [i,(jl,AB)]
+            c1 = be.gemm(x, self.V1)                                             # [i,(jl,AB)]
             be.packed_fold_occ(S, c1, no, nv, alpha=0.5, j_begin=self.j0, nj=self.nj)
             del c1
-        if self.rank == 0:
-            c2 = be.gemm(self.G2, be.permute(x, (1, 0)))
-            be.packed_fold_virt(S, nv, nv, c2, self._off_rows, alpha=-0.5)
+        if nij > 0:
+            c2 = be.gemm(self.G2[ij0 * nv:ij1 * nv], be.permute(x, (1, 0)))      # [(IJ slab,a),b]
+            be.packed_fold_virt(S, nv, nv, c2, self._off_rows[:nij], alpha=-0.5, rows=self._rows_ij)
             del c2
-        self._mark("allreduce", 0)
-        dist.all_reduce(buf)
-        self._mark("allreduce", 1)
+        # ---- all-reduce of the partial sums, overlapped with the vvvv GEMM
+        main = torch.cuda.current_stream() if buf.is_cuda else None
+        work = None
+        if main is not None:
+            if getattr(self, "_comm_stream", None) is None:
+                self._comm_stream = torch.cuda.Stream(priority=-1)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            self._comm_stream.wait_event(ready)
+            with torch.cuda.stream(self._comm_stream):
+                dist.all_reduce(buf)
+                done = torch.cuda.Event()
+                done.record(self._comm_stream)
+        else:
+            dist.all_reduce(buf)
+        if self.order_dd == 1:
+            wmax = self._wmax
+            slab = be.empty((npo, wmax)) if wmax > 0 else None
+            w = self.ab1 - self.ab0
+            if w < wmax or w == 0:
+                be.fill(slab, 0.0)
+            if w > 0:
+                self._mark("vvvv", 0)
+                be.gemm(U, self.W, out=slab[:, :w])
+                self._mark("vvvv", 1)
+            gathered = be.empty((world * npo, wmax))
+            dist.all_gather_into_tensor(gathered, slab)
+            gathered = gathered.view(world, npo, wmax)
+        if main is not None:
+            main.wait_event(done)
+            buf.record_stream(self._comm_stream)
+        if self.order_dd == 1:
+            for r in range(world):
+                wr = self._cuts[r + 1] - self._cuts[r]
+                if wr > 0:
+                    be.add_columns(S, self._cuts[r], gathered[r], wr)
         return AmplitudeVector(ph=self._wrap_ph(s1.view(no, nv)), pphh=self._wrap_pphh(S))
 
     def matvec(self, v):

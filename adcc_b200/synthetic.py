@@ -18,10 +18,27 @@ SHAPES = {
 }
 
 
-def restricted_scf_dict(n_orb, n_occ, seed=1001, scale=0.05, conv_tol=1e-12):
+def molecule_like_levels(lo, hi, n, dense_end="hi"):
+    """n levels in [lo, hi] with square-root spacing: sparse near the frontier end, dense far from
+    it, so that the lowest excitations are well separated like in a molecule (a uniform ladder
+    gives hundreds of near-degenerate e_a - e_i and a Davidson that crawls)."""
+    if n == 1:
+        return np.array([lo if dense_end == "hi" else hi])
+    t = np.sqrt(np.arange(n) / (n - 1.0))
+    return lo + (hi - lo) * t if dense_end == "hi" else hi - (hi - lo) * t[::-1]
+
+
+def restricted_scf_dict(n_orb, n_occ, seed=1001, scale=None, conv_tol=1e-12):
+    """scale=None: 0.35 / (number of virtual spin orbitals), which keeps the spectral radius of the
+    random <ab||cd> block (~0.85 * scale * n_virt_spin) a perturbation of the orbital-energy gaps."""
     rng = np.random.default_rng(seed)
-    occ_e = np.concatenate(([-20.0], np.linspace(-1.6, -0.4, n_occ - 1))) if n_occ > 1 else np.array([-0.5])
-    virt_e = np.linspace(0.15, 4.0, n_orb - n_occ)
+    if scale is None:
+        scale = 0.35 / (2 * (n_orb - n_occ))
+    if n_occ > 1:
+        occ_e = np.concatenate(([-20.0], molecule_like_levels(-1.6, -0.4, n_occ - 1, dense_end="lo")))
+    else:
+        occ_e = np.array([-0.5])
+    virt_e = molecule_like_levels(0.15, 4.0, n_orb - n_occ, dense_end="hi")
     orben = np.concatenate((occ_e, virt_e))
     g = rng.standard_normal((n_orb,) * 4)
     # 8-fold symmetry of real chemists' integrals (pq|rs)
@@ -105,5 +122,7 @@ def synthetic_eri_block(seed, block, no, nv, scale):
 
 
 def synthetic_orbital_energies(no, nv):
-    """e_occ = linspace(-2.0, -0.3, no), e_virt = linspace(0.2, 4.0, nv)."""
-    return np.linspace(-2.0, -0.3, no), np.linspace(0.2, 4.0, nv)
+    """Spin-orbital energies of the synthetic workload: occupied in [-2.0, -0.3], virtual in
+    [0.2, 4.0] (the ranges of SURVEY.md 8(d)) with molecule-like square-root spacing."""
+    return (molecule_like_levels(-2.0, -0.3, no, dense_end="lo"),
+            molecule_like_levels(0.2, 4.0, nv, dense_end="hi"))

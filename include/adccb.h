@@ -57,6 +57,11 @@ int adccb_elementwise(void* stream, int op, int64_t n, double alpha, const doubl
 int adccb_direct_sum(void* stream, int64_t na, int64_t nb, double sa, const double* a, double sb,
                      const double* b, double* out);
 
+/* S[i, col0 + c] += G[i, c] for i < nrows, c < ncols (row-major, leading dims lds / ldg): merges the
+ * column slab a peer rank computed into the local sigma vector after the all-gather. */
+int adccb_add_columns(void* stream, int64_t nrows, int64_t ncols, double* S, int64_t lds, int64_t col0,
+                      const double* G, int64_t ldg);
+
 /* out = beta * out + sum_k host_coeff[k] * host_ptrs[k][:] (one pass over all inputs).
  * libadcc_src/TensorImpl.cc:604-624 (add_linear_combination) reached from
  * libadcc_src/pyiface/export_Tensor.cc:260-277 (linear_combination_strict). */
@@ -93,7 +98,7 @@ int adccb_packed_unpack(void* stream, int no, int nv, const double* U, double* o
  * symmetrisation of adcc/AdcMatrix.py:449-455 in one pass. */
 int adccb_packed_pack(void* stream, int no, int nv, const double* T, double* U);
 /* GEMM-ready expansions of packed U: which = 0: X[i,a,k,c] = u[ikac]; 1: Ue[i,j,AB] = u[ij,AB];
- * 2: Uh[a,JK,b] = u[JK,ab]. */
+ * 2: Uh[a,JK,b] = u[JK,ab] (no < 0: U holds a slab of -no JK rows). */
 int adccb_packed_expand(void* stream, int which, int no, int nv, const double* U, double* out);
 /* S[rows[r], AB] += alpha * (F_r[a,b] - F_r[b,a]), F_r[a,b] = P1[off1[r] + a*sa + b] - P2[off2[r] + a*sa + b]
  * (P2/off2 may be NULL; rows NULL = identity); off1/off2/rows: device int64 arrays of length nrows.  Folds the ovov-type

@@ -114,7 +114,15 @@ def install(monkeypatch):
             return torch.zeros((len(po), len(pv)), dtype=F64)
         return from_numpy(t[ii[:, None], jj[:, None], aa[None, :], bb[None, :]])
 
-    def packed_expand(which, U, no, nv, out=None):
+    def packed_expand(which, U, no, nv, out=None, n_pairs_o=None):
+        if n_pairs_o is not None:
+            assert which == 2
+            pv = _pairs(nv)
+            res = torch.zeros((nv, n_pairs_o, nv), dtype=F64)
+            for A, (a, b) in enumerate(pv):
+                res[a, :, b] = U[:, A]
+                res[b, :, a] = -U[:, A]
+            return res.reshape(nv, -1)
         d = packed_unpack(U, no, nv)
         if which == 0:
             return d.permute(0, 2, 1, 3).contiguous().reshape(no * nv, no * nv)
@@ -178,6 +186,10 @@ def install(monkeypatch):
         # advanced indices adjacent -> result axis stays in place
         return res.contiguous()
 
+    def add_columns(S, col0, G, ncols):
+        S[:, col0:col0 + ncols] += G[:, :ncols]
+        return S
+
     def int64_tensor(values):
         return torch.tensor([int(v) for v in values], dtype=torch.int64)
 
@@ -228,6 +240,6 @@ def install(monkeypatch):
                          spin_singlet_=spin_singlet_, packed_unpack=packed_unpack, packed_pack=packed_pack,
                          packed_expand=packed_expand, packed_fold_virt=packed_fold_virt,
                          packed_fold_occ=packed_fold_occ, packed_diagonal=packed_diagonal,
-                         pair_select=pair_select, int64_tensor=int64_tensor, synth_fill=synth_fill).items():
+                         pair_select=pair_select, int64_tensor=int64_tensor, add_columns=add_columns, synth_fill=synth_fill).items():
         monkeypatch.setattr(be, name, fn)
     monkeypatch.setattr(be, "device", lambda: cpu)
