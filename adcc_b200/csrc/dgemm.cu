@@ -81,116 +81,17 @@ struct TileCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;
 };
 
-template <int WARPS_M, int WARPS_N, int MB, int NB, int STAGES>
-__global__ void __launch_bounds__((WARPS_M * WARPS_N + 1) * 32, 1)
-dgemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA,
-                    const __grid_constant__ CUtensorMap tmB, double* __restrict__ C,
-                    long long ldc, int M, int N, int K, int k_per_split, double alpha,
-                    double beta, double* __restrict__ partial) {
-  using Cfg = TileCfg<WARPS_M, WARPS_N, MB, NB, STAGES>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
-  // full[s] at bar_base + 8*s, empty[s] at bar_base + 8*(STAGES+s)
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int tile_m = blockIdx.x, tile_n = blockIdx.y, split = blockIdx.z;
-  const int k_begin = split * k_per_split;
-  const int k_end = min(K, k_begin + k_per_split);
-  const int n_iters = (k_end - k_begin + kBK - 1) / kBK;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_base + 8 * s, 1);
-      mbar_init(bar_base + 8 * (STAGES + s), Cfg::kConsumerWarps);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (warp == Cfg::kConsumerWarps) {
-    // ===== TMA producer (one elected lane) =====
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-      for (int it = 0; it < n_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(bar_base + 8 * (STAGES + s), ph ^ 1);
-        const uint32_t full = bar_base + 8 * s;
-        mbar_expect_tx(full, Cfg::STAGE_BYTES);
-        const uint32_t dst = smem_base + s * Cfg::STAGE_BYTES;
-        const int k0 = k_begin + it * kBK;
-        tma_load_2d(dst, &tmA, full, k0, tile_m * Cfg::BM);
-        tma_load_2d(dst + Cfg::A_BYTES, &tmB, full, k0, tile_n * Cfg::BN);
-      }
-    }
-    return;
-  }
-
-  // ===== DMMA consumers =====
+// epilogue shared by the main kernel and the stream-K fix-up: thread (warp, lane) holds
+// C[row pg][cols t, t+4] of each 8x8 block of its warp tile
+template <int WARPS_N, int MB, int NB, int BM, int BN>
+__device__ __forceinline__ void store_tile(const double (&acc)[MB][NB][2], int warp, int lane,
+                                           int tile_m, int tile_n, double* __restrict__ C,
+                                           long long ldc, int M, int N, double alpha, double beta) {
   const int wm = warp / WARPS_N, wn = warp % WARPS_N;
   const int g = lane >> 2, t = lane & 3;
-  // fragment row g of every 8-row block lives in tile row pg: lanes of one quarter warp then
-  // hit rows r and r^4, whose swizzled 16B chunks fall into disjoint bank groups
   const int pg = (g >> 1) | ((g & 1) << 2);
-  const uint32_t a_off = (uint32_t)((wm * MB * 8 + pg) * 128 + ((t ^ pg) << 4));
-  const uint32_t b_off = (uint32_t)(Cfg::A_BYTES + (wn * NB * 8 + pg) * 128 + ((t ^ pg) << 4));
-
-  double acc[MB][NB][2];
-#pragma unroll
-  for (int i = 0; i < MB; ++i)
-#pragma unroll
-    for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  for (int it = 0; it < n_iters; ++it) {
-    const int s = it % STAGES;
-    const uint32_t ph = (it / STAGES) & 1;
-    mbar_wait(bar_base + 8 * s, ph);
-    const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES + a_off;
-    const uint32_t sb = smem_base + s * Cfg::STAGE_BYTES + b_off;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      // logical 16B chunk t + 4h of the row: doubles k = 8h + 2t, 8h + 2t + 1.  The same
-      // k <-> (h, t, slot) relabelling is used for A and B, which leaves the dot product intact.
-      double2 af[MB], bf[NB];
-#pragma unroll
-      for (int i = 0; i < MB; ++i) af[i] = lds128((sa + i * 1024) ^ (h << 6));
-#pragma unroll
-      for (int j = 0; j < NB; ++j) bf[j] = lds128((sb + j * 1024) ^ (h << 6));
-#pragma unroll
-      for (int i = 0; i < MB; ++i)
-#pragma unroll
-        for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x);
-#pragma unroll
-      for (int i = 0; i < MB; ++i)
-#pragma unroll
-        for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i].y, bf[j].y);
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + s));
-  }
-
-  // ===== epilogue: thread holds C[row pg][cols t, t+4] of each 8x8 block =====
-  const int row0 = tile_m * Cfg::BM + wm * MB * 8 + pg;
-  const int col0 = tile_n * Cfg::BN + wn * NB * 8 + t;
-  if (partial != nullptr) {
-    double* P = partial + (size_t)split * (size_t)M * (size_t)N;
-#pragma unroll
-    for (int i = 0; i < MB; ++i) {
-      const int r = row0 + i * 8;
-      if (r >= M) continue;
-#pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        const int c = col0 + j * 8;
-        if (c < N) P[(size_t)r * N + c] = acc[i][j][0];
-        if (c + 4 < N) P[(size_t)r * N + c + 4] = acc[i][j][1];
-      }
-    }
-    return;
-  }
+  const int row0 = tile_m * BM + wm * MB * 8 + pg;
+  const int col0 = tile_n * BN + wn * NB * 8 + t;
 #pragma unroll
   for (int i = 0; i < MB; ++i) {
     const int r = row0 + i * 8;
@@ -206,17 +107,198 @@ dgemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA,
   }
 }
 
-// fixed-order reduction of split-K partials
-__global__ void splitk_reduce_kernel(const double* __restrict__ partial, int splits, long long MN,
-                                     int N, double* __restrict__ C, long long ldc, double alpha,
-                                     double beta) {
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < MN;
-       idx += (long long)gridDim.x * blockDim.x) {
-    double s = 0.0;
-    for (int k = 0; k < splits; ++k) s += partial[(size_t)k * MN + idx];
-    const long long r = idx / N, c = idx % N;
-    double* dst = C + r * ldc + c;
-    *dst = (beta == 0.0) ? alpha * s : alpha * s + beta * (*dst);
+// Work distribution (persistent, one CTA per SM): tiles are ordered M-fastest.
+//   * data-parallel phase: `dp_waves` rounds in which CTA b owns the whole tile  w * gridDim.x + b
+//     (the CTAs running together cover neighbouring tiles, so A/B slabs are shared through L2);
+//   * stream-K phase: the remaining tiles' (tile, k-slab) space is cut into equal contiguous
+//     spans, one per CTA.  A span segment that covers a tile completely stores it directly; the
+//     (at most two) partially covered tiles at the ends of a span go to `partial` (slot 2*cta for
+//     the span's first segment, 2*cta+1 for its last) and dgemm_fixup_kernel sums the segments of
+//     each such tile in CTA order (deterministic).
+// One scheme thus covers plain tiling, split-K for skinny outputs and the partial last wave.
+struct SegIter {
+  int w, dp_waves, tiles_m, k_iters, rem, k_next;
+  long long tile_next;
+  bool first_sk;
+  __device__ __forceinline__ void init(int dp_waves_, int tiles_m_, int k_iters_, long long sk_tile0,
+                                       long long sk_total, long long ipc) {
+    w = 0; dp_waves = dp_waves_; tiles_m = tiles_m_; k_iters = k_iters_;
+    const long long g0 = (long long)blockIdx.x * ipc;
+    const long long g1 = min(g0 + ipc, sk_total);
+    rem = g1 > g0 ? (int)(g1 - g0) : 0;
+    const long long tl = g0 / k_iters;
+    tile_next = sk_tile0 + tl;
+    k_next = (int)(g0 - tl * k_iters);
+    first_sk = true;
+  }
+  // returns false when the CTA has no more work
+  __device__ __forceinline__ bool next(int& tm, int& tn, int& k_start, int& n_seg, int& slot) {
+    long long tile;
+    if (w < dp_waves) {
+      tile = (long long)w * gridDim.x + blockIdx.x;
+      ++w;
+      k_start = 0; n_seg = k_iters; slot = -1;
+    } else if (rem > 0) {
+      tile = tile_next++;
+      k_start = k_next;
+      n_seg = min(rem, k_iters - k_next);
+      slot = (n_seg == k_iters) ? -1 : (first_sk ? 0 : 1);
+      rem -= n_seg; k_next = 0; first_sk = false;
+    } else {
+      return false;
+    }
+    tm = (int)(tile % tiles_m);
+    tn = (int)(tile / tiles_m);
+    return true;
+  }
+};
+
+template <int WARPS_M, int WARPS_N, int MB, int NB, int STAGES>
+__global__ void __launch_bounds__((WARPS_M * WARPS_N + 1) * 32, 1)
+dgemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA,
+                    const __grid_constant__ CUtensorMap tmB, double* __restrict__ C,
+                    long long ldc, int M, int N, int tiles_m, int k_iters, int dp_waves,
+                    long long sk_tile0, long long sk_total, long long ipc, double alpha, double beta,
+                    double* __restrict__ partial) {
+  using Cfg = TileCfg<WARPS_M, WARPS_N, MB, NB, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  // full[s] at bar_base + 8*s, empty[s] at bar_base + 8*(STAGES+s)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_base + 8 * s, 1);
+      mbar_init(bar_base + 8 * (STAGES + s), Cfg::kConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  SegIter seg;
+  seg.init(dp_waves, tiles_m, k_iters, sk_tile0, sk_total, ipc);
+  int tm, tn, k_start, n_seg, slot;
+  int it = 0;
+
+  if (warp == Cfg::kConsumerWarps) {
+    // ===== TMA producer (one elected lane) =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+      while (seg.next(tm, tn, k_start, n_seg, slot)) {
+        for (int n = 0; n < n_seg; ++n, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(bar_base + 8 * (STAGES + s), ph ^ 1);
+          const uint32_t full = bar_base + 8 * s;
+          mbar_expect_tx(full, Cfg::STAGE_BYTES);
+          const uint32_t dst = smem_base + s * Cfg::STAGE_BYTES;
+          tma_load_2d(dst, &tmA, full, (k_start + n) * kBK, tm * Cfg::BM);
+          tma_load_2d(dst + Cfg::A_BYTES, &tmB, full, (k_start + n) * kBK, tn * Cfg::BN);
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== DMMA consumers =====
+  const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+  const int g = lane >> 2, t = lane & 3;
+  // fragment row g of every 8-row block lives in tile row pg: lanes of one quarter warp then
+  // hit rows r and r^4, whose swizzled 16B chunks fall into disjoint bank groups
+  const int pg = (g >> 1) | ((g & 1) << 2);
+  const uint32_t a_off = (uint32_t)((wm * MB * 8 + pg) * 128 + ((t ^ pg) << 4));
+  const uint32_t b_off = (uint32_t)(Cfg::A_BYTES + (wn * NB * 8 + pg) * 128 + ((t ^ pg) << 4));
+
+  double acc[MB][NB][2];
+  while (seg.next(tm, tn, k_start, n_seg, slot)) {
+#pragma unroll
+    for (int i = 0; i < MB; ++i)
+#pragma unroll
+      for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int n = 0; n < n_seg; ++n, ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(bar_base + 8 * s, ph);
+      const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES + a_off;
+      const uint32_t sb = smem_base + s * Cfg::STAGE_BYTES + b_off;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        // logical 16B chunk t + 4h of the row: doubles k = 8h + 2t, 8h + 2t + 1.  The same
+        // k <-> (h, t, slot) relabelling is used for A and B, which leaves the dot product intact.
+        double2 af[MB], bf[NB];
+#pragma unroll
+        for (int i = 0; i < MB; ++i) af[i] = lds128((sa + i * 1024) ^ (h << 6));
+#pragma unroll
+        for (int j = 0; j < NB; ++j) bf[j] = lds128((sb + j * 1024) ^ (h << 6));
+#pragma unroll
+        for (int i = 0; i < MB; ++i)
+#pragma unroll
+          for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x);
+#pragma unroll
+        for (int i = 0; i < MB; ++i)
+#pragma unroll
+          for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i].y, bf[j].y);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + s));
+    }
+
+    if (slot < 0) {
+      store_tile<WARPS_N, MB, NB, Cfg::BM, Cfg::BN>(acc, warp, lane, tm, tn, C, ldc, M, N, alpha, beta);
+    } else {
+      // fragment-ordered partial: element (reg, consumer thread) -> coalesced
+      constexpr int kCT = Cfg::kConsumerWarps * 32;
+      double* P = partial + ((size_t)2 * blockIdx.x + slot) * (size_t)(MB * NB * 2) * kCT;
+      const int ctid = threadIdx.x;
+#pragma unroll
+      for (int i = 0; i < MB; ++i)
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          P[(size_t)((i * NB + j) * 2 + 0) * kCT + ctid] = acc[i][j][0];
+          P[(size_t)((i * NB + j) * 2 + 1) * kCT + ctid] = acc[i][j][1];
+        }
+    }
+  }
+}
+
+// sums the partial segments of every stream-K tile that no single CTA covered, in CTA order
+template <int WARPS_M, int WARPS_N, int MB, int NB, int STAGES>
+__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32)
+dgemm_fixup_kernel(double* __restrict__ C, long long ldc, int M, int N, int tiles_m, int k_iters,
+                   long long sk_tile0, long long sk_tiles, long long ipc, double alpha, double beta,
+                   const double* __restrict__ partial) {
+  using Cfg = TileCfg<WARPS_M, WARPS_N, MB, NB, STAGES>;
+  constexpr int kThreads = Cfg::kConsumerWarps * 32;
+  for (long long tl = blockIdx.x; tl < sk_tiles; tl += gridDim.x) {
+    const long long t0 = tl * (long long)k_iters, t1 = t0 + k_iters;
+    const long long b_first = t0 / ipc, b_last = (t1 - 1) / ipc;
+    if (b_first == b_last && b_first * ipc <= t0 && (b_first + 1) * ipc >= t1) continue;  // stored directly
+    double acc[MB][NB][2];
+#pragma unroll
+    for (int i = 0; i < MB; ++i)
+#pragma unroll
+      for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (long long b = b_first; b <= b_last; ++b) {
+      const int slot = ((b * ipc) / k_iters == tl) ? 0 : 1;   // first or last segment of CTA b
+      const double* P = partial + ((size_t)2 * b + slot) * (size_t)(MB * NB * 2) * kThreads;
+#pragma unroll
+      for (int i = 0; i < MB; ++i)
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          acc[i][j][0] += P[(size_t)((i * NB + j) * 2 + 0) * kThreads + threadIdx.x];
+          acc[i][j][1] += P[(size_t)((i * NB + j) * 2 + 1) * kThreads + threadIdx.x];
+        }
+    }
+    const long long tile = sk_tile0 + tl;
+    store_tile<WARPS_N, MB, NB, Cfg::BM, Cfg::BN>(acc, threadIdx.x >> 5, threadIdx.x & 31,
+                                                 (int)(tile % tiles_m), (int)(tile / tiles_m), C, ldc,
+                                                 M, N, alpha, beta);
   }
 }
 
@@ -339,30 +421,39 @@ static int launch_tma(cudaStream_t st, int M, int N, int K, double alpha, const 
     return fail("cuTensorMapEncodeTiled failed");
   const int tm = (M + Cfg::BM - 1) / Cfg::BM, tn = (N + Cfg::BN - 1) / Cfg::BN;
   const long long tiles = (long long)tm * tn;
-  // split K when the output has too few tiles to fill the machine
-  int splits = 1;
+  const int k_iters = (K + kBK - 1) / kBK;
   const int nsm = sm_count();
-  const int k_slabs = (K + kBK - 1) / kBK;
-  if (tiles < nsm && k_slabs >= 64 && ws != nullptr) {
-    splits = (int)((2LL * nsm + tiles - 1) / tiles);
-    if (splits > k_slabs / 16) splits = k_slabs / 16;
-    const long long per = (long long)M * N * 8;
-    if (per > 0 && (long long)splits * per > ws_bytes) splits = (int)(ws_bytes / per);
-    if (splits < 1) splits = 1;
+  const long long slot_bytes = (long long)MB * NB * 2 * Cfg::kConsumerWarps * 32 * 8;
+  const bool can_sk = ws != nullptr && 2LL * nsm * slot_bytes <= ws_bytes;
+  // data-parallel rounds of whole tiles, stream-K for the rest (see SegIter)
+  long long n_ctas, sk_tile0, sk_tiles, ipc;
+  int dp_waves;
+  if (!can_sk) {                       // whole tiles only, one CTA per tile
+    n_ctas = tiles; dp_waves = 1; sk_tile0 = tiles; sk_tiles = 0; ipc = k_iters;
+  } else if (tiles >= nsm) {
+    const long long q = tiles / nsm, r = tiles % nsm;
+    n_ctas = nsm;
+    dp_waves = (int)((r == 0) ? q : q - 1);
+    sk_tile0 = (long long)dp_waves * nsm;
+    sk_tiles = tiles - sk_tile0;
+    ipc = (sk_tiles * k_iters + n_ctas - 1) / n_ctas;
+  } else {                             // fewer tiles than SMs: split K, spans of >= 8 k-slabs
+    const long long total = tiles * k_iters;
+    n_ctas = std::min<long long>(nsm, std::max<long long>(tiles, total / 8));
+    dp_waves = 0; sk_tile0 = 0; sk_tiles = tiles;
+    ipc = (total + n_ctas - 1) / n_ctas;
+    n_ctas = (total + ipc - 1) / ipc;
   }
-  int k_per_split = ((k_slabs + splits - 1) / splits) * kBK;
-  splits = (K + k_per_split - 1) / k_per_split;
-  dim3 grid(tm, tn, splits);
-  if (tn > 65535) return fail("dgemm: too many N tiles");
-  double* partial = splits > 1 ? ws : nullptr;
-  kern<<<grid, Cfg::kThreads, Cfg::SMEM_BYTES, st>>>(tmA, tmB, C, ldc, M, N, K, k_per_split, alpha,
-                                                    beta, partial);
+  const long long sk_total = sk_tiles * k_iters;
+  const bool has_partials = sk_tiles > 0 && (ipc % k_iters) != 0;
+  kern<<<(unsigned)n_ctas, Cfg::kThreads, Cfg::SMEM_BYTES, st>>>(tmA, tmB, C, ldc, M, N, tm, k_iters, dp_waves,
+                                                                 sk_tile0, sk_total, ipc, alpha, beta, ws);
   ADCCB_LAUNCH_OK();
   count_launch();
-  if (splits > 1) {
-    const long long MN = (long long)M * N;
-    int blocks = (int)std::min<long long>((MN + 255) / 256, 4LL * nsm);
-    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(partial, splits, MN, N, C, ldc, alpha, beta);
+  if (has_partials) {
+    const int blocks = (int)std::min<long long>(sk_tiles, 4LL * nsm);
+    dgemm_fixup_kernel<WARPS_M, WARPS_N, MB, NB, STAGES><<<blocks, Cfg::kConsumerWarps * 32, 0, st>>>(
+        C, ldc, M, N, tm, k_iters, sk_tile0, sk_tiles, ipc, alpha, beta, ws);
     ADCCB_LAUNCH_OK();
     count_launch();
   }
