@@ -266,7 +266,10 @@ class PackedAdcEngine:
         self._off_ovov_2 = be.int64_tensor([(j * nv * no + i) * nv for i, j in pairs])
         self._off_rows = be.int64_tensor([r * nv * nv for r in range(self.npo)])
         self._rows_ij = be.int64_tensor(list(range(self.ij0, self.ij1)))
+        self._reduce_group = None
         if self.world > 1:
+            import torch.distributed as dist
+            self._reduce_group = dist.new_group(ranks=list(range(self.world)))
             # ovov fold of a j-slab: T_r[(i,a),(jl,b)], offset (i*nv + a)*(nj*nv) + jl*nv + b
             njv = self.nj * nv
             own = range(self.j0, self.j0 + self.nj)
@@ -426,7 +429,9 @@ class PackedAdcEngine:
             be.packed_fold_virt(S, nv, nv, c2, self._off_rows[:nij], alpha=-0.5, rows=self._rows_ij)
             del c2
         # ---- all-reduce of the partial sums, overlapped with the vvvv GEMM
-        main = torch.cuda.current_stream() if buf.is_cuda else None
+        import os
+        overlap = buf.is_cuda and os.environ.get("ADCCB_NO_OVERLAP", "0") != "1"
+        main = torch.cuda.current_stream() if overlap else None
         work = None
         if main is not None:
             if getattr(self, "_comm_stream", None) is None:
@@ -435,7 +440,9 @@ class PackedAdcEngine:
             ready.record(main)
             self._comm_stream.wait_event(ready)
             with torch.cuda.stream(self._comm_stream):
-                dist.all_reduce(buf)
+                # own communicator: NCCL does not allow two collectives of ONE communicator in
+                # flight on different streams (the all-gather below runs on the main stream)
+                dist.all_reduce(buf, group=self._reduce_group)
                 done = torch.cuda.Event()
                 done.record(self._comm_stream)
         else:

@@ -267,6 +267,9 @@ def run_gpu(args):
         mw = matrix.matvec(w)
         lhs, rhs = v @ mw, sig @ w
         checks["hermiticity_rel"] = abs(lhs - rhs) / max(abs(lhs), 1e-300)
+        again = matrix.matvec(v)
+        checks["run_to_run_identical"] = bool(torch.equal(again.pphh._data, sig.pphh._data)
+                                              and torch.equal(again.ph._data, sig.ph._data))
 
     # ---- time to converged states ----------------------------------------------------------------
     davidson = None
