@@ -69,14 +69,14 @@ def check_matvec_parity(data, method, core, seed=42):
     return matrix, omatrix
 
 
-def check_run_parity(data, method, kind, core, n=None):
+def check_run_parity(data, method, kind, core, n=None, conv_tol=1e-9):
     import adcc_b200 as adcc
     if n is None:
         n = len(SINGLETS[method]) if method in SINGLETS else 3
     kw = {"singlet": {"n_singlets": n}, "triplet": {"n_triplets": n}, "any": {"n_states": n}}[kind]
-    state = adcc.run_adc(data, method=method, conv_tol=1e-9, core_orbitals=core, output=None, **kw)
+    state = adcc.run_adc(data, method=method, conv_tol=conv_tol, core_orbitals=core, output=None, **kw)
     okw = dict(kw)
-    ostate = oracle.run_adc(data, method, conv_tol=1e-9, core_orbitals=core,
+    ostate = oracle.run_adc(data, method, conv_tol=conv_tol, core_orbitals=core,
                             kind="any" if kind == "any" else kind, **okw)
     assert state.converged and ostate.converged
     np.testing.assert_allclose(state.excitation_energy, ostate.eigenvalues, atol=ENERGY_ATOL, rtol=0)
