@@ -331,3 +331,71 @@ class AdcMatrix(AdcMatrixlike):
             for blk in res.blocks:
                 mat[offs[blk]:offs[blk] + self.axis_lengths[blk], col] = res[blk].to_ndarray().ravel()
         return mat
+
+
+class AdcMatrixShifted(AdcMatrix):
+    """``matrix @ v + shift * v`` (adcc/AdcMatrix.py:649-693)."""
+
+    def __init__(self, matrix, shift=0.0):
+        super().__init__(matrix.method, matrix.ground_state, block_orders=matrix.block_orders,
+                         intermediates=matrix.intermediates, doubles_storage=matrix.doubles_storage)
+        self.shift = shift
+
+    def matvec(self, in_ampl):
+        return super().matvec(in_ampl) + self.shift * in_ampl
+
+    def block_apply(self, block, in_vec):
+        ret = super().block_apply(block, in_vec)
+        inblock, outblock = block.split("_")
+        if inblock == outblock:
+            ret = ret + self.shift * in_vec
+        return ret
+
+    def diagonal(self):
+        return super().diagonal() + self.shift
+
+    def to_ndarray(self, out=None):
+        return super().to_ndarray() + self.shift * np.eye(self.shape[0])
+
+    def block_view(self, block):
+        raise NotImplementedError("Block-view not yet implemented for shifted ADC matrices.")
+
+
+class AdcMatrixProjected(AdcMatrix):
+    """``P @ M @ P`` with P a projector onto selected excitation blocks, e.g. ["cv", "ccvv", "ocvv"]
+    (adcc/AdcMatrix.py:696-780)."""
+
+    def __init__(self, matrix, excitation_blocks, core_orbitals=None, outer_virtuals=None):
+        from .projection import Projector, SubspacePartitioning
+        for sp in excitation_blocks:
+            if not any(len(sp) == len(ax_sp) for ax_sp in matrix.axis_spaces.values()):
+                raise ValueError(f"Invalid partition block {sp}.")
+        super().__init__(matrix.method, matrix.ground_state, block_orders=matrix.block_orders,
+                         intermediates=matrix.intermediates, doubles_storage="dense")
+        partitioning = SubspacePartitioning(matrix.mospaces, core_orbitals, outer_virtuals)
+        self.projectors = {}
+        for block in matrix.axis_spaces:
+            keep = [sp for sp in excitation_blocks if len(sp) == len(matrix.axis_spaces[block])]
+            self.projectors[block] = Projector(matrix.axis_spaces[block], partitioning, keep)
+
+    def apply_projection(self, in_ampl):
+        return AmplitudeVector(**{block: self.projectors[block] @ in_ampl[block] for block in in_ampl.keys()})
+
+    def matvec(self, in_ampl):
+        return self.apply_projection(super().matvec(self.apply_projection(in_ampl)))
+
+    def block_apply(self, block, in_vec):
+        outblock, inblock = block.split("_")
+        ret = super().block_apply(block, self.projectors[inblock].apply(in_vec))
+        return self.projectors[outblock].apply(ret)
+
+    def diagonal(self):
+        blocks = {}
+        for block, diagblock in super().diagonal().items():
+            P = self.projectors[block]
+            one = diagblock.ones_like()
+            blocks[block] = P @ diagblock + 100000 * (one - P @ one)
+        return AmplitudeVector(**blocks)
+
+    def block_view(self, block):
+        raise NotImplementedError("Block-view not yet implemented for projected ADC matrices.")

@@ -7,7 +7,7 @@ API.  Usage mirrors adcc:
 """
 from functools import wraps as _wraps
 
-from .AdcMatrix import AdcMatrix, AdcMatrixlike  # noqa: F401
+from .AdcMatrix import AdcMatrix, AdcMatrixlike, AdcMatrixProjected, AdcMatrixShifted  # noqa: F401
 from .AdcMethod import AdcMethod  # noqa: F401
 from .AmplitudeVector import AmplitudeVector  # noqa: F401
 from .DataHfProvider import DataHfProvider, HartreeFockProvider  # noqa: F401
@@ -21,6 +21,7 @@ from .guess import (guess_symmetries, guess_zero, guesses_any, guesses_singlet, 
 from .Intermediates import Intermediates, register_as_intermediate  # noqa: F401
 from .LazyMp import LazyMp  # noqa: F401
 from .MoSpaces import MoSpaces  # noqa: F401
+from .projection import Projector, SubspacePartitioning  # noqa: F401
 from .ReferenceState import ReferenceState  # noqa: F401
 from .solver.davidson import jacobi_davidson  # noqa: F401
 from .Symmetry import Symmetry  # noqa: F401

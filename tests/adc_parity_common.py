@@ -98,3 +98,41 @@ def check_oscillator_strengths(data, method, core, n=3):
     np.testing.assert_allclose(f, of, rtol=1e-6, atol=1e-10)
     assert np.all(f >= 0)
     return f
+
+
+def check_shifted_projected(data):
+    import adcc_b200 as adcc
+    matrix, omatrix = build_pair(data, "adc2x", None)
+    v, ov = random_vector(matrix, omatrix, 7)
+    osig = omatrix.matvec(ov)
+    # shifted
+    sh = adcc.AdcMatrixShifted(matrix, shift=-0.35)
+    ssig = sh.matvec(v)
+    for k in osig:
+        assert rel_err(ssig[k].to_ndarray(), osig[k] - 0.35 * ov[k]) < SIGMA_RTOL
+        assert rel_err(sh.diagonal()[k].to_ndarray(), omatrix.diagonal()[k] - 0.35) < SIGMA_RTOL
+    # projected onto core excitations (1 core orbital per spin)
+    pm = adcc.AdcMatrixProjected(matrix, ["cv", "ccvv", "ocvv"], core_orbitals=1)
+    no, na = omatrix.shapes["ph"][0], omatrix.hf.n_alpha_of["o1"]
+    core = np.zeros(no)
+    core[[0, na]] = 1.0
+    val = 1.0 - core
+    m1 = core[:, None] * np.ones(omatrix.shapes["ph"][1])[None, :]
+    m2o = np.maximum(np.maximum(np.multiply.outer(core, core), np.multiply.outer(val, core)),
+                     np.multiply.outer(core, val))
+    m2 = m2o[:, :, None, None] * np.ones(omatrix.shapes["pphh"][2:])[None, None]
+    masks = {"ph": m1, "pphh": m2}
+    for k in masks:
+        assert np.array_equal(pm.projectors[k].kernel.to_ndarray(), masks[k])
+    pov = {k: masks[k] * ov[k] for k in ov}
+    posig = omatrix.matvec(pov)
+    psig = pm.matvec(v)
+    for k in posig:
+        assert rel_err(psig[k].to_ndarray(), masks[k] * posig[k]) < SIGMA_RTOL
+        expect_d = masks[k] * omatrix.diagonal()[k] + 100000 * (1 - masks[k])
+        assert rel_err(pm.diagonal()[k].to_ndarray(), expect_d) < SIGMA_RTOL
+    # core-excited states through the projected full matrix: lowest singlet close to CVS-ADC(2)-x
+    state = adcc.run_adc(pm, n_singlets=2, n_guesses=2, conv_tol=1e-7, output=None)
+    assert state.converged
+    assert abs(state.excitation_energy[0] - 19.90528006) < 0.05
+    return state

@@ -70,3 +70,14 @@ def test_any_kind_unrestricted_style(h2o):
 def test_oscillator_strengths_vs_oracle(h2o, method):
     from adc_parity_common import check_oscillator_strengths
     check_oscillator_strengths(h2o, method, 1 if method.startswith("cvs") else None)
+
+
+@pytest.mark.parametrize("case", ["gen", "cvs", "fc-fv-cvs"])
+def test_import_blocks_device(case):
+    from import_common import check_imports
+    check_imports(case)
+
+
+def test_shifted_and_projected_matrix_device(h2o):
+    from adc_parity_common import check_shifted_projected
+    check_shifted_projected(h2o)

@@ -123,3 +123,11 @@ def test_tensor_algebra_semantics(h2o):
 def test_oscillator_strengths_vs_oracle(h2o, method):
     from adc_parity_common import check_oscillator_strengths
     check_oscillator_strengths(h2o, method, 1 if method.startswith("cvs") else None)
+
+
+def test_shifted_and_projected_matrix(h2o):
+    """AdcMatrixShifted / AdcMatrixProjected (adcc/AdcMatrix.py:649-780) against the
+    oracle matvec plus NumPy masks; core excitations by projection converge to the CVS energies'
+    neighbourhood (examples/2_core_excitations/water_core_by_projection.py)."""
+    from adc_parity_common import check_shifted_projected
+    check_shifted_projected(h2o)
