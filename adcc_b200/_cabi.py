@@ -34,6 +34,7 @@ def _declare(lib):
                                   ctypes.POINTER(c_ptr), c_i64, c_dbl, c_ptr]
     lib.adccb_dot_many.argtypes = [c_ptr, ctypes.c_int, c_ptr, ctypes.POINTER(c_ptr), c_i64,
                                    c_dbl, c_dbl, c_ptr, c_ptr, c_i64]
+    lib.adccb_spin_expand4.argtypes = [c_ptr, ctypes.POINTER(ctypes.c_int), c_ptr, c_ptr]
     lib.adccb_spin_project.argtypes = [c_ptr, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
                                        ctypes.POINTER(ctypes.c_int), c_dbl, c_ptr, c_ptr]
     lib.adccb_spin_singlet.argtypes = [c_ptr, ctypes.POINTER(ctypes.c_int),
@@ -57,7 +58,7 @@ def _declare(lib):
 EXPORTS = [
     "adccb_version", "adccb_last_error", "adccb_launch_count", "adccb_device_info",
     "adccb_dgemm", "adccb_strided_gather", "adccb_elementwise", "adccb_direct_sum",
-    "adccb_add_columns", "adccb_lincomb", "adccb_dot_many", "adccb_spin_project", "adccb_spin_singlet",
+    "adccb_add_columns", "adccb_lincomb", "adccb_dot_many", "adccb_spin_expand4", "adccb_spin_project", "adccb_spin_singlet",
     "adccb_packed_unpack", "adccb_packed_pack", "adccb_packed_expand", "adccb_packed_fold_virt",
     "adccb_packed_fold_occ", "adccb_packed_diagonal", "adccb_pair_select", "adccb_synth_fill",
 ]

@@ -212,6 +212,15 @@ def dot(x, y):
 
 
 # --------------------------------------------------------------------------------- spin
+def spin_expand4(T):
+    """Spatial chemists' block (p'q'|r's') -> spin-orbital block, axes [alpha|beta], spin-forbidden = 0."""
+    T = contiguous(T)
+    n = (ctypes.c_int * 4)(*[int(x) for x in T.shape])
+    out = empty(tuple(2 * int(x) for x in T.shape))
+    _cabi.check(_cabi.lib().adccb_spin_expand4(_stream(), n, _ptr(T), _ptr(out)))
+    return out
+
+
 def spin_project(t, n_alpha, fac):
     t = contiguous(t)
     nd = t.dim()

@@ -43,6 +43,7 @@ int lincomb(cudaStream_t st, int nvec, const double* coeff, const double* const*
             double beta, double* out);
 int dot_many(cudaStream_t st, int nvec, const double* x, const double* const* ys, long long n,
              double scale, double beta, double* out_dev, double* ws, long long ws_bytes);
+int spin_expand4(cudaStream_t st, const int* n, const double* T, double* out);
 int spin_project(cudaStream_t st, int nd, const int* shape, const int* nalpha, double fac,
                  const double* in, double* out);
 int spin_singlet(cudaStream_t st, const int* shape, const int* nalpha, double* T);
@@ -118,6 +119,10 @@ int adccb_lincomb(void* stream, int nvec, const double* host_coeff, const double
 int adccb_dot_many(void* stream, int nvec, const double* x, const double* const* host_ys, int64_t n,
                    double scale, double beta, double* out_dev, double* ws, int64_t ws_bytes) {
   return dot_many((cudaStream_t)stream, nvec, x, host_ys, n, scale, beta, out_dev, ws, ws_bytes);
+}
+
+int adccb_spin_expand4(void* stream, const int* n_spatial, const double* T, double* out) {
+  return spin_expand4((cudaStream_t)stream, n_spatial, T, out);
 }
 
 int adccb_spin_project(void* stream, int ndim, const int* shape, const int* n_alpha, double fac,

@@ -382,6 +382,37 @@ __global__ void spin_singlet_kernel(SpinDesc d, double* __restrict__ T) {
   }
 }
 
+// Spin expansion of a restricted (spatial) two-electron block in chemists' order:
+// out[p,q,r,s] = T[p',q',r',s'] if spin(p)==spin(q) and spin(r)==spin(s), else 0, where every output
+// axis is [alpha | beta] over the same n[k] spatial orbitals (adcc/backends/EriBuilder.py:117-119).
+__global__ void spin_expand4_kernel(int n0, int n1, int n2, int n3, const double* __restrict__ T,
+                                    double* __restrict__ out) {
+  const long long total = 16LL * n0 * n1 * n2 * n3;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long rem = idx;
+    const int s = (int)(rem % (2 * n3)); rem /= 2 * n3;
+    const int r = (int)(rem % (2 * n2)); rem /= 2 * n2;
+    const int q = (int)(rem % (2 * n1)); rem /= 2 * n1;
+    const int p = (int)rem;
+    const bool bp = p >= n0, bq = q >= n1, br = r >= n2, bs = s >= n3;
+    double v = 0.0;
+    if (bp == bq && br == bs)
+      v = T[(((long long)(bp ? p - n0 : p) * n1 + (bq ? q - n1 : q)) * n2 + (br ? r - n2 : r)) * n3 +
+            (bs ? s - n3 : s)];
+    out[idx] = v;
+  }
+}
+
+int spin_expand4(cudaStream_t st, const int* n, const double* T, double* out) {
+  const long long total = 16LL * n[0] * n[1] * n[2] * n[3];
+  if (total <= 0) return 0;
+  spin_expand4_kernel<<<grid_for(total, 256, 2), 256, 0, st>>>(n[0], n[1], n[2], n[3], T, out);
+  ADCCB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
 int spin_project(cudaStream_t st, int nd, const int* shape, const int* nalpha, double fac,
                  const double* in, double* out) {
   if (nd != 2 && nd != 4) return fail("spin_project: rank must be 2 or 4");

@@ -74,6 +74,12 @@ int adccb_lincomb(void* stream, int nvec, const double* host_coeff, const double
 int adccb_dot_many(void* stream, int nvec, const double* x, const double* const* host_ys, int64_t n,
                    double scale, double beta, double* out_dev, double* ws, int64_t ws_bytes);
 
+/* out[p,q,r,s] = T[p',q',r',s'] * [spin(p)==spin(q)] * [spin(r)==spin(s)]: expands a spatial chemists'
+ * (pq|rs) block of a restricted reference (extents n_spatial[4]) to spin orbitals, every output axis
+ * being [alpha | beta] over the same spatial orbitals.  Device counterpart of the spin pattern
+ * adcc/backends/EriBuilder.py:117-119 applies on the host during ReferenceState::eri import. */
+int adccb_spin_expand4(void* stream, const int* n_spatial, const double* T, double* out);
+
 /* Spin-block symmetry of restricted singlet (fac=+1) / triplet (fac=-1) vectors on dense
  * [alpha|beta]^rank tensors (rank 2 or 4): out = (T + fac * flip(T)) / 2, spin-changing blocks
  * zeroed.  Dense counterpart of the spin-block maps adcc/guess/guess_zero.py:121-161 that

@@ -190,6 +190,14 @@ def install(monkeypatch):
         S[:, col0:col0 + ncols] += G[:, :ncols]
         return S
 
+    def spin_expand4(T):
+        n = T.shape
+        out = torch.zeros(tuple(2 * x for x in n), dtype=F64)
+        for a in (0, 1):
+            for b in (0, 1):
+                out[a * n[0]:(a + 1) * n[0], a * n[1]:(a + 1) * n[1], b * n[2]:(b + 1) * n[2], b * n[3]:(b + 1) * n[3]] = T
+        return out
+
     def int64_tensor(values):
         return torch.tensor([int(v) for v in values], dtype=torch.int64)
 
@@ -240,6 +248,6 @@ def install(monkeypatch):
                          spin_singlet_=spin_singlet_, packed_unpack=packed_unpack, packed_pack=packed_pack,
                          packed_expand=packed_expand, packed_fold_virt=packed_fold_virt,
                          packed_fold_occ=packed_fold_occ, packed_diagonal=packed_diagonal,
-                         pair_select=pair_select, int64_tensor=int64_tensor, add_columns=add_columns, synth_fill=synth_fill).items():
+                         pair_select=pair_select, int64_tensor=int64_tensor, add_columns=add_columns, spin_expand4=spin_expand4, synth_fill=synth_fill).items():
         monkeypatch.setattr(be, name, fn)
     monkeypatch.setattr(be, "device", lambda: cpu)
