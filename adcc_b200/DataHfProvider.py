@@ -201,6 +201,9 @@ def import_scf_results(res):
     if isinstance(res, HartreeFockProvider):
         return res
     if isinstance(res, dict):
+        if "eri_bbbb" in res:
+            from .AoEriProvider import AoDataHfProvider
+            return AoDataHfProvider(res)
         return DataHfProvider(res)
     raise NotImplementedError("No means to import an SCF result of type " + str(type(res)) +
                               " (supported here: dict, HartreeFockProvider).")

@@ -107,14 +107,16 @@ class ReferenceState:
             return be.from_numpy(blk)
         # (pr|qs) goes to the device once; the exchange part re-uses it when an index pair
         # shares its subspace (import_eri.cc:123-144), otherwise (ps|qr) is staged as well
-        c1 = be.from_numpy(hf.eri_chem_block(P, R, Q, S))           # [p,r,q,s]
+        on_device = hasattr(hf, "eri_chem_block_device")     # AO->MO transformed in HBM (8(f4))
+        chem = hf.eri_chem_block_device if on_device else (lambda *ix: be.from_numpy(hf.eri_chem_block(*ix)))
+        c1 = chem(P, R, Q, S)                                        # [p,r,q,s]
         out = be.permute(c1, (0, 2, 1, 3))                           # <pq|rs>
         if sp[2] == sp[3]:
             be.permute(c1, (0, 2, 3, 1), alpha=-1.0, out=out, beta=1.0)       # c1[p,s,q,r]
         elif sp[0] == sp[1]:
             be.permute(c1, (2, 0, 1, 3), alpha=-1.0, out=out, beta=1.0)       # c1[q,r,p,s]
         else:
-            c2 = be.from_numpy(hf.eri_chem_block(P, S, Q, R))       # [p,s,q,r]
+            c2 = chem(P, S, Q, R)                                    # [p,s,q,r]
             be.permute(c2, (0, 2, 3, 1), alpha=-1.0, out=out, beta=1.0)
         if self.symmetry_check_on_import:
             self._check_eri_symmetry(sp, out.cpu().numpy())

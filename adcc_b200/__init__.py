@@ -10,6 +10,7 @@ from functools import wraps as _wraps
 from .AdcMatrix import AdcMatrix, AdcMatrixlike, AdcMatrixProjected, AdcMatrixShifted  # noqa: F401
 from .AdcMethod import AdcMethod  # noqa: F401
 from .AmplitudeVector import AmplitudeVector  # noqa: F401
+from .AoEriProvider import AoDataHfProvider  # noqa: F401
 from .DataHfProvider import DataHfProvider, HartreeFockProvider  # noqa: F401
 from .exceptions import InputError  # noqa: F401
 from .ExcitedStates import ExcitedStates  # noqa: F401

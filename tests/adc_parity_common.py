@@ -136,3 +136,41 @@ def check_shifted_projected(data):
     assert state.converged
     assert abs(state.excitation_energy[0] - 19.90528006) < 0.05
     return state
+
+
+def ao_version_of(data, seed=3):
+    """Same SCF data expressed in a rotated 'AO' basis: AO ERIs + non-trivial MO coefficients."""
+    from oracle.hfdata import OracleHf
+    na = np.asarray(data["orbcoeff_fb"]).shape[0] // 2
+    rng = np.random.default_rng(seed)
+    q, _ = np.linalg.qr(rng.standard_normal((na, na)))     # orthogonal: C = q, AO = back-rotated MO
+    if "eri_ffff_spatial" in data:
+        mo = np.asarray(data["eri_ffff_spatial"])
+    else:
+        mo = np.asarray(data["eri_ffff"])[:na, :na, :na, :na]
+    ao = np.einsum("pqrs,pm,qn,rl,sk->mnlk", mo, q, q, q, q, optimize=True)
+    out = {k: v for k, v in data.items() if k not in ("eri_ffff", "eri_ffff_spatial")}
+    out["eri_bbbb"] = ao
+    out["orbcoeff_fb"] = np.vstack([q, q])
+    if "multipoles" in data and "elec_1" in data["multipoles"]:
+        mm = dict(data["multipoles"])
+        c_old = np.asarray(data["orbcoeff_fb"])[:na]
+        d_mo = np.einsum("pm,xmn,qn->xpq", c_old, mm["elec_1"], c_old)
+        mm["elec_1"] = np.einsum("xpq,pm,qn->xmn", d_mo, q, q)
+        out["multipoles"] = mm
+    return out
+
+
+def check_ao_import(data, method="adc2", core=None):
+    """8(f4): ERIs given in the AO basis, transformed on the device, must give the same matrix."""
+    import adcc_b200 as adcc
+    ao = ao_version_of(data)
+    ref_ao = adcc.ReferenceState(ao, core_orbitals=core)
+    ref_mo = adcc.ReferenceState(data, core_orbitals=core)
+    for blk in ("o1o1v1v1", "o1v1o1v1", "o1v1v1v1", "v1v1v1v1", "o1o1o1v1"):
+        a, b = ref_ao.eri(blk).to_ndarray(), ref_mo.eri(blk).to_ndarray()
+        assert np.max(np.abs(a - b)) < 1e-12 * max(1.0, np.max(np.abs(b))), blk
+    state = adcc.run_adc(ref_ao, method=method, n_singlets=2, conv_tol=1e-8, output=None)
+    ostate = oracle.run_adc(data, method, n_singlets=2, conv_tol=1e-8, core_orbitals=core)
+    np.testing.assert_allclose(state.excitation_energy, ostate.eigenvalues, atol=ENERGY_ATOL, rtol=0)
+    return state

@@ -81,3 +81,10 @@ def test_import_blocks_device(case):
 def test_shifted_and_projected_matrix_device(h2o):
     from adc_parity_common import check_shifted_projected
     check_shifted_projected(h2o)
+
+
+def test_ao_basis_import_device(h2o):
+    from adc_parity_common import check_ao_import
+    check_ao_import(h2o, "adc2")
+    from adcc_b200.synthetic import restricted_scf_dict
+    check_ao_import(restricted_scf_dict(12, 4, seed=2), "adc2x")

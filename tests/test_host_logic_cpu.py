@@ -131,3 +131,8 @@ def test_shifted_and_projected_matrix(h2o):
     neighbourhood (examples/2_core_excitations/water_core_by_projection.py)."""
     from adc_parity_common import check_shifted_projected
     check_shifted_projected(h2o)
+
+
+def test_ao_basis_import(h2o):
+    from adc_parity_common import check_ao_import
+    check_ao_import(h2o, "adc2")
