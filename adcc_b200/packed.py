@@ -369,15 +369,15 @@ class PackedAdcEngine:
     def _matvec_sharded(self, u1, U):
         """Per-rank partial sigma from this rank's operand slabs.
 
-        Everything except the vvvv term is accumulated into one packed (pphh + ph) buffer whose
-        all-reduce runs on a high-priority side stream WHILE the vvvv GEMM (disjoint AB-column
-        slab per rank, the longest kernel) computes; the column slabs are then all-gathered and
-        added.  Slabs: vvvv: AB rows of W; ovov / ovvv: occupied j; oooo, D0, ooov terms: IJ
+        Everything except the vvvv term is accumulated into one packed (pphh + ph) buffer that is
+        all-reduced (optionally on a side stream while the vvvv GEMM runs, see below); the vvvv
+        GEMM computes a disjoint AB-column slab per rank, the slabs are all-gathered and added.  Slabs: vvvv: AB rows of W; ovov / ovvv: occupied j; oooo, D0, ooov terms: IJ
         pairs; ph_ph: rows of M1.  All ranks end with the identical, complete sigma."""
         import torch
         import torch.distributed as dist
         no, nv, npo, npv = self.no, self.nv, self.npo, self.npv
         world = self.world
+        self._mark("step", 0)
         buf = be.zeros((npo * npv + no * nv,))
         S = buf[:npo * npv].view(npo, npv)
         s1 = buf[npo * npv:].view(1, no * nv)
@@ -430,7 +430,10 @@ class PackedAdcEngine:
             del c2
         # ---- all-reduce of the partial sums, overlapped with the vvvv GEMM
         import os
-        overlap = buf.is_cuda and os.environ.get("ADCCB_NO_OVERLAP", "0") != "1"
+        # Overlapping the all-reduce with the vvvv GEMM is OFF by default: the GEMM is persistent
+        # (one CTA per SM, static stream-K spans), so SMs taken by the NCCL kernel delay some of its
+        # CTAs by a whole span (measured at 4 GPUs: GEMM 68 -> 96 ms).  ADCCB_OVERLAP=1 enables it.
+        overlap = buf.is_cuda and os.environ.get("ADCCB_OVERLAP", "0") == "1"
         main = torch.cuda.current_stream() if overlap else None
         work = None
         if main is not None:
@@ -458,7 +461,9 @@ class PackedAdcEngine:
                 be.gemm(U, self.W, out=slab[:, :w])
                 self._mark("vvvv", 1)
             gathered = be.empty((world * npo, wmax))
+            self._mark("gather", 0)
             dist.all_gather_into_tensor(gathered, slab)
+            self._mark("gather", 1)
             gathered = gathered.view(world, npo, wmax)
         if main is not None:
             main.wait_event(done)
@@ -468,6 +473,7 @@ class PackedAdcEngine:
                 wr = self._cuts[r + 1] - self._cuts[r]
                 if wr > 0:
                     be.add_columns(S, self._cuts[r], gathered[r], wr)
+        self._mark("step", 1)
         return AmplitudeVector(ph=self._wrap_ph(s1.view(no, nv)), pphh=self._wrap_pphh(S))
 
     def matvec(self, v):

@@ -308,6 +308,7 @@ def run_gpu(args):
                           "ms_per_launch": t_ovov,
                           "achieved": eng.flops["pphh_pphh/ovov"] / (t_ovov * 1e-3) * 1e-12 if t_ovov else None},
         "share_of_step": (t_vvvv / ms_step) if t_vvvv else None,
+        "section_ms": {k: float(np.mean(v)) for k, v in ktimes.items()},
     }
     cpu = cpu_sample() if (world == 1 and not args.no_cpu_baseline) else None
     line = {
