@@ -282,11 +282,78 @@ class AdcMatrix(AdcMatrixlike):
     def rmatvec(self, v):
         return self.matvec(v)
 
+    # ------------------------------------------------------------------ batched matvec (8(f2))
+    def _eval_batched(self, expr, ampl):
+        """Like _eval for trial vectors that carry a leading batch axis 'Z' (several vectors stacked):
+        returns (tensor, has_batch_axis)."""
+        kind = expr[0]
+        if kind == "einsum":
+            ins, out = expr[1].split("->")
+            ins = ins.split(",")
+            ops, new_ins, batched = [], [], False
+            for idx, o in zip(ins, expr[2]):
+                if isinstance(o, tuple):
+                    t, b = self._eval_batched(o, ampl)
+                else:
+                    t, b = self._operand(o, ampl), o in ("u1", "u2")
+                ops.append(t)
+                new_ins.append(("Z" + idx) if b else idx)
+                batched = batched or b
+            subs = ",".join(new_ins) + "->" + (("Z" + out) if batched else out)
+            return einsum(subs, *ops), batched
+        t, batched = self._eval_batched(expr[1], ampl)
+        shift = 1 if batched else 0
+        if kind == "asym":
+            for pair in expr[2]:
+                t = t.antisymmetrise(*[p + shift for p in pair])
+            return t, batched
+        if kind == "sym":
+            return t.symmetrise(*[tuple(p + shift for p in pair) for pair in expr[2]]), batched
+        raise ValueError(kind)
+
+    def matvec_batch(self, vectors):
+        """[M v for v in vectors] with ONE pass over every constant operand: the trial vectors are
+        stacked along a leading batch axis, so each term of the block tables is a single GEMM with
+        n-times more rows (adcc/AdcMatrix.py:402-408 loops over the list instead)."""
+        from . import backend as be
+        n = len(vectors)
+        if n == 0:
+            return []
+        blocks = vectors[0].blocks
+        if (n == 1 or self.extra_terms or self._engine is not None
+                or any(v.blocks != blocks for v in vectors)
+                or type(self).matvec is not AdcMatrix.matvec):
+            return [self.matvec(v) for v in vectors]
+        with self.timer.record("matvec_batch"):
+            stacked = {}
+            for blk in blocks:
+                first = vectors[0][blk]
+                data = be.empty((n,) + tuple(first.shape))
+                for k, v in enumerate(vectors):
+                    be.axpby(1.0, v[blk]._contig(), 0.0, data[k])
+                stacked[blk] = Tensor._wrap(self.mospaces, ["B"] + list(first.subspaces), data)
+            collected = {}
+            for blk in self._tables:
+                inb, outb, terms = self._tables[blk]
+                if inb is None or inb not in stacked:
+                    continue
+                for c, e in terms:
+                    t, batched = self._eval_batched(e, stacked)
+                    assert batched
+                    collected.setdefault(outb, []).append((c, t))
+            out = [dict() for _ in range(n)]
+            for outb, terms in collected.items():
+                res = linear_combination_strict([c for c, _ in terms], [t for _, t in terms])
+                sub = res.subspaces[1:]
+                for k in range(n):
+                    out[k][outb] = Tensor._wrap(self.mospaces, sub, res._data[k])
+            return [AmplitudeVector(**o) for o in out]
+
     def __matmul__(self, other):
         if isinstance(other, AmplitudeVector):
             return self.matvec(other)
         if isinstance(other, list) and all(isinstance(e, AmplitudeVector) for e in other):
-            return [self.matvec(ov) for ov in other]
+            return self.matvec_batch(other)
         return NotImplemented
 
     def block_view(self, block):

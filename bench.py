@@ -270,6 +270,12 @@ def run_gpu(args):
         again = matrix.matvec(v)
         checks["run_to_run_identical"] = bool(torch.equal(again.pphh._data, sig.pphh._data)
                                               and torch.equal(again.ph._data, sig.ph._data))
+        if rank == 0 and args.verify_samples > 0:
+            # sampled sigma entries recomputed on the CPU from the definition of the inputs
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from verify_headline import verify
+            res = verify(matrix, v, sig, n_pphh=args.verify_samples, n_ph=max(1, args.verify_samples // 4))
+            checks.update({k: float(x) for k, x in res.items()})
 
     # ---- time to converged states ----------------------------------------------------------------
     davidson = None
@@ -351,6 +357,8 @@ def main():
     ap.add_argument("--nvirt", type=int, default=NV)
     ap.add_argument("--n-states", type=int, default=5)
     ap.add_argument("--max-iter", type=int, default=40)
+    ap.add_argument("--verify-samples", type=int, default=8,
+                    help="sigma entries re-derived on the CPU from the input definition (0 = off)")
     ap.add_argument("--no-davidson", dest="davidson", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -174,3 +174,47 @@ def check_ao_import(data, method="adc2", core=None):
     ostate = oracle.run_adc(data, method, n_singlets=2, conv_tol=1e-8, core_orbitals=core)
     np.testing.assert_allclose(state.excitation_energy, ostate.eigenvalues, atol=ENERGY_ATOL, rtol=0)
     return state
+
+
+def check_unrestricted_kinds(no=6, nv=8):
+    import adcc_b200 as adcc
+    from adcc_b200.packed import synthetic_reference_state
+    from oracle.synthetic import OracleSyntheticRef
+    ref = synthetic_reference_state(no, nv, seed=9, scale=0.02)
+    assert not ref.restricted
+    with pytest_raises(adcc.InputError):
+        adcc.run_adc(ref, method="adc2", n_singlets=2, output=None)       # restricted-only keyword
+    for method in ("adc1", "adc2"):
+        om = oracle.OracleAdcMatrix(method, OracleSyntheticRef(no, nv, seed=9, scale=0.02))
+        m = adcc.AdcMatrix(method, ref, doubles_storage="dense")
+        st = adcc.run_adc(m, n_states=3, conv_tol=1e-8, output=None)
+        ost = oracle.run_adc(om, method, n_states=3, conv_tol=1e-8)
+        np.testing.assert_allclose(st.excitation_energy, ost.eigenvalues, atol=ENERGY_ATOL, rtol=0)
+        sf = adcc.run_adc(m, n_spin_flip=2, conv_tol=1e-8, output=None)
+        osf = oracle.run_adc(om, method, n_states=2, kind="spin_flip", conv_tol=1e-8)
+        assert sf.converged and osf.converged
+        np.testing.assert_allclose(sf.excitation_energy, osf.eigenvalues, atol=ENERGY_ATOL, rtol=0)
+
+
+class pytest_raises:
+    def __init__(self, exc): self.exc = exc
+    def __enter__(self): return self
+    def __exit__(self, et, ev, tb):
+        if et is None or not issubclass(et, self.exc):
+            raise AssertionError(f"{self.exc} not raised")
+        return True
+
+
+def check_batched_matvec(data, method, core):
+    """8(f2): matrix @ [v1..vn] (stacked, one GEMM per term) equals the per-vector products."""
+    import adcc_b200 as adcc
+    matrix, omatrix = build_pair(data, method, core)
+    vecs = [random_vector(matrix, omatrix, 100 + k) for k in range(3)]
+    batched = matrix @ [v for v, _ in vecs]
+    assert len(batched) == 3
+    for (v, ov), res in zip(vecs, batched):
+        osig = omatrix.matvec(ov)
+        single = matrix.matvec(v)
+        for k in osig:
+            assert rel_err(res[k].to_ndarray(), osig[k]) < SIGMA_RTOL
+            assert rel_err(res[k].to_ndarray(), single[k].to_ndarray()) < 1e-13

@@ -88,3 +88,9 @@ def test_ao_basis_import_device(h2o):
     check_ao_import(h2o, "adc2")
     from adcc_b200.synthetic import restricted_scf_dict
     check_ao_import(restricted_scf_dict(12, 4, seed=2), "adc2x")
+
+
+@pytest.mark.parametrize("method", ["adc2", "adc3", "cvs-adc2x"])
+def test_batched_matvec_device(h2o, method):
+    from adc_parity_common import check_batched_matvec
+    check_batched_matvec(h2o, method, 1 if method.startswith("cvs") else None)

@@ -136,3 +136,16 @@ def test_shifted_and_projected_matrix(h2o):
 def test_ao_basis_import(h2o):
     from adc_parity_common import check_ao_import
     check_ao_import(h2o, "adc2")
+
+
+def test_unrestricted_style_kinds():
+    """Unrestricted-style reference (no spin-block maps): kind='any' and kind='spin_flip' through the
+    dense engine against the oracle (adcc/workflow.py:288-348, guess kwargs adcc/guess/__init__.py:30-45)."""
+    from adc_parity_common import check_unrestricted_kinds
+    check_unrestricted_kinds()
+
+
+@pytest.mark.parametrize("method", ["adc1", "adc2x", "adc3", "cvs-adc3"])
+def test_batched_matvec(h2o, method):
+    from adc_parity_common import check_batched_matvec
+    check_batched_matvec(h2o, method, 1 if method.startswith("cvs") else None)
