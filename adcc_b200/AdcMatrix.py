@@ -320,7 +320,9 @@ class AdcMatrix(AdcMatrixlike):
         if n == 0:
             return []
         blocks = vectors[0].blocks
+        import os
         if (n == 1 or self.extra_terms or self._engine is not None
+                or os.environ.get("ADCCB_NO_BATCH", "0") == "1"
                 or any(v.blocks != blocks for v in vectors)
                 or type(self).matvec is not AdcMatrix.matvec):
             return [self.matvec(v) for v in vectors]

@@ -45,7 +45,9 @@ def install(monkeypatch):
 
     def contiguous(t): return t.contiguous()
     def fill(t, v): t.fill_(float(v)); return t
-    def axpby(a, x, b, y): y.copy_(a * x.reshape(y.shape) + b * y); return y
+    def axpby(a, x, b, y):
+        y.copy_(a * x.reshape(y.shape) + (b * y if b != 0.0 else 0.0))   # beta == 0 never reads y
+        return y
     def scaled_copy(x, alpha=1.0): return (alpha * x).contiguous()
     def mul(x, y, alpha=1.0): return (alpha * x * y).contiguous()
     def div(x, y, alpha=1.0): return (alpha * x / y).contiguous()

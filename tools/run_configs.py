@@ -39,6 +39,9 @@ for name, method, kw in CASES:
              launches=_cabi.launch_count() - n0, mem_gb=round(torch.cuda.max_memory_allocated() / 1e9, 2),
              e0=float(state.excitation_energy[0]))
     print(json.dumps(r), flush=True)
+    if os.environ.get("SHOW_TIMERS"):
+        print(state.solver_state.timer.describe())
+        print(matrix.timer.describe())
     res.append(r)
     del matrix, ref, state
     torch.cuda.empty_cache()
