@@ -65,54 +65,71 @@ __global__ void pack_dense_kernel(int no, int nv, const double* __restrict__ T,
 // ---------------------------------------------------------------------------------------
 // GEMM-ready expansions of the packed trial vector
 // ---------------------------------------------------------------------------------------
-// X[i,a,k,c] = u[i,k,a,c]   (ovov-term operand, o*v x o*v); one CTA per (i,k)
-__global__ void expand_iakc_kernel(int no, int nv, const double* __restrict__ U,
-                                   double* __restrict__ X) {
+// Antisymmetric expansion of packed virtual-pair rows, 32x32 tiles through shared memory:
+//   out[base_r + a*sA + c] = +s_r * row_r[pair(a,c)],  out[base_r + c*sA + a] = -s_r * row_r[pair(a,c)]
+// for a < c, zero on the diagonal.  The packed row is read once, coalesced along a (pair(a,c) is
+// contiguous in a for fixed c); both output triangles are written coalesced (c resp. a fastest).
+//   mode 0: X[i,a,k,c] = u[i,k,a,c]  (ovov-term operand): r = (i,k), row = U[pair(i,k)], s = sign(k-i),
+//           base = (i*nv*no + k)*nv, sA = no*nv; r with i == k is zero-filled
+//   mode 2: Uh[a,JK,b] = u[JK,a,b]   : r = JK, row = U[JK], s = +1, base = JK*nv, sA = npo*nv
+__global__ void expand_antisym_kernel(int mode, int no, long long npo, int nv,
+                                      const double* __restrict__ U, double* __restrict__ out) {
+  __shared__ double tile[32][33];
   const long long npv = (long long)nv * (nv - 1) / 2;
-  const int i = blockIdx.x / no, k = blockIdx.x % no;
-  double* dst = X + ((long long)i * nv * no + k) * nv;     // + a*(no*nv) + c
-  const long long astride = (long long)no * nv;
-  if (i == k) {
-    for (int e = threadIdx.x; e < nv * nv; e += blockDim.x) dst[(e / nv) * astride + (e % nv)] = 0.0;
-    return;
+  const int a0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  if (a0 > c0) return;                          // tiles below the diagonal are produced as mirrors
+  const long long r = blockIdx.z;
+  const double* row;
+  double sgn;
+  long long base, sA;
+  if (mode == 0) {
+    const int i = (int)(r / no), k = (int)(r % no);
+    sA = (long long)no * nv;
+    base = ((long long)i * nv * no + k) * nv;
+    if (i == k) { row = nullptr; sgn = 0.0; }
+    else { row = U + pair_index(min(i, k), max(i, k)) * npv; sgn = (i < k) ? 1.0 : -1.0; }
+  } else {
+    row = U + r * npv; sgn = 1.0;
+    sA = npo * nv;
+    base = r * nv;
   }
-  const double sik = (i < k) ? 1.0 : -1.0;
-  const double* row = U + pair_index(min(i, k), max(i, k)) * npv;
-  for (int e = threadIdx.x; e < nv * nv; e += blockDim.x) {
-    const int a = e / nv, c = e % nv;
+  // tile[cc][aa] = sgn * row[pair(a0+aa, c0+cc)]  (0 unless a < c)
+  for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {
+    const int c = c0 + cc, a = a0 + threadIdx.x;
     double v = 0.0;
-    if (a != c) v = ((a < c) ? sik : -sik) * row[pair_index(min(a, c), max(a, c))];
-    dst[a * astride + c] = v;
+    if (row != nullptr && a < c && c < nv) v = sgn * row[pair_index(a, c)];
+    tile[cc][threadIdx.x] = v;
+  }
+  __syncthreads();
+  // upper triangle out[a, c]: c fastest
+  for (int aa = threadIdx.y; aa < 32; aa += blockDim.y) {
+    const int a = a0 + aa, c = c0 + threadIdx.x;
+    if (a < nv && c < nv && (a0 != c0 || a <= c)) out[base + (long long)a * sA + c] = tile[threadIdx.x][aa];
+  }
+  // lower triangle out[c, a] = -value: a fastest
+  for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {
+    const int c = c0 + cc, a = a0 + threadIdx.x;
+    if (a < nv && c < nv && a < c) out[base + (long long)c * sA + a] = -tile[cc][threadIdx.x];
   }
 }
 
-// Ue[i,j,AB] = s_ij U[pair(ij),AB]; one CTA per (i,j)
+// Ue[i,j,AB] = s_ij U[pair(ij),AB]; one CTA per (i,j), 16-byte accesses when the row length is even
 __global__ void expand_occ_kernel(int no, long long npv, const double* __restrict__ U,
                                   double* __restrict__ Ue) {
   const int i = blockIdx.x / no, j = blockIdx.x % no;
   double* dst = Ue + (long long)blockIdx.x * npv;
-  if (i == j) {
-    for (long long e = threadIdx.x; e < npv; e += blockDim.x) dst[e] = 0.0;
-    return;
-  }
-  const double s = (i < j) ? 1.0 : -1.0;
-  const double* row = U + pair_index(min(i, j), max(i, j)) * npv;
-  for (long long e = threadIdx.x; e < npv; e += blockDim.x) dst[e] = s * row[e];
-}
-
-// Uh[a,JK,b] = u[JK,a,b] = s_ab U[JK,pair(ab)]; grid (npo, a-chunks)
-__global__ void expand_virt_t_kernel(long long npo, int nv, const double* __restrict__ U,
-                                     double* __restrict__ Uh) {
-  const long long npv = (long long)nv * (nv - 1) / 2;
-  const long long JK = blockIdx.x;
-  const double* row = U + JK * npv;
-  for (int a = blockIdx.y; a < nv; a += gridDim.y) {
-    double* dst = Uh + ((long long)a * npo + JK) * nv;
-    for (int b = threadIdx.x; b < nv; b += blockDim.x) {
-      double v = 0.0;
-      if (a != b) v = ((a < b) ? 1.0 : -1.0) * row[pair_index(min(a, b), max(a, b))];
-      dst[b] = v;
+  const double s = (i == j) ? 0.0 : ((i < j) ? 1.0 : -1.0);
+  const double* row = (i == j) ? U : U + pair_index(min(i, j), max(i, j)) * npv;
+  if ((npv & 1) == 0) {
+    const double2* src2 = reinterpret_cast<const double2*>(row);
+    double2* dst2 = reinterpret_cast<double2*>(dst);
+    for (long long e = threadIdx.x; e < npv / 2; e += blockDim.x) {
+      double2 v = src2[e];
+      v.x *= s; v.y *= s;
+      dst2[e] = v;
     }
+  } else {
+    for (long long e = threadIdx.x; e < npv; e += blockDim.x) dst[e] = s * row[e];
   }
 }
 
@@ -359,12 +376,14 @@ int packed_expand(cudaStream_t st, int which, int no, int nv, const double* U, d
   if (no < 0 && which != 2) return fail("packed_expand: row slabs are supported for layout 2 only");
   if (npv == 0 || npo == 0) return 0;
   if (which == 0) {
-    expand_iakc_kernel<<<no * no, 256, 0, st>>>(no, nv, U, out);
+    const int t = (nv + 31) / 32;
+    expand_antisym_kernel<<<dim3(t, t, no * no), dim3(32, 8), 0, st>>>(0, no, npo, nv, U, out);
   } else if (which == 1) {
-    expand_occ_kernel<<<no * no, 256, 0, st>>>(no, npv, U, out);
+    expand_occ_kernel<<<no * no, 512, 0, st>>>(no, npv, U, out);
   } else if (which == 2) {
-    dim3 grid((unsigned)npo, (unsigned)std::min(nv, 8));
-    expand_virt_t_kernel<<<grid, 128, 0, st>>>(npo, nv, U, out);
+    const int t = (nv + 31) / 32;
+    if (npo > 65535) return fail("packed_expand: too many pair rows");
+    expand_antisym_kernel<<<dim3(t, t, (unsigned)npo), dim3(32, 8), 0, st>>>(2, no, npo, nv, U, out);
   } else {
     return fail("packed_expand: unknown layout");
   }

@@ -275,8 +275,32 @@ int lincomb(cudaStream_t st, int nvec, const double* coeff, const double* const*
 // dot_many: out[j] = scale * <x, y_j>, j < nvec (<= kMaxVec per launch).  Stage 1 writes one
 // partial per block and vector, stage 2 sums the partials in block order (deterministic).
 // ---------------------------------------------------------------------------------------
-constexpr int kDotBlocks = 592;   // 4 x 148
+constexpr int kDotBlocks = 4736;  // 32 x 148 (full occupancy like the other streaming kernels)
 constexpr int kDotChunk = 8;      // vectors accumulated in registers per sweep
+
+// one sweep over x and NV vectors (pointers hoisted, no predicates, 2 elements per iteration)
+template <int NV>
+__device__ __forceinline__ void dot_sweep(const VecList& v, int j0, const double* __restrict__ x,
+                                          long long n, double (&acc)[kDotChunk]) {
+  const double* p[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) p[j] = v.ptr[j0 + j];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (; i + stride < n; i += 2 * stride) {
+    const double x0 = x[i], x1 = x[i + stride];
+    double y0[NV], y1[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) { y0[j] = p[j][i]; y1[j] = p[j][i + stride]; }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc[j] += x0 * y0[j] + x1 * y1[j];
+  }
+  if (i < n) {
+    const double x0 = x[i];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc[j] += x0 * p[j][i];
+  }
+}
 
 __global__ void __launch_bounds__(256)
 dot_stage1_kernel(VecList v, const double* __restrict__ x, long long n, double* __restrict__ partial) {
@@ -286,12 +310,15 @@ dot_stage1_kernel(VecList v, const double* __restrict__ x, long long n, double* 
     double acc[kDotChunk];
 #pragma unroll
     for (int j = 0; j < kDotChunk; ++j) acc[j] = 0.0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-         i += (long long)gridDim.x * blockDim.x) {
-      const double xv = x[i];
-#pragma unroll
-      for (int j = 0; j < kDotChunk; ++j)
-        if (j0 + j < v.n) acc[j] += xv * v.ptr[j0 + j][i];
+    switch (min(kDotChunk, v.n - j0)) {
+      case 1: dot_sweep<1>(v, j0, x, n, acc); break;
+      case 2: dot_sweep<2>(v, j0, x, n, acc); break;
+      case 3: dot_sweep<3>(v, j0, x, n, acc); break;
+      case 4: dot_sweep<4>(v, j0, x, n, acc); break;
+      case 5: dot_sweep<5>(v, j0, x, n, acc); break;
+      case 6: dot_sweep<6>(v, j0, x, n, acc); break;
+      case 7: dot_sweep<7>(v, j0, x, n, acc); break;
+      default: dot_sweep<8>(v, j0, x, n, acc); break;
     }
 #pragma unroll
     for (int j = 0; j < kDotChunk; ++j) {
@@ -309,6 +336,119 @@ dot_stage1_kernel(VecList v, const double* __restrict__ x, long long n, double* 
   }
 }
 
+// ---- bulk-copy variant: the register file cannot keep enough loads in flight for 9 concurrent
+// streams (ncu: 114 regs -> 25 % occupancy, long-scoreboard stalls, 43 % of DRAM peak), so x and the NV
+// vectors are streamed into a shared-memory ring with cp.async.bulk (1-D TMA, SASS UBLKCP) whose
+// completion is tracked by mbarrier transaction bytes: ~180 KB in flight per SM, no register cost.
+constexpr int kBulkStages = 5;
+// doubles per vector per stage: few vectors -> bigger chunks, so that ~180 KB stay in flight per SM
+__host__ __device__ constexpr int bulk_chunk(int nv) { return nv <= 1 ? 2048 : (nv <= 3 ? 1024 : 512); }
+constexpr int kBulkThreads = 256;
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ bool bar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kBulkThreads + 32, 1)
+dot_bulk_kernel(VecList v, int j0, const double* __restrict__ x, long long n_chunks,
+                double* __restrict__ partial) {
+  constexpr int kBulkChunk = bulk_chunk(NV);
+  extern __shared__ __align__(128) unsigned char dsm[];
+  constexpr int kStageBytes = (NV + 1) * kBulkChunk * 8;
+  const uint32_t base = smem_u32(dsm);
+  const uint32_t bar_base = base + kBulkStages * kStageBytes;       // full[s], then empty[s]
+  __shared__ double red[kBulkThreads / 32][NV];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < kBulkStages; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_base + 8 * s), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_base + 8 * (kBulkStages + s)),
+                   "r"(kBulkThreads / 32));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid >= kBulkThreads) {                       // producer warp
+    if (tid == kBulkThreads) {
+      int it = 0;
+      for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it) {
+        const int s = it % kBulkStages;
+        const uint32_t ph = (it / kBulkStages) & 1;
+        while (!bar_try_wait(bar_base + 8 * (kBulkStages + s), ph ^ 1)) {}
+        const uint32_t full = bar_base + 8 * s;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(kStageBytes)
+                     : "memory");
+        const uint32_t dst = base + s * kStageBytes;
+        const long long off = c * kBulkChunk;
+        bulk_load(dst, x + off, kBulkChunk * 8, full);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) bulk_load(dst + (j + 1) * kBulkChunk * 8, v.ptr[j0 + j] + off, kBulkChunk * 8, full);
+      }
+    }
+    return;
+  }
+  double acc[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) acc[j] = 0.0;
+  int it = 0;
+  for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it) {
+    const int s = it % kBulkStages;
+    const uint32_t ph = (it / kBulkStages) & 1;
+    while (!bar_try_wait(bar_base + 8 * s, ph)) {}
+    const double* st = reinterpret_cast<const double*>(dsm + s * kStageBytes);
+#pragma unroll
+    for (int e = 0; e < kBulkChunk / (2 * kBulkThreads); ++e) {
+      const double2 xv = reinterpret_cast<const double2*>(st)[tid + e * kBulkThreads];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const double2 yv = reinterpret_cast<const double2*>(st + (j + 1) * kBulkChunk)[tid + e * kBulkThreads];
+        acc[j] += xv.x * yv.x + xv.y * yv.y;
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0)
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_base + 8 * (kBulkStages + s)) : "memory");
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    double a = acc[j];
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) red[warp][j] = a;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kBulkThreads));      // consumers only (producer warp has left)
+  if (tid < NV) {
+    double sum = 0.0;
+    for (int w = 0; w < kBulkThreads / 32; ++w) sum += red[w][tid];
+    partial[(size_t)(j0 + tid) * gridDim.x + blockIdx.x] = sum;
+  }
+}
+
+template <int NV>
+static int launch_dot_bulk(cudaStream_t st, const VecList& v, int j0, const double* x, long long n_chunks,
+                           int blocks, double* partial) {
+  constexpr int smem = kBulkStages * (NV + 1) * bulk_chunk(NV) * 8 + 2 * kBulkStages * 8;
+  static bool attr = false;
+  if (!attr) {
+    ADCCB_CUDA_OK(cudaFuncSetAttribute(dot_bulk_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  dot_bulk_kernel<NV><<<blocks, kBulkThreads + 32, smem, st>>>(v, j0, x, n_chunks, partial);
+  ADCCB_LAUNCH_OK();
+  return 0;
+}
+
 __global__ void dot_stage2_kernel(const double* __restrict__ partial, int nblocks, int nvec, double scale,
                                   double beta, double* __restrict__ out) {
   const int j = blockIdx.x;
@@ -320,6 +460,16 @@ __global__ void dot_stage2_kernel(const double* __restrict__ partial, int nblock
   if (threadIdx.x == 0) out[j] = (beta != 0.0 ? beta * out[j] : 0.0) + scale * s;
 }
 
+// tail elements [n0, n) of the bulk path, added on top of the stage-2 result
+__global__ void dot_tail_kernel(VecList v, const double* __restrict__ x, long long n0, long long n,
+                                double scale, double* __restrict__ out) {
+  const int j = blockIdx.x;
+  double s = 0.0;
+  for (long long i = n0 + threadIdx.x; i < n; i += 32) s += x[i] * v.ptr[j][i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (threadIdx.x == 0) out[j] += scale * s;
+}
+
 int dot_many(cudaStream_t st, int nvec, const double* x, const double* const* ys, long long n,
              double scale, double beta, double* out_dev, double* ws, long long ws_bytes) {
   if (nvec <= 0) return 0;
@@ -327,7 +477,53 @@ int dot_many(cudaStream_t st, int nvec, const double* x, const double* const* ys
   for (int k0 = 0; k0 < nvec; k0 += kMaxVec) {
     VecList v;
     v.n = std::min(kMaxVec, nvec - k0);
-    for (int k = 0; k < v.n; ++k) v.ptr[k] = ys[k0 + k];
+    bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    for (int k = 0; k < v.n; ++k) {
+      v.ptr[k] = ys[k0 + k];
+      aligned = aligned && (reinterpret_cast<uintptr_t>(v.ptr[k]) & 15) == 0;
+    }
+    if (aligned && n / 2048 >= 4LL * sm_count()) {
+      // streamed through shared memory: one CTA per SM, sweeps of up to 8 vectors
+      const int blocks = sm_count();
+      long long done_min = n;          // elements covered by every sweep's whole chunks
+      for (int j0 = 0; j0 < v.n; j0 += kDotChunk) {
+        const int nv_sweep = std::min(kDotChunk, v.n - j0);
+        const long long ch = bulk_chunk(nv_sweep), n_chunks = n / ch;
+        int rc = 0;
+        switch (nv_sweep) {
+          case 1: rc = launch_dot_bulk<1>(st, v, j0, x, n_chunks, blocks, ws); break;
+          case 2: rc = launch_dot_bulk<2>(st, v, j0, x, n_chunks, blocks, ws); break;
+          case 3: rc = launch_dot_bulk<3>(st, v, j0, x, n_chunks, blocks, ws); break;
+          case 4: rc = launch_dot_bulk<4>(st, v, j0, x, n_chunks, blocks, ws); break;
+          case 5: rc = launch_dot_bulk<5>(st, v, j0, x, n_chunks, blocks, ws); break;
+          case 6: rc = launch_dot_bulk<6>(st, v, j0, x, n_chunks, blocks, ws); break;
+          case 7: rc = launch_dot_bulk<7>(st, v, j0, x, n_chunks, blocks, ws); break;
+          default: rc = launch_dot_bulk<8>(st, v, j0, x, n_chunks, blocks, ws); break;
+        }
+        if (rc) return rc;
+        count_launch();
+        done_min = std::min(done_min, n_chunks * ch);
+        // the elements between this sweep's coverage and the common tail start are added below
+        (void)done_min;
+      }
+      dot_stage2_kernel<<<v.n, 32, 0, st>>>(ws, blocks, v.n, scale, beta, out_dev + k0);
+      ADCCB_LAUNCH_OK();
+      count_launch();
+      // tails: sweep with chunk ch covered [0, (n/ch)*ch); every vector's remainder is summed here
+      for (int j0 = 0; j0 < v.n; j0 += kDotChunk) {
+        const int nv_sweep = std::min(kDotChunk, v.n - j0);
+        const long long ch = bulk_chunk(nv_sweep), n0 = (n / ch) * ch;
+        if (n0 < n) {
+          VecList t;
+          t.n = nv_sweep;
+          for (int k = 0; k < nv_sweep; ++k) t.ptr[k] = v.ptr[j0 + k];
+          dot_tail_kernel<<<nv_sweep, 32, 0, st>>>(t, x, n0, n, scale, out_dev + k0 + j0);
+          ADCCB_LAUNCH_OK();
+          count_launch();
+        }
+      }
+      continue;
+    }
     int blocks = (int)std::min<long long>(kDotBlocks, std::max<long long>(1, (n + 255) / 256));
     dot_stage1_kernel<<<blocks, 256, 0, st>>>(v, x, n, ws);
     ADCCB_LAUNCH_OK();

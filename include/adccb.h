@@ -69,7 +69,7 @@ int adccb_lincomb(void* stream, int nvec, const double* host_coeff, const double
                   int64_t n, double beta, double* out);
 
 /* out_dev[j] = beta * out_dev[j] + scale * <x, y_j>, j < nvec, in one pass over x and every
- * y_j with a fixed-order two-stage reduction.  ws: >= 32*592*8 bytes of device scratch.
+ * y_j with a fixed-order two-stage reduction.  ws: >= 32*4736*8 bytes of device scratch.
  * libadcc_src/TensorImpl.cc:1120-1144 (dot with a list), libadcc_src/Tensor.hh:198-206. */
 int adccb_dot_many(void* stream, int nvec, const double* x, const double* const* host_ys, int64_t n,
                    double scale, double beta, double* out_dev, double* ws, int64_t ws_bytes);
