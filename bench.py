@@ -37,6 +37,7 @@ NO, NV = 40, 400
 # states are singles-dominated and the solver converges.  Matvec cost does not depend on it.
 SEED, SCALE = 20261019, 5e-4
 FP64_DMMA_PEAK_TFLOPS = 37.17          # tools/microbench/fp64_peak.cu on this pool's B200
+EXEC_FLOPS = 1.8448e13                 # executed flops of one packed ADC(2)-x matvec at nocc=40/nvirt=400
 METRIC = "adc2x_matvecs_per_second"
 UNIT = "matvec/s"
 
@@ -115,6 +116,7 @@ def cpu_sample(no_s=16, nv_s=96, n_matvec=3):
         times.append(time.perf_counter() - t0)
     t = float(np.median(times))
     ratio = dense_flops(no_s, nv_s) / dense_flops(NO, NV)
+    sample_gflops = dense_flops(no_s, nv_s) / t * 1e-9
     return {
         "value": ratio / t,                        # matvec/s extrapolated to nocc=40 / nvirt=400
         "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
@@ -122,7 +124,10 @@ def cpu_sample(no_s=16, nv_s=96, n_matvec=3):
                    f"nocc={no_s}, nvirt={nv_s}: {t:.3f} s/matvec over {n_matvec} reps "
                    f"(build {t_build:.1f} s); EXTRAPOLATED to nocc={NO}, nvirt={NV} by the dense "
                    f"flop ratio {1 / ratio:.0f}x (the dense vvvv block, 204.8 GB, cannot exist on "
-                   f"this host); libtensor itself is not installable offline"),
+                   f"this host); libtensor itself is not installable offline. Note: this port executes the "
+                   f"equations as written (dense spin orbitals); a symmetry-exploiting CPU code would execute "
+                   f"~{EXEC_FLOPS / 1e12:.1f} TFLOP per matvec like the GPU path, i.e. {sample_gflops:.0f} GFLOP/s "
+                   f"sustained here would give ~{sample_gflops * 1e9 / EXEC_FLOPS:.4f} matvec/s"),
         "seconds_per_matvec_sample": t,
     }
 

@@ -218,3 +218,29 @@ def check_batched_matvec(data, method, core):
         for k in osig:
             assert rel_err(res[k].to_ndarray(), osig[k]) < SIGMA_RTOL
             assert rel_err(res[k].to_ndarray(), single[k].to_ndarray()) < 1e-13
+
+
+def open_shell_dict(n_orb=6, n_alpha=3, n_beta=2, seed=4, scale=0.03):
+    """Unrestricted open-shell reference (n_alpha != n_beta) given directly as <pq||rs>
+    (key eri_phys_asym_ffff, adcc/DataHfProvider.py:121-132)."""
+    rng = np.random.default_rng(seed)
+    nf = 2 * n_orb
+    g = rng.standard_normal((nf,) * 4) * scale
+    g = g - g.transpose(1, 0, 2, 3)
+    g = g - g.transpose(0, 1, 3, 2)
+    g = g + g.transpose(2, 3, 0, 1)
+    ea = np.sort(rng.uniform(-1.5, -0.4, n_alpha)).tolist() + np.sort(rng.uniform(0.2, 2.5, n_orb - n_alpha)).tolist()
+    eb = np.sort(rng.uniform(-1.5, -0.4, n_beta)).tolist() + np.sort(rng.uniform(0.2, 2.5, n_orb - n_beta)).tolist()
+    orben = np.array(ea + eb)
+    occ = np.array([1.0] * n_alpha + [0.0] * (n_orb - n_alpha) + [1.0] * n_beta + [0.0] * (n_orb - n_beta))
+    return {"restricted": False, "conv_tol": 1e-12, "spin_multiplicity": n_alpha - n_beta + 1,
+            "orbcoeff_fb": np.vstack([np.eye(n_orb)] * 2), "occupation_f": occ, "orben_f": orben,
+            "fock_ff": np.diag(orben), "eri_phys_asym_ffff": g}
+
+
+def check_open_shell():
+    data = open_shell_dict()
+    for method in ("adc2", "adc2x", "adc3"):
+        matrix, omatrix = check_matvec_parity(data, method, None)
+        assert matrix.mospaces.n_orbs_alpha("o1") == 3 and matrix.mospaces.n_orbs_beta("o1") == 2
+    check_run_parity(data, "adc2", "any", None, n=3, conv_tol=1e-8)

@@ -11,6 +11,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """Make sure libadccb.so exists and is current (nvcc cross-compiles without a GPU); a failure here
+    is not swallowed by a fallback: every test that needs the library then fails loudly."""
+    try:
+        import __graft_entry__
+        __graft_entry__.build()
+    except Exception as exc:        # pragma: no cover
+        print(f"[conftest] build() failed: {exc}")
+
+
 def pytest_collection_modifyitems(config, items):
     try:
         import torch

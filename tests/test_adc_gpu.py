@@ -94,3 +94,8 @@ def test_ao_basis_import_device(h2o):
 def test_batched_matvec_device(h2o, method):
     from adc_parity_common import check_batched_matvec
     check_batched_matvec(h2o, method, 1 if method.startswith("cvs") else None)
+
+
+def test_open_shell_unrestricted_reference_device():
+    from adc_parity_common import check_open_shell
+    check_open_shell()

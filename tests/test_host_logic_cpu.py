@@ -149,3 +149,9 @@ def test_unrestricted_style_kinds():
 def test_batched_matvec(h2o, method):
     from adc_parity_common import check_batched_matvec
     check_batched_matvec(h2o, method, 1 if method.startswith("cvs") else None)
+
+
+def test_open_shell_unrestricted_reference():
+    """n_alpha != n_beta (ragged alpha/beta halves on every axis), <pq||rs> import path."""
+    from adc_parity_common import check_open_shell
+    check_open_shell()
