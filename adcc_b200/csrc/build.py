@@ -24,7 +24,8 @@ def build(force=False, verbose=False):
            "-Xcompiler", "-fPIC", "-shared", "-o", OUT] + SOURCES + ["-lcudart"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
-    subprocess.run(cmd, cwd=HERE, check=True)
+    # compiler chatter goes to stderr: bench.py must print exactly one JSON line on stdout
+    subprocess.run(cmd, cwd=HERE, check=True, stdout=sys.stderr)
     return OUT
 
 
