@@ -131,3 +131,61 @@ def test_spin_kernels(be):
     t = be.from_numpy(T)
     be.spin_singlet_(t, na)
     assert np.array_equal(t.cpu().numpy(), ref)
+
+
+def test_gemm_randomised_shapes(be):
+    """Ragged / prime extents, tile-boundary cases and stream-K splits, incl. beta accumulation."""
+    rng = np.random.default_rng(123)
+    shapes = [(1, 1, 1), (7, 3, 5), (113, 127, 131), (112, 128, 16), (129, 257, 1000), (780, 2048, 4096),
+              (40, 4001, 402), (2, 100003, 64), (300, 300, 30002), (17, 19, 100000), (1000, 9, 2050)]
+    for M, N, K in shapes:
+        A = rng.standard_normal((M, K))
+        B = rng.standard_normal((N, K))
+        C0 = rng.standard_normal((M, N))
+        out = be.from_numpy(C0)
+        be.gemm(be.from_numpy(A), be.from_numpy(B), out=out, alpha=0.7, beta=-1.3)
+        ref = 0.7 * (A @ B.T) - 1.3 * C0
+        assert _rel(out.cpu().numpy(), ref) < 1e-12, (M, N, K)
+
+
+def test_gemm_views_and_unaligned(be):
+    import torch
+    rng = np.random.default_rng(5)
+    big = be.from_numpy(rng.standard_normal((70, 300)))
+    A = big[3:60, 10:210]          # row-strided view, 16B-aligned start (offset 10 doubles -> 80 B)
+    B = big[5:33, 11:211]          # start offset 11 doubles = 88 B: not 16B aligned -> generic path
+    C = be.gemm(A, B)
+    assert _rel(C.cpu().numpy(), A.cpu().numpy() @ B.cpu().numpy().T) < 1e-13
+    # output into a column slab of a wider matrix (ldc > N)
+    wide = be.from_numpy(np.zeros((57, 100)))
+    be.gemm(A, big[0:28, 10:210], out=wide[:, 30:58])
+    assert _rel(wide.cpu().numpy()[:, 30:58], A.cpu().numpy() @ big[0:28, 10:210].cpu().numpy().T) < 1e-13
+    assert torch.count_nonzero(wide[:, :30]).item() == 0 and torch.count_nonzero(wide[:, 58:]).item() == 0
+
+
+def test_vector_kernels_odd_sizes_and_offsets(be):
+    rng = np.random.default_rng(8)
+    for n in (1, 31, 2049, 1_000_003, 3_000_000):
+        k = 11
+        flat = be.from_numpy(rng.standard_normal(k * (n + 1) + 3))
+        # vectors that start at odd element offsets (8-byte but not 16-byte aligned) and aligned ones
+        for start in (0, 1):
+            vs = [flat[start + j * (n + 1): start + j * (n + 1) + n] for j in range(k)]
+            ref = np.stack([v.cpu().numpy() for v in vs])
+            d = be.dot_many(vs[0], vs)
+            assert _rel(d, ref @ ref[0]) < 1e-12, (n, start)
+            c = rng.standard_normal(k)
+            out = be.lincomb(c, vs)
+            assert _rel(out.cpu().numpy(), c @ ref) < 1e-13
+
+
+def test_gather_randomised_permutations(be):
+    rng = np.random.default_rng(21)
+    for trial in range(12):
+        nd = int(rng.integers(1, 7))
+        shape = tuple(int(x) for x in rng.integers(1, 9 if nd > 4 else 40, size=nd))
+        perm = tuple(int(x) for x in rng.permutation(nd))
+        T = rng.standard_normal(shape)
+        add = rng.standard_normal(tuple(shape[p] for p in perm))
+        out = be.permute(be.from_numpy(T), perm, alpha=2.0, add=be.from_numpy(add), gamma=-0.5).cpu().numpy()
+        assert np.allclose(out, 2.0 * T.transpose(perm) - 0.5 * add, atol=1e-14), (shape, perm)
