@@ -51,6 +51,20 @@ class Symmetry:
             parsed.append((axes, sign))
         self._perms, self._perm_strings = parsed, perms
 
+    def permutation_group(self):
+        """Closure of the listed (axes, sign) permutations under composition."""
+        group = {tuple(range(self.ndim)): 1.0}
+        gens = [g for g in self._perms[1:]]
+        todo = list(group.items())
+        while todo:
+            axes, sign = todo.pop()
+            for gaxes, gsign in gens:
+                new = tuple(axes[a] for a in gaxes)
+                if new not in group:
+                    group[new] = sign * gsign
+                    todo.append((new, sign * gsign))
+        return list(group.items())
+
     @property
     def has_permutations(self):
         return len(self._perms) > 1

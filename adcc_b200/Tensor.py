@@ -135,10 +135,11 @@ class Tensor:
         arr = rng.uniform(-1.0, 1.0, size=self.shape)
         sym = self.symmetry
         if sym is not None and sym.has_permutations:
+            group = sym.permutation_group()
             acc = np.zeros_like(arr)
-            for axes, sign in sym._perms:
+            for axes, sign in group:
                 acc += sign * arr.transpose(axes)
-            arr = acc / len(sym._perms)
+            arr = acc / len(group)
         self._data = be.from_numpy(arr)
         return self
 
@@ -379,18 +380,36 @@ class Tensor:
             if self.ndim != 2:
                 raise ValueError("symmetrise without arguments is only valid for matrices")
             perms = [(0, 1)]
-        if any(len(p) != 2 for p in perms):
-            raise NotImplementedError("only pair (anti)symmetrisation is implemented")
         flat = [a for p in perms for a in p]
         if len(set(flat)) != len(flat):
-            raise ValueError("index pairs need to be disjoint")
-        axes = list(range(self.ndim))
-        for a, b in perms:
-            if self.subspaces[a] != self.subspaces[b]:
+            raise ValueError("index groups need to be disjoint")
+        if any(len(p) != len(perms[0]) for p in perms) or len(perms[0]) not in (2, 3):
+            raise NotImplementedError("only pair and triple (anti)symmetrisation is implemented")
+        for p in perms:
+            if len({self.subspaces[a] for a in p}) != 1:
                 raise ValueError("(anti)symmetrisation needs axes of the same subspace")
-            axes[a], axes[b] = axes[b], axes[a]
         base = self._contig()
-        out = be.permute(base, axes, alpha=0.5 * sign, add=base, gamma=0.5)
+        if len(perms[0]) == 2:
+            axes = list(range(self.ndim))
+            for a, b in perms:
+                axes[a], axes[b] = axes[b], axes[a]
+            out = be.permute(base, axes, alpha=0.5 * sign, add=base, gamma=0.5)
+            return Tensor._wrap(self.mospaces, self.subspaces, out)
+        # triples: 1/6 sum over the 6 permutations of the group (applied simultaneously to all
+        # groups), odd permutations weighted by `sign` (libadcc_src/Tensor.hh:229-244)
+        import itertools
+        out = None
+        for sigma in itertools.permutations(range(3)):
+            inversions = sum(1 for x in range(3) for y in range(x + 1, 3) if sigma[x] > sigma[y])
+            weight = (sign if inversions % 2 else 1.0) / 6.0
+            axes = list(range(self.ndim))
+            for grp in perms:
+                for k in range(3):
+                    axes[grp[k]] = grp[sigma[k]]
+            if out is None:
+                out = be.permute(base, axes, alpha=weight)
+            else:
+                be.permute(base, axes, alpha=weight, out=out, beta=1.0)
         return Tensor._wrap(self.mospaces, self.subspaces, out)
 
     def symmetrise(self, *perms):

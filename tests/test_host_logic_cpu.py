@@ -155,3 +155,66 @@ def test_open_shell_unrestricted_reference():
     """n_alpha != n_beta (ragged alpha/beta halves on every axis), <pq||rs> import path."""
     from adc_parity_common import check_open_shell
     check_open_shell()
+
+
+def test_tensor_symmetrise_reference_goldens():
+    from tensor_golden_common import check_tensor_goldens
+    check_tensor_goldens()
+
+
+def test_tensor_ops_closed_form(h2o):
+    """More of the closed-form expectations of libadcc_src/tests/TensorTest.cc:99-970: trace, set_mask,
+    select_n_*, matmul, direct_sum of three operands, copy / *_like, in-place ops, random fill."""
+    import adcc_b200 as adcc
+    from adcc_b200.functions import einsum, direct_sum, trace
+    ref = adcc.ReferenceState(h2o)
+    ms = ref.mospaces
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal((10, 10))
+    A = adcc.Tensor.from_ndarray(ms, "o1o1", a)
+    B = adcc.Tensor.from_ndarray(ms, "o1o1", a.T.copy())
+    # trace / full contractions
+    assert abs(trace("ii", A) - np.trace(a)) < 1e-13
+    oooo = ref.oooo
+    assert abs(trace("ijij", oooo) - np.einsum("ijij->", oooo.to_ndarray())) < 1e-12
+    # matmul contracts axis 1 of a with axis 0 of b (export_Tensor.cc:420-422)
+    np.testing.assert_allclose((A @ B).to_ndarray(), a @ a.T, atol=1e-13)
+    np.testing.assert_allclose(A.T.to_ndarray(), a.T)
+    # set_mask: Kronecker delta and general masks
+    d = A.zeros_like()
+    d.set_mask("ii", 1.0)
+    np.testing.assert_array_equal(d.to_ndarray(), np.eye(10))
+    t4 = ref.oovv.zeros_like()
+    t4.set_mask("ijab", 2.0)
+    assert np.all(t4.to_ndarray() == 2.0)
+    t4.set_mask("iiab", 7.0)
+    arr = t4.to_ndarray()
+    assert np.all(arr[np.arange(10), np.arange(10)] == 7.0) and arr[0, 1, 0, 0] == 2.0
+    # select_n_* (TensorImpl.cc:260-282): sorted, index + value
+    sel = A.select_n_min(3)
+    flat = np.sort(a, axis=None)
+    assert [v for _, v in sel] == list(flat[:3])
+    assert all(a[idx] == v for idx, v in sel)
+    assert A.select_n_absmax(1)[0][1] == a.flat[np.argmax(np.abs(a))]
+    # direct_sum with three operands and a permutation
+    fo, fv = ref.foo.diagonal(), ref.fvv.diagonal()
+    ds = direct_sum("-i+a-j->jai", fo, fv, fo).to_ndarray()
+    o, v = fo.to_ndarray(), fv.to_ndarray()
+    np.testing.assert_allclose(ds, (-o[:, None, None] + v[None, :, None] - o[None, None, :]).transpose(2, 1, 0))
+    # copies, *_like, in-place arithmetic
+    C = A.copy()
+    C *= 2.0
+    C += A
+    C -= B
+    C /= 4.0
+    np.testing.assert_allclose(C.to_ndarray(), (3.0 * a - a.T) / 4.0, atol=1e-15)
+    assert np.all(A.ones_like().to_ndarray() == 1.0) and np.all(A.empty_like().to_ndarray() == 0.0)
+    assert A.nosym_like().symmetry is None
+    r = adcc.Tensor(adcc.Symmetry(ms, "o1o1v1v1", permutations=["ijab", "-jiab", "-ijba"])).set_random()
+    rr = r.to_ndarray()
+    assert np.allclose(rr, -rr.transpose(1, 0, 2, 3)) and np.allclose(rr, -rr.transpose(0, 1, 3, 2))
+    # partial traces are not supported (opt_einsum_integration.py:68-71); extent mismatch is an error
+    with pytest.raises(NotImplementedError):
+        einsum("iiab->ab", ref.oovv)
+    with pytest.raises(ValueError):
+        einsum("ij,jk->ik", A, ref.fvv)

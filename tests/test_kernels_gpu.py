@@ -189,3 +189,8 @@ def test_gather_randomised_permutations(be):
         add = rng.standard_normal(tuple(shape[p] for p in perm))
         out = be.permute(be.from_numpy(T), perm, alpha=2.0, add=be.from_numpy(add), gamma=-0.5).cpu().numpy()
         assert np.allclose(out, 2.0 * T.transpose(perm) - 0.5 * add, atol=1e-14), (shape, perm)
+
+
+def test_tensor_symmetrise_reference_goldens_device(be):
+    from tensor_golden_common import check_tensor_goldens
+    check_tensor_goldens()

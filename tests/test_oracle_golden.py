@@ -94,3 +94,14 @@ def test_singlet_fixed_point_of_spin_enforcement(h2o):
     before = u2.copy()
     enforce_spin_kind(u2, [5, 5, 2, 2], "singlet")
     np.testing.assert_allclose(u2, before, atol=1e-9)
+
+
+def test_oracle_symmetrisers_against_reference_goldens():
+    """oracle.mp.sym / asym / sym_pairs vs libadcc_src/tests/TensorTestData.cc."""
+    from oracle.mp import sym, asym, sym_pairs
+    from tensor_golden_common import GOLD
+    a = GOLD["a"]
+    np.testing.assert_allclose(sym(a, 0, 1), GOLD["a_sym_01"], atol=1e-15)
+    np.testing.assert_allclose(asym(a, 0, 1), GOLD["a_asym_01"], atol=1e-15)
+    np.testing.assert_allclose(sym_pairs(a, (0, 1), (2, 3)), GOLD["a_sym_01_23"], atol=1e-15)
+    np.testing.assert_allclose(0.5 * (a - a.transpose(1, 0, 3, 2)), GOLD["a_asym_01_23"], atol=1e-15)
