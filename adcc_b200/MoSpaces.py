@@ -160,7 +160,11 @@ class MoSpaces:
             self._n[s] = len(idx)
         self.map_block_start, self.map_block_spin, self.map_block_irrep = {}, {}, {}
         for s in ["f"] + self.subspaces:
-            starts = construct_blocks([0, self._n_alpha[s]], self._n[s], max_block_size)
+            # a block starts wherever spin or subspace changes (libadcc_src/MoSpaces.cc:462-481)
+            idx = self.map_index_hf_provider[s]
+            crude = [k for k in range(len(idx))
+                     if k == 0 or (spin[idx[k]], sub[idx[k]]) != (spin[idx[k - 1]], sub[idx[k - 1]])]
+            starts = construct_blocks(crude, self._n[s], max_block_size)
             self.map_block_start[s] = starts
             self.map_block_spin[s] = ["a" if st < self._n_alpha[s] else "b" for st in starts]
             self.map_block_irrep[s] = ["A"] * len(starts)
