@@ -7,6 +7,8 @@ diagonal_precomputed)``, ``matvec`` / ``@`` / ``rmatvec``, ``block_apply``, ``di
 :74-130.  The blocks are the contraction tables of adcc_b200/adc_pp.py; ``matvec`` evaluates
 all terms of all blocks and merges the terms of each output block in one fused lincomb launch.
 """
+import os
+
 import numpy as np
 
 from . import adc_pp
@@ -80,6 +82,8 @@ class AdcMatrix(AdcMatrixlike):
         self._validate_block_orders()
         self._variant = "cvs" if self.is_core_valence_separated else ""
         self._const = {}
+        self._graphs = {}
+        self._graph_seen = {}
         self.doubles_storage = self._select_storage(doubles_storage)
         if shard is not None and (shard[1] > 1) and self.doubles_storage != "packed":
             raise NotImplementedError("multi-GPU sharding is implemented for the packed doubles store")
@@ -263,6 +267,15 @@ class AdcMatrix(AdcMatrixlike):
             ret = self.blocks[block](AmplitudeVector(**{inblock: tensor}))
             return getattr(ret, outblock)
 
+    def _matvec_terms(self, v):
+        collected = {}
+        for blk in self._tables:
+            outb, terms = self._terms(blk, v)
+            if terms:
+                collected.setdefault(outb, []).extend(terms)
+        return {outb: linear_combination_strict([c for c, _ in terms], [t for _, t in terms])
+                for outb, terms in collected.items()}
+
     def matvec(self, v):
         """sigma = M v  (adcc/AdcMatrix.py:390-396)."""
         with self.timer.record("matvec"):
@@ -270,14 +283,66 @@ class AdcMatrix(AdcMatrixlike):
                 return self._engine.matvec(v)
             if self.extra_terms:
                 return sum(block(v) for block in self.blocks.values())
-            collected = {}
-            for blk in self._tables:
-                outb, terms = self._terms(blk, v)
-                if terms:
-                    collected.setdefault(outb, []).extend(terms)
-            return AmplitudeVector(**{
-                outb: linear_combination_strict([c for c, _ in terms], [t for _, t in terms])
-                for outb, terms in collected.items()})
+            if self._graphs_enabled():
+                res = self._graph_matvec([v])
+                if res is not None:
+                    return res[0]
+            return AmplitudeVector(**self._matvec_terms(v))
+
+    # ------------------------------------------------------------------ CUDA-graph replay
+    GRAPH_MAX_ELEMENTS = 1 << 25      # dense vectors up to 256 MiB: host launch cost matters
+    GRAPH_MAX_CACHED = 8              # distinct (blocks, batch size) signatures kept
+    GRAPH_CAPTURE_AFTER = 2           # eager uses of a signature before it is captured
+
+    def _graphs_enabled(self):
+        from . import backend as be
+        # Opt-in: measured on B200 (tools/diag_small.py) one capture costs about as much as the
+        # host time it saves over a single run_adc (9-13 Davidson iterations); it pays when one
+        # matrix serves many solves.
+        return (os.environ.get("ADCCB_GRAPHS") == "1" and be.graphs_supported()
+                and len(self) <= self.GRAPH_MAX_ELEMENTS)
+
+    def _graph_matvec(self, vectors):
+        """Replay the captured launch sequence of matvec (one vector) or matvec_batch (several).
+        Returns None if no further graph should be cached for this signature."""
+        from . import backend as be
+        n = len(vectors)
+        blocks = tuple(vectors[0].blocks)
+        key = (n, blocks)
+        graph = self._graphs.get(key)
+        lead = () if n == 1 else (n,)
+        subspaces = {blk: list(vectors[0][blk].subspaces) for blk in blocks}
+
+        def fill(bufs):
+            for blk in blocks:
+                for k, v in enumerate(vectors):
+                    be.axpby(1.0, v[blk]._contig(), 0.0, bufs[blk] if n == 1 else bufs[blk][k])
+
+        def run(bufs):
+            if n == 1:
+                ampl = AmplitudeVector(**{blk: Tensor._wrap(self.mospaces, subspaces[blk], bufs[blk])
+                                          for blk in blocks})
+                return self._matvec_terms(ampl)
+            stacked = {blk: Tensor._wrap(self.mospaces, ["B"] + subspaces[blk], bufs[blk])
+                       for blk in blocks}
+            return self._matvec_stacked(stacked)
+
+        if graph is None:
+            # capture costs about ten eager matvecs: only signatures that keep coming back pay off
+            seen = self._graph_seen[key] = self._graph_seen.get(key, 0) + 1
+            if seen <= self.GRAPH_CAPTURE_AFTER or len(self._graphs) >= self.GRAPH_MAX_CACHED:
+                return None
+            shapes = {blk: lead + tuple(vectors[0][blk].shape) for blk in blocks}
+            graph = self._graphs[key] = be.ReplayGraph(shapes, fill, run)
+        outputs = graph.run(fill)
+        ret = []
+        for k in range(n):
+            ret.append(AmplitudeVector(**{
+                outb: Tensor._wrap(self.mospaces, res.subspaces[len(lead):],
+                                   be.clone(res._data if n == 1 else res._data[k]),
+                                   symmetry=res.symmetry if n == 1 else None)
+                for outb, res in outputs.items()}))
+        return ret
 
     def rmatvec(self, v):
         return self.matvec(v)
@@ -320,13 +385,16 @@ class AdcMatrix(AdcMatrixlike):
         if n == 0:
             return []
         blocks = vectors[0].blocks
-        import os
         if (n == 1 or self.extra_terms or self._engine is not None
                 or os.environ.get("ADCCB_NO_BATCH", "0") == "1"
                 or any(v.blocks != blocks for v in vectors)
                 or type(self).matvec is not AdcMatrix.matvec):
             return [self.matvec(v) for v in vectors]
         with self.timer.record("matvec_batch"):
+            if self._graphs_enabled():
+                res = self._graph_matvec(vectors)
+                if res is not None:
+                    return res
             stacked = {}
             for blk in blocks:
                 first = vectors[0][blk]
@@ -334,22 +402,25 @@ class AdcMatrix(AdcMatrixlike):
                 for k, v in enumerate(vectors):
                     be.axpby(1.0, v[blk]._contig(), 0.0, data[k])
                 stacked[blk] = Tensor._wrap(self.mospaces, ["B"] + list(first.subspaces), data)
-            collected = {}
-            for blk in self._tables:
-                inb, outb, terms = self._tables[blk]
-                if inb is None or inb not in stacked:
-                    continue
-                for c, e in terms:
-                    t, batched = self._eval_batched(e, stacked)
-                    assert batched
-                    collected.setdefault(outb, []).append((c, t))
             out = [dict() for _ in range(n)]
-            for outb, terms in collected.items():
-                res = linear_combination_strict([c for c, _ in terms], [t for _, t in terms])
+            for outb, res in self._matvec_stacked(stacked).items():
                 sub = res.subspaces[1:]
                 for k in range(n):
                     out[k][outb] = Tensor._wrap(self.mospaces, sub, res._data[k])
             return [AmplitudeVector(**o) for o in out]
+
+    def _matvec_stacked(self, stacked):
+        collected = {}
+        for blk in self._tables:
+            inb, outb, terms = self._tables[blk]
+            if inb is None or inb not in stacked:
+                continue
+            for c, e in terms:
+                t, batched = self._eval_batched(e, stacked)
+                assert batched
+                collected.setdefault(outb, []).append((c, t))
+        return {outb: linear_combination_strict([c for c, _ in terms], [t for _, t in terms])
+                for outb, terms in collected.items()}
 
     def __matmul__(self, other):
         if isinstance(other, AmplitudeVector):

@@ -6,6 +6,8 @@ blocks that sum to the integer 0, ``dot`` with one vector (float) or a list (nda
 """
 import numpy as np
 
+from . import backend as be
+
 
 class AmplitudeVector(dict):
     def __init__(self, **blocks):
@@ -51,9 +53,21 @@ class AmplitudeVector(dict):
         return self
 
     def dot(self, other):
-        if isinstance(other, list):
+        """Scalar product(s) summed over the blocks on the device: one host read per call."""
+        from .Tensor import Tensor
+        single = not isinstance(other, list)
+        others = [other] if single else other
+        if any(type(t) is not Tensor for t in self.values()):     # packed doubles weigh their dot
+            if single:
+                return sum(self[b].dot(other[b]) for b in self.keys())
             return sum(np.asarray(self[b].dot([av[b] for av in other])) for b in self.keys())
-        return sum(self[b].dot(other[b]) for b in self.keys())
+        pairs = []
+        for b in self.keys():
+            for av in others:
+                self[b]._check_same(av[b])
+            pairs.append((self[b]._contig(), [av[b]._contig() for av in others]))
+        res = be.dot_many_blocks(pairs)
+        return float(res[0]) if single else res
 
     def __matmul__(self, other):
         if isinstance(other, AmplitudeVector):
@@ -103,3 +117,24 @@ class AmplitudeVector(dict):
 
     def __repr__(self):
         return "AmplitudeVector(" + "=..., ".join(self.blocks) + "=...)"
+
+
+def dot_rows(rows):
+    """[x @ ys for x, ys in rows] with a single device-to-host read: every row's batched dot writes
+    its slice of one device array (used for the Davidson subspace-matrix update)."""
+    from .Tensor import Tensor
+    rows = [(x, list(ys)) for x, ys in rows]
+    if not rows:
+        return []
+    if any(type(t) is not Tensor for x, _ in rows for t in x.values()):
+        return [np.asarray(x @ ys) for x, ys in rows]
+    out = be.empty((sum(len(ys) for _, ys in rows),))
+    pos, cuts = 0, []
+    for x, ys in rows:
+        if ys:
+            be.dot_many_blocks([(x[b]._contig(), [av[b]._contig() for av in ys]) for b in x.keys()],
+                               out=out[pos:pos + len(ys)])
+        cuts.append((pos, pos + len(ys)))
+        pos += len(ys)
+    host = be.to_host(out)
+    return [host[a:b] for a, b in cuts]

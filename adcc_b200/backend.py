@@ -21,7 +21,12 @@ def device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    if _raw_stream is not None:        # same handle as current_stream().cuda_stream, ~10x cheaper
+        return ctypes.c_void_p(_raw_stream(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -59,6 +64,42 @@ def _check_dev(*ts):
     for t in ts:
         if t is not None and (not t.is_cuda or t.dtype != F64):
             raise ValueError("expected CUDA float64 tensors")
+
+
+# --------------------------------------------------------------------------------- graphs
+def graphs_supported():
+    return torch.cuda.is_available()
+
+
+class ReplayGraph:
+    """A fixed launch sequence captured once into a CUDA graph (stream capture) and replayed:
+    ``fn(inputs) -> outputs`` over static input buffers.  For small systems the matvec is a few
+    dozen microsecond-sized kernels and the host cost of issuing them dominates; one graph launch
+    replaces them.  ``fn`` must not synchronise or read device data on the host."""
+
+    def __init__(self, shapes, fill, fn):
+        self.inputs = {k: empty(shape) for k, shape in shapes.items()}
+        fill(self.inputs)
+        workspace()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            fn(self.inputs)            # eager pass: operand layout caches fill outside the capture
+        cur.wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = fn(self.inputs)
+
+    def run(self, fill):
+        fill(self.inputs)
+        self.graph.replay()
+        return self.outputs
+
+
+def clone(t):
+    """Device-to-device copy of a contiguous array (cudaMemcpyAsync on the current stream)."""
+    return t.clone()
 
 
 # --------------------------------------------------------------------------------- GEMM
@@ -205,6 +246,35 @@ def dot_many(x, ys, scale=1.0):
     _cabi.check(_cabi.lib().adccb_dot_many(_stream(), k, _ptr(x), ps, n, float(scale), 0.0,
                                            _ptr(out), _ptr(ws), ws.numel() * 8))
     return out.cpu().numpy()
+
+
+def dot_many_blocks(pairs, scale=1.0, out=None):
+    """sum over blocks b of <x_b, y_bj> for pairs = [(x_b, [y_b0 .. y_bk-1]), ...]: the partial sums
+    accumulate on the device (beta = 1 from the second block on), ONE D2H copy at the end.
+    With ``out`` (device array of length k) the result stays on the device and nothing is read."""
+    k = len(pairs[0][1])
+    if k == 0:
+        return np.zeros(0)
+    keep = out is not None
+    if not keep:
+        out = torch.empty(k, dtype=F64, device=pairs[0][0].device)
+    ws = workspace()
+    for ib, (x, ys) in enumerate(pairs):
+        n = x.numel()
+        if len(ys) != k:
+            raise ValueError("dot_many_blocks: every block needs the same number of vectors")
+        for t in [x] + list(ys):
+            if not t.is_contiguous() or t.numel() != n:
+                raise ValueError("dot_many: tensors must be contiguous and equally sized")
+        ps = (ctypes.c_void_p * k)(*[t.data_ptr() for t in ys])
+        _cabi.check(_cabi.lib().adccb_dot_many(_stream(), k, _ptr(x), ps, n, float(scale),
+                                               0.0 if ib == 0 else 1.0, _ptr(out), _ptr(ws),
+                                               ws.numel() * 8))
+    return out if keep else out.cpu().numpy()
+
+
+def to_host(t):
+    return t.cpu().numpy()
 
 
 def dot(x, y):

@@ -19,7 +19,7 @@ import numpy as np
 import scipy.linalg as la
 
 from ..AdcMatrix import AdcMatrixlike
-from ..AmplitudeVector import AmplitudeVector
+from ..AmplitudeVector import AmplitudeVector, dot_rows
 from ..functions import evaluate, lincomb
 from ..timings import strtime, strtime_short
 from .common import select_eigenpairs
@@ -56,13 +56,13 @@ def default_print(state, identifier, file=sys.stdout):
 
 def _project(Ass, SS, Ax, rows, upper):
     """Fill rows (and, by symmetry, columns) of the subspace matrix: one batched dot per row."""
-    for i in rows:
+    rows = list(rows)
+    allvals = dot_rows([(SS[i], Ax[i:] if upper else Ax[:i + 1]) for i in rows])
+    for i, vals in zip(rows, allvals):
         if upper:
-            vals = np.asarray(SS[i] @ Ax[i:])
             Ass[i, i:] = vals
             Ass[i:, i] = vals
         else:
-            vals = np.asarray(SS[i] @ Ax[:i + 1])
             Ass[i, :i + 1] = vals
             Ass[:i + 1, i] = vals
 
@@ -120,7 +120,8 @@ def davidson_iterations(matrix, state, max_subspace, max_iter, n_ep, n_block, is
             epair_mask = select_eigenpairs(rvals, n_ep, which)
             state.eigenvalues = rvals[epair_mask]
             state.residuals = [residuals[i] for i in epair_mask]
-            state.residual_norms = np.array([np.sqrt(r @ r) for r in state.residuals])
+            state.residual_norms = np.sqrt(np.array(
+                [float(d[0]) for d in dot_rows([(r, [r]) for r in state.residuals])]))
 
         callback(state, "next_iter")
         state.timer.restart("iteration")
@@ -166,11 +167,12 @@ def davidson_iterations(matrix, state, max_subspace, max_iter, n_ep, n_block, is
                 pvec = preconds[i]
                 coefficients = np.hstack(([1], -np.asarray(pvec @ SS)))
                 pvec = lincomb(coefficients, [pvec] + SS, evaluate=True)
-                pnorm = np.sqrt(pvec @ pvec)
+                overlaps = np.array(pvec @ ([pvec] + SS))      # norm and re-check in one pass
+                pnorm = np.sqrt(overlaps[0])
                 if pnorm < residual_min_norm:
                     continue
                 with state.timer.record("reorthogonalisation"):
-                    ss_overlap = np.array(pvec @ SS)
+                    ss_overlap = overlaps[1:]
                     max_ortho_loss = np.max(np.abs(ss_overlap)) / pnorm
                     if max_ortho_loss > n_problem * eps:
                         coefficients = np.hstack(([1], -ss_overlap))

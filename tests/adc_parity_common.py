@@ -244,3 +244,33 @@ def check_open_shell():
         matrix, omatrix = check_matvec_parity(data, method, None)
         assert matrix.mospaces.n_orbs_alpha("o1") == 3 and matrix.mospaces.n_orbs_beta("o1") == 2
     check_run_parity(data, "adc2", "any", None, n=3, conv_tol=1e-8)
+
+
+def check_graph_replay(data, method, core, monkeypatch):
+    """Captured-graph matvec (single and batched) equals the eagerly launched one on fresh inputs
+    each replay, and the oracle."""
+    matrix, omatrix = build_pair(data, method, core)
+    matrix.GRAPH_CAPTURE_AFTER = 1
+    vecs = [random_vector(matrix, omatrix, 300 + k) for k in range(5)]
+    monkeypatch.setenv("ADCCB_GRAPHS", "0")
+    eager = [matrix.matvec(v) for v, _ in vecs]
+    assert not matrix._graphs
+    monkeypatch.setenv("ADCCB_GRAPHS", "1")
+    replayed = [matrix.matvec(v) for v, _ in vecs]                # eager, capture, 3 replays
+    sets = [vecs[:3], vecs[3:], vecs[1:4], vecs[:2], vecs[2:5]]   # n=3: eager, capture, replay
+    batched = [matrix @ [v for v, _ in vs] for vs in sets]
+    assert set(matrix._graphs) == {(n, tuple(vecs[0][0].blocks)) for n in (1, 2, 3)}
+    for k, (v, ov) in enumerate(vecs):
+        osig = omatrix.matvec(ov)
+        for b in osig:
+            assert rel_err(replayed[k][b].to_ndarray(), osig[b]) < SIGMA_RTOL
+            assert np.array_equal(replayed[k][b].to_ndarray(), eager[k][b].to_ndarray())
+    for vs, res in zip(sets, batched):
+        for (v, ov), sig in zip(vs, res):
+            k = [id(x) for x, _ in vecs].index(id(v))
+            for b in eager[k].blocks:
+                assert rel_err(sig[b].to_ndarray(), eager[k][b].to_ndarray()) < 1e-13
+    # outputs are copies: a later replay must not overwrite an earlier result
+    first = replayed[2]["ph"].to_ndarray().copy()
+    matrix.matvec(vecs[1][0])
+    assert np.array_equal(replayed[2]["ph"].to_ndarray(), first)

@@ -69,6 +69,15 @@ def install(monkeypatch):
 
     def dot(x, y): return float(torch.dot(x.reshape(-1), y.reshape(-1)))
 
+    def dot_many_blocks(pairs, scale=1.0, out=None):
+        res = sum(dot_many(x, ys, scale) for x, ys in pairs)
+        if out is None:
+            return res
+        out.copy_(torch.from_numpy(np.asarray(res)))
+        return out
+
+    def to_host(t): return t.numpy()
+
     def spin_project(t, n_alpha, fac):
         f = t
         for ax, na in enumerate(n_alpha):
@@ -246,10 +255,27 @@ def install(monkeypatch):
                          permute=permute, contiguous=contiguous, fill=fill, axpby=axpby,
                          scaled_copy=scaled_copy, mul=mul, div=div, div_shift=div_shift,
                          add_scalar=add_scalar, direct_sum=direct_sum, lincomb=lincomb,
-                         dot_many=dot_many, dot=dot, spin_project=spin_project,
+                         dot_many=dot_many, dot=dot, dot_many_blocks=dot_many_blocks, to_host=to_host, spin_project=spin_project,
                          spin_singlet_=spin_singlet_, packed_unpack=packed_unpack, packed_pack=packed_pack,
                          packed_expand=packed_expand, packed_fold_virt=packed_fold_virt,
                          packed_fold_occ=packed_fold_occ, packed_diagonal=packed_diagonal,
                          pair_select=pair_select, int64_tensor=int64_tensor, add_columns=add_columns, spin_expand4=spin_expand4, synth_fill=synth_fill).items():
         monkeypatch.setattr(be, name, fn)
     monkeypatch.setattr(be, "device", lambda: cpu)
+
+    class ReplayGraph:
+        """Host-logic stand-in: same static-buffer protocol, the launch sequence re-runs eagerly."""
+        def __init__(self, shapes, fill, fn):
+            self.inputs = {k: empty(shape) for k, shape in shapes.items()}
+            self.fn = fn
+            fill(self.inputs)
+            fn(self.inputs)
+
+        def run(self, fill):
+            fill(self.inputs)
+            self.outputs = self.fn(self.inputs)
+            return self.outputs
+
+    import os
+    monkeypatch.setattr(be, "ReplayGraph", ReplayGraph)
+    monkeypatch.setattr(be, "graphs_supported", lambda: os.environ.get("ADCCB_SHIM_GRAPHS") == "1")

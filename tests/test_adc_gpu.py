@@ -99,3 +99,10 @@ def test_batched_matvec_device(h2o, method):
 def test_open_shell_unrestricted_reference_device():
     from adc_parity_common import check_open_shell
     check_open_shell()
+
+
+@pytest.mark.parametrize("method", ["adc1", "adc2", "adc2x", "adc3", "cvs-adc2x"])
+def test_graph_replay_device(h2o, method, monkeypatch):
+    """CUDA-graph capture of the dense matvec: bit-identical to the eager launches, parity with the oracle."""
+    from adc_parity_common import check_graph_replay
+    check_graph_replay(h2o, method, 1 if method.startswith("cvs") else None, monkeypatch)

@@ -218,3 +218,11 @@ def test_tensor_ops_closed_form(h2o):
         einsum("iiab->ab", ref.oovv)
     with pytest.raises(ValueError):
         einsum("ij,jk->ik", A, ref.fvv)
+
+
+@pytest.mark.parametrize("method", ["adc2", "cvs-adc2x"])
+def test_graph_replay_host_logic(h2o, method, monkeypatch):
+    """Static-buffer / replay / copy-out protocol of the captured matvec (the shim re-runs eagerly)."""
+    from adc_parity_common import check_graph_replay
+    monkeypatch.setenv("ADCCB_SHIM_GRAPHS", "1")
+    check_graph_replay(h2o, method, 1 if method.startswith("cvs") else None, monkeypatch)
