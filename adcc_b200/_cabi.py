@@ -23,6 +23,13 @@ def _declare(lib):
     lib.adccb_device_info.argtypes = [ctypes.POINTER(ctypes.c_int)] * 3
     lib.adccb_dgemm.argtypes = [c_ptr, c_i64, c_i64, c_i64, c_dbl, c_ptr, c_i64, c_i64, c_ptr,
                                 c_i64, c_i64, c_dbl, c_ptr, c_i64, c_ptr, c_i64, ctypes.c_int]
+    lib.adccb_dgemm_peers.argtypes = [c_ptr, c_i64, c_i64, c_i64, c_dbl, c_ptr, c_i64, c_ptr, c_i64,
+                                      c_ptr, ctypes.c_int, ctypes.POINTER(c_ptr), c_i64, c_ptr, c_i64,
+                                      ctypes.c_int]
+    lib.adccb_peer_alloc.argtypes = [c_i64, ctypes.POINTER(c_ptr), c_ptr]
+    lib.adccb_peer_open.argtypes = [c_ptr, ctypes.POINTER(c_ptr)]
+    lib.adccb_peer_close.argtypes = [c_ptr]
+    lib.adccb_peer_free.argtypes = [c_ptr]
     lib.adccb_strided_gather.argtypes = [c_ptr, ctypes.c_int, ctypes.POINTER(c_i64),
                                          ctypes.POINTER(c_i64), c_dbl, c_ptr, c_dbl, c_ptr, c_dbl,
                                          c_ptr]
@@ -57,7 +64,8 @@ def _declare(lib):
 
 EXPORTS = [
     "adccb_version", "adccb_last_error", "adccb_launch_count", "adccb_device_info",
-    "adccb_dgemm", "adccb_strided_gather", "adccb_elementwise", "adccb_direct_sum",
+    "adccb_dgemm", "adccb_dgemm_peers", "adccb_peer_alloc", "adccb_peer_open", "adccb_peer_close",
+    "adccb_peer_free", "adccb_strided_gather", "adccb_elementwise", "adccb_direct_sum",
     "adccb_add_columns", "adccb_lincomb", "adccb_dot_many", "adccb_spin_expand4", "adccb_spin_project", "adccb_spin_singlet",
     "adccb_packed_unpack", "adccb_packed_pack", "adccb_packed_expand", "adccb_packed_fold_virt",
     "adccb_packed_fold_occ", "adccb_packed_diagonal", "adccb_pair_select", "adccb_synth_fill",

@@ -124,6 +124,101 @@ def gemm(A, B, out=None, alpha=1.0, beta=0.0, tile_hint=0):
     return out
 
 
+# --------------------------------------------------------------------------------- peer exchange
+class _RawDeviceArray:
+    """__cuda_array_interface__ view of memory this library allocated (wrapped as a torch tensor)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def peer_exchange_supported():
+    return torch.cuda.is_available()
+
+
+class PeerBuffer:
+    """One FP64 buffer of ``n`` elements per rank, each mapped into every other rank's address space
+    (CUDA IPC; one process per GPU on one NVSwitch box).  ``local`` is this rank's buffer as a
+    torch tensor, ``peer_ptrs[r]`` the device address of rank r's buffer as seen from here.
+    Construction is collective; ``PeerBuffer.create`` returns None on EVERY rank if any rank could
+    not allocate, export or map (the caller then keeps the NCCL exchange)."""
+
+    def __init__(self):
+        self.n, self._own, self._opened, self.peer_ptrs, self.local = 0, None, [], [], None
+        self.error = None
+
+    @classmethod
+    def create(cls, n, group=None):
+        import torch.distributed as dist
+        self = cls()
+        self.n = int(n)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        handle = ctypes.create_string_buffer(64)
+        try:
+            ptr = ctypes.c_void_p()
+            _cabi.check(_cabi.lib().adccb_peer_alloc(self.n * 8, ctypes.byref(ptr), handle))
+            self._own = ptr.value
+            self.local = torch.as_tensor(_RawDeviceArray(self._own, self.n), device=device())
+        except Exception as exc:      # noqa: BLE001 - reported, decided collectively below
+            self.error = f"rank {self.rank}: {exc}"
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (self.error, handle.raw), group=group)
+        if all(err is None for err, _ in handles):
+            try:
+                for r, (_, h) in enumerate(handles):
+                    if r == self.rank:
+                        self.peer_ptrs.append(self._own)
+                        continue
+                    p = ctypes.c_void_p()
+                    _cabi.check(_cabi.lib().adccb_peer_open(ctypes.create_string_buffer(h, 64),
+                                                            ctypes.byref(p)))
+                    self.peer_ptrs.append(p.value)
+                    self._opened.append(p.value)
+            except Exception as exc:  # noqa: BLE001
+                self.error = f"rank {self.rank}: {exc}"
+        errors = [None] * self.world
+        dist.all_gather_object(errors, self.error or next((e for e, _ in handles if e), None),
+                               group=group)
+        failed = [e for e in errors if e]
+        if failed:
+            self.close()
+            if self.rank == 0:
+                import sys
+                print(f"adcc_b200: peer-memory exchange unavailable ({failed[0]}); using the NCCL "
+                      "all-gather", file=sys.stderr)
+            return None
+        return self
+
+    def close(self):
+        for p in self._opened:
+            _cabi.lib().adccb_peer_close(ctypes.c_void_p(p))
+        self._opened, self.peer_ptrs = [], []
+        if self._own:
+            self.local = None
+            _cabi.lib().adccb_peer_free(ctypes.c_void_p(self._own))
+            self._own = None
+
+
+def gemm_peers(A, B, local_out, peer_ptrs, col_offset, ldc, tile_hint=0):
+    """local_out[:, :] = A B^T, also written to address peer_ptrs[d] + col_offset (same leading
+    dimension) for every d: the column-slab GEMM whose epilogue does the slab exchange."""
+    _check_dev(A, B, local_out)
+    M, K = A.shape
+    N, K2 = B.shape
+    if K != K2 or tuple(local_out.shape) != (M, N) or local_out.stride(1) != 1 or local_out.stride(0) != ldc:
+        raise ValueError("gemm_peers: shape mismatch")
+    if A.stride(1) != 1 or B.stride(1) != 1:
+        raise ValueError("gemm_peers: operands must be K-contiguous")
+    k = len(peer_ptrs)
+    ps = (ctypes.c_void_p * max(k, 1))(*[int(p) + 8 * int(col_offset) for p in peer_ptrs])
+    ws = workspace()
+    _cabi.check(_cabi.lib().adccb_dgemm_peers(
+        _stream(), M, N, K, 1.0, _ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(local_out), k, ps,
+        int(ldc), _ptr(ws), ws.numel() * 8, int(tile_hint)))
+    return local_out
+
+
 # --------------------------------------------------------------------------------- gather
 def gather(inp, shape, in_strides, alpha=1.0, add=None, gamma=0.0, out=None, beta=0.0):
     """out[o] = alpha*inp.flat[sum o_d*in_strides[d]] + gamma*add[o] + beta*out[o]."""

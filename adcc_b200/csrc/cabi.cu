@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "../../include/adccb.h"
 #include <atomic>
+#include <cstring>
 
 namespace adccb {
 
@@ -30,6 +31,10 @@ int dgemm_strided(cudaStream_t st, long long M, long long N, long long K, double
                   const double* A, long long ars, long long acs, const double* B, long long brs,
                   long long bcs, double beta, double* C, long long ldc, double* ws,
                   long long ws_bytes, int tile_hint);
+int dgemm_peers(cudaStream_t st, long long M, long long N, long long K, double alpha,
+                const double* A, long long lda, const double* B, long long ldb, double* C,
+                int n_peers, double* const* peer_C, long long ldc, double* ws, long long ws_bytes,
+                int tile_hint);
 int strided_gather(cudaStream_t st, int nd, const long long* shape, const long long* istride,
                    double alpha, const double* in, double gamma, const double* add, double beta,
                    double* out);
@@ -87,6 +92,50 @@ int adccb_dgemm(void* stream, int64_t M, int64_t N, int64_t K, double alpha, con
                 double beta, double* C, int64_t ldc, double* ws, int64_t ws_bytes, int tile_hint) {
   return dgemm_strided((cudaStream_t)stream, M, N, K, alpha, A, a_rs, a_cs, B, b_rs, b_cs, beta, C,
                        ldc, ws, ws_bytes, tile_hint);
+}
+
+int adccb_dgemm_peers(void* stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A,
+                      int64_t lda, const double* B, int64_t ldb, double* C, int n_peers,
+                      double* const* host_peer_C, int64_t ldc, double* ws, int64_t ws_bytes,
+                      int tile_hint) {
+  return dgemm_peers((cudaStream_t)stream, M, N, K, alpha, A, lda, B, ldb, C, n_peers, host_peer_C,
+                     ldc, ws, ws_bytes, tile_hint);
+}
+
+int adccb_peer_alloc(int64_t bytes, void** dev_ptr, void* host_handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (bytes <= 0 || dev_ptr == nullptr || host_handle64 == nullptr) return fail("peer_alloc: bad arguments");
+  void* p = nullptr;
+  ADCCB_CUDA_OK(cudaMalloc(&p, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  }
+  memcpy(host_handle64, &h, sizeof(h));
+  *dev_ptr = p;
+  return 0;
+}
+
+int adccb_peer_open(const void* host_handle64, void** dev_ptr) {
+  if (dev_ptr == nullptr || host_handle64 == nullptr) return fail("peer_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, host_handle64, sizeof(h));
+  void* p = nullptr;
+  ADCCB_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *dev_ptr = p;
+  return 0;
+}
+
+int adccb_peer_close(void* dev_ptr) {
+  ADCCB_CUDA_OK(cudaIpcCloseMemHandle(dev_ptr));
+  return 0;
+}
+
+int adccb_peer_free(void* dev_ptr) {
+  ADCCB_CUDA_OK(cudaFree(dev_ptr));
+  return 0;
 }
 
 int adccb_strided_gather(void* stream, int ndim, const int64_t* shape, const int64_t* in_stride,

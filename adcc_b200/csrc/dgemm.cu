@@ -81,12 +81,46 @@ struct TileCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;
 };
 
+// Additional destinations of every finished C tile: the same (row, col) of buffers in PEER GPUs'
+// memory (mapped through CUDA IPC, written over NVLink).  This fuses the exchange step that follows
+// a column-slab GEMM (all-gather of the slabs) into the epilogue: the tile goes out while the
+// other CTAs are still in their DMMA loops, so no collective is left on the critical path.
+constexpr int kMaxPeers = 7;
+struct PeerDests {
+  int n;
+  double* ptr[kMaxPeers];
+};
+
 // epilogue shared by the main kernel and the stream-K fix-up: thread (warp, lane) holds
 // C[row pg][cols t, t+4] of each 8x8 block of its warp tile
-template <int WARPS_N, int MB, int NB, int BM, int BN>
+template <int WARPS_N, int MB, int NB, int BM, int BN, bool PEERS>
 __device__ __forceinline__ void store_tile(const double (&acc)[MB][NB][2], int warp, int lane,
                                            int tile_m, int tile_n, double* __restrict__ C,
-                                           long long ldc, int M, int N, double alpha, double beta) {
+                                           long long ldc, int M, int N, double alpha, double beta,
+                                           const PeerDests& peers) {
+  if constexpr (PEERS) {   // beta == 0 by contract; one pass per destination keeps the stores streaming
+    const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+    const int g = lane >> 2, t = lane & 3;
+    const int pg = (g >> 1) | ((g & 1) << 2);
+    const int row0 = tile_m * BM + wm * MB * 8 + pg;
+    const int col0 = tile_n * BN + wn * NB * 8 + t;
+    for (int d = -1; d < peers.n; ++d) {
+      double* dst = d < 0 ? C : peers.ptr[d];
+#pragma unroll
+      for (int i = 0; i < MB; ++i) {
+        const int r = row0 + i * 8;
+        if (r >= M) continue;
+        double* Crow = dst + (size_t)r * ldc;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const int c = col0 + j * 8;
+          if (c < N) Crow[c] = alpha * acc[i][j][0];
+          if (c + 4 < N) Crow[c + 4] = alpha * acc[i][j][1];
+        }
+      }
+    }
+    return;
+  }
   const int wm = warp / WARPS_N, wn = warp % WARPS_N;
   const int g = lane >> 2, t = lane & 3;
   const int pg = (g >> 1) | ((g & 1) << 2);
@@ -153,13 +187,13 @@ struct SegIter {
   }
 };
 
-template <int WARPS_M, int WARPS_N, int MB, int NB, int STAGES>
+template <int WARPS_M, int WARPS_N, int MB, int NB, int STAGES, bool PEERS>
 __global__ void __launch_bounds__((WARPS_M * WARPS_N + 1) * 32, 1)
 dgemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA,
                     const __grid_constant__ CUtensorMap tmB, double* __restrict__ C,
                     long long ldc, int M, int N, int tiles_m, int k_iters, int dp_waves,
                     long long sk_tile0, long long sk_total, long long ipc, double alpha, double beta,
-                    double* __restrict__ partial) {
+                    double* __restrict__ partial, const __grid_constant__ PeerDests peers) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, MB, NB, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -250,7 +284,7 @@ dgemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA,
     }
 
     if (slot < 0) {
-      store_tile<WARPS_N, MB, NB, Cfg::BM, Cfg::BN>(acc, warp, lane, tm, tn, C, ldc, M, N, alpha, beta);
+      store_tile<WARPS_N, MB, NB, Cfg::BM, Cfg::BN, PEERS>(acc, warp, lane, tm, tn, C, ldc, M, N, alpha, beta, peers);
     } else {
       // fragment-ordered partial: element (reg, consumer thread) -> coalesced
       constexpr int kCT = Cfg::kConsumerWarps * 32;
@@ -268,11 +302,11 @@ dgemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA,
 }
 
 // sums the partial segments of every stream-K tile that no single CTA covered, in CTA order
-template <int WARPS_M, int WARPS_N, int MB, int NB, int STAGES>
+template <int WARPS_M, int WARPS_N, int MB, int NB, int STAGES, bool PEERS>
 __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32)
 dgemm_fixup_kernel(double* __restrict__ C, long long ldc, int M, int N, int tiles_m, int k_iters,
                    long long sk_tile0, long long sk_tiles, long long ipc, double alpha, double beta,
-                   const double* __restrict__ partial) {
+                   const double* __restrict__ partial, const __grid_constant__ PeerDests peers) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, MB, NB, STAGES>;
   constexpr int kThreads = Cfg::kConsumerWarps * 32;
   for (long long tl = blockIdx.x; tl < sk_tiles; tl += gridDim.x) {
@@ -296,9 +330,9 @@ dgemm_fixup_kernel(double* __restrict__ C, long long ldc, int M, int N, int tile
         }
     }
     const long long tile = sk_tile0 + tl;
-    store_tile<WARPS_N, MB, NB, Cfg::BM, Cfg::BN>(acc, threadIdx.x >> 5, threadIdx.x & 31,
+    store_tile<WARPS_N, MB, NB, Cfg::BM, Cfg::BN, PEERS>(acc, threadIdx.x >> 5, threadIdx.x & 31,
                                                  (int)(tile % tiles_m), (int)(tile / tiles_m), C, ldc,
-                                                 M, N, alpha, beta);
+                                                 M, N, alpha, beta, peers);
   }
 }
 
@@ -405,12 +439,12 @@ static bool make_map_2d(CUtensorMap* tm, const double* base, long long rows, lon
   return r == CUDA_SUCCESS;
 }
 
-template <int WARPS_M, int WARPS_N, int MB, int NB, int STAGES>
+template <int WARPS_M, int WARPS_N, int MB, int NB, int STAGES, bool PEERS>
 static int launch_tma(cudaStream_t st, int M, int N, int K, double alpha, const double* A,
                       long long lda, const double* B, long long ldb, double beta, double* C,
-                      long long ldc, double* ws, long long ws_bytes) {
+                      long long ldc, double* ws, long long ws_bytes, const PeerDests& peers) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, MB, NB, STAGES>;
-  auto kern = dgemm_tn_tma_kernel<WARPS_M, WARPS_N, MB, NB, STAGES>;
+  auto kern = dgemm_tn_tma_kernel<WARPS_M, WARPS_N, MB, NB, STAGES, PEERS>;
   static bool attr_set = false;
   if (!attr_set) {
     ADCCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -447,24 +481,25 @@ static int launch_tma(cudaStream_t st, int M, int N, int K, double alpha, const 
   const long long sk_total = sk_tiles * k_iters;
   const bool has_partials = sk_tiles > 0 && (ipc % k_iters) != 0;
   kern<<<(unsigned)n_ctas, Cfg::kThreads, Cfg::SMEM_BYTES, st>>>(tmA, tmB, C, ldc, M, N, tm, k_iters, dp_waves,
-                                                                 sk_tile0, sk_total, ipc, alpha, beta, ws);
+                                                                 sk_tile0, sk_total, ipc, alpha, beta, ws, peers);
   ADCCB_LAUNCH_OK();
   count_launch();
   if (has_partials) {
     const int blocks = (int)std::min<long long>(sk_tiles, 4LL * nsm);
-    dgemm_fixup_kernel<WARPS_M, WARPS_N, MB, NB, STAGES><<<blocks, Cfg::kConsumerWarps * 32, 0, st>>>(
-        C, ldc, M, N, tm, k_iters, sk_tile0, sk_tiles, ipc, alpha, beta, ws);
+    dgemm_fixup_kernel<WARPS_M, WARPS_N, MB, NB, STAGES, PEERS><<<blocks, Cfg::kConsumerWarps * 32, 0, st>>>(
+        C, ldc, M, N, tm, k_iters, sk_tile0, sk_tiles, ipc, alpha, beta, ws, peers);
     ADCCB_LAUNCH_OK();
     count_launch();
   }
   return 0;
 }
 
-int dgemm_strided(cudaStream_t st, long long M, long long N, long long K, double alpha,
-                  const double* A, long long ars, long long acs, const double* B, long long brs,
-                  long long bcs, double beta, double* C, long long ldc, double* ws,
-                  long long ws_bytes, int tile_hint) {
+static int dgemm_impl(cudaStream_t st, long long M, long long N, long long K, double alpha,
+                      const double* A, long long ars, long long acs, const double* B, long long brs,
+                      long long bcs, double beta, double* C, long long ldc, double* ws,
+                      long long ws_bytes, int tile_hint, const PeerDests& peers) {
   if (M <= 0 || N <= 0) return 0;
+  if (peers.n > 0 && (beta != 0.0 || K <= 0)) return fail("dgemm_peers: needs beta == 0 and K > 0");
   if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff) return fail("dgemm: extent exceeds int32");
   if (K <= 0) {
     // C = beta * C
@@ -477,14 +512,17 @@ int dgemm_strided(cudaStream_t st, long long M, long long N, long long K, double
   const bool tma_ok = acs == 1 && bcs == 1 && (ars % 2 == 0) && (brs % 2 == 0) &&
                       ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && get_encode_fn() != nullptr &&
-                      ((long long)M * N * K >= 32LL * 32 * 32);
+                      (peers.n > 0 || (long long)M * N * K >= 32LL * 32 * 32);
   if (tma_ok) {
     // row-tile height: the smallest tile that covers M for skinny outputs (these are HBM-bound
     // streams over the big operand, so DMMA rows spent on zero padding would make them
     // tensor-bound instead), else whichever of 112 / 128 pads M less
     // (e.g. 780 occupied pairs -> 7 x 112 = 784 instead of 7 x 128 = 896)
-#define ADCCB_TMA(WM, WN, MB, NB) \
-  return launch_tma<WM, WN, MB, NB, 6>(st, (int)M, (int)N, (int)K, alpha, A, ars, B, brs, beta, C, ldc, ws, ws_bytes)
+#define ADCCB_TMA(WM, WN, MB, NB)                                                                    \
+  return peers.n > 0 ? launch_tma<WM, WN, MB, NB, 6, true>(st, (int)M, (int)N, (int)K, alpha, A, ars, B, \
+                                                           brs, beta, C, ldc, ws, ws_bytes, peers)      \
+                     : launch_tma<WM, WN, MB, NB, 6, false>(st, (int)M, (int)N, (int)K, alpha, A, ars, B, \
+                                                            brs, beta, C, ldc, ws, ws_bytes, peers)
     if (tile_hint == 0 || tile_hint == 16 || tile_hint == 40 || tile_hint == 64) {
       if (tile_hint == 16 || (tile_hint == 0 && M <= 16)) ADCCB_TMA(1, 8, 2, 2);
       if (tile_hint == 40 || (tile_hint == 0 && M <= 40)) ADCCB_TMA(1, 8, 5, 2);
@@ -495,12 +533,39 @@ int dgemm_strided(cudaStream_t st, long long M, long long N, long long K, double
     ADCCB_TMA(2, 4, 8, 4);
 #undef ADCCB_TMA
   }
+  if (peers.n > 0) return fail("dgemm_peers: operands must be K-contiguous and 16-byte aligned (TMA path)");
   dim3 grid((unsigned)((M + GB - 1) / GB), (unsigned)((N + GB - 1) / GB));
   if (grid.y > 65535) return fail("dgemm(generic): too many N tiles");
   dgemm_generic_kernel<<<grid, 128, 0, st>>>((int)M, (int)N, (int)K, alpha, A, ars, acs, B, brs, bcs, beta, C, ldc);
   ADCCB_LAUNCH_OK();
   count_launch();
   return 0;
+}
+
+int dgemm_strided(cudaStream_t st, long long M, long long N, long long K, double alpha,
+                  const double* A, long long ars, long long acs, const double* B, long long brs,
+                  long long bcs, double beta, double* C, long long ldc, double* ws,
+                  long long ws_bytes, int tile_hint) {
+  PeerDests none;
+  none.n = 0;
+  return dgemm_impl(st, M, N, K, alpha, A, ars, acs, B, brs, bcs, beta, C, ldc, ws, ws_bytes,
+                    tile_hint, none);
+}
+
+// C = alpha * A B^T written to the local C AND to the same offsets of n_peers peer buffers
+int dgemm_peers(cudaStream_t st, long long M, long long N, long long K, double alpha,
+                const double* A, long long lda, const double* B, long long ldb, double* C,
+                int n_peers, double* const* peer_C, long long ldc, double* ws, long long ws_bytes,
+                int tile_hint) {
+  if (n_peers < 0 || n_peers > kMaxPeers) return fail("dgemm_peers: at most 7 peer destinations");
+  PeerDests peers;
+  peers.n = n_peers;
+  for (int d = 0; d < n_peers; ++d) {
+    if (peer_C[d] == nullptr) return fail("dgemm_peers: null peer destination");
+    peers.ptr[d] = peer_C[d];
+  }
+  return dgemm_impl(st, M, N, K, alpha, A, lda, 1, B, ldb, 1, 0.0, C, ldc, ws, ws_bytes, tile_hint,
+                    peers);
 }
 
 }  // namespace adccb

@@ -267,9 +267,23 @@ class PackedAdcEngine:
         self._off_rows = be.int64_tensor([r * nv * nv for r in range(self.npo)])
         self._rows_ij = be.int64_tensor(list(range(self.ij0, self.ij1)))
         self._reduce_group = None
+        self._peer = None
         if self.world > 1:
+            import os
             import torch.distributed as dist
             self._reduce_group = dist.new_group(ranks=list(range(self.world)))
+            # slab exchange of the vvvv term through peer memory, written by the GEMM epilogue
+            # (two buffers, alternating per matvec: a rank that runs ahead never overwrites a
+            # buffer its peer is still reading)
+            if (self.order_dd == 1 and be.peer_exchange_supported()
+                    and os.environ.get("ADCCB_P2P", "1") != "0"):
+                bufs = [be.PeerBuffer.create(self.npo * self.npv) for _ in range(2)]
+                if all(b is not None for b in bufs):
+                    self._peer, self._peer_flip = bufs, 0
+                else:
+                    for b in bufs:
+                        if b is not None:
+                            b.close()
             # ovov fold of a j-slab: T_r[(i,a),(jl,b)], offset (i*nv + a)*(nj*nv) + jl*nv + b
             njv = self.nj * nv
             own = range(self.j0, self.j0 + self.nj)
@@ -448,8 +462,35 @@ class PackedAdcEngine:
                 dist.all_reduce(buf, group=self._reduce_group)
                 done = torch.cuda.Event()
                 done.record(self._comm_stream)
-        else:
+        elif self._peer is None or self.order_dd != 1:
             dist.all_reduce(buf)
+        if self.order_dd == 1 and self._peer is not None:
+            # vvvv term: this rank's column slab, written by the GEMM epilogue into the exchange
+            # buffer of EVERY rank (own memory + NVLink stores to the peers).  The all-reduce of the
+            # other terms that follows on the same stream is the cross-rank ordering point.
+            peer = self._peer[self._peer_flip]
+            self._peer_flip ^= 1
+            R = peer.local.view(npo, npv)
+            w = self.ab1 - self.ab0
+            if w > 0:
+                self._mark("vvvv", 0)
+                be.gemm_peers(U, self.W, R[:, self.ab0:self.ab1],
+                              [p for r, p in enumerate(peer.peer_ptrs) if r != self.rank],
+                              col_offset=self.ab0, ldc=npv)
+                self._mark("vvvv", 1)
+            self._mark("gather", 0)
+            if main is None:
+                dist.all_reduce(buf)
+            else:
+                main.wait_event(done)
+                buf.record_stream(self._comm_stream)
+                if getattr(self, "_token", None) is None:
+                    self._token = be.zeros((1,))
+                dist.all_reduce(self._token)          # ordering point on the main stream
+            self._mark("gather", 1)
+            be.axpby(1.0, R, 1.0, S)
+            self._mark("step", 1)
+            return AmplitudeVector(ph=self._wrap_ph(s1.view(no, nv)), pphh=self._wrap_pphh(S))
         if self.order_dd == 1:
             wmax = self._wmax
             slab = be.empty((npo, wmax)) if wmax > 0 else None

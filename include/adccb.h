@@ -38,6 +38,31 @@ int adccb_dgemm(void* stream, int64_t M, int64_t N, int64_t K, double alpha, con
                 int64_t a_rs, int64_t a_cs, const double* B, int64_t b_rs, int64_t b_cs,
                 double beta, double* C, int64_t ldc, double* ws, int64_t ws_bytes, int tile_hint);
 
+/* Column-slab GEMM fused with the exchange that follows it in a sharded matvec:
+ * C[m,n] = alpha * sum_k A[m*lda + k] * B[n*ldb + k] is written to the local C AND, tile by tile
+ * from the same epilogue, to the same offsets of n_peers (<= 7) buffers that live in PEER GPUs'
+ * memory (host array `host_peer_C` of device pointers obtained from adccb_peer_open).  Every rank
+ * of a sharded sigma build calls this with its own column slab (C and the peer pointers already
+ * offset to the slab's first column, common leading dimension ldc); after a stream-ordered
+ * cross-rank synchronisation (any collective on the same stream) all ranks hold all slabs.  It
+ * replaces "GEMM, then all-gather of the slabs" (SURVEY 8(e) fusion target); in the reference
+ * the corresponding step is the shared-memory libtensor contraction writing one result tensor
+ * (libadcc_src/TensorImpl.cc:901-1117).  A and B must be K-contiguous and 16-byte aligned. */
+int adccb_dgemm_peers(void* stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A,
+                      int64_t lda, const double* B, int64_t ldb, double* C, int n_peers,
+                      double* const* host_peer_C, int64_t ldc, double* ws, int64_t ws_bytes,
+                      int tile_hint);
+/* Peer-visible device memory for adccb_dgemm_peers (one process per GPU, CUDA IPC):
+ * adccb_peer_alloc allocates `bytes` on the current device and writes the 64-byte IPC handle the
+ * host side passes to the other ranks (any transport, e.g. torch.distributed all_gather_object);
+ * adccb_peer_open maps a peer's buffer into this process and enables peer access to its device;
+ * adccb_peer_close unmaps it; adccb_peer_free releases an own allocation.  These are the only
+ * entry points that own memory, because IPC export needs a dedicated allocation. */
+int adccb_peer_alloc(int64_t bytes, void** dev_ptr, void* host_handle64);
+int adccb_peer_open(const void* host_handle64, void** dev_ptr);
+int adccb_peer_close(void* dev_ptr);
+int adccb_peer_free(void* dev_ptr);
+
 /* out[o] = alpha * in[sum_d o_d * in_stride[d]] + gamma * add[o] + beta * out[o] for a
  * contiguous `out` of the given shape (rank <= 8); `add` may be NULL.
  * Covers transpose / copy / diagonal extraction / (anti)symmetrisation:

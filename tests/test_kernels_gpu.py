@@ -43,6 +43,32 @@ def test_gemm_tile_variants(be, hint):
     assert _rel(C, A @ B.T) < 1e-13
 
 
+@pytest.mark.parametrize("M,N,K,hint,ndest", [(780, 640, 2050, 0, 3), (100, 36, 130, 0, 1), (6, 28, 28, 0, 7),
+                                              (300, 333, 514, 128, 2), (300, 333, 514, 64, 2),
+                                              (45, 128, 40000, 0, 2)])
+def test_gemm_peer_destinations(be, M, N, K, hint, ndest):
+    """adccb_dgemm_peers: every tile (direct and stream-K fix-up) lands in the local slab and in the
+    same columns of every additional destination; bit-identical to the plain GEMM.  The extra
+    destinations here are ordinary buffers on this GPU (the kernel only sees addresses)."""
+    import torch
+    rng = np.random.default_rng(M + N + K + ndest)
+    A, B = be.from_numpy(rng.standard_normal((M, K))), be.from_numpy(rng.standard_normal((N, K)))
+    plain = be.gemm(A, B, tile_hint=hint)
+    ld, c0 = N + 256, 128                          # slab columns [c0, c0+N) of wider result buffers
+    bufs = [be.from_numpy(np.full((M, ld), -7.0)) for _ in range(ndest + 1)]
+    be.gemm_peers(A, B, bufs[0][:, c0:c0 + N], [b.data_ptr() for b in bufs[1:]], col_offset=c0,
+                  ldc=ld, tile_hint=hint)
+    same_path = M * N * K >= 32 ** 3               # below that the plain GEMM takes the generic kernel
+    for b in bufs:
+        if same_path:
+            assert torch.equal(b[:, c0:c0 + N], plain)
+        else:
+            assert _rel(b[:, c0:c0 + N].cpu().numpy(), plain.cpu().numpy()) < 1e-13
+        assert bool((b[:, :c0] == -7.0).all()) and bool((b[:, c0 + N:] == -7.0).all())
+    with pytest.raises(RuntimeError):              # more than 7 peers
+        be.gemm_peers(A, B, bufs[0][:, c0:c0 + N], [bufs[0].data_ptr()] * 8, col_offset=c0, ldc=ld)
+
+
 def test_gemm_generic_strides(be):
     rng = np.random.default_rng(7)
     # odd leading dimension -> generic path; transposed operands
