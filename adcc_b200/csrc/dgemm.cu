@@ -60,7 +60,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
 }
 __device__ __forceinline__ double2 lds128(uint32_t addr) {
   double2 v;
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
   return v;
 }
 
@@ -249,6 +249,13 @@ dgemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA,
   const uint32_t b_off = (uint32_t)(Cfg::A_BYTES + (wn * NB * 8 + pg) * 128 + ((t ^ pg) << 4));
 
   double acc[MB][NB][2];
+  // A stage is handed back to the producer ONE iteration late, after the wait for the next
+  // stage: by then every DMMA that consumed the stage's fragments has been issued, so all of its
+  // shared-memory reads (of every lane) have completed.  Releasing right behind the last LDS is
+  // not enough: the arrive of lane 0 does not order the other lanes' reads, and the TMA refill of
+  // an L2-resident slab was observed to overtake a delayed read (wrong rows of the last-loaded
+  // fragment, about once per 10^4 tiles, first tiles of a launch).
+  uint32_t release_bar = 0;
   while (seg.next(tm, tn, k_start, n_seg, slot)) {
 #pragma unroll
     for (int i = 0; i < MB; ++i)
@@ -259,6 +266,11 @@ dgemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA,
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
       mbar_wait(bar_base + 8 * s, ph);
+      if (release_bar != 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(release_bar);
+      }
+      release_bar = bar_base + 8 * (STAGES + s);
       const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES + a_off;
       const uint32_t sb = smem_base + s * Cfg::STAGE_BYTES + b_off;
 #pragma unroll
@@ -279,8 +291,6 @@ dgemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
           for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i].y, bf[j].y);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + s));
     }
 
     if (slot < 0) {

@@ -402,10 +402,18 @@ dot_bulk_kernel(VecList v, int j0, const double* __restrict__ x, long long n_chu
 #pragma unroll
   for (int j = 0; j < NV; ++j) acc[j] = 0.0;
   int it = 0;
+  uint32_t release_bar = 0;   // stages are released one iteration late (see dgemm.cu: the reads of
+                              // every lane must have completed before the refill may start)
   for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it) {
     const int s = it % kBulkStages;
     const uint32_t ph = (it / kBulkStages) & 1;
     while (!bar_try_wait(bar_base + 8 * s, ph)) {}
+    if (release_bar != 0) {
+      __syncwarp();
+      if ((tid & 31) == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(release_bar) : "memory");
+    }
+    release_bar = bar_base + 8 * (kBulkStages + s);
     const double* st = reinterpret_cast<const double*>(dsm + s * kStageBytes);
 #pragma unroll
     for (int e = 0; e < kBulkChunk / (2 * kBulkThreads); ++e) {
@@ -416,9 +424,6 @@ dot_bulk_kernel(VecList v, int j0, const double* __restrict__ x, long long n_chu
         acc[j] += xv.x * yv.x + xv.y * yv.y;
       }
     }
-    __syncwarp();
-    if ((tid & 31) == 0)
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_base + 8 * (kBulkStages + s)) : "memory");
   }
   const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll

@@ -313,6 +313,12 @@ class PackedAdcEngine:
         """Record CUDA events around the two dominant GEMM launches (bench.py roofline)."""
         self._events = {} if on else None
 
+    def _trace_add(self, name, t):
+        """Debug aid (ADCCB_TRACE=1): keep a copy of an intermediate of the sharded matvec."""
+        tr = getattr(self, "_trace", None)
+        if tr is not None and t is not None:
+            tr.append((name, t.clone()))
+
     def _mark(self, name, which):
         ev = getattr(self, "_events", None)
         if ev is None:
@@ -403,44 +409,59 @@ class PackedAdcEngine:
         r0, r1 = self.j0 * nv, (self.j0 + self.nj) * nv
         if r1 > r0:
             be.gemm(x.reshape(1, -1), self.M1[r0:r1], out=s1[:, r0:r1])
+        self._trace_add("s1_phph", s1)
         # ---- ph_pphh
         if self.nj > 0:
             Ue = be.packed_expand(1, U, no, nv)
             k0, k1 = self.j0 * npv, (self.j0 + self.nj) * npv
             be.gemm(Ue[:, k0:k1], self.V2, out=s1m, alpha=2.0, beta=1.0)
+            self._trace_add("Ue", Ue)
             del Ue
+        self._trace_add("s1_V2", s1)
         if nij > 0:
             Uh = be.packed_expand(2, U[ij0:ij1], nij, nv, n_pairs_o=nij)        # [a,(JK slab,b)]
             be.gemm(self.G1[:, ij0 * nv:ij1 * nv], Uh, out=s1m, alpha=2.0, beta=1.0)
+            self._trace_add("Uh", Uh)
             del Uh
+        self._trace_add("s1_G1", s1)
         # ---- pphh_pphh without the vvvv term
         if nij > 0:
             be.mul(U[ij0:ij1], self.D0[ij0:ij1], out=S[ij0:ij1])
+        self._trace_add("S_D0", S)
         if self.order_dd == 1:
             if nij > 0:
                 Ut = be.permute(U[ij0:ij1], (1, 0))                               # [AB, KL slab]
                 be.gemm(self.O[:, ij0:ij1], Ut, out=S, alpha=1.0, beta=1.0)
                 del Ut
+            self._trace_add("S_oooo", S)
             if self.nj > 0:
                 X = be.packed_expand(0, U, no, nv)
                 self._mark("ovov", 0)
                 T = be.gemm(X, self.Y)                                           # [(i,a),(jl,b)]
                 self._mark("ovov", 1)
+                self._trace_add("X", X)
+                self._trace_add("T", T)
                 del X
                 njv = self.nj * nv
                 off, rows = self._sl_hi
                 be.packed_fold_virt(S, nv, njv, T, off, alpha=-1.0, rows=rows)
+                self._trace_add("S_hi", S)
                 off, rows = self._sl_lo
                 be.packed_fold_virt(S, nv, njv, T, off, alpha=+1.0, rows=rows)
+                self._trace_add("S_lo", S)
                 del T
         # ---- pphh_ph
         if self.nj > 0:
             c1 = be.gemm(x, self.V1)                                             # [i,(jl,AB)]
             be.packed_fold_occ(S, c1, no, nv, alpha=0.5, j_begin=self.j0, nj=self.nj)
+            self._trace_add("c1", c1)
+            self._trace_add("S_c1", S)
             del c1
         if nij > 0:
             c2 = be.gemm(self.G2[ij0 * nv:ij1 * nv], be.permute(x, (1, 0)))      # [(IJ slab,a),b]
             be.packed_fold_virt(S, nv, nv, c2, self._off_rows[:nij], alpha=-0.5, rows=self._rows_ij)
+            self._trace_add("c2", c2)
+            self._trace_add("S_c2", S)
             del c2
         # ---- all-reduce of the partial sums, overlapped with the vvvv GEMM
         import os
@@ -506,6 +527,9 @@ class PackedAdcEngine:
             dist.all_gather_into_tensor(gathered, slab)
             self._mark("gather", 1)
             gathered = gathered.view(world, npo, wmax)
+            self._trace_add("S_reduced", S)
+            self._trace_add("slab", slab)
+            self._trace_add("gathered", gathered)
         if main is not None:
             main.wait_event(done)
             buf.record_stream(self._comm_stream)

@@ -331,7 +331,10 @@ def run_gpu(args):
                                "random antisymmetrised FP64 ERIs from a counter-based hash",
                    "storage": "antisymmetry-packed doubles + vvvv (50.9 GB instead of 204.8 GB dense)",
                    "l2": "inputs (vvvv 50.9 GB, ovvv 2x10.2 GB) exceed the 126 MB L2 every step",
-                   "seed": SEED, "parallelism": f"virtual-pair slabs x{world}" if world > 1 else "single GPU"},
+                   "seed": SEED, "parallelism": f"virtual-pair slabs x{world}" if world > 1 else "single GPU",
+                   "slab_exchange": ("none" if world == 1 else
+                                     "GEMM epilogue -> peer memory (NVLink stores)" if eng._peer is not None
+                                     else "NCCL all-gather")},
         "executed_tflop_per_step": eng.flops_per_matvec * 1e-12,
         "dense_tflop_per_step": dense_flops(no, nv) * 1e-12,
         "achieved_tflops_executed": eng.flops_per_matvec / (ms_step * 1e-3) * 1e-12,
@@ -352,7 +355,24 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def _reserve_stdout():
+    """The contract is ONE JSON line on stdout, but libraries write there too (NCCL prints its
+    version banner on stdout): route fd 1 to stderr for the whole run and keep the real stdout for
+    the result line."""
+    global print
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    builtin_print = print
+
+    def print(*a, **kw):      # noqa: A001 - module-level print() calls emit the result line
+        kw.setdefault("file", real)
+        kw.setdefault("flush", True)
+        builtin_print(*a, **kw)
+
+
 def main():
+    _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -9,6 +9,22 @@ import adcc_b200 as adcc
 from adcc_b200.packed import PackedDoubles, synthetic_reference_state
 no, nv = int(sys.argv[1]), int(sys.argv[2])
 overlap = os.environ.get("ADCCB_NO_OVERLAP", "0") != "1"
+def poison():
+    """NaN-fill the allocator's free blocks and the GEMM workspace (uninitialised-read hunt)."""
+    if not os.environ.get("ADCCB_POISON"):
+        return
+    from adcc_b200 import backend as be
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    blocks = [torch.full((2 ** 26,), float("nan"), dtype=torch.float64, device="cuda") for _ in range(16)]
+    small = [torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+             for n in (64, 512, 4096, 65536, 2 ** 20) for _ in range(8)]
+    be.workspace().fill_(float("nan"))
+    torch.cuda.synchronize()
+    del blocks, small
+
+
+poison()
 ref = synthetic_reference_state(no, nv, seed=7, scale=5e-4)
 m = adcc.AdcMatrix("adc2x", ref, doubles_storage="packed", shard=(rank, world))
 eng = m._engine
@@ -18,12 +34,22 @@ u2 = torch.randn(eng.npo, eng.npv, generator=g, dtype=torch.float64).cuda()
 v = adcc.AmplitudeVector(ph=adcc.Tensor._wrap(ref.mospaces, ["o1", "v1"], u1),
                          pphh=PackedDoubles._wrap(ref.mospaces, ["o1", "o1", "v1", "v1"], u2))
 outs = []
+traces = []
 for rep in range(3):
+    poison()
+    if os.environ.get("ADCCB_TRACE"):
+        eng._trace = []
     s = m.matvec(v)
+    if os.environ.get("ADCCB_TRACE"):
+        traces.append(eng._trace + [("final_ph", s.ph._data.clone()), ("final_pphh", s.pphh._data.clone())])
     torch.cuda.synchronize()
     outs.append((s.ph._data.clone(), s.pphh._data.clone()))
 same = all(torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1]) for o in outs[1:])
 res = {"rank": rank, "run_to_run_identical": bool(same)}
+if os.environ.get("ADCCB_POISON"):
+    res["nan"] = [[int(torch.isnan(o[0]).sum().item()), int(torch.isnan(o[1]).sum().item())] for o in outs]
+    res["nan_build"] = {k: int(torch.isnan(getattr(eng, k)).sum().item())
+                        for k in ("M1", "V1", "V2", "G1", "G2", "D0", "W", "O", "Y")}
 if rank == 0:
     m1 = adcc.AdcMatrix("adc2x", ref, doubles_storage="packed")
     s1 = m1.matvec(v)
@@ -31,6 +57,31 @@ if rank == 0:
     d2 = (s1.pphh._data - outs[0][1]).abs().max().item() / s1.pphh._data.abs().max().item()
     d1 = (s1.ph._data - outs[0][0]).abs().max().item() / s1.ph._data.abs().max().item()
     res.update(rel_err_ph=d1, rel_err_pphh=d2)
+    if os.environ.get("ADCCB_CHECK_VERBOSE"):
+        res["cuts"] = eng._cuts
+        res["per_rep"] = []
+        for o in outs:
+            bad = (~(o[1] == outs[-1][1])).nonzero()
+            badph = (~(o[0] == outs[-1][0])).nonzero()
+            info = {"n_pphh": int(bad.shape[0]), "n_ph": int(badph.shape[0]),
+                    "vs_single_pphh": (s1.pphh._data - o[1]).abs().max().item(),
+                    "vs_single_ph": (s1.ph._data - o[0]).abs().max().item()}
+            if bad.shape[0]:
+                info["rows"] = [int(bad[:, 0].min()), int(bad[:, 0].max())]
+                info["cols"] = [int(bad[:, 1].min()), int(bad[:, 1].max())]
+            res["per_rep"].append(info)
+if traces:
+    torch.cuda.synchronize()
+    res["trace_diff"] = []
+    for rep in range(1, len(traces)):
+        for (name, t0), (_, t1) in zip(traces[0], traces[rep]):
+            ne = (t0 != t1)
+            n = int(ne.sum().item())
+            if n:
+                idx = ne.reshape(t0.shape).nonzero()
+                res["trace_diff"].append({"rep": rep, "stage": name, "n": n, "shape": list(t0.shape),
+                                          "idx_head": idx[:12].tolist(), "idx_tail": idx[-4:].tolist(),
+                                          "d": float((t0 - t1).abs().max().item())})
 flat = torch.cat((outs[0][0].reshape(-1), outs[0][1].reshape(-1)))
 ref0 = flat.clone()
 dist.broadcast(ref0, 0)
