@@ -314,7 +314,7 @@ def run_gpu(args):
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture
         # profiles/r01_vvvv_gemm.ncu-rep (1 GPU, nocc=40/nvirt=400): 114.43 GB + 0.52 GB per launch;
         # algorithmic: W 50.9 GB once + U 0.5 GB per round of N tiles + sigma RMW 1 GB
-        "traffic": 1.1495e11 if (world == 1 and no == NO and nv == NV) else None,
+        "traffic": 1.2325e11 if (world == 1 and no == NO and nv == NV) else None,
         "second_kernel": {"name": "dgemm_tn_tma_kernel (ovov term)", "flops_per_launch": eng.flops["pphh_pphh/ovov"],
                           "ms_per_launch": t_ovov,
                           "achieved": eng.flops["pphh_pphh/ovov"] / (t_ovov * 1e-3) * 1e-12 if t_ovov else None},
