@@ -139,10 +139,12 @@ class AdcMatrix(AdcMatrixlike):
         adcc_b200/packed.py).  'auto' packs when the dense doubles vector would exceed 1 GiB."""
         if requested not in ("auto", "dense", "packed"):
             raise ValueError("doubles_storage needs to be 'auto', 'dense' or 'packed'")
-        packable = (not self.is_core_valence_separated and self.method.level == 2
-                    and self.block_orders.get("pphh_pphh") in (0, 1))
+        orders = tuple(self.block_orders.get(b) for b in ("ph_ph", "ph_pphh", "pphh_ph", "pphh_pphh"))
+        packable = (not self.is_core_valence_separated
+                    and orders in ((2, 1, 1, 0), (2, 1, 1, 1), (3, 2, 2, 1)))
         if requested == "packed" and not packable:
-            raise NotImplementedError("packed doubles storage is implemented for ADC(2) and ADC(2)-x")
+            raise NotImplementedError("packed doubles storage is implemented for ADC(2), ADC(2)-x "
+                                      "and ADC(3)")
         if requested == "auto":
             no, nv = self.mospaces.n_orbs("o1"), self.mospaces.n_orbs("v1")
             return "packed" if (packable and no * no * nv * nv * 8 >= (1 << 30)) else "dense"

@@ -154,9 +154,13 @@ def torch_like_ones(t):
 class DenseSource:
     """Stages the packed / GEMM-ready operands from a ReferenceState's dense device blocks."""
 
-    def __init__(self, hf, mp):
+    def __init__(self, hf, mp, ooov=None, ovvv=None):
+        """``ooov`` / ``ovvv``: tensors with the same (anti)symmetry used instead of the ERI blocks
+        in the coupling operands (ADC(3): adc3_pia / adc3_pib, adcc/adc_pp/matrix.py:490-532)."""
         self.hf, self.mp = hf, mp
         self.no, self.nv = hf.mospaces.n_orbs("o1"), hf.mospaces.n_orbs("v1")
+        self._ooov = ooov if ooov is not None else hf.ooov
+        self._ovvv = ovvv if ovvv is not None else hf.ovvv
 
     def vvvv_packed(self, row_begin=0, n_rows=None):
         full = be.packed_pack(self.hf.vvvv._contig(), self.nv, self.nv)
@@ -175,19 +179,19 @@ class DenseSource:
         return be.contiguous(full[self._jslice(j_begin, nj)]).reshape(-1, self.no * self.nv)
 
     def ovvv_jabc(self, j_begin=0, nj=None):     # V1[(j,AB),c] = <jc||ab>
-        sel = be.pair_select(self.hf.ovvv._contig(), 2)              # [j,c,AB]
+        sel = be.pair_select(self._ovvv._contig(), 2)              # [j,c,AB]
         return be.permute(sel[self._jslice(j_begin, nj)], (0, 2, 1)).reshape(-1, self.nv)
 
     def ovvv_ajbc(self, j_begin=0, nj=None):     # V2[a,(j,BC)] = <ja||bc>
-        sel = be.pair_select(self.hf.ovvv._contig(), 2)              # [j,a,BC]
+        sel = be.pair_select(self._ovvv._contig(), 2)              # [j,a,BC]
         return be.permute(sel[self._jslice(j_begin, nj)], (1, 0, 2)).reshape(self.nv, -1)
 
     def ooov_ijkb(self):     # G1[i,(JK,b)] = <jk||ib>
-        sel = be.pair_select(self.hf.ooov._contig(), 0)              # [JK,i,b]
+        sel = be.pair_select(self._ooov._contig(), 0)              # [JK,i,b]
         return be.permute(sel, (1, 0, 2)).reshape(self.no, -1)
 
     def ooov_ijak(self):     # G2[(IJ,a),k] = <ij||ka>
-        sel = be.pair_select(self.hf.ooov._contig(), 0)              # [IJ,k,a]
+        sel = be.pair_select(self._ooov._contig(), 0)              # [IJ,k,a]
         return be.permute(sel, (0, 2, 1)).reshape(-1, self.no)
 
     def diag_vv(self):
@@ -196,7 +200,7 @@ class DenseSource:
 
 
 class PackedAdcEngine:
-    """ADC(2) / ADC(2)-x matvec on the packed doubles store (see module docstring)."""
+    """ADC(2) / ADC(2)-x / ADC(3) matvec on the packed doubles store (see module docstring)."""
 
     def __init__(self, matrix, source=None, shard=None):
         from .functions import einsum, direct_sum
@@ -208,23 +212,47 @@ class PackedAdcEngine:
         no, nv = self.no, self.nv
         self.npo, self.npv = be.n_pairs(no), be.n_pairs(nv)
         self.order_dd = matrix.block_orders["pphh_pphh"]
-        if matrix.block_orders["ph_ph"] != 2 or matrix.block_orders["ph_pphh"] != 1:
-            raise NotImplementedError("packed engine: ADC(2) and ADC(2)-x only")
+        orders = (matrix.block_orders["ph_ph"], matrix.block_orders["ph_pphh"],
+                  matrix.block_orders["pphh_ph"], self.order_dd)
+        if orders not in ((2, 1, 1, 0), (2, 1, 1, 1), (3, 2, 2, 1)):
+            raise NotImplementedError("packed engine: ADC(2), ADC(2)-x and ADC(3) block orders only")
+        self.level3 = orders[0] == 3
         foo, fvv = hf.foo.to_ndarray(), hf.fvv.to_ndarray()
         offdiag = max(np.max(np.abs(foo - np.diag(np.diag(foo)))), np.max(np.abs(fvv - np.diag(np.diag(fvv)))))
         if offdiag > 1e-12:
             raise NotImplementedError("packed engine needs canonical orbitals (diagonal Fock)")
         src = source if source is not None else getattr(hf, "packed_source", None)
-        if src is None:
+        if self.level3:
+            # ADC(3): the couplings keep their first-order structure with adc3_pia / adc3_pib in
+            # place of ooov / ovvv (matrix.py:490-532); the second-order singles block is the
+            # ov x ov matrix adc3_m11 (matrix.py:606-618).  The intermediates come from the dense
+            # builders, so the dense ERI blocks must exist.
+            if src is not None or self.world > 1:
+                raise NotImplementedError("packed ADC(3) needs dense ERI blocks for its intermediates "
+                                          "and is not sharded yet")
+            src = DenseSource(hf, mp, ooov=im.adc3_pia, ovvv=im.adc3_pib)
+        elif src is None:
             src = DenseSource(hf, mp)
         self.flops = {}
 
         # ---- singles-singles block folded into one (ov x ov) matrix  (matrix.py:353-375)
-        i1, i2 = im.adc2_i1, im.adc2_i2
-        m1 = einsum("ij,ab->iajb", _delta_like(hf.foo), i1) - einsum("ij,ab->iajb", i2, _delta_like(hf.fvv))
-        m1 = m1 - hf.ovov.transpose((2, 1, 0, 3))               # - <ja||ib>
-        m1 = m1 - 0.5 * im.term_t2_eri.transpose((0, 2, 1, 3))  # - 1/2 term[ikac] -> [i,a,k,c]
-        self.M1 = m1._contig().reshape(no * nv, no * nv)
+        if self.level3:
+            self.M1 = im.adc3_m11._contig().reshape(no * nv, no * nv)
+        else:
+            i1, i2 = im.adc2_i1, im.adc2_i2
+            m1 = einsum("ij,ab->iajb", _delta_like(hf.foo), i1) - einsum("ij,ab->iajb", i2, _delta_like(hf.fvv))
+            m1 = m1 - hf.ovov.transpose((2, 1, 0, 3))               # - <ja||ib>
+            m1 = m1 - 0.5 * im.term_t2_eri.transpose((0, 2, 1, 3))  # - 1/2 term[ikac] -> [i,a,k,c]
+            self.M1 = m1._contig().reshape(no * nv, no * nv)
+        # second-order coupling terms without a first-order counterpart (three-operand terms with
+        # t2): evaluated by the table interpreter on the unpacked doubles
+        self._extra = {"ph_pphh": [], "pphh_ph": []}
+        if self.level3:
+            for blk in self._extra:
+                for c, e in matrix._tables[blk][2]:
+                    if not _mentions(e, ("adc3_pia", "adc3_pib")):
+                        matrix._resolve_constants(e)
+                        self._extra[blk].append((c, e))
 
         # ---- couplings (matrix.py:270-276, 288-294)
         # slabs owned by this rank (world == 1: everything)
@@ -554,21 +582,53 @@ class PackedAdcEngine:
         S = be.empty((self.npo, self.npv))
         self.apply_pphh_pphh(U, S, 0.0)
         self.apply_pphh_ph(u1, S)
+        self._extra_ph_pphh(u2, s1)
+        self._extra_pphh_ph(u1, S)
         return AmplitudeVector(ph=self._wrap_ph(s1), pphh=self._wrap_pphh(S))
+
+    def _extra_ph_pphh(self, u2, s1):
+        """s1 += table terms of ph_pphh that have no packed kernel (ADC(3) only)."""
+        if not self._extra["ph_pphh"]:
+            return
+        ampl = AmplitudeVector(pphh=u2.to_dense())
+        terms = [(c, self.matrix._eval(e, ampl)) for c, e in self._extra["ph_pphh"]]
+        be.lincomb([c for c, _ in terms], [t._contig() for _, t in terms], out=s1, beta=1.0)
+
+    def _extra_pphh_ph(self, u1, S):
+        """S += packed(table terms of pphh_ph without a packed kernel) (ADC(3) only)."""
+        if not self._extra["pphh_ph"]:
+            return
+        ampl = AmplitudeVector(ph=u1)
+        terms = [(c, self.matrix._eval(e, ampl)) for c, e in self._extra["pphh_ph"]]
+        dense = be.lincomb([c for c, _ in terms], [t._contig() for _, t in terms])
+        be.axpby(1.0, be.packed_pack(dense, self.no, self.nv), 1.0, S)
 
     def block_apply(self, block, tensor):
         if block == "ph_ph":
             return self._wrap_ph(self.apply_ph_ph(tensor))
         if block == "ph_pphh":
             t = tensor if isinstance(tensor, PackedDoubles) else PackedDoubles.from_dense(tensor)
-            return self._wrap_ph(self.apply_ph_pphh(t._contig()))
+            s1 = self.apply_ph_pphh(t._contig())
+            self._extra_ph_pphh(t, s1)
+            return self._wrap_ph(s1)
         S = be.zeros((self.npo, self.npv))
         if block == "pphh_ph":
-            return self._wrap_pphh(self.apply_pphh_ph(tensor, S))
+            self.apply_pphh_ph(tensor, S)
+            self._extra_pphh_ph(tensor, S)
+            return self._wrap_pphh(S)
         if block == "pphh_pphh":
             t = tensor if isinstance(tensor, PackedDoubles) else PackedDoubles.from_dense(tensor)
             return self._wrap_pphh(self.apply_pphh_pphh(t._contig(), S, 0.0))
         raise ValueError(block)
+
+
+def _mentions(expr, names):
+    """True if a block-table expression (adc_pp.E / A / S tuples) uses one of the operand names."""
+    if isinstance(expr, str):
+        return expr in names
+    if expr[0] == "einsum":
+        return any(_mentions(op, names) for op in expr[2])
+    return _mentions(expr[1], names)
 
 
 def _delta_like(t):

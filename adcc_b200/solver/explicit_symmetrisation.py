@@ -53,15 +53,28 @@ class IndexSpinSymmetrisation(IndexSymmetrisation):
     def symmetrise(self, new_vectors):
         if isinstance(new_vectors, AmplitudeVector):
             return self.symmetrise([new_vectors])[0]
+        from ..packed import PackedDoubles
         fac = 1.0 if self.enforce_spin_kind == "singlet" else -1.0
+        packed_done = []
         for vec in new_vectors:
             for b in vec.blocks:
                 t = vec[b]
                 n_alpha = [t.mospaces.n_orbs_alpha(s) for s in t.subspaces]
+                if isinstance(t, PackedDoubles):
+                    # packed doubles: project and purify on the unpacked tensor, pack again (index
+                    # antisymmetry is structural in this store, both steps preserve it)
+                    dense = be.spin_project(t.to_dense()._contig(), n_alpha, fac)
+                    if self.enforce_spin_kind == "singlet":
+                        be.spin_singlet_(dense, n_alpha)
+                    new = PackedDoubles.from_dense(Tensor._wrap(t.mospaces, t.subspaces, dense))
+                    new.symmetry = t.symmetry
+                    vec[b] = new
+                    packed_done.append(id(vec))
+                    continue
                 vec[b] = Tensor._wrap(t.mospaces, t.subspaces,
                                       be.spin_project(t._contig(), n_alpha, fac), t.symmetry)
         new_vectors = super().symmetrise(new_vectors)
         for vec in new_vectors:
-            if "pphh" in vec.blocks:
+            if "pphh" in vec.blocks and id(vec) not in packed_done:
                 amplitude_vector_enforce_spin_kind(vec.pphh, "d", self.enforce_spin_kind)
         return new_vectors

@@ -57,6 +57,19 @@ def check_packed_run(method, n=4):
     assert st.n_iter == ost.n_iter
 
 
+def check_packed_spin_kinds(method, n=3):
+    """Restricted singlets / triplets on the packed store: the spin projector and the singlet
+    purification act on the unpacked tensor (solver/explicit_symmetrisation.py)."""
+    import adcc_b200 as adcc
+    data = load_h2o_sto3g()
+    for kw in (dict(n_singlets=n), dict(n_triplets=n)):
+        m = adcc.AdcMatrix(method, adcc.ReferenceState(data), doubles_storage="packed")
+        st = adcc.run_adc(m, conv_tol=1e-8, output=None, **kw)
+        ost = oracle.run_adc(data, method, conv_tol=1e-8, **kw)
+        assert st.converged and st.n_iter == ost.n_iter
+        np.testing.assert_allclose(st.excitation_energy, ost.eigenvalues, atol=ENERGY_ATOL, rtol=0)
+
+
 def check_synthetic(no, nv, seed=5, run=True):
     import adcc_b200 as adcc
     from adcc_b200.packed import synthetic_reference_state

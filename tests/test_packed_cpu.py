@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import cpu_shim
-from packed_parity_common import check_packed_matrix, check_packed_run, check_synthetic
+from packed_parity_common import check_packed_matrix, check_packed_run, check_packed_spin_kinds, check_synthetic
 
 
 @pytest.fixture(autouse=True)
@@ -12,14 +12,19 @@ def shim(monkeypatch):
     cpu_shim.install(monkeypatch)
 
 
-@pytest.mark.parametrize("method", ["adc2", "adc2x"])
+@pytest.mark.parametrize("method", ["adc2", "adc2x", "adc3"])
 def test_packed_matvec_h2o(method):
     check_packed_matrix(method)
 
 
-@pytest.mark.parametrize("method", ["adc2", "adc2x"])
+@pytest.mark.parametrize("method", ["adc2", "adc2x", "adc3"])
 def test_packed_davidson_h2o(method):
     check_packed_run(method)
+
+
+@pytest.mark.parametrize("method", ["adc2", "adc2x", "adc3"])
+def test_packed_singlets_triplets_h2o(method):
+    check_packed_spin_kinds(method)
 
 
 def test_synthetic_workload_small():

@@ -2,7 +2,8 @@
 import numpy as np
 import pytest
 
-from packed_parity_common import check_packed_matrix, check_packed_run, check_synthetic
+from packed_parity_common import (check_packed_matrix, check_packed_run, check_packed_spin_kinds,
+                                  check_synthetic)
 
 pytestmark = pytest.mark.gpu
 
@@ -81,16 +82,22 @@ def test_synth_fill_matches_definition(be):
     assert np.array_equal(part, full[7:17])
 
 
-@pytest.mark.parametrize("method", ["adc2", "adc2x"])
+@pytest.mark.parametrize("method", ["adc2", "adc2x", "adc3"])
 def test_packed_engine_h2o(method):
     check_packed_matrix(method)
     check_packed_run(method)
 
 
-def test_packed_engine_c1_shape():
+@pytest.mark.parametrize("method", ["adc2x", "adc3"])
+def test_packed_singlets_triplets_h2o(method):
+    check_packed_spin_kinds(method)
+
+
+@pytest.mark.parametrize("method", ["adc2x", "adc3"])
+def test_packed_engine_c1_shape(method):
     from adcc_b200.synthetic import named_case
     data, _ = named_case("h2o_ccpvdz")
-    check_packed_matrix("adc2x", data)
+    check_packed_matrix(method, data)
 
 
 @pytest.mark.parametrize("no,nv", [(6, 10), (10, 38), (16, 48)])

@@ -11,6 +11,7 @@ import adcc_b200 as adcc
 from adcc_b200 import _cabi
 from adcc_b200.synthetic import named_case
 
+STORAGE = os.environ.get("ADCCB_STORAGE", "auto")      # auto | dense | packed (ADC(2), ADC(2)-x, ADC(3))
 CASES = [("h2o_ccpvdz", "adc2", dict(n_singlets=3, conv_tol=1e-6)),
          ("h2o_ccpvtz", "adc2", dict(n_singlets=10)),
          ("methyloxirane_ccpvdz", "adc3", dict(n_singlets=8)),
@@ -25,7 +26,8 @@ for name, method, kw in CASES:
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     ref = adcc.ReferenceState(data, core_orbitals=core or None)
-    matrix = adcc.AdcMatrix(method, ref)
+    storage = STORAGE if not method.startswith("cvs") else "auto"
+    matrix = adcc.AdcMatrix(method, ref, doubles_storage=storage)
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t0
     n0 = _cabi.launch_count()
@@ -34,7 +36,7 @@ for name, method, kw in CASES:
     torch.cuda.synchronize()
     t_solve = time.perf_counter() - t0
     mv = state.solver_state.timer.total("projection")
-    r = dict(case=name, method=method, converged=bool(state.converged), n_iter=state.n_iter,
+    r = dict(case=name, method=method, storage=matrix.doubles_storage, converged=bool(state.converged), n_iter=state.n_iter,
              n_applies=state.n_applies, build_s=round(t_build, 3), solve_s=round(t_solve, 3),
              launches=_cabi.launch_count() - n0, mem_gb=round(torch.cuda.max_memory_allocated() / 1e9, 2),
              e0=float(state.excitation_energy[0]))
