@@ -132,6 +132,12 @@ class DataHfProvider(HartreeFockProvider):
             opprov.electric_dipole = np.asarray(mmp["elec_1"])
         self.operator_integral_provider = opprov
         self._spin = np.array([0] * na + [1] * na)
+        self._spatial_dev = None
+        if ("eri_ffff_spatial" in data and "eri_ffff" not in data
+                and not hasattr(type(self), "eri_chem_block_device")):
+            # restricted spatial ERI: blocks are cut and spin-expanded in HBM (ReferenceState
+            # looks for this attribute), the host only uploads the spatial array once
+            self.eri_chem_block_device = self._spatial_block_device
 
     def get_restricted(self): return bool(np.asarray(self.data["restricted"]))
 
@@ -189,6 +195,32 @@ class DataHfProvider(HartreeFockProvider):
             m2 = (self._spin[R][:, None] == self._spin[S][None, :]).astype(float)
             return blk * m1[:, :, None, None] * m2[None, None, :, :]
         raise ValueError("chemists' ERI not available from this data")
+
+    def _spatial_block_device(self, P, Q, R, S):
+        """(pq|rs) for spin-orbital index lists of the form [alpha subset | the same beta subset]:
+        the spatial block is cut out of the device copy of ``eri_ffff_spatial`` and expanded with
+        the spin pattern of adcc/backends/EriBuilder.py:117-119 by one kernel."""
+        from . import backend as be
+        na = self.n_orbs_alpha
+        spatial_idx = []
+        for x in (np.asarray(v, dtype=int) for v in (P, Q, R, S)):
+            a, b = x[x < na], x[x >= na]
+            if len(a) != len(b) or not np.array_equal(a, b - na) or not np.array_equal(x, np.concatenate((a, b))):
+                return be.from_numpy(self.eri_chem_block(P, Q, R, S))       # ragged: host path
+            spatial_idx.append(a)
+        if all(len(a) > 0 and np.array_equal(a, np.arange(a[0], a[0] + len(a))) for a in spatial_idx):
+            if self._spatial_dev is None:
+                self._spatial_dev = be.from_numpy(np.asarray(self.data["eri_ffff_spatial"]))
+            view = self._spatial_dev
+            for ax, a in enumerate(spatial_idx):
+                view = view.narrow(ax, int(a[0]), len(a))
+            block = be.contiguous(view)
+        else:
+            block = be.from_numpy(np.asarray(self.data["eri_ffff_spatial"])[np.ix_(*spatial_idx)])
+        return be.spin_expand4(block)
+
+    def release_device_cache(self):
+        self._spatial_dev = None
 
     def eri_asym_block(self, P, Q, R, S):
         if "eri_phys_asym_ffff" in self.data:

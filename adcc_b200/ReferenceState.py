@@ -141,6 +141,7 @@ class ReferenceState:
                        "o1v1o2o2", "o1o1o2v1", "o2v1v1v1", "o1o2o1v1"]
         for w in wanted:
             self.eri(w)
+        self.flush_hf_cache()
 
     @property
     def cached_eri_blocks(self):
@@ -160,6 +161,8 @@ class ReferenceState:
 
     def flush_hf_cache(self):
         self._hf.flush_cache()
+        if hasattr(self._hf, "release_device_cache"):
+            self._hf.release_device_cache()
 
     def __getattr__(self, attr):
         if attr.startswith("_"):

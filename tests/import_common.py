@@ -55,11 +55,20 @@ def expected_spaces(n_orb, n_occ, core, fc, fv):
     return out
 
 
-def check_imports(case):
+def check_imports(case, spatial=False):
+    """spatial=True hands over the restricted spatial ERI (key eri_ffff_spatial): the blocks are then
+    cut and spin-expanded on the device (DataHfProvider._spatial_block_device)."""
     import adcc_b200 as adcc
     core, fc, fv = CASES[case]
     data, n_orb, n_occ = counter_data()
-    ref = adcc.ReferenceState(data, core_orbitals=core, frozen_core=fc, frozen_virtual=fv)
+    if spatial:
+        given = dict(data)
+        given["eri_ffff_spatial"] = np.ascontiguousarray(data["eri_ffff"][:n_orb, :n_orb, :n_orb, :n_orb])
+        del given["eri_ffff"]
+        ref = adcc.ReferenceState(given, core_orbitals=core, frozen_core=fc, frozen_virtual=fv)
+        assert hasattr(ref._hf, "eri_chem_block_device")
+    else:
+        ref = adcc.ReferenceState(data, core_orbitals=core, frozen_core=fc, frozen_virtual=fv)
     spaces = expected_spaces(n_orb, n_occ, core, fc, fv)
     ms = ref.mospaces
     assert sorted(ms.subspaces) == sorted(spaces)

@@ -78,6 +78,12 @@ def test_import_blocks_device(case):
     check_imports(case)
 
 
+@pytest.mark.parametrize("case", ["gen", "fc-fv-cvs", "fv-cvs"])
+def test_import_blocks_from_spatial_eri_device(case):
+    from import_common import check_imports
+    check_imports(case, spatial=True)
+
+
 def test_shifted_and_projected_matrix_device(h2o):
     from adc_parity_common import check_shifted_projected
     check_shifted_projected(h2o)

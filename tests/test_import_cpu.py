@@ -15,6 +15,11 @@ def test_import_blocks(case):
     check_imports(case)
 
 
+@pytest.mark.parametrize("case", ["gen", "fc-fv-cvs", "fv-cvs"])
+def test_import_blocks_from_spatial_eri(case):
+    check_imports(case, spatial=True)
+
+
 def test_invalid_spaces():
     import adcc_b200 as adcc
     from import_common import counter_data
