@@ -248,7 +248,7 @@ class Tensor:
         if type(self) is not type(other):
             raise ValueError("Cannot combine tensors with different storage "
                              f"({type(self).__name__} vs {type(other).__name__})")
-        if self.shape != other.shape:
+        if self._data.shape != other._data.shape:
             raise ValueError(f"Shape mismatch: {self.shape} vs {other.shape}")
         if self.subspaces != other.subspaces:
             raise ValueError(f"Subspace mismatch: {self.space} vs {other.space}")
