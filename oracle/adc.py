@@ -27,8 +27,13 @@ def _dsum4(a, b, c, d):
 
 
 class OracleAdcMatrix:
-    def __init__(self, method, refstate_or_mp):
+    def __init__(self, method, refstate_or_mp, unique_pairs=False):
+        """unique_pairs: evaluate the oooo / vvvv terms of the first-order pphh_pphh block over the
+        canonical index pairs only (i<j, a<b, c<d), the way libtensor works on the symmetry-unique
+        blocks of an antisymmetric tensor (libadcc_src/TensorImpl/as_lt_symmetry.cc:37-55);
+        same result, 8x fewer flops in the dominant term.  Used for the CPU timing baseline."""
         mp = refstate_or_mp if isinstance(refstate_or_mp, OracleMp) else OracleMp(refstate_or_mp)
+        self.unique_pairs = unique_pairs
         self.mp = mp
         self.hf = mp.hf
         self.method = method
@@ -288,11 +293,36 @@ class OracleAdcMatrix:
                              - es("JK,iKab->iJab", hf.fcc, u))}
         return apply, self._diag_pphh_0()
 
+    def _pair_terms(self, u):
+        """1/2 <ij||kl> u[klab] + 1/2 u[ijcd] <ab||cd> as two GEMMs over canonical pairs."""
+        hf = self.hf
+        no, nv = u.shape[0], u.shape[2]
+        if not hasattr(self, "_pairs"):
+            i, j = np.triu_indices(no, 1)
+            a, b = np.triu_indices(nv, 1)
+            W = np.ascontiguousarray(hf.vvvv[a[:, None], b[:, None], a[None, :], b[None, :]])
+            O = np.ascontiguousarray(hf.oooo[i[:, None], j[:, None], i[None, :], j[None, :]])
+            self._pairs = (i, j, a, b, W, O)
+        i, j, a, b, W, O = self._pairs
+        U = u[i[:, None], j[:, None], a[None, :], b[None, :]]          # [IJ, AB]
+        S = U @ W.T + O @ U
+        out = np.zeros_like(u)
+        out[i[:, None], j[:, None], a[None, :], b[None, :]] = S
+        out[j[:, None], i[:, None], a[None, :], b[None, :]] = -S
+        out[i[:, None], j[:, None], b[None, :], a[None, :]] = -S
+        out[j[:, None], i[:, None], b[None, :], a[None, :]] = S
+        return out
+
     def _block_pphh_pphh_1(self):
         hf = self.hf
 
         def apply(v):
             u = v["pphh"]
+            if self.unique_pairs:
+                return {"pphh": (2 * asym(es("ijac,bc->ijab", u, hf.fvv), 2, 3)
+                                 - 2 * asym(es("ik,kjab->ijab", hf.foo, u), 0, 1)
+                                 + asym(asym(-4 * es("ikac,kbjc->ijab", u, hf.ovov), 0, 1), 2, 3)
+                                 + self._pair_terms(u))}
             return {"pphh": (2 * asym(es("ijac,bc->ijab", u, hf.fvv), 2, 3)
                              - 2 * asym(es("ik,kjab->ijab", hf.foo, u), 0, 1)
                              + asym(asym(-4 * es("ikac,kbjc->ijab", u, hf.ovov), 0, 1), 2, 3)
@@ -415,3 +445,29 @@ class OracleAdcMatrix:
                                              - es("Ic,jcab->jIab", u, pib)
                                              - es("lKIc,Kc,jlab->jIab", occv, u, mp.t2oo))}
         return apply, None
+
+
+def dominant_terms_sample(no, nv, ab_slab, jb_slab, reps=2):
+    """Bounded sample of the two dominant contractions of the first-order pphh_pphh block AT FULL
+    operand extents, for the CPU timing baseline (test infrastructure, never the product path):
+    a column slab of  S[IJ,AB] += sum_CD U[IJ,CD] W[AB,CD]  (vvvv term over canonical pairs, as in
+    ``_pair_terms``) and of  T[(i,a),(j,b)] = sum_kc X[(i,a),(k,c)] Y[(j,b),(k,c)]  (ovov term,
+    ``ikac,kbjc->ijab`` of _block_pphh_pphh_1).  Operand values do not matter for a DGEMM timing.
+    Returns (flops, seconds) of the best of ``reps`` repetitions."""
+    import time
+    npo, npv = no * (no - 1) // 2, nv * (nv - 1) // 2
+    ab_slab, jb_slab = min(ab_slab, npv), min(jb_slab, no * nv)
+    U = np.full((npo, npv), 0.5)
+    W = np.full((ab_slab, npv), 0.25)
+    X = np.full((no * nv, no * nv), 0.5)
+    Y = np.full((jb_slab, no * nv), 0.25)
+    flops = 2.0 * npo * ab_slab * npv + 2.0 * (no * nv) * jb_slab * (no * nv)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        S = U @ W.T
+        T = X @ Y.T
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    assert S.shape == (npo, ab_slab) and T.shape == (no * nv, jb_slab)
+    return flops, best

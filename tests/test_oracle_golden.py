@@ -105,3 +105,23 @@ def test_oracle_symmetrisers_against_reference_goldens():
     np.testing.assert_allclose(asym(a, 0, 1), GOLD["a_asym_01"], atol=1e-15)
     np.testing.assert_allclose(sym_pairs(a, (0, 1), (2, 3)), GOLD["a_sym_01_23"], atol=1e-15)
     np.testing.assert_allclose(0.5 * (a - a.transpose(1, 0, 3, 2)), GOLD["a_asym_01_23"], atol=1e-15)
+
+
+def test_oracle_unique_pairs_mode_is_the_same_matrix():
+    """The CPU timing baseline evaluates the oooo / vvvv terms over canonical index pairs (like
+    libtensor's symmetry-unique blocks): identical sigma, and the slab sampler returns sane numbers."""
+    import numpy as np
+    import oracle
+    from oracle.adc import dominant_terms_sample
+    from oracle.synthetic import OracleSyntheticRef
+    ref = OracleSyntheticRef(6, 10, seed=3, scale=0.02)
+    dense = oracle.OracleAdcMatrix("adc2x", ref)
+    pairs = oracle.OracleAdcMatrix("adc2x", ref, unique_pairs=True)
+    rng = np.random.default_rng(1)
+    v = {k: rng.standard_normal(s) for k, s in dense.shapes.items()}
+    v["pphh"] = dense.symmetrise_doubles(v["pphh"])
+    sd, sp = dense.matvec(v), pairs.matvec(v)
+    for k in sd:
+        assert np.max(np.abs(sd[k] - sp[k])) < 1e-13 * np.max(np.abs(sd[k]))
+    flops, seconds = dominant_terms_sample(6, 10, 16, 16)
+    assert flops == 2.0 * 15 * 16 * 45 + 2.0 * 60 * 16 * 60 and seconds > 0
