@@ -362,6 +362,16 @@ class AdcMatrix(AdcMatrixlike):
     def rmatvec(self, v):
         return self.matvec(v)
 
+    def matvec_host(self, u_host, sigma_host):
+        """sigma = M u between PINNED host buffers (dicts {"ph": [no, nv], "pphh": packed
+        [npo, npv]} of torch CPU tensors): the end-to-end form of ``matvec`` for callers whose
+        vectors live on the host.  On the packed single-GPU engine the PCIe transfers are
+        pipelined with the vvvv GEMM (PackedAdcEngine.matvec_host)."""
+        if self._engine is None:
+            raise NotImplementedError("matvec_host is implemented for the packed doubles store")
+        with self.timer.record("matvec_host"):
+            self._engine.matvec_host(u_host["ph"], u_host["pphh"], sigma_host["ph"], sigma_host["pphh"])
+
     # ------------------------------------------------------------------ batched matvec (8(f2))
     def _eval_batched(self, expr, ampl):
         """Like _eval for trial vectors that carry a leading batch axis 'Z' (several vectors stacked):

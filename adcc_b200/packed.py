@@ -603,6 +603,85 @@ class PackedAdcEngine:
         dense = be.lincomb([c for c, _ in terms], [t._contig() for _, t in terms])
         be.axpby(1.0, be.packed_pack(dense, self.no, self.nv), 1.0, S)
 
+    def matvec_host(self, u1_host, U_host, s1_host, S_host, edge_rows=112):
+        """sigma = M u for a trial vector in PINNED host buffers, result into pinned host buffers
+        (ph: [no, nv]; pphh: packed [npo, npv]).  Same kernels as ``matvec``; the vvvv GEMM is cut
+        into three row slabs so that most of the PCIe traffic hides behind it: the first slab starts
+        as soon as its ``edge_rows`` rows of U have arrived (the rest of U is uploaded meanwhile), the
+        last slab runs while all finished rows of sigma are already downloading.  Exposed transfer:
+        2 x edge_rows/npo of the vector instead of all of it.  Returns after the downloads are done."""
+        import torch
+        if self.world > 1 or self.order_dd != 1 or self.npo < 4 * edge_rows:
+            v = AmplitudeVector(ph=self._wrap_ph(u1_host.to("cuda", non_blocking=True)),
+                                pphh=self._wrap_pphh(U_host.to("cuda", non_blocking=True)))
+            s = self.matvec(v)
+            s1_host.copy_(s.ph._data, non_blocking=True)
+            S_host.copy_(s.pphh._data, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return
+        no, nv, npo, npv = self.no, self.nv, self.npo, self.npv
+        r1, r2 = edge_rows, npo - edge_rows
+        main = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+        cs = self._copy_stream
+        x = be.empty((no, nv))
+        U = be.empty((npo, npv))
+        S = be.empty((npo, npv))
+        start = torch.cuda.Event()
+        start.record(main)
+        cs.wait_event(start)                      # the fresh buffers may recycle memory still in use on main
+        with torch.cuda.stream(cs):
+            x.copy_(u1_host, non_blocking=True)
+            U[:r1].copy_(U_host[:r1], non_blocking=True)
+            got_first = torch.cuda.Event()
+            got_first.record(cs)
+            U[r1:].copy_(U_host[r1:], non_blocking=True)
+            got_all = torch.cuda.Event()
+            got_all.record(cs)
+        # rows [0, r1): diagonal part + vvvv term while the rest of U is still on its way
+        main.wait_event(got_first)
+        be.mul(U[:r1], self.D0[:r1], out=S[:r1])
+        self._mark("vvvv", 0)
+        be.gemm(U[:r1], self.W, out=S[:r1], alpha=1.0, beta=1.0)
+        main.wait_event(got_all)
+        be.mul(U[r1:], self.D0[r1:], out=S[r1:])
+        be.gemm(U[r1:r2], self.W, out=S[r1:r2], alpha=1.0, beta=1.0)
+        self._mark("vvvv", 1)
+        # every other term, all rows
+        Ut = be.permute(U, (1, 0))
+        be.gemm(self.O, Ut, out=S, alpha=1.0, beta=1.0)
+        del Ut
+        X = be.packed_expand(0, U, no, nv)
+        self._mark("ovov", 0)
+        T = be.gemm(X, self.Y)
+        self._mark("ovov", 1)
+        del X
+        be.packed_fold_virt(S, nv, no * nv, T, self._off_ovov_1, T, self._off_ovov_2, alpha=-1.0)
+        del T
+        u1 = self._wrap_ph(x)
+        self.apply_pphh_ph(u1, S)
+        self._extra_pphh_ph(u1, S)
+        s1 = self.apply_ph_ph(u1)
+        be.axpby(1.0, self.apply_ph_pphh(U), 1.0, s1)
+        self._extra_ph_pphh(self._wrap_pphh(U), s1)
+        head_done = torch.cuda.Event()
+        head_done.record(main)
+        # rows [r2, npo): vvvv term last, while rows [0, r2) and the ph part are downloading
+        be.gemm(U[r2:], self.W, out=S[r2:], alpha=1.0, beta=1.0)
+        tail_done = torch.cuda.Event()
+        tail_done.record(main)
+        with torch.cuda.stream(cs):
+            cs.wait_event(head_done)
+            s1_host.copy_(s1, non_blocking=True)
+            S_host[:r2].copy_(S[:r2], non_blocking=True)
+            cs.wait_event(tail_done)
+            S_host[r2:].copy_(S[r2:], non_blocking=True)
+            finished = torch.cuda.Event()
+            finished.record(cs)
+        main.wait_event(finished)
+        finished.synchronize()
+
     def block_apply(self, block, tensor):
         if block == "ph_ph":
             return self._wrap_ph(self.apply_ph_ph(tensor))

@@ -35,6 +35,26 @@ def test_sampled_sigma_medium_size():
     assert res["sampled_rel_err_pphh"] < 1e-11 and res["sampled_rel_err_ph"] < 1e-11
 
 
+@pytest.mark.parametrize("no,nv,edge", [(34, 60, 112), (34, 60, 96), (12, 40, 112)])
+def test_matvec_between_host_buffers(no, nv, edge):
+    """AdcMatrix.matvec_host (PCIe transfers pipelined with three row slabs of the vvvv GEMM; small
+    systems take the plain path) fills the pinned result buffers with the same sigma as matvec."""
+    import torch
+    m, vec = _setup(no, nv, 0.02)
+    v = vec()
+    sig = m.matvec(v)
+    u = {"ph": v.ph._data.cpu().pin_memory(), "pphh": v.pphh._data.cpu().pin_memory()}
+    out = {"ph": torch.full_like(u["ph"], float("nan")).pin_memory(),
+           "pphh": torch.full_like(u["pphh"], float("nan")).pin_memory()}
+    for _ in range(3):                       # repeated: buffers are recycled across streams
+        out["pphh"].fill_(float("nan"))
+        m._engine.matvec_host(u["ph"], u["pphh"], out["ph"], out["pphh"], edge_rows=edge)
+        for k, ref in (("ph", sig.ph._data), ("pphh", sig.pphh._data)):
+            ref = ref.cpu()
+            assert float((out[k] - ref).abs().max() / ref.abs().max()) < 1e-13
+    m.matvec_host(u, out)
+
+
 def test_headline_size_invariants_and_samples():
     import torch
     if torch.cuda.get_device_properties(0).total_memory < 120e9:
