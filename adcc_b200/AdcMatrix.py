@@ -365,10 +365,13 @@ class AdcMatrix(AdcMatrixlike):
     def matvec_host(self, u_host, sigma_host):
         """sigma = M u between PINNED host buffers (dicts {"ph": [no, nv], "pphh": packed
         [npo, npv]} of torch CPU tensors): the end-to-end form of ``matvec`` for callers whose
-        vectors live on the host.  On the packed single-GPU engine the PCIe transfers are
-        pipelined with the vvvv GEMM (PackedAdcEngine.matvec_host)."""
+        vectors live on the host.  The PCIe transfers are pipelined with row slabs of the vvvv GEMM
+        (PackedAdcEngine.matvec_host).  Sharded matrices: rank 0 passes the buffers, the other
+        ranks pass None; all ranks must call."""
         if self._engine is None:
             raise NotImplementedError("matvec_host is implemented for the packed doubles store")
+        u_host = u_host or {"ph": None, "pphh": None}              # sharded: only rank 0 holds buffers
+        sigma_host = sigma_host or {"ph": None, "pphh": None}
         with self.timer.record("matvec_host"):
             self._engine.matvec_host(u_host["ph"], u_host["pphh"], sigma_host["ph"], sigma_host["pphh"])
 

@@ -201,8 +201,9 @@ class PeerBuffer:
 
 
 def gemm_peers(A, B, local_out, peer_ptrs, col_offset, ldc, tile_hint=0):
-    """local_out[:, :] = A B^T, also written to address peer_ptrs[d] + col_offset (same leading
-    dimension) for every d: the column-slab GEMM whose epilogue does the slab exchange."""
+    """local_out[:, :] = A B^T, also written to address peer_ptrs[d] + col_offset elements (same
+    leading dimension) for every d: the column-slab GEMM whose epilogue does the slab exchange
+    (col_offset = first_row * ldc + first_column of the slab inside the peers' buffers)."""
     _check_dev(A, B, local_out)
     M, K = A.shape
     N, K2 = B.shape

@@ -13,6 +13,8 @@ blocks of adcc/adc_pp/matrix.py:127-133 (pphh_pphh_0), :234-246 (pphh_pphh_1), :
 (ph_pphh_1), :288-294 (pphh_ph_1) and :353-375 (ph_ph_2) on that store.  Requires canonical
 orbitals (diagonal Fock), which every SCF reference adcc accepts provides.
 """
+import os
+
 import numpy as np
 
 from . import backend as be
@@ -414,8 +416,14 @@ class PackedAdcEngine:
     def _wrap_pphh(self, data):
         return PackedDoubles._wrap(self.mospaces, ["o1", "o1", "v1", "v1"], data)
 
-    def _matvec_sharded(self, u1, U):
+    def _matvec_sharded(self, u1, U, host_out=None, pipelined=False, arrive=None):
         """Per-rank partial sigma from this rank's operand slabs.
+
+        ``pipelined`` (all ranks alike; end-to-end calls): the vvvv term is produced in three row
+        slabs [0, r1), [r1, r2), [r2, npo).  The first one starts as soon as its rows of U are on
+        every rank (``arrive(0, r1)`` uploads / broadcasts them; ``arrive(r1, npo)`` follows while
+        it computes), the last one runs while the rank holding ``host_out`` (pinned ph / pphh
+        result buffers) already downloads all other rows.
 
         Everything except the vvvv term is accumulated into one packed (pphh + ph) buffer that is
         all-reduced (optionally on a side stream while the vvvv GEMM runs, see below); the vvvv
@@ -426,6 +434,32 @@ class PackedAdcEngine:
         no, nv, npo, npv = self.no, self.nv, self.npo, self.npv
         world = self.world
         self._mark("step", 0)
+        pipe = None
+        if pipelined and self.order_dd == 1 and self._peer is not None \
+                and os.environ.get("ADCCB_OVERLAP", "0") != "1":
+            # row slabs of the vvvv term: sizes from the time model (GEMM at 36 TFLOP/s, PCIe at
+            # 50 GB/s): the last slab must cover the download of everything before it
+            # (identical on every rank: the widest column slab decides)
+            t_gemm = 2.0 * npo * max(self._wmax, 1) * npv / 36e12
+            t_copy = npo * npv * 8 / 50e9
+            tile = 112
+            last = int(np.ceil(npo * t_copy / (t_gemm + t_copy) / tile)) * tile
+            if npo >= 4 * tile and tile + last < npo:
+                peer = self._peer[self._peer_flip]
+                self._peer_flip ^= 1
+                pipe = {"cuts": [0, tile, npo - last, npo], "peer": peer,
+                        "R": peer.local.view(npo, npv),
+                        "others": [p for r, p in enumerate(peer.peer_ptrs) if r != self.rank]}
+        self._last_pipelined = pipe is not None
+        if arrive is not None:
+            arrive(0, pipe["cuts"][1] if pipe else npo)
+        if pipe is not None:
+            a, b = pipe["cuts"][0], pipe["cuts"][1]
+            if self.ab1 > self.ab0:
+                be.gemm_peers(U[a:b], self.W, pipe["R"][a:b, self.ab0:self.ab1], pipe["others"],
+                              col_offset=a * npv + self.ab0, ldc=npv)
+            if arrive is not None:
+                arrive(b, npo)
         buf = be.zeros((npo * npv + no * nv,))
         S = buf[:npo * npv].view(npo, npv)
         s1 = buf[npo * npv:].view(1, no * nv)
@@ -513,6 +547,8 @@ class PackedAdcEngine:
                 done.record(self._comm_stream)
         elif self._peer is None or self.order_dd != 1:
             dist.all_reduce(buf)
+        if pipe is not None:
+            return self._vvvv_exchange_pipelined(U, buf, S, s1, pipe, host_out)
         if self.order_dd == 1 and self._peer is not None:
             # vvvv term: this rank's column slab, written by the GEMM epilogue into the exchange
             # buffer of EVERY rank (own memory + NVLink stores to the peers).  The all-reduce of the
@@ -569,6 +605,110 @@ class PackedAdcEngine:
         self._mark("step", 1)
         return AmplitudeVector(ph=self._wrap_ph(s1.view(no, nv)), pphh=self._wrap_pphh(S))
 
+    def _vvvv_exchange_pipelined(self, U, buf, S, s1, pipe, host_out):
+        """Tail of the pipelined sharded matvec.  The first vvvv row slab was computed before the
+        other terms (peer-destination epilogue); here: all-reduce of the other terms (which is also
+        the ordering point of that first slab), middle slab, ordering point, ``S += R`` for both,
+        download of those rows on the copy stream while the last slab computes, last slab, ordering
+        point, ``S += R``, download of the last rows."""
+        import torch
+        import torch.distributed as dist
+        no, nv, npo, npv = self.no, self.nv, self.npo, self.npv
+        c0, c1, c2, c3 = pipe["cuts"]
+        R, others = pipe["R"], pipe["others"]
+        w = self.ab1 - self.ab0
+        if getattr(self, "_token", None) is None:
+            self._token = be.zeros((1,))
+        main = torch.cuda.current_stream()
+        dist.all_reduce(buf)                                  # every term but vvvv; orders slab [c0, c1)
+        events = []
+        for a, b, lo in ((c1, c2, c0), (c2, c3, c2)):
+            if w > 0:
+                be.gemm_peers(U[a:b], self.W, R[a:b, self.ab0:self.ab1], others,
+                              col_offset=a * npv + self.ab0, ldc=npv)
+            dist.all_reduce(self._token)                      # ordering point of this row slab
+            be.axpby(1.0, R[lo:b], 1.0, S[lo:b])
+            ev = torch.cuda.Event()
+            ev.record(main)
+            events.append((ev, lo, b))
+        if host_out is not None:
+            s1_host, S_host = host_out
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream()
+            cs = self._copy_stream
+            with torch.cuda.stream(cs):
+                for k, (ev, lo, b) in enumerate(events):
+                    cs.wait_event(ev)
+                    if k == 0:
+                        s1_host.copy_(s1.view(no, nv), non_blocking=True)
+                    S_host[lo:b].copy_(S[lo:b], non_blocking=True)
+                finished = torch.cuda.Event()
+                finished.record(cs)
+            main.wait_event(finished)
+            finished.synchronize()
+        self._mark("step", 1)
+        return AmplitudeVector(ph=self._wrap_ph(s1.view(no, nv)), pphh=self._wrap_pphh(S))
+
+    def _matvec_host_sharded(self, u1_host, U_host, s1_host, S_host):
+        """Rank 0 holds the pinned host buffers (the other ranks pass None): the trial vector is
+        uploaded and broadcast (NCCL) in two row chunks, the second one crossing PCIe while the
+        first vvvv slab computes; sigma is downloaded on rank 0 while the last slab computes."""
+        import torch
+        import torch.distributed as dist
+        x = be.empty((self.no, self.nv))
+        U = be.empty((self.npo, self.npv))
+        streams = U.is_cuda
+        if not streams:                       # host-logic runs (gloo): no streams to pipeline
+            if self.rank == 0:
+                x.copy_(u1_host)
+                U.copy_(U_host)
+            dist.broadcast(x, 0)
+            dist.broadcast(U, 0)
+            sig = self._matvec_sharded(self._wrap_ph(x), U)
+            if self.rank == 0:
+                s1_host.copy_(sig.ph._data)
+                S_host.copy_(sig.pphh._data)
+            return sig
+        main = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+        cs = self._copy_stream
+        uploaded = {}
+        if self.rank == 0:
+            start = torch.cuda.Event()
+            start.record(main)
+            cs.wait_event(start)              # fresh buffers may recycle memory still in use on main
+
+        def queue_upload(a, b):
+            with torch.cuda.stream(cs):
+                if a == 0:
+                    x.copy_(u1_host, non_blocking=True)
+                U[a:b].copy_(U_host[a:b], non_blocking=True)
+                uploaded[(a, b)] = torch.cuda.Event()
+                uploaded[(a, b)].record(cs)
+
+        def arrive(a, b):
+            """Rows [a, b) of U on every rank.  Rank 0 queues ALL uploads at the first call, so the
+            second chunk crosses PCIe while the first vvvv slab computes; the broadcasts stay on
+            the main stream in program order."""
+            if self.rank == 0:
+                if not uploaded:
+                    queue_upload(a, b)
+                    if b < self.npo:
+                        queue_upload(b, self.npo)
+                main.wait_event(uploaded[(a, b)])
+            if a == 0:
+                dist.broadcast(x, 0)
+            dist.broadcast(U[a:b], 0)
+
+        host_out = (s1_host, S_host) if self.rank == 0 else None
+        sig = self._matvec_sharded(self._wrap_ph(x), U, host_out=host_out, pipelined=True, arrive=arrive)
+        if self.rank == 0 and not self._last_pipelined:
+            s1_host.copy_(sig.ph._data, non_blocking=True)     # plain exchange: download at the end
+            S_host.copy_(sig.pphh._data, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return sig
+
     def matvec(self, v):
         u1, u2 = v["ph"], v["pphh"]
         if not isinstance(u2, PackedDoubles):
@@ -611,7 +751,10 @@ class PackedAdcEngine:
         last slab runs while all finished rows of sigma are already downloading.  Exposed transfer:
         2 x edge_rows/npo of the vector instead of all of it.  Returns after the downloads are done."""
         import torch
-        if self.world > 1 or self.order_dd != 1 or self.npo < 4 * edge_rows:
+        if self.world > 1:
+            self._matvec_host_sharded(u1_host, U_host, s1_host, S_host)
+            return
+        if self.order_dd != 1 or self.npo < 4 * edge_rows:
             v = AmplitudeVector(ph=self._wrap_ph(u1_host.to("cuda", non_blocking=True)),
                                 pphh=self._wrap_pphh(U_host.to("cuda", non_blocking=True)))
             s = self.matvec(v)

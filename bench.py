@@ -274,15 +274,11 @@ def run_gpu(args):
     ms_step = ms_total / args.steps
 
     # ---- end to end: host buffers in, host buffers out -------------------------------------------
-    if world == 1:
-        u_host = {"ph": u1_host, "pphh": u2_host}
-        s_host = {"ph": sig1_host, "pphh": sig2_host}
+    u_host = {"ph": u1_host, "pphh": u2_host} if rank == 0 else None
+    s_host = {"ph": sig1_host, "pphh": sig2_host} if rank == 0 else None
 
-        def e2e_step():                       # public API: AdcMatrix.matvec_host (pipelined PCIe)
-            matrix.matvec_host(u_host, s_host)
-    else:
-        def e2e_step():
-            to_host(matrix.matvec(to_vec(u1_host, u2_host)))
+    def e2e_step():                           # public API: AdcMatrix.matvec_host (pipelined PCIe);
+        matrix.matvec_host(u_host, s_host)    # N > 1: rank 0 owns the host buffers
     e2e_step()
     barrier()
     e0.record()

@@ -41,6 +41,12 @@ def _worker(rank, world, port, no, nv, out):
     gathered = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
     same = all(torch.equal(gathered[0], g) for g in gathered)
+    # end-to-end form: rank 0 owns the host buffers, every rank calls (plain exchange on CPU)
+    host_in = {"ph": vp.ph._data.clone(), "pphh": vp.pphh._data.clone()} if rank == 0 else None
+    host_out = {"ph": torch.zeros_like(vp.ph._data), "pphh": torch.zeros_like(vp.pphh._data)} if rank == 0 else None
+    m.matvec_host(host_in, host_out)
+    if rank == 0:
+        same = same and torch.equal(host_out["ph"], sig.ph._data) and torch.equal(host_out["pphh"], sig.pphh._data)
     # Davidson on the sharded matrix (replicated vectors)
     st = adcc.run_adc(m, n_states=2, conv_tol=1e-7, output=None)
     if rank == 0:

@@ -28,3 +28,4 @@ def test_sharded_matches_single_gpu():
         assert r["run_to_run_identical"] and r["identical_to_rank0"]
         if r["rank"] == 0:
             assert r["rel_err_ph"] < 1e-11 and r["rel_err_pphh"] < 1e-11
+            assert r["host_path_rel_diff"] < 1e-13

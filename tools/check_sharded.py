@@ -46,6 +46,18 @@ for rep in range(3):
     outs.append((s.ph._data.clone(), s.pphh._data.clone()))
 same = all(torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1]) for o in outs[1:])
 res = {"rank": rank, "run_to_run_identical": bool(same)}
+# end-to-end form: rank 0 owns pinned host buffers, all ranks call (pipelined exchange + download)
+h_in = {"ph": u1.cpu().pin_memory(), "pphh": u2.cpu().pin_memory()} if rank == 0 else None
+h_out = {"ph": torch.full((no, nv), float("nan"), dtype=torch.float64).pin_memory(),
+         "pphh": torch.full((eng.npo, eng.npv), float("nan"), dtype=torch.float64).pin_memory()} if rank == 0 else None
+for rep in range(3):
+    m.matvec_host(h_in, h_out)
+    torch.cuda.synchronize()
+    if rank == 0:
+        d = max(((h_out["ph"] - outs[0][0].cpu()).abs().max() / outs[0][0].abs().max()).item(),
+                ((h_out["pphh"] - outs[0][1].cpu()).abs().max() / outs[0][1].abs().max()).item())
+        res["host_path_rel_diff"] = max(res.get("host_path_rel_diff", 0.0), d)
+        h_out["pphh"].fill_(float("nan"))
 if os.environ.get("ADCCB_POISON"):
     res["nan"] = [[int(torch.isnan(o[0]).sum().item()), int(torch.isnan(o[1]).sum().item())] for o in outs]
     res["nan_build"] = {k: int(torch.isnan(getattr(eng, k)).sum().item())
