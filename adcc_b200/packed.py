@@ -299,7 +299,6 @@ class PackedAdcEngine:
         self._reduce_group = None
         self._peer = None
         if self.world > 1:
-            import os
             import torch.distributed as dist
             self._reduce_group = dist.new_group(ranks=list(range(self.world)))
             # slab exchange of the vvvv term through peer memory, written by the GEMM epilogue
@@ -526,7 +525,6 @@ class PackedAdcEngine:
             self._trace_add("S_c2", S)
             del c2
         # ---- all-reduce of the partial sums, overlapped with the vvvv GEMM
-        import os
         # Overlapping the all-reduce with the vvvv GEMM is OFF by default: the GEMM is persistent
         # (one CTA per SM, static stream-K spans), so SMs taken by the NCCL kernel delay some of its
         # CTAs by a whole span (measured at 4 GPUs: GEMM 68 -> 96 ms).  ADCCB_OVERLAP=1 enables it.
