@@ -274,3 +274,23 @@ def check_graph_replay(data, method, core, monkeypatch):
     first = replayed[2]["ph"].to_ndarray().copy()
     matrix.matvec(vecs[1][0])
     assert np.array_equal(replayed[2]["ph"].to_ndarray(), first)
+
+
+def check_frozen_spaces(data, method, core, frozen_core, frozen_virtual, n=2):
+    """Frozen-core / frozen-virtual subspaces (the reference's fc, fv, fc-fv, *-cvs cases,
+    adcc/tests/testcases.py:199-301): sigma and converged singlets against the oracle."""
+    import adcc_b200 as adcc
+    ref = adcc.ReferenceState(data, core_orbitals=core, frozen_core=frozen_core, frozen_virtual=frozen_virtual)
+    matrix = adcc.AdcMatrix(method, ref)
+    oref = oracle.OracleRefState(oracle.OracleHf(data), core_orbitals=core, frozen_core=frozen_core,
+                                 frozen_virtual=frozen_virtual)
+    omatrix = oracle.OracleAdcMatrix(method, oref)
+    assert matrix.shape == omatrix.shape
+    v, ov = random_vector(matrix, omatrix, 11)
+    sig, osig = matrix.matvec(v), omatrix.matvec(ov)
+    for k in osig:
+        assert rel_err(sig[k].to_ndarray(), osig[k]) < SIGMA_RTOL, f"sigma {k}"
+    state = adcc.run_adc(matrix, n_singlets=n, conv_tol=1e-8, output=None)
+    ostate = oracle.run_adc(omatrix, method, n_singlets=n, conv_tol=1e-8)
+    assert state.converged and ostate.converged and state.n_iter == ostate.n_iter
+    np.testing.assert_allclose(state.excitation_energy, ostate.eigenvalues, atol=ENERGY_ATOL, rtol=0)

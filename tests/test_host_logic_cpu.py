@@ -226,3 +226,11 @@ def test_graph_replay_host_logic(h2o, method, monkeypatch):
     from adc_parity_common import check_graph_replay
     monkeypatch.setenv("ADCCB_SHIM_GRAPHS", "1")
     check_graph_replay(h2o, method, 1 if method.startswith("cvs") else None, monkeypatch)
+
+
+@pytest.mark.parametrize("method,core,fc,fv", [("adc2", None, 1, None), ("adc2x", None, None, 1),
+                                               ("adc3", None, 1, 1), ("cvs-adc2x", 1, 1, None),
+                                               ("cvs-adc2", 1, None, 1), ("cvs-adc3", 1, 1, 1)])
+def test_frozen_spaces_vs_oracle(h2o, method, core, fc, fv):
+    from adc_parity_common import check_frozen_spaces
+    check_frozen_spaces(h2o, method, core, fc, fv)
