@@ -234,3 +234,46 @@ def test_graph_replay_host_logic(h2o, method, monkeypatch):
 def test_frozen_spaces_vs_oracle(h2o, method, core, fc, fv):
     from adc_parity_common import check_frozen_spaces
     check_frozen_spaces(h2o, method, core, fc, fv)
+
+
+def test_einsum_planner_random_expressions(h2o):
+    """Randomly generated 2- and 3-operand contractions over occupied / virtual axes (with
+    transposed views as inputs, outer products, full contractions) against numpy.einsum; the
+    reference's own einsum tests use the same oracle and tolerance (adcc/tests/einsum_test.py:36)."""
+    import adcc_b200 as adcc
+    from adcc_b200.functions import einsum
+    ref = adcc.ReferenceState(h2o)
+    rng = np.random.default_rng(2024)
+    letters = {"o1": "ijklmn", "v1": "abcdef"}
+
+    def rand_tensor(spaces):
+        shape = [ref.mospaces.n_orbs(s) for s in spaces]
+        arr = rng.standard_normal(shape)
+        return adcc.Tensor.from_ndarray(ref.mospaces, spaces, arr), arr
+
+    n_done = 0
+    while n_done < 40:
+        n_ops = int(rng.integers(2, 4))
+        pool = {sp: list(letters[sp][:int(rng.integers(2, 5))]) for sp in letters}
+        space_of = {c: sp for sp, cs in pool.items() for c in cs}
+        ops, arrays, subs = [], [], []
+        for _ in range(n_ops):
+            nd = int(rng.integers(1, 5))
+            idx = list(rng.choice(sorted(space_of), size=nd, replace=False))
+            t, a = rand_tensor([space_of[c] for c in idx])
+            if nd > 1 and rng.random() < 0.4:               # hand over a transposed (strided) view
+                perm = [int(p) for p in rng.permutation(nd)]
+                t, a, idx = t.transpose(perm), a.transpose(perm), [idx[p] for p in perm]
+            ops.append(t), arrays.append(a), subs.append("".join(idx))
+        flat = "".join(subs)
+        counts = {c: flat.count(c) for c in set(flat)}
+        if any(v > 2 for v in counts.values()):
+            continue                                        # an index on three operands: not a pair contraction
+        free = [c for c in dict.fromkeys(flat) if counts[c] == 1]
+        out = "".join(rng.permutation(free)) if free else ""
+        expr = ",".join(subs) + "->" + out
+        expected = np.einsum(expr, *arrays)
+        got = einsum(expr, *ops)
+        got = got.to_ndarray() if hasattr(got, "to_ndarray") else got
+        np.testing.assert_allclose(got, expected, rtol=1e-10, atol=1e-12, err_msg=expr)
+        n_done += 1
