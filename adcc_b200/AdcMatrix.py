@@ -8,6 +8,7 @@ diagonal_precomputed)``, ``matvec`` / ``@`` / ``rmatvec``, ``block_apply``, ``di
 all terms of all blocks and merges the terms of each output block in one fused lincomb launch.
 """
 import os
+from collections import namedtuple
 
 import numpy as np
 
@@ -22,6 +23,27 @@ from .Tensor import Tensor
 from .timings import Timer
 
 _SPECIAL_ORDERS = {"adc2x": {"ph_ph": 2, "ph_pphh": 1, "pphh_ph": 1, "pphh_pphh": 1}}
+
+
+AdcBlock = namedtuple("AdcBlock", ["apply", "diagonal"])      # adcc/adc_pp/matrix.py:41
+
+
+class AdcExtraTerm:
+    """Custom terms added to the blocks of an existing AdcMatrix (adcc/AdcMatrix.py:36-65): the
+    plug-in point environment couplings use.  ``blocks``: {"ph_ph": callable(hf, mp, intermediates)
+    -> AdcBlock(apply, diagonal)}."""
+
+    def __init__(self, matrix, blocks):
+        self.ground_state = matrix.ground_state
+        self.reference_state = matrix.reference_state
+        self.intermediates = matrix.intermediates
+        self.blocks = {}
+        if not isinstance(blocks, dict):
+            raise TypeError("blocks needs to be a dict.")
+        for space, block_fun in blocks.items():
+            if not callable(block_fun):
+                raise TypeError("Items in additional_blocks must be callable.")
+            self.blocks[space] = block_fun(self.reference_state, self.ground_state, self.intermediates)
 
 
 class AdcMatrixlike:
@@ -294,10 +316,10 @@ class AdcMatrix(AdcMatrixlike):
     def matvec(self, v):
         """sigma = M v  (adcc/AdcMatrix.py:390-396)."""
         with self.timer.record("matvec"):
-            if self._engine is not None:
-                return self._engine.matvec(v)
             if self.extra_terms:
                 return sum(block(v) for block in self.blocks.values())
+            if self._engine is not None:
+                return self._engine.matvec(v)
             if self._graphs_enabled():
                 res = self._graph_matvec([v])
                 if res is not None:
@@ -361,6 +383,37 @@ class AdcMatrix(AdcMatrixlike):
 
     def rmatvec(self, v):
         return self.matvec(v)
+
+    # ------------------------------------------------------------------ extra terms
+    def __iadd__(self, other):
+        """In-place addition of an AdcExtraTerm (adcc/AdcMatrix.py:286-311)."""
+        if not isinstance(other, AdcExtraTerm):
+            return NotImplemented
+        if not all(k in self.blocks for k in other.blocks):
+            raise ValueError("Can only add to blocks of AdcMatrix that already exist.")
+        for sp in other.blocks:
+            orig_app, other_app = self.blocks[sp], other.blocks[sp].apply
+
+            def patched_apply(ampl, original=orig_app, other=other_app):
+                return sum(app(ampl) for app in (original, other))
+            self.blocks[sp] = patched_apply
+        other_diagonal = sum(bl.diagonal for bl in other.blocks.values() if bl.diagonal)
+        self._diagonal = (self._diagonal + other_diagonal).evaluate()
+        self.extra_terms.append(other)
+        return self
+
+    def __add__(self, other):
+        """matrix + AdcExtraTerm: a copy with the term added (adcc/AdcMatrix.py:313-336)."""
+        if not isinstance(other, AdcExtraTerm):
+            return NotImplemented
+        ret = AdcMatrix(self.method, self.ground_state, block_orders=self.block_orders,
+                        intermediates=self.intermediates, diagonal_precomputed=self.diagonal(),
+                        doubles_storage=self.doubles_storage)
+        ret += other
+        return ret
+
+    def __radd__(self, other):
+        return self.__add__(other)
 
     def matvec_host(self, u_host, sigma_host):
         """sigma = M u between PINNED host buffers (dicts {"ph": [no, nv], "pphh": packed

@@ -7,7 +7,8 @@ API.  Usage mirrors adcc:
 """
 from functools import wraps as _wraps
 
-from .AdcMatrix import AdcMatrix, AdcMatrixlike, AdcMatrixProjected, AdcMatrixShifted  # noqa: F401
+from .AdcMatrix import (AdcBlock, AdcExtraTerm, AdcMatrix, AdcMatrixlike,  # noqa: F401
+                        AdcMatrixProjected, AdcMatrixShifted)
 from .AdcMethod import AdcMethod  # noqa: F401
 from .AmplitudeVector import AmplitudeVector  # noqa: F401
 from .AoEriProvider import AoDataHfProvider  # noqa: F401

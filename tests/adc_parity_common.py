@@ -294,3 +294,56 @@ def check_frozen_spaces(data, method, core, frozen_core, frozen_virtual, n=2):
     ostate = oracle.run_adc(omatrix, method, n_singlets=n, conv_tol=1e-8)
     assert state.converged and ostate.converged and state.n_iter == ostate.n_iter
     np.testing.assert_allclose(state.excitation_energy, ostate.eigenvalues, atol=ENERGY_ATOL, rtol=0)
+
+
+def check_extra_term(data):
+    """AdcExtraTerm / matrix + term / term + matrix / matrix += term, following the reference's
+    own test (adcc/tests/AdcMatrix_test.py:403-470): a shift added through the plug-in interface
+    equals AdcMatrixShifted."""
+    import pytest
+    import adcc_b200 as adcc
+    from adcc_b200 import AdcBlock, AdcExtraTerm, AdcMatrixShifted
+    ground_state = adcc.LazyMp(adcc.ReferenceState(data))
+    matrix_adc1 = adcc.AdcMatrix("adc1", ground_state)
+    with pytest.raises(TypeError):
+        matrix_adc1 += 42
+    matrix = adcc.AdcMatrix("adc2", ground_state)
+    with pytest.raises(TypeError):
+        adcc.AdcMatrix("adc2", ground_state, diagonal_precomputed=42)
+    with pytest.raises(TypeError):
+        AdcExtraTerm(matrix, "fail")
+    with pytest.raises(TypeError):
+        AdcExtraTerm(matrix, {"fail": "not_callable"})
+    shift = -0.3
+    shifted = AdcMatrixShifted(matrix, shift)
+    ones = matrix.diagonal().ones_like()
+
+    def shift_ph(hf, mp, intermediates):
+        return AdcBlock(lambda invec: adcc.AmplitudeVector(ph=shift * invec.ph),
+                        adcc.AmplitudeVector(ph=shift * ones.ph))
+
+    def shift_pphh(hf, mp, intermediates):
+        return AdcBlock(lambda invec: adcc.AmplitudeVector(pphh=shift * invec.pphh),
+                        adcc.AmplitudeVector(pphh=shift * ones.pphh))
+    extra = AdcExtraTerm(matrix, {"ph_ph": shift_ph, "pphh_pphh": shift_pphh})
+    with pytest.raises(ValueError):          # ADC(1) has no pphh_pphh block
+        matrix_adc1 += extra
+    omatrix = oracle.OracleAdcMatrix("adc2", oracle.OracleRefState(oracle.OracleHf(data)))
+    vec, ovec = random_vector(matrix, omatrix, 21)
+    ref = shifted @ vec
+    osig = omatrix.matvec(ovec)
+    for manual in (matrix + extra, extra + matrix):
+        assert len(manual.extra_terms) == 1 and not matrix.extra_terms
+        for b in ("ph", "pphh"):
+            np.testing.assert_allclose(manual.diagonal()[b].to_ndarray(), shifted.diagonal()[b].to_ndarray(),
+                                       atol=1e-12)
+            np.testing.assert_allclose((manual @ vec)[b].to_ndarray(), ref[b].to_ndarray(), atol=1e-12)
+            assert rel_err((manual @ vec)[b].to_ndarray(), osig[b] + shift * ovec[b]) < SIGMA_RTOL
+    # lists of vectors go through the per-vector path when extra terms are present
+    many = (matrix + extra) @ [vec, vec]
+    np.testing.assert_allclose(many[1].pphh.to_ndarray(), ref.pphh.to_ndarray(), atol=1e-12)
+    matrix += extra
+    np.testing.assert_allclose((matrix @ vec).ph.to_ndarray(), ref.ph.to_ndarray(), atol=1e-12)
+    state = adcc.run_adc(matrix, n_singlets=2, conv_tol=1e-8, output=None)
+    plain = oracle.run_adc(data, "adc2", n_singlets=2, conv_tol=1e-8)
+    np.testing.assert_allclose(state.excitation_energy, plain.eigenvalues + shift, atol=ENERGY_ATOL)

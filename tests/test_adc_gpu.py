@@ -112,3 +112,8 @@ def test_graph_replay_device(h2o, method, monkeypatch):
     """CUDA-graph capture of the dense matvec: bit-identical to the eager launches, parity with the oracle."""
     from adc_parity_common import check_graph_replay
     check_graph_replay(h2o, method, 1 if method.startswith("cvs") else None, monkeypatch)
+
+
+def test_extra_terms_plugin_interface_device(h2o):
+    from adc_parity_common import check_extra_term
+    check_extra_term(h2o)

@@ -277,3 +277,8 @@ def test_einsum_planner_random_expressions(h2o):
         got = got.to_ndarray() if hasattr(got, "to_ndarray") else got
         np.testing.assert_allclose(got, expected, rtol=1e-10, atol=1e-12, err_msg=expr)
         n_done += 1
+
+
+def test_extra_terms_plugin_interface(h2o):
+    from adc_parity_common import check_extra_term
+    check_extra_term(h2o)
