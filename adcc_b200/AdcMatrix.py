@@ -531,27 +531,98 @@ class AdcMatrix(AdcMatrixlike):
             ret["pphh"] = symmetrise_generic_adc_doubles
         return ret
 
+    def dense_basis(self, axis_blocks=None, ordering="adcc"):
+        """Basis in which ``to_ndarray`` expresses the matrix (adcc/AdcMatrix.py:474-558): a list of
+        basis vectors, each a list of (index, factor).  Singles: unit vectors; doubles: the
+        orthonormal antisymmetrised combinations (+-1/2 on the four images of i>j, a>b; CVS:
+        +-1/sqrt(2) on a>b).  ordering: "adcc" (index order), "spin" or "spatial"."""
+        if axis_blocks is None:
+            axis_blocks = self.axis_blocks
+        if not isinstance(axis_blocks, list):
+            axis_blocks = [axis_blocks]
+        if ordering not in ("adcc", "spin", "spatial"):
+            raise ValueError("ordering needs to be 'adcc', 'spin' or 'spatial'")
+        if any(b not in ("ph", "pphh") for b in axis_blocks):
+            raise NotImplementedError("Blocks other than ph and pphh not implemented")
+
+        def key_of(n_alpha, idx):
+            if ordering == "adcc":
+                return (idx, idx)
+            is_beta = [idx[k] >= n_alpha[k] for k in range(len(idx))]
+            spatial = [idx[k] - n_alpha[k] if is_beta[k] else idx[k] for k in range(len(idx))]
+            return (is_beta, spatial) if ordering == "spin" else (spatial, is_beta)
+
+        def ordered(vectors, spaces):
+            n_alpha = [self.mospaces.n_orbs_alpha(sp) for sp in spaces]
+            return sorted(vectors, key=lambda vec: min(key_of(n_alpha, idx) for idx, _ in vec))
+
+        ret = []
+        if "ph" in axis_blocks:
+            sp = self.axis_spaces["ph"]
+            n = [self.mospaces.n_orbs(x) for x in sp]
+            ret.extend(ordered([[((i, a), 1)] for i in range(n[0]) for a in range(n[1])], sp))
+        if "pphh" in axis_blocks:
+            sp = self.axis_spaces["pphh"]
+            n = [self.mospaces.n_orbs(x) for x in sp]
+            if sp[0] == sp[1] and sp[2] == sp[3]:
+                vecs = [[((i, j, a, b), +0.5), ((j, i, a, b), -0.5), ((i, j, b, a), -0.5), ((j, i, b, a), +0.5)]
+                        for i in range(n[0]) for j in range(i) for a in range(n[2]) for b in range(a)]
+            elif sp[2] == sp[3]:
+                f = 1 / np.sqrt(2)
+                vecs = [[((i, j, a, b), +f), ((i, j, b, a), -f)]
+                        for i in range(n[0]) for j in range(n[1]) for a in range(n[2]) for b in range(a)]
+            else:
+                vecs = [[((i, j, a, b), 1)] for i in range(n[0]) for j in range(n[1])
+                        for a in range(n[2]) for b in range(n[3])]
+            ret.extend(ordered(vecs, sp))
+        return ret
+
     def to_ndarray(self, out=None):
-        """Dense matrix in the plain (non-orthonormalised) product basis; tests only."""
-        n = self.shape[0]
-        mat = np.zeros((n, n))
-        diag = self._diagonal
+        """The matrix as a dense array in the ``dense_basis`` (adcc/AdcMatrix.py:560-644; debugging /
+        visualisation: one matvec per basis vector).  No spin symmetry is imposed: the spectrum
+        contains singlets and triplets and, for restricted references, spin-mixed combinations."""
+        if any(b not in ("ph", "pphh") for b in self.axis_blocks):
+            raise NotImplementedError("Blocks other than ph and pphh not implemented")
+        if "ph" not in self.axis_blocks:
+            raise NotImplementedError("Block 'ph' needs to be present")
+        basis = {b: self.dense_basis(b) for b in self.axis_blocks}
+        mat_len = sum(len(v) for v in basis.values())
+        if out is None:
+            out = np.zeros((mat_len, mat_len))
+        elif out.shape != (mat_len, mat_len):
+            raise ValueError(f"Output array has shape ({out.shape[0]}, {out.shape[1]}), but shape "
+                             f"({mat_len}, {mat_len}) is required.")
+        else:
+            out[:] = 0
+        shapes = {b: tuple(self.mospaces.n_orbs(sp) for sp in self.axis_spaces[b]) for b in self.axis_blocks}
+        # basis vectors as columns of a (dense length) x (basis length) array per block
+        expand = {}
+        for b in self.axis_blocks:
+            E = np.zeros((int(np.prod(shapes[b])), len(basis[b])))
+            for j, vec in enumerate(basis[b]):
+                for idx, val in vec:
+                    E[np.ravel_multi_index(idx, shapes[b]), j] = val
+            expand[b] = E
         offs, off = {}, 0
-        for blk in self.axis_blocks:
-            offs[blk] = off
-            off += self.axis_lengths[blk]
-        for col in range(n):
-            vec = diag.zeros_like()
-            for blk in self.axis_blocks:
-                if offs[blk] <= col < offs[blk] + self.axis_lengths[blk]:
-                    arr = np.zeros(self.axis_lengths[blk])
-                    arr[col - offs[blk]] = 1.0
-                    vec[blk] = Tensor.from_ndarray(self.mospaces, self.axis_spaces[blk],
-                                                   arr.reshape(diag[blk].shape))
-            res = self.matvec(vec)
-            for blk in res.blocks:
-                mat[offs[blk]:offs[blk] + self.axis_lengths[blk], col] = res[blk].to_ndarray().ravel()
-        return mat
+        for b in self.axis_blocks:
+            offs[b] = off
+            off += len(basis[b])
+        chunk = 16
+        for b in self.axis_blocks:
+            for j0 in range(0, len(basis[b]), chunk):
+                cols = range(j0, min(j0 + chunk, len(basis[b])))
+                vectors = []
+                for j in cols:
+                    data = {}
+                    for blk in self.axis_blocks:
+                        arr = expand[b][:, j].reshape(shapes[b]) if blk == b else np.zeros(shapes[blk])
+                        data[blk] = Tensor.from_ndarray(self.mospaces, self.axis_spaces[blk], arr)
+                    vectors.append(AmplitudeVector(**data))
+                for j, res in zip(cols, self @ vectors):
+                    for blk in res.blocks:
+                        dense = res[blk].to_ndarray().reshape(-1)
+                        out[offs[blk]:offs[blk] + len(basis[blk]), offs[b] + j] = expand[blk].T @ dense
+        return out
 
 
 class AdcMatrixShifted(AdcMatrix):
@@ -576,7 +647,9 @@ class AdcMatrixShifted(AdcMatrix):
         return super().diagonal() + self.shift
 
     def to_ndarray(self, out=None):
-        return super().to_ndarray() + self.shift * np.eye(self.shape[0])
+        dense = super().to_ndarray(out)
+        dense += self.shift * np.eye(dense.shape[0])
+        return dense
 
     def block_view(self, block):
         raise NotImplementedError("Block-view not yet implemented for shifted ADC matrices.")

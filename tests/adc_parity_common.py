@@ -347,3 +347,21 @@ def check_extra_term(data):
     state = adcc.run_adc(matrix, n_singlets=2, conv_tol=1e-8, output=None)
     plain = oracle.run_adc(data, "adc2", n_singlets=2, conv_tol=1e-8)
     np.testing.assert_allclose(state.excitation_energy, plain.eigenvalues + shift, atol=ENERGY_ATOL)
+
+
+def check_dense_export(data, method, core, n_states):
+    """AdcMatrix.to_ndarray in the antisymmetrised dense basis: symmetric, and its lowest distinct
+    eigenvalues are the converged states -- the reference's own dense-export test
+    (adcc/tests/AdcMatrix_dense_export_test.py:33-68)."""
+    import adcc_b200 as adcc
+    matrix = adcc.AdcMatrix(method, adcc.ReferenceState(data, core_orbitals=core))
+    conv_tol = 1e-8
+    state = adcc.run_adc(matrix, conv_tol=conv_tol, n_states=n_states, max_subspace=7 * n_states, output=None)
+    dense = matrix.to_ndarray()
+    basis = matrix.dense_basis()
+    assert dense.shape == (len(basis), len(basis))
+    np.testing.assert_allclose(dense, dense.T, rtol=1e-10, atol=1e-12)
+    spectrum = np.linalg.eigvalsh(dense)
+    rounded = np.unique(np.round(spectrum, 10))[:n_states]
+    np.testing.assert_allclose(state.excitation_energy, rounded, atol=10 * conv_tol)
+    return spectrum

@@ -117,3 +117,16 @@ def test_graph_replay_device(h2o, method, monkeypatch):
 def test_extra_terms_plugin_interface_device(h2o):
     from adc_parity_common import check_extra_term
     check_extra_term(h2o)
+
+
+@pytest.mark.parametrize("method,core,n_states", [("adc2", None, 7), ("adc3", None, 7), ("cvs-adc2x", 1, 7)])
+def test_dense_export_device(h2o, method, core, n_states):
+    """to_ndarray in the reference's dense basis: spectrum = converged states, and it contains the
+    reference's in-source known answers (smoke_test.py:32-58)."""
+    import numpy as np
+    from adc_parity_common import check_dense_export
+    from test_oracle_golden import SINGLETS, TRIPLETS
+    spectrum = check_dense_export(h2o, method, core, n_states)
+    for table in (SINGLETS, TRIPLETS):
+        for val in table[method]:
+            assert np.min(np.abs(spectrum - val)) < 1e-6, (method, val)

@@ -282,3 +282,16 @@ def test_einsum_planner_random_expressions(h2o):
 def test_extra_terms_plugin_interface(h2o):
     from adc_parity_common import check_extra_term
     check_extra_term(h2o)
+
+
+@pytest.mark.parametrize("method,core,n_states", [("adc1", None, 5), ("adc2", None, 7), ("adc2x", None, 7),
+                                                  ("adc3", None, 7), ("cvs-adc1", 1, 2),
+                                                  ("cvs-adc2", 1, 3), ("cvs-adc2x", 1, 7)])
+def test_dense_export(h2o, method, core, n_states):
+    from adc_parity_common import check_dense_export
+    spectrum = check_dense_export(h2o, method, core, n_states)
+    # the dense spectrum also contains the reference's in-source known answers (smoke_test.py:32-58)
+    from test_oracle_golden import SINGLETS, TRIPLETS
+    for table in (SINGLETS, TRIPLETS):
+        for val in table[method]:
+            assert np.min(np.abs(spectrum - val)) < 1e-6, (method, val)
