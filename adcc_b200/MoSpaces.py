@@ -170,6 +170,16 @@ class MoSpaces:
             self.map_block_irrep[s] = ["A"] * len(starts)
 
     @property
+    def occupied_orbitals(self):
+        """Active valence-occupied spin orbitals in host-provider indexing (adcc/MoSpaces.py:173-179)."""
+        return self.map_index_hf_provider["o1"]
+
+    @property
+    def virtual_orbitals(self):
+        """Active virtual spin orbitals in host-provider indexing (adcc/MoSpaces.py:181-187)."""
+        return self.map_index_hf_provider["v1"]
+
+    @property
     def has_core_occupied_space(self):
         return "o2" in self.subspaces_occupied
 

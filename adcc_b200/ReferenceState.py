@@ -53,6 +53,13 @@ class ReferenceState:
         return self.mospaces.has_core_occupied_space
 
     @property
+    def is_aufbau_occupation(self):
+        """Lowest-energy orbitals occupied? (adcc/ReferenceState.py:184-194)"""
+        e_homo = max(float(np.max(self.orbital_energies_host(s))) for s in self.mospaces.subspaces_occupied)
+        e_lumo = min(float(np.min(self.orbital_energies_host(s))) for s in self.mospaces.subspaces_virtual)
+        return e_homo < e_lumo
+
+    @property
     def hf_provider(self):
         return self._hf
 

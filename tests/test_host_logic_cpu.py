@@ -42,6 +42,15 @@ def test_synthetic_restricted_small():
     check_run_parity(data, "cvs-adc2", "singlet", 1, n=2)
 
 
+def test_space_and_reference_properties(h2o):
+    import adcc_b200 as adcc
+    ref = adcc.ReferenceState(h2o, core_orbitals=1, frozen_virtual=1)
+    ms = ref.mospaces
+    assert ms.core_orbitals == [0, 7] and ms.occupied_orbitals == [1, 2, 3, 4, 8, 9, 10, 11]
+    assert ms.virtual_orbitals == [5, 12] and ms.frozen_virtual == [6, 13] and ms.frozen_core == []
+    assert ref.is_aufbau_occupation
+
+
 def test_api_surface_and_errors(h2o):
     import adcc_b200 as adcc
     with pytest.raises(adcc.InputError):
