@@ -3,16 +3,27 @@ adcc/ElectronicStates.py: energies, vectors, solver bookkeeping, ``describe``; t
 properties of SURVEY 8(f1) live in adcc_b200/properties.py)."""
 import numpy as np
 
+from .AdcMethod import AdcMethod
+
 from .timings import Timer
 
 
 class ExcitedStates:
-    def __init__(self, data):
+    def __init__(self, data, method=None, property_method=None):
+        """``data``: solver state or another ExcitedStates; ``property_method``: level of the ISR
+        used for properties ("isr0" / "isr1" / "isr2" or an ADC method name; default: the
+        method's own level, ADC(3) -> second order) (adcc/ElectronicStates.py:39-96)."""
         self.matrix = data.matrix
         self.reference_state = self.matrix.reference_state
         self.ground_state = self.matrix.ground_state
-        self.method = self.matrix.method
-        self.property_method = self.method.property_method
+        self.method = self.matrix.method if method is None else AdcMethod(method)
+        if property_method is None:
+            property_method = self.method.property_method
+        elif str(property_method).startswith("isr"):
+            prefix = "cvs-" if self.method.is_core_valence_separated else ""
+            property_method = prefix + "adc" + str(property_method)[3:]
+        self.property_method = AdcMethod(property_method).name
+        data = getattr(data, "solver_state", data)
         self.timer = Timer()
         if hasattr(data, "timer"):
             self.timer.attach(data.timer, "solver")

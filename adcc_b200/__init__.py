@@ -49,6 +49,13 @@ def _method_shortcut(name):
     return inner
 
 
+@with_runadc_doc
+def cis(*args, **kwargs):
+    """ADC(1) states with zeroth-order (CIS) properties (adcc/__init__.py:93-96)."""
+    from .ExcitedStates import ExcitedStates
+    return ExcitedStates(run_adc(*args, **kwargs, method="adc1"), property_method="isr0")
+
+
 adc0 = _method_shortcut("adc0")
 adc1 = _method_shortcut("adc1")
 adc2 = _method_shortcut("adc2")
@@ -59,6 +66,15 @@ cvs_adc1 = _method_shortcut("cvs-adc1")
 cvs_adc2 = _method_shortcut("cvs-adc2")
 cvs_adc2x = _method_shortcut("cvs-adc2x")
 cvs_adc3 = _method_shortcut("cvs-adc3")
+
+
+def banner(colour=False):
+    """Version / backend summary (the reference prints its own banner, adcc/__init__.py:149-200)."""
+    line = "+" + 70 * "-" + "+\n"
+    rows = ["adcc_b200: adcc's ADC(n) matvec + Jacobi-Davidson path on NVIDIA B200",
+            f"version {__version__}",
+            f"backend: {__backend__['name']}"]
+    return line + "".join("|{0:^70s}|\n".format(r) for r in rows) + line
 
 
 def set_n_threads(n):

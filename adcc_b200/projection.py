@@ -119,3 +119,82 @@ class Projector:
         if isinstance(other, list) and all(isinstance(e, Tensor) for e in other):
             return [self.matvec(o) for o in other]
         return NotImplemented
+
+
+def transfer_amplitude_cvs_to_full(mospaces_cvs, cvs, symmetry_full, tol=1e-12):
+    """Copy a CVS amplitude (spaces o2 v1 / o1 o2 v1 v1) into a full-space amplitude with the
+    symmetry ``symmetry_full`` (adcc/projection.py:238-314).  The core orbitals have to be the
+    lowest occupied orbitals of each spin (``core_orbitals`` given as an integer).  The ocvv part
+    enters twice in the full doubles amplitude (oc and co), hence the factor 1/sqrt(2)."""
+    from .AmplitudeVector import AmplitudeVector
+    from .Tensor import Tensor
+    if cvs.keys() != symmetry_full.keys():
+        raise ValueError("Blocks present in CVS and full vector should agree.")
+    if not mospaces_cvs.has_core_occupied_space:
+        raise ValueError("Should have CVS enabled in mospaces_cvs")
+    if not isinstance(cvs, AmplitudeVector):
+        raise TypeError("Expected cvs to be an AmplitudeVector.")
+    mospaces_full = symmetry_full["ph"].mospaces
+    nca, noa = mospaces_cvs.n_orbs_alpha("o2"), mospaces_cvs.n_orbs_alpha("o1")
+    nfa = mospaces_full.n_orbs_alpha("o1")
+    core, occ_full = list(mospaces_cvs.core_orbitals), list(mospaces_full.occupied_orbitals)
+    if core[:nca] != occ_full[:nca] or core[nca:] != occ_full[nfa:nfa + nca]:
+        raise NotImplementedError(
+            "For transfer CVS to full only the case where the CVS space is contiguous in the full "
+            "space has been implemented, i.e. when the `core_orbitals` are chosen as an integer in "
+            "the run_adc routines.")
+    full = AmplitudeVector(**{block: Tensor(sym) for block, sym in symmetry_full.items()})
+    if cvs.ph.subspaces != ["o2", "v1"] or full.ph.subspaces != ["o1", "v1"]:
+        raise ValueError("Unexpected subspaces of the singles blocks")
+    # where the core (alpha, beta) and valence (alpha, beta) orbitals sit on a full occupied axis
+    c_a, c_b = slice(0, nca), slice(nfa, nfa + nca)
+    o_a, o_b = slice(nca, nfa), slice(nfa + nca, None)
+    src_ph = cvs.ph.to_ndarray()
+    dst_ph = np.zeros(full.ph.shape)
+    dst_ph[c_a] = src_ph[:nca]
+    dst_ph[c_b] = src_ph[nca:]
+    full.ph.set_from_ndarray(dst_ph, tol)
+    if "pphh" in cvs:
+        if cvs.pphh.subspaces != ["o1", "o2", "v1", "v1"] or full.pphh.subspaces != ["o1", "o1", "v1", "v1"]:
+            raise ValueError("Unexpected subspaces of the doubles blocks")
+        src = cvs.pphh.to_ndarray() / np.sqrt(2)
+        dst = np.zeros(full.pphh.shape)
+        for o_full, o_cvs in ((o_a, slice(0, noa)), (o_b, slice(noa, None))):
+            for c_full, c_cvs in ((c_a, slice(0, nca)), (c_b, slice(nca, None))):
+                part = src[o_cvs, c_cvs]
+                dst[o_full, c_full] = part
+                dst[c_full, o_full] = -part.transpose(1, 0, 2, 3)
+        full.pphh.set_from_ndarray(dst, tol)
+    return full
+
+
+def transfer_cvs_to_full(state_matrix_cvs, matrix_full, vector=None, kind=None, spin_change=0,
+                         spin_block_symmetrisation="none"):
+    """Transfer ``vector`` (or a list of vectors) from the CVS space to the full space of
+    ``matrix_full`` (adcc/projection.py:317-359); ``state_matrix_cvs`` is the CVS matrix or the
+    ExcitedStates holding the solved CVS excitations (then the spin symmetry is taken from it).
+    Typical use: CVS eigenvectors as guesses for a projected full matrix."""
+    from .AdcMatrix import AdcMatrixlike
+    from .guess import guess_kwargs_kind, guess_symmetries
+    if kind is None and hasattr(state_matrix_cvs, "kind"):
+        kind = state_matrix_cvs.kind
+    if spin_change is None and spin_block_symmetrisation is None:
+        if kind is None:
+            raise ValueError("kind needs to be given if first argument is not an ExcitedStates "
+                             "object and spin symmetry setup is not explicitly given.")
+        return transfer_cvs_to_full(state_matrix_cvs, matrix_full, vector, kind, **guess_kwargs_kind(kind))
+    if vector is None:
+        if hasattr(state_matrix_cvs, "excitation_vector"):
+            vector = state_matrix_cvs.excitation_vector
+        else:
+            raise ValueError("vector needs to be given if first argument is not an ExcitedStates object.")
+    if isinstance(vector, list):
+        return [transfer_cvs_to_full(state_matrix_cvs, matrix_full, v, kind, **guess_kwargs_kind(kind))
+                for v in vector]
+    if isinstance(state_matrix_cvs, AdcMatrixlike):
+        mospaces_cvs = state_matrix_cvs.mospaces
+    else:
+        mospaces_cvs = state_matrix_cvs.matrix.mospaces
+    sym = guess_symmetries(matrix_full, spin_change=spin_change,
+                           spin_block_symmetrisation=spin_block_symmetrisation)
+    return transfer_amplitude_cvs_to_full(mospaces_cvs, vector, sym)

@@ -10,10 +10,12 @@ import numpy as np
 from .mp import es
 
 
-def transition_dm(matrix, vec):
+def transition_dm(matrix, vec, level=None):
+    """level: ISR order of the density (default: the method's own, at most 2; adcc.cis uses 0)."""
     mp, cvs = matrix.mp, matrix.cvs
     base = matrix.method[4:] if cvs else matrix.method
-    level = min(int(base[3]), 2)
+    if level is None:
+        level = min(int(base[3]), 2)
     u1 = vec["ph"]
     C = "c" if cvs else "o"
     dm = {"v" + C: u1.T.copy()}
@@ -38,12 +40,12 @@ def transition_dm(matrix, vec):
     return dm
 
 
-def oscillator_strengths(matrix, state):
+def oscillator_strengths(matrix, state, level=None):
     hf = matrix.hf
     sp = {"o": "o1", "v": "v1", "c": "o2"}
     res, mus = [], []
     for vec, omega in zip(state.eigenvectors, state.eigenvalues):
-        dm = transition_dm(matrix, vec)
+        dm = transition_dm(matrix, vec, level)
         mu = np.zeros(3)
         for blk, rho in dm.items():
             s1, s2 = sp[blk[0]], sp[blk[1]]

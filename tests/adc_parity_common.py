@@ -365,3 +365,38 @@ def check_dense_export(data, method, core, n_states):
     rounded = np.unique(np.round(spectrum, 10))[:n_states]
     np.testing.assert_allclose(state.excitation_energy, rounded, atol=10 * conv_tol)
     return spectrum
+
+
+def check_transfer_cvs_to_full(data, kind="singlet"):
+    """transfer_cvs_to_full (adcc/projection.py:238-359): scalar products are preserved
+    (adcc/tests/projection_test.py:223-251), and CVS eigenvectors serve as guesses for the
+    projected full matrix (examples/2_core_excitations/water_core_by_projection.py:30-46)."""
+    import pytest
+    import adcc_b200 as adcc
+    from adcc_b200.projection import transfer_cvs_to_full
+    kw = {"n_singlets": 2} if kind == "singlet" else {"n_triplets": 2}
+    state_cvs = adcc.run_adc(data, method="cvs-adc2x", core_orbitals=1, conv_tol=1e-8, output=None, **kw)
+    matrix = adcc.AdcMatrix("adc2x", adcc.ReferenceState(data))
+    gram = np.array([[v @ w for v in state_cvs.excitation_vector] for w in state_cvs.excitation_vector])
+    full = transfer_cvs_to_full(state_cvs, matrix)
+    gram_full = np.array([[v @ w for v in full] for w in full])
+    np.testing.assert_allclose(gram, gram_full, atol=1e-14)
+    for v in full:
+        assert v.ph.subspaces == ["o1", "v1"] and v.pphh.subspaces == ["o1", "o1", "v1", "v1"]
+        d = v.pphh.to_ndarray()
+        assert np.max(np.abs(d + d.transpose(1, 0, 2, 3))) < 1e-15
+    # random vectors of the CVS space, explicit kind
+    rnd = [v.copy().set_random() for v in state_cvs.excitation_vector]
+    gram = np.array([[v @ w for v in rnd] for w in rnd])
+    full_rnd = transfer_cvs_to_full(state_cvs.matrix, matrix, rnd, kind)
+    np.testing.assert_allclose(gram, np.array([[v @ w for v in full_rnd] for w in full_rnd]), rtol=1e-14)
+    with pytest.raises(ValueError):
+        transfer_cvs_to_full(state_cvs.matrix, matrix)            # neither states nor vectors
+    # the transferred eigenvectors as guesses of the projected matrix
+    pm = adcc.AdcMatrixProjected(matrix, ["cv", "ccvv", "ocvv"], core_orbitals=1)
+    by_guess = adcc.run_adc(pm, conv_tol=1e-8, guesses=transfer_cvs_to_full(state_cvs, pm), output=None, **kw)
+    plain = adcc.run_adc(pm, conv_tol=1e-8, n_guesses=2, n_guesses_doubles=0, output=None, **kw)
+    assert by_guess.converged and plain.converged
+    np.testing.assert_allclose(by_guess.excitation_energy, plain.excitation_energy, atol=1e-7)
+    assert by_guess.n_iter <= plain.n_iter
+    assert np.max(np.abs(by_guess.excitation_energy - state_cvs.excitation_energy)) < 0.05

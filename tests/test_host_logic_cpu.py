@@ -304,3 +304,26 @@ def test_dense_export(h2o, method, core, n_states):
     for table in (SINGLETS, TRIPLETS):
         for val in table[method]:
             assert np.min(np.abs(spectrum - val)) < 1e-6, (method, val)
+
+
+@pytest.mark.parametrize("kind", ["singlet", "triplet"])
+def test_transfer_cvs_to_full(h2o, kind):
+    from adc_parity_common import check_transfer_cvs_to_full
+    check_transfer_cvs_to_full(h2o, kind)
+
+
+def test_cis_is_adc1_with_zeroth_order_properties(h2o):
+    """adcc.cis (adcc/__init__.py:93-96): ADC(1) energies, ISR(0) transition densities."""
+    import adcc_b200 as adcc
+    import oracle
+    from oracle.properties import oscillator_strengths
+    state = adcc.cis(h2o, n_singlets=3, conv_tol=1e-9, output=None)
+    ostate = oracle.run_adc(h2o, "adc1", n_singlets=3, conv_tol=1e-9)
+    omatrix = oracle.OracleAdcMatrix("adc1", oracle.OracleRefState(oracle.OracleHf(h2o)))
+    np.testing.assert_allclose(state.excitation_energy, ostate.eigenvalues, atol=1e-8)
+    assert state.property_method == "adc0" and state.method.name == "adc1"
+    f0, _ = oscillator_strengths(omatrix, ostate, level=0)
+    f1, _ = oscillator_strengths(omatrix, ostate)
+    np.testing.assert_allclose(state.oscillator_strength, f0, rtol=1e-6, atol=1e-10)
+    assert np.max(np.abs(f0 - f1)) > 1e-4                  # the two levels really differ
+    assert "adcc_b200" in adcc.banner()
