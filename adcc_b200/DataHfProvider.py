@@ -237,5 +237,12 @@ def import_scf_results(res):
             from .AoEriProvider import AoDataHfProvider
             return AoDataHfProvider(res)
         return DataHfProvider(res)
+    if isinstance(res, str):
+        # on-disk hfdata dictionary (adcc/backends/__init__.py:100-106; read without h5py)
+        import os
+        if os.path.isfile(res) and (res.endswith(".h5") or res.endswith(".hdf5")):
+            from .hdf5io import load
+            return import_scf_results(load(res))
+        raise ValueError(f"Unrecognised path or file extension: {res}")
     raise NotImplementedError("No means to import an SCF result of type " + str(type(res)) +
                               " (supported here: dict, HartreeFockProvider).")

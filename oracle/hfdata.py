@@ -101,3 +101,24 @@ def load_h2o_sto3g(path=None):
         z["orben"], int(z["n_occ_alpha"]), z["eri_spatial_chem"], orbcoeff=z["orbcoeff"],
         dipole_ao=z["dipole_ao"], energy_scf=float(z["energy_scf"]),
         conv_tol=float(z["conv_tol"]), nuclear_dipole=z["nuclear_dipole"])
+
+
+def load_h2o_sto3g_pyscf(path=None):
+    """The reference's second offline fixture (examples/0_basics/h2o_sto3g_hfdata.hdf5, PySCF RHF)
+    as the nested hfdata dict adcc's DataHfProvider takes (tests/golden/make_h2o_sto3g_pyscf.py)."""
+    if path is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests",
+                            "golden", "h2o_sto3g_pyscf_hfdata.npz")
+    z = np.load(path, allow_pickle=False)
+    out = {}
+    for key in z.files:
+        val = z[key]
+        val = val[()] if val.shape == () else val
+        if isinstance(val, np.str_):
+            val = str(val)
+        node = out
+        parts = key.split("/")
+        for part in parts[:-1]:
+            node = node.setdefault(part, {})
+        node[parts[-1]] = val
+    return out
