@@ -327,3 +327,20 @@ def test_cis_is_adc1_with_zeroth_order_properties(h2o):
     np.testing.assert_allclose(state.oscillator_strength, f0, rtol=1e-6, atol=1e-10)
     assert np.max(np.abs(f0 - f1)) > 1e-4                  # the two levels really differ
     assert "adcc_b200" in adcc.banner()
+
+
+def test_chained_methods_reuse_ground_state_and_vectors(h2o):
+    """The overview notebook's flow (examples/0_basics/00_Overview.ipynb): ADC(2) vectors as guesses
+    for ADC(2)-x on the same ground state, those for ADC(3); a ReferenceState as first argument."""
+    import adcc_b200 as adcc
+    from test_oracle_golden import SINGLETS
+    state = adcc.adc2(h2o, n_singlets=3, conv_tol=1e-8, output=None)
+    s2x = adcc.adc2x(state.ground_state, n_singlets=3, guesses=state.excitation_vector, conv_tol=1e-8, output=None)
+    s3 = adcc.adc3(s2x.ground_state, n_singlets=3, guesses=s2x.excitation_vector, conv_tol=1e-8, output=None)
+    assert s2x.ground_state is state.ground_state and s3.ground_state is state.ground_state
+    np.testing.assert_allclose(s2x.excitation_energy, SINGLETS["adc2x"], atol=1e-6)
+    np.testing.assert_allclose(s3.excitation_energy, SINGLETS["adc3"], atol=1e-6)
+    s1 = adcc.adc1(state.reference_state, n_singlets=3, conv_tol=1e-8, output=None)
+    np.testing.assert_allclose(s1.excitation_energy, SINGLETS["adc1"], atol=1e-6)
+    with pytest.raises(adcc.exceptions.InputError):
+        adcc.adc2x(state.ground_state, n_singlets=3, guesses=state.excitation_vector[:2], output=None)
