@@ -121,6 +121,9 @@ def _all_host_threads():
 def cpu_sample(no_s=16, nv_s=96, n_matvec=3):
     import oracle
     _all_host_threads()
+    quick = os.environ.get("ADCCB_BENCH_QUICK") == "1"      # contract tests: tiny sample, same code path
+    if quick:
+        no_s, nv_s = 6, 10
     from oracle.synthetic import OracleSyntheticRef
     t0 = time.perf_counter()
     om = oracle.OracleAdcMatrix("adc2x", OracleSyntheticRef(no_s, nv_s, seed=SEED, scale=SCALE),
@@ -139,7 +142,7 @@ def cpu_sample(no_s=16, nv_s=96, n_matvec=3):
     small_gflops = pair_flops(no_s, nv_s) / t * 1e-9
     # the two GEMMs that carry 98 % of the flops, at FULL operand extents, on column slabs
     from oracle.adc import dominant_terms_sample
-    ab_slab, jb_slab = 4096, 1024
+    ab_slab, jb_slab = (16, 8) if quick else (4096, 1024)
     fl, dt = dominant_terms_sample(NO, NV, ab_slab, jb_slab)
     gemm_gflops = fl / dt * 1e-9
     full = pair_flops(NO, NV)
