@@ -34,3 +34,29 @@ def test_no_cpu_fallback_in_product():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/adccb.h compiles as C99 (no C++ / torch types in the signatures) and a C program that
+    takes the address of every declared entry point links against libadccb.so: the boundary a cgo /
+    JNI / ctypes binding would use."""
+    import shutil
+    import subprocess
+    import __graft_entry__ as g
+    g.build()
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the image"
+    names = _declared()
+    src = tmp_path / "probe.c"
+    body = "\n".join(f"    table[{k}] = (fn_t){name};" for k, name in enumerate(names))
+    src.write_text('#include "adccb.h"\n#include <stdio.h>\ntypedef void (*fn_t)(void);\n'
+                   f"int main(void) {{\n    fn_t table[{len(names)}];\n{body}\n"
+                   f'    printf("%d %d\\n", {len(names)}, table[0] != 0);\n    return 0;\n}}\n')
+    libdir = os.path.join(ROOT, "adcc_b200")
+    exe = tmp_path / "probe"
+    cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+           "-L", libdir, "-ladccb", "-Wl,-rpath," + libdir, "-Wl,--unresolved-symbols=ignore-in-shared-libs",
+           "-o", str(exe)]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert os.path.exists(exe)
