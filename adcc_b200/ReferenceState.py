@@ -77,6 +77,32 @@ class ReferenceState:
         """numpy (n_space, n_bas): rows follow the adcc order of `space`."""
         return self._orbcoeff_fb[self._host_index(space)]
 
+    def _coefficients(self, space, keep):
+        if not (isinstance(space, str) and space.endswith("b") and len(space) == 3):
+            raise ValueError(f"Invalid space string {space}: an object orbital_coefficients({space}) "
+                             "is not known (expected e.g. 'o1b').")
+        sub = space[:2]
+        idx = self._host_index(sub)
+        coeff = np.array(self._orbcoeff_fb[idx])
+        is_alpha = idx < self._hf.n_orbs_alpha
+        if keep == "a":
+            coeff[~is_alpha] = 0.0
+        elif keep == "b":
+            coeff[is_alpha] = 0.0
+        return coeff
+
+    def orbital_coefficients(self, space):
+        """MO coefficients C[p, mu] of subspace ``space[:2]`` as a host array (n_space, n_bas)
+        (libadcc_src/ReferenceState.cc:380-390; the basis axis "b" is not a tensor space here)."""
+        return self._coefficients(space, "ab")
+
+    def orbital_coefficients_alpha(self, space):
+        """Like orbital_coefficients with the rows of beta orbitals zeroed (ReferenceState.cc:392-403)."""
+        return self._coefficients(space, "a")
+
+    def orbital_coefficients_beta(self, space):
+        return self._coefficients(space, "b")
+
     # ------------------------------------------------------------------ Fock / ERI
     def fock(self, space):
         sp = split_spaces(space)

@@ -49,6 +49,12 @@ def test_space_and_reference_properties(h2o):
     assert ms.core_orbitals == [0, 7] and ms.occupied_orbitals == [1, 2, 3, 4, 8, 9, 10, 11]
     assert ms.virtual_orbitals == [5, 12] and ms.frozen_virtual == [6, 13] and ms.frozen_core == []
     assert ref.is_aufbau_occupation
+    c, ca, cb = (f("o1b") for f in (ref.orbital_coefficients, ref.orbital_coefficients_alpha,
+                                    ref.orbital_coefficients_beta))
+    assert c.shape == (8, 7) and np.array_equal(ca + cb, c)
+    assert not ca[4:].any() and not cb[:4].any() and np.array_equal(ca[:4], cb[4:])     # restricted
+    with pytest.raises(ValueError):
+        ref.orbital_coefficients("o1")
 
 
 def test_api_surface_and_errors(h2o):
