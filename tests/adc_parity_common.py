@@ -400,3 +400,50 @@ def check_transfer_cvs_to_full(data, kind="singlet"):
     np.testing.assert_allclose(by_guess.excitation_energy, plain.excitation_energy, atol=1e-7)
     assert by_guess.n_iter <= plain.n_iter
     assert np.max(np.abs(by_guess.excitation_energy - state_cvs.excitation_energy)) < 0.05
+
+
+def check_davidson_edge_cases(data):
+    """Solver control flow beyond the happy path (adcc/solver/davidson.py:225-245, 330-350,
+    adcc/tests/solver/davidson_test.py): subspace collapse on a small max_subspace, the
+    max_iter warning with converged=False, callbacks, and n_block > n_ep."""
+    import warnings
+    import pytest
+    import adcc_b200 as adcc
+    from adcc_b200.solver.davidson import jacobi_davidson
+    from adcc_b200.guess import guesses_singlet
+    from adcc_b200.solver.explicit_symmetrisation import IndexSpinSymmetrisation
+    matrix, omatrix = build_pair(data, "adc2", None)
+    # (1) restarts: max_subspace barely above the block size
+    events, oevents = [], []
+    state = adcc.run_adc(matrix, n_singlets=3, conv_tol=1e-8, max_subspace=7, output=None)
+    ostate = oracle.run_adc(omatrix, "adc2", n_singlets=3, conv_tol=1e-8, max_subspace=7,
+                            callback=lambda st, ident: oevents.append(ident))
+    direct = jacobi_davidson(matrix, guesses_singlet(matrix, 6, block="ph"), n_ep=3, conv_tol=1e-8,
+                             max_subspace=7, callback=lambda st, ident: events.append(ident),
+                             explicit_symmetrisation=IndexSpinSymmetrisation(matrix, "singlet"))
+    assert events[0] == "start" and events[-1] == "is_converged" and events.count("restart") >= 3
+    assert events.count("next_iter") == oevents.count("next_iter") == state.n_iter
+    assert direct.n_iter == state.n_iter
+    with pytest.raises(TypeError):            # like the reference: run_adc owns the solver callback
+        adcc.run_adc(matrix, n_singlets=3, output=None, callback=lambda st, ident: None)
+    assert state.converged and state.n_iter == ostate.n_iter and state.n_applies == ostate.n_applies
+    np.testing.assert_allclose(state.excitation_energy, ostate.eigenvalues, atol=ENERGY_ATOL, rtol=0)
+    # (2) too few iterations: warning, converged False, best estimates returned
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        short = adcc.run_adc(matrix, n_singlets=3, conv_tol=1e-10, max_iter=2, output=None)
+    assert not short.converged and short.n_iter == 2
+    assert any("Maximum number of iterations" in str(w.message) for w in caught)
+    assert np.all(np.abs(short.excitation_energy - state.excitation_energy) < 1e-2)
+    # (3) more guesses than states and a block size of its own through the solver interface
+    guesses = guesses_singlet(matrix, 6, block="ph")
+    res = jacobi_davidson(matrix, guesses, n_ep=2, n_block=4, conv_tol=1e-8,
+                          explicit_symmetrisation=IndexSpinSymmetrisation(matrix, "singlet"))
+    assert res.converged and len(res.eigenvalues) == 2
+    np.testing.assert_allclose(res.eigenvalues, state.excitation_energy[:2], atol=1e-7)
+    # (4) invalid solver arguments
+    from adcc_b200.solver.davidson import eigsh
+    with pytest.raises(ValueError):
+        eigsh(matrix, guesses, n_ep=2, conv_tol=1e-8, preconditioning_method="nonsense")
+    with pytest.raises(ValueError):
+        eigsh(matrix, guesses[:1], n_ep=2, conv_tol=1e-8)            # fewer guesses than states

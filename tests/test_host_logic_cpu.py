@@ -350,3 +350,8 @@ def test_chained_methods_reuse_ground_state_and_vectors(h2o):
     np.testing.assert_allclose(s1.excitation_energy, SINGLETS["adc1"], atol=1e-6)
     with pytest.raises(adcc.exceptions.InputError):
         adcc.adc2x(state.ground_state, n_singlets=3, guesses=state.excitation_vector[:2], output=None)
+
+
+def test_davidson_edge_cases(h2o):
+    from adc_parity_common import check_davidson_edge_cases
+    check_davidson_edge_cases(h2o)
