@@ -5,7 +5,6 @@ like "-jiab" (sign + permuted index letters relative to the identity string), sp
 are (from, to, factor) with spin strings like "aaaa", forbidden spin blocks a list of spin
 strings.  The point group is C1 (libadcc_src/MoSpaces.cc:136), so irreps_allowed is ["A"].
 """
-import itertools
 from .MoSpaces import split_spaces
 
 

@@ -1,6 +1,5 @@
 """Shorthand space strings: b.oovv -> "o1o1v1v1" (o -> o1, v -> v1, c -> o2), the helper the
 reference defines in adcc/block.py:30-38."""
-import sys
 
 _MAP = {"o": "o1", "v": "v1", "c": "o2"}
 
