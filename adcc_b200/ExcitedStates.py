@@ -8,6 +8,15 @@ from .AdcMethod import AdcMethod
 from .timings import Timer
 
 
+def _column(header, values, unit="", width=None):
+    """One column of the describe() table: every cell centred in a common width."""
+    need = max(len(header), len(unit), *(len(v) for v in values)) if values else max(len(header), len(unit))
+    if width is None or width < need:
+        width = need + 1
+    return {"width": width, "header": f"{header:^{width}s}", "unit": f"{unit:^{width}s}",
+            "values": [f"{v:^{width}s}" for v in values]}
+
+
 class ExcitedStates:
     def __init__(self, data, method=None, property_method=None):
         """``data``: solver state or another ExcitedStates; ``property_method``: level of the ISR
@@ -23,6 +32,7 @@ class ExcitedStates:
             prefix = "cvs-" if self.method.is_core_valence_separated else ""
             property_method = prefix + "adc" + str(property_method)[3:]
         self.property_method = AdcMethod(property_method).name
+        outer = data
         data = getattr(data, "solver_state", data)
         self.timer = Timer()
         if hasattr(data, "timer"):
@@ -33,7 +43,7 @@ class ExcitedStates:
         self.residual_norm = np.array(data.residual_norms) if data.residual_norms is not None else None
         self._excitation_energy_uncorrected = np.array(data.eigenvalues)
         self.excitation_vector = data.eigenvectors
-        self.kind = getattr(data, "kind", "any")
+        self.kind = getattr(outer, "kind", getattr(data, "kind", "any"))
         self.spin_change = None
         self.solver_state = data
 
@@ -73,18 +83,48 @@ class ExcitedStates:
         return 2.0 / 3.0 * np.array([np.linalg.norm(t) ** 2 * e
                                      for t, e in zip(tdm, self.excitation_energy)])
 
-    def describe(self, oscillator_strengths=False):
+    def describe(self, oscillator_strengths=True, rotatory_strengths=False, state_dipole_moments=False,
+                 transition_dipole_moments=False, block_norms=True, ssq=False):
+        """Human-readable table of the states (adcc/ExcitedStates.py:50-166): one column group per
+        requested quantity, each column as wide as its widest entry plus one, header line
+        ``method (property method)    kind, converged``.  Rotatory strengths, state dipole
+        moments and <S^2> belong to subsystems outside this path and are not shown."""
         eV = 27.211386245988
-        kind = {"singlet": "singlet", "triplet": "triplet", "any": "any", "spin_flip": "spin_flip"}.get(self.kind, "")
-        conv = "converged" if self.converged else "NOT CONVERGED"
-        lines = ["+" + "-" * 52 + "+",
-                 "| {0:<30s} {1:>19s} |".format(self.method.name + "  " + kind, conv),
-                 "+" + "-" * 52 + "+",
-                 "|  #        excitation energy     " + ("osc str " if oscillator_strengths else "        ") + "           |",
-                 "|          (au)           (eV)                       |"]
-        osc = self.oscillator_strength if oscillator_strengths else None
-        for i, e in enumerate(self.excitation_energy):
-            extra = f"{osc[i]:8.4f}" if osc is not None else " " * 8
-            lines.append("| {0:2d} {1:13.7g} {2:13.7g}   {3}           |".format(i, e, e * eV, extra))
-        lines.append("+" + "-" * 52 + "+")
+        has_dipole = hasattr(self.reference_state.operator_integral_provider, "electric_dipole")
+        columns = [_column("#", [str(i) for i in range(self.size)])]
+        columns.append(_column("excitation energy", [f"{e:^13.7g} {e * eV:^13.7g}" for e in self.excitation_energy],
+                               unit="(au)         (eV)"))
+        if transition_dipole_moments and has_dipole:
+            vals = [f"{t[0]:^8.4f} {t[1]:^8.4f} {t[2]:^8.4f}{np.linalg.norm(t):^8.4f}"
+                    for t in self.transition_dipole_moment]
+            columns.append(_column("transition dipole moment", vals, unit="x(au)    y(au)    z(au)    abs(au)"))
+        if oscillator_strengths and has_dipole:
+            columns.append(_column("osc str", [f"{f:^8.4f}" for f in self.oscillator_strength], unit="(au)"))
+        if block_norms:
+            for block, label in (("ph", "|v1|^2"), ("pphh", "|v2|^2")):
+                if block in self.matrix.axis_blocks:
+                    columns.append(_column(label, [f"{v[block].dot(v[block]):^9.4f}"
+                                                   for v in self.excitation_vector]))
+        width = sum(c["width"] for c in columns)
+        method = self.method.name
+        if self.property_method != self.method.name:
+            method += f" ({self.property_method})"
+        info = []
+        if self.kind:
+            info.append(self.kind + ",")
+        info.append("converged" if self.converged else "NOT CONVERGED")
+        info = " ".join(info)
+        header = f"{method}    {info:>{max(width - len(method) - 4, 0)}s}"
+        if len(header) > width:                                   # few narrow columns: pad the last one
+            columns[-1] = _column(columns[-1]["header"].strip(), [v.strip() for v in columns[-1]["values"]],
+                                  unit=columns[-1]["unit"].strip(),
+                                  width=columns[-1]["width"] + len(header) - width)
+            width = len(header)
+        hline = "+" + "-" * (width + 2) + "+"
+        lines = [hline, f"| {header} |", hline,
+                 "| " + "".join(c["header"] for c in columns) + " |",
+                 "| " + "".join(c["unit"] for c in columns) + " |"]
+        for row in zip(*[c["values"] for c in columns]):
+            lines.append("| " + "".join(row) + " |")
+        lines.append(hline)
         return "\n".join(lines)

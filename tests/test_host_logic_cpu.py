@@ -333,6 +333,15 @@ def test_cis_is_adc1_with_zeroth_order_properties(h2o):
     np.testing.assert_allclose(state.oscillator_strength, f0, rtol=1e-6, atol=1e-10)
     assert np.max(np.abs(f0 - f1)) > 1e-4                  # the two levels really differ
     assert "adcc_b200" in adcc.banner()
+    assert state.kind == "singlet"
+    # describe(): the reference's table layout (adcc/ExcitedStates.py:50-166)
+    lines = state.describe().splitlines()
+    assert len({len(ln) for ln in lines}) == 1                      # a proper frame
+    assert lines[1].startswith("| adc1 (adc0)") and lines[1].rstrip(" |").endswith("singlet, converged")
+    assert "excitation energy" in lines[3] and "osc str" in lines[3] and "|v1|^2" in lines[3]
+    assert "|v2|^2" not in lines[3] and "(au)" in lines[4] and len(lines) == 5 + 3 + 1
+    assert "transition dipole moment" in state.describe(transition_dipole_moments=True)
+    assert "osc str" not in state.describe(oscillator_strengths=False)
 
 
 def test_chained_methods_reuse_ground_state_and_vectors(h2o):
