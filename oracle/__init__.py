@@ -7,7 +7,10 @@ legs of ``bench.py`` use it, and there only as the checker / the CPU arm.
 Parity status: PINNED.  The restatement reproduces the reference's in-source known
 answers for H2O/STO-3G (adcc/tests/smoke_test.py:32-58: adc0..adc3 and cvs-adc0..3,
 3 singlets + 3 triplets, atol 1e-6) from the reference's own fixture
-(examples/water/data.py -> tests/golden/h2o_sto3g.npz), see tests/test_oracle_golden.py.
+(examples/water/data.py -> tests/golden/h2o_sto3g.npz), see tests/test_oracle_golden.py, and
+again from its second, PySCF-generated fixture (examples/0_basics/h2o_sto3g_hfdata.hdf5 ->
+tests/golden/h2o_sto3g_pyscf_hfdata.npz, full 14^4 eri_ffff), see tests/test_hdf5_cpu.py; the
+(anti)symmetrisers are checked against the reference's vendored tensor goldens.
 Sigma vectors are not dumped anywhere in the reference tree, so per-entry sigma parity
 between the reference and this oracle is pinned only through those eigenvalues and
 through hermiticity / symmetry invariants.
