@@ -50,3 +50,21 @@ def test_streamed_dot_uses_bulk_copies(sass):
     dot = _body(sass, "dot_bulk_kernel")
     assert "UBLKCP" in dot and "SYNCS.ARRIVE.TRANS64" in dot
     assert "DFMA" in dot
+
+
+def test_headline_gemm_register_budget():
+    """The 112x128 tile (vvvv GEMM of the headline workload) must stay within the 168 registers a
+    288-thread CTA can have (3 warps on one SM sub-partition) WITHOUT spilling: accumulators are
+    112 of them, a spill in the main loop costs DMMA issue slots."""
+    import re
+    import __graft_entry__ as g
+    g.build()
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([tool, "-res-usage", os.path.join(ROOT, "adcc_b200", "libadccb.so")],
+                         capture_output=True, text=True, timeout=600).stdout
+    m = re.search(r"dgemm_tn_tma_kernelILi1ELi8ELi14ELi2ELi6ELb0E[^\n]*\n\s*REG:(\d+) STACK:(\d+)", out)
+    assert m, "headline GEMM instantiation not found"
+    regs, stack = int(m.group(1)), int(m.group(2))
+    assert regs <= 168 and stack == 0
