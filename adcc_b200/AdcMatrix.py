@@ -418,11 +418,20 @@ class AdcMatrix(AdcMatrixlike):
     def matvec_host(self, u_host, sigma_host):
         """sigma = M u between PINNED host buffers (dicts {"ph": [no, nv], "pphh": packed
         [npo, npv]} of torch CPU tensors): the end-to-end form of ``matvec`` for callers whose
-        vectors live on the host.  The PCIe transfers are pipelined with row slabs of the vvvv GEMM
+        vectors live on the host (dense store: tensors of the dense block shapes, plain upload /
+        download).  Packed store: the PCIe transfers are pipelined with row slabs of the vvvv GEMM
         (PackedAdcEngine.matvec_host).  Sharded matrices: rank 0 passes the buffers, the other
         ranks pass None; all ranks must call."""
         if self._engine is None:
-            raise NotImplementedError("matvec_host is implemented for the packed doubles store")
+            # dense store: plain upload / matvec / download (the vectors have the dense block shapes)
+            from . import backend as be
+            with self.timer.record("matvec_host"):
+                ampl = AmplitudeVector(**{
+                    blk: Tensor._wrap(self.mospaces, self.axis_spaces[blk], be.upload(t)) for blk, t in u_host.items()})
+                sigma = self.matvec(ampl)
+                for blk, out in sigma_host.items():
+                    be.download(sigma[blk]._contig(), out)
+            return
         u_host = u_host or {"ph": None, "pphh": None}              # sharded: only rank 0 holds buffers
         sigma_host = sigma_host or {"ph": None, "pphh": None}
         with self.timer.record("matvec_host"):

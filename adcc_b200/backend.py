@@ -56,6 +56,19 @@ def from_numpy(arr):
     return torch.from_numpy(arr).to(device())
 
 
+def upload(host_tensor):
+    """Host (ideally pinned) FP64 torch tensor -> device copy on the current stream."""
+    return host_tensor.to(device(), non_blocking=True)
+
+
+def download(dev_tensor, host_tensor):
+    """Device array -> existing host tensor; returns after the copy has finished."""
+    host_tensor.copy_(dev_tensor, non_blocking=True)
+    if dev_tensor.is_cuda:
+        torch.cuda.current_stream().synchronize()
+    return host_tensor
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 

@@ -77,6 +77,8 @@ def install(monkeypatch):
         return out
 
     def to_host(t): return t.numpy()
+    def upload(t): return t.clone()
+    def download(dev, host): host.copy_(dev); return host
 
     def spin_project(t, n_alpha, fac):
         f = t
@@ -255,7 +257,7 @@ def install(monkeypatch):
                          permute=permute, contiguous=contiguous, fill=fill, axpby=axpby,
                          scaled_copy=scaled_copy, mul=mul, div=div, div_shift=div_shift,
                          add_scalar=add_scalar, direct_sum=direct_sum, lincomb=lincomb,
-                         dot_many=dot_many, dot=dot, dot_many_blocks=dot_many_blocks, to_host=to_host, spin_project=spin_project,
+                         dot_many=dot_many, dot=dot, dot_many_blocks=dot_many_blocks, to_host=to_host, upload=upload, download=download, spin_project=spin_project,
                          spin_singlet_=spin_singlet_, packed_unpack=packed_unpack, packed_pack=packed_pack,
                          packed_expand=packed_expand, packed_fold_virt=packed_fold_virt,
                          packed_fold_occ=packed_fold_occ, packed_diagonal=packed_diagonal,

@@ -364,3 +364,18 @@ def test_chained_methods_reuse_ground_state_and_vectors(h2o):
 def test_davidson_edge_cases(h2o):
     from adc_parity_common import check_davidson_edge_cases
     check_davidson_edge_cases(h2o)
+
+
+@pytest.mark.parametrize("method", ["adc2", "cvs-adc2x"])
+def test_matvec_between_host_buffers_dense_store(h2o, method):
+    """AdcMatrix.matvec_host on the dense store: sigma lands in the caller's host buffers."""
+    import torch
+    from adc_parity_common import build_pair, random_vector, rel_err, SIGMA_RTOL
+    matrix, omatrix = build_pair(h2o, method, 1 if method.startswith("cvs") else None)
+    v, ov = random_vector(matrix, omatrix, 5)
+    u_host = {b: torch.from_numpy(ov[b].copy()) for b in ov}
+    s_host = {b: torch.full_like(u_host[b], float("nan")) for b in ov}
+    matrix.matvec_host(u_host, s_host)
+    osig = omatrix.matvec(ov)
+    for b in osig:
+        assert rel_err(s_host[b].numpy(), osig[b]) < SIGMA_RTOL
