@@ -130,3 +130,17 @@ def test_dense_export_device(h2o, method, core, n_states):
     for table in (SINGLETS, TRIPLETS):
         for val in table[method]:
             assert np.min(np.abs(spectrum - val)) < 1e-6, (method, val)
+
+
+@pytest.mark.parametrize("method", ["adc2", "cvs-adc2x"])
+def test_matvec_between_host_buffers_dense_store_device(h2o, method):
+    import torch
+    from adc_parity_common import build_pair, random_vector, rel_err, SIGMA_RTOL
+    matrix, omatrix = build_pair(h2o, method, 1 if method.startswith("cvs") else None)
+    v, ov = random_vector(matrix, omatrix, 5)
+    u_host = {b: torch.from_numpy(ov[b].copy()).pin_memory() for b in ov}
+    s_host = {b: torch.full_like(u_host[b], float("nan")).pin_memory() for b in ov}
+    matrix.matvec_host(u_host, s_host)
+    osig = omatrix.matvec(ov)
+    for b in osig:
+        assert rel_err(s_host[b].numpy(), osig[b]) < SIGMA_RTOL
