@@ -14,14 +14,14 @@ def cutlass_root():
 
 
 def build(force=False):
-    src = os.path.join(HERE, "cutlass_i8_gemm.cu")
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) > os.path.getmtime(src):
+    srcs = [os.path.join(HERE, "cutlass_i8_gemm.cu"), os.path.join(HERE, "slices.cu")]
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) > os.path.getmtime(f) for f in srcs):
         return OUT
     root = cutlass_root()
     cmd = [os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc"), "-gencode", "arch=compute_100a,code=sm_100a",
            "-std=c++17", "-O3", "--expt-relaxed-constexpr", "-lineinfo",
            "-I", os.path.join(root, "include"), "-I", os.path.join(root, "tools", "util", "include"),
-           "-Xcompiler", "-fPIC", "-shared", "-o", OUT, src]
+           "-Xcompiler", "-fPIC", "-shared", "-o", OUT] + srcs
     subprocess.run(cmd, check=True, stdout=sys.stderr)
     return OUT
 

@@ -14,8 +14,8 @@ import numpy as np
 
 def slices(X, beta, s):
     """X[r, :] = 2^e[r] * sum_p 2^(-beta (p+1)) X_p[r, :] + remainder, X_p integer in (-2^beta, 2^beta)."""
-    e = np.ceil(np.log2(np.max(np.abs(X), axis=1, keepdims=True)))
-    R = X / 2.0 ** e                                   # |R| <= 1
+    e = np.frexp(np.max(np.abs(X), axis=1, keepdims=True))[1].astype(float)   # max = f 2^e, 0.5 <= f < 1
+    R = X / 2.0 ** e                                   # |R| < 1 strictly (no int8 overflow of slice 0)
     out = []
     for _ in range(s):
         R = R * 2.0 ** beta

@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 def slice_rows(X, beta, s):
     """Row exponents e and s int8 planes with X ~= 2^e * sum_p 2^(-beta (p+1)) X_p (|X_p| < 2^beta)."""
     amax = X.abs().amax(dim=1, keepdim=True).clamp_min(torch.finfo(X.dtype).tiny)
-    e = torch.ceil(torch.log2(amax))
+    e = torch.frexp(amax)[1].to(X.dtype)            # amax = f * 2^e, 0.5 <= f < 1: |X / 2^e| < 1 strictly
     R = X * torch.exp2(-e)
     planes = []
     for _ in range(s):
