@@ -53,6 +53,52 @@ def main():
     from adcc_b200 import backend as be
     exact, ms_dmma = timed(lambda: be.gemm(U, W), reps=3)
     print(f"adccb_dgemm (DMMA): {ms_dmma:.2f} ms = {2.0 * M * N * K / ms_dmma * 1e-9:.2f} TFLOP/s")
+    # the CUDA slicing kernel against the torch statement of the same arithmetic
+    lib.study_slice_rows.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong,
+                                     ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_void_p, ctypes.c_void_p]
+    lib.study_recombine.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p,
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double,
+                                    ctypes.c_void_p, ctypes.c_longlong]
+    stream = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)      # noqa: E731
+
+    def cuda_slices(X, s):
+        rows, kk = X.shape
+        planes = torch.empty((s, rows, kk), dtype=torch.int8, device=dev)
+        expo = torch.empty(rows, dtype=torch.int32, device=dev)
+        st = lib.study_slice_rows(stream(), rows, kk, kk, X.data_ptr(), X.stride(0), 7, s, planes.data_ptr(),
+                                  expo.data_ptr())
+        assert st == 0
+        return expo, planes
+
+    for name, X in (("U", U), ("W", W)):
+        (expo, planes), ms_sl = timed(lambda: cuda_slices(X, 6), reps=3)
+        e_t, planes_t = slice_rows(X, 7, 6)
+        same = bool(torch.equal(expo.double().reshape(-1, 1), e_t)) and all(
+            torch.equal(planes[p], planes_t[p]) for p in range(6))
+        print(f"slice kernel on {name} {tuple(X.shape)}: {ms_sl:.3f} ms, identical to the torch statement = {same}")
+
+    def emulated_cuda(s):
+        ea, As = cuda_slices(U, s)
+        eb, Bs = cuda_slices(W, s)
+        C = torch.empty((M, N), dtype=torch.float64, device=dev)
+        tmp = torch.empty((M, N), dtype=torch.int32, device=dev)
+        first = True
+        for p in range(s):
+            for q in range(s - p):
+                i8_gemm(As[p], Bs[q], tmp)
+                st = lib.study_recombine(stream(), M, N, tmp.data_ptr(), ea.data_ptr(), eb.data_ptr(),
+                                         7 * (p + q + 2), 0.0 if first else 1.0, C.data_ptr(), N)
+                assert st == 0
+                first = False
+        return C
+
+    for s in (6, 7):
+        C, ms_em = timed(lambda: emulated_cuda(s), reps=2)
+        err = float((C - exact).abs().max() / exact.abs().max())
+        print(f"emulated FP64 (CUDA slices + tcgen05 INT8 GEMMs + recombine), 7-bit x {s}: {ms_em:.2f} ms "
+              f"= {2.0 * M * N * K / ms_em * 1e-9:.1f} TFLOP/s FP64-equivalent, max|C - dmma| / max = {err:.2e}")
+
     for s in (6, 7):
         t0 = time.perf_counter()
         ea, As = slice_rows(U, 7, s)
