@@ -22,6 +22,7 @@ from .guess import (guess_symmetries, guess_zero, guesses_any, guesses_singlet, 
                     guesses_spin_flip, guesses_triplet)
 from .Intermediates import Intermediates, register_as_intermediate  # noqa: F401
 from .LazyMp import LazyMp  # noqa: F401
+from .memory_pool import memory_pool  # noqa: F401
 from .MoSpaces import MoSpaces  # noqa: F401
 from .projection import Projector, SubspacePartitioning  # noqa: F401
 from .ReferenceState import ReferenceState  # noqa: F401

@@ -16,13 +16,21 @@ int fail(const std::string& msg) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+
+// SM count of the CURRENT device (cached per device: a one-process-many-GPU host may mix parts)
 int sm_count() {
-  static int n = 0;
+  static std::atomic<int> cache[64];
+  const int dev = current_device();
+  int n = (dev >= 0 && dev < 64) ? cache[dev].load(std::memory_order_relaxed) : 0;
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
 }

@@ -28,7 +28,8 @@ int fail(const std::string& msg);   // sets the error and returns a non-zero sta
     }                                                                                    \
   } while (0)
 
-int sm_count();
+int sm_count();        // of the current device
+int current_device();
 
 // launch counter (bench.py reports it as gpu_launches)
 void count_launch(int n = 1);

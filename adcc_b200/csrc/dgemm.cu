@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include <vector>
 #include <mutex>
+#include <atomic>
 
 namespace adccb {
 
@@ -455,10 +456,13 @@ static int launch_tma(cudaStream_t st, int M, int N, int K, double alpha, const 
                       long long ldc, double* ws, long long ws_bytes, const PeerDests& peers) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, MB, NB, STAGES>;
   auto kern = dgemm_tn_tma_kernel<WARPS_M, WARPS_N, MB, NB, STAGES, PEERS>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the attribute belongs to the (function, device) pair: set it once per device
+  // (one-process-many-GPU hosts launch the same instantiation on several devices)
+  static std::atomic<unsigned long long> attr_devices{0};
+  const int dev = current_device();
+  if (dev >= 64 || !((attr_devices.load(std::memory_order_acquire) >> dev) & 1ULL)) {
     ADCCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+    if (dev < 64) attr_devices.fetch_or(1ULL << dev, std::memory_order_release);
   }
   CUtensorMap tmA, tmB;
   if (!make_map_2d(&tmA, A, M, K, lda, Cfg::BM) || !make_map_2d(&tmB, B, N, K, ldb, Cfg::BN))

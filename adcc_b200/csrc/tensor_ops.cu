@@ -12,6 +12,7 @@
 // All are HBM-bound: coalesced 16-byte accesses where alignment allows, shared-memory tiles
 // for transposes, warp-shuffle + fixed-order two-stage reductions (deterministic).
 #include "common.cuh"
+#include <atomic>
 #include <algorithm>
 
 namespace adccb {
@@ -444,10 +445,11 @@ template <int NV>
 static int launch_dot_bulk(cudaStream_t st, const VecList& v, int j0, const double* x, long long n_chunks,
                            int blocks, double* partial) {
   constexpr int smem = kBulkStages * (NV + 1) * bulk_chunk(NV) * 8 + 2 * kBulkStages * 8;
-  static bool attr = false;
-  if (!attr) {
+  static std::atomic<unsigned long long> attr_devices{0};      // per (function, device), see dgemm.cu
+  const int dev = current_device();
+  if (dev >= 64 || !((attr_devices.load(std::memory_order_acquire) >> dev) & 1ULL)) {
     ADCCB_CUDA_OK(cudaFuncSetAttribute(dot_bulk_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
+    if (dev < 64) attr_devices.fetch_or(1ULL << dev, std::memory_order_release);
   }
   dot_bulk_kernel<NV><<<blocks, kBulkThreads + 32, smem, st>>>(v, j0, x, n_chunks, partial);
   ADCCB_LAUNCH_OK();

@@ -304,7 +304,10 @@ class PackedAdcEngine:
             # slab exchange of the vvvv term through peer memory, written by the GEMM epilogue
             # (two buffers, alternating per matvec: a rank that runs ahead never overwrites a
             # buffer its peer is still reading)
-            if (self.order_dd == 1 and be.peer_exchange_supported()
+            # (the peer-destination epilogue exists on the TMA path only: row stride npv of U and
+            # W must be even - 16-byte aligned rows; nv = 2, 3 mod 4, e.g. 38, 50, 106, gives an odd
+            # npv and keeps the NCCL all-gather)
+            if (self.order_dd == 1 and be.peer_exchange_supported() and self.npv % 2 == 0
                     and os.environ.get("ADCCB_P2P", "1") != "0"):
                 bufs = [be.PeerBuffer.create(self.npo * self.npv) for _ in range(2)]
                 if all(b is not None for b in bufs):

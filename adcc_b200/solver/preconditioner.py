@@ -1,3 +1,25 @@
+## ---------------------------------------------------------------------
+##
+## This file is derived from adcc v0.18.0 (adcc/solver/preconditioner.py).
+## Copyright (C) 2018 by the adcc authors
+##
+## adcc is free software: you can redistribute it and/or modify
+## it under the terms of the GNU General Public License as published
+## by the Free Software Foundation, either version 3 of the License, or
+## (at your option) any later version.
+##
+## adcc is distributed in the hope that it will be useful,
+## but WITHOUT ANY WARRANTY; without even the implied warranty of
+## MERCHANTABILITY or FITNESS FOR A PARTICULAR PURPOSE.  See the
+## GNU General Public License for more details.
+##
+## You should have received a copy of the GNU General Public License
+## along with adcc. If not, see <http://www.gnu.org/licenses/>.
+##
+## Changes with respect to adcc: condensed; the vector algebra is mapped onto
+## batched device kernels of libadccb.so (see the module docstring).
+##
+## ---------------------------------------------------------------------
 """Jacobi preconditioner (D - sigma)^-1 (adcc/solver/preconditioner.py:29-87).
 
 The reference evaluates ``v / (D - sigma)`` through a temporary filled tensor

@@ -43,6 +43,12 @@ def rel_err(a, b):
 
 def check_matvec_parity(data, method, core, seed=42):
     matrix, omatrix = build_pair(data, method, core)
+    return compare_matrices(matrix, omatrix, seed)
+
+
+def compare_matrices(matrix, omatrix, seed=42):
+    """diagonal, sigma, per-block applies and hermiticity of a dense-store product matrix against an
+    oracle matrix of the same method / reference (adcc/tests/AdcMatrix_test.py:213-285)."""
     # diagonal
     for k, d in omatrix.diagonal().items():
         assert rel_err(matrix.diagonal()[k].to_ndarray(), d) < SIGMA_RTOL, f"diagonal {k}"
@@ -84,13 +90,14 @@ def check_run_parity(data, method, kind, core, n=None, conv_tol=1e-9):
     return state, ostate
 
 
-def check_oscillator_strengths(data, method, core, n=3):
+def check_oscillator_strengths(data, method, core, n=3, conv_tol=1e-9):
     """transition dipoles / oscillator strengths, product vs oracle (<= 1e-6 rel)."""
     import adcc_b200 as adcc
     from oracle.properties import oscillator_strengths
     n = 2 if method.startswith("cvs") else n
-    state = adcc.run_adc(data, method=method, n_singlets=n, conv_tol=1e-9, core_orbitals=core, output=None)
-    ostate = oracle.run_adc(data, method, n_singlets=n, conv_tol=1e-9, core_orbitals=core)
+    state = adcc.run_adc(data, method=method, n_singlets=n, conv_tol=conv_tol, core_orbitals=core, output=None)
+    ostate = oracle.run_adc(data, method, n_singlets=n, conv_tol=conv_tol, core_orbitals=core)
+    assert state.converged and ostate.converged
     oref = oracle.OracleRefState(oracle.OracleHf(data), core_orbitals=core)
     of, omu = oscillator_strengths(oracle.OracleAdcMatrix(method, oref), ostate)
     f = state.oscillator_strength

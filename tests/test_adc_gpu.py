@@ -144,3 +144,64 @@ def test_matvec_between_host_buffers_dense_store_device(h2o, method):
     osig = omatrix.matvec(ov)
     for b in osig:
         assert rel_err(s_host[b].numpy(), osig[b]) < SIGMA_RTOL
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[1..3] at their exact spin-orbital shapes: restricted
+# synthetic SCF data of the molecule's dimensions (real cc-pVXZ SCF data cannot be produced offline,
+# SURVEY 8(d)); sigma + diagonal + per-block parity against the oracle as in the reference's
+# adcc/tests/AdcMatrix_test.py:213-285.
+# ------------------------------------------------------------------------------------------------
+_ORACLE_CACHE = {}
+
+
+def _oracle_matrix(case, method):
+    """Oracle matrices of the larger shapes are expensive (ADC(3) at o=32/v=140: about a minute of
+    host time); dense and packed product tests share one."""
+    import oracle
+    from adcc_b200.synthetic import named_case
+    key = (case, method)
+    if key not in _ORACLE_CACHE:
+        data, core = named_case(case)
+        oref = oracle.OracleRefState(oracle.OracleHf(data), core_orbitals=core or None)
+        _ORACLE_CACHE[key] = (data, core or None, oracle.OracleAdcMatrix(method, oref))
+    return _ORACLE_CACHE[key]
+
+
+def test_c2_shape_adc2_sigma_and_oscillator_strengths():
+    """configs[1]: H2O cc-pVTZ shape (o=10, v=106), ADC(2) + oscillator strengths."""
+    import adcc_b200 as adcc
+    from adc_parity_common import compare_matrices, check_oscillator_strengths
+    data, core, om = _oracle_matrix("h2o_ccpvtz", "adc2")
+    m = adcc.AdcMatrix("adc2", adcc.ReferenceState(data), doubles_storage="dense")
+    assert m.axis_lengths == {"ph": 1060, "pphh": 1123600}
+    compare_matrices(m, om)
+    f = check_oscillator_strengths(data, "adc2", None, n=3, conv_tol=1e-7)
+    assert f.shape == (3,)
+
+
+@pytest.mark.parametrize("storage", ["dense", "packed"])
+def test_c3_shape_adc3_sigma(storage):
+    """configs[2]: methyloxirane cc-pVDZ shape (o=32, v=140), ADC(3) incl. the vvvv intermediates,
+    on the dense store and on the antisymmetry-packed store."""
+    import adcc_b200 as adcc
+    from adc_parity_common import compare_matrices
+    data, core, om = _oracle_matrix("methyloxirane_ccpvdz", "adc3")
+    m = adcc.AdcMatrix("adc3", adcc.ReferenceState(data), doubles_storage=storage)
+    assert m.axis_lengths == {"ph": 4480, "pphh": 20070400}
+    if storage == "dense":
+        compare_matrices(m, om)
+    else:
+        from packed_parity_common import _compare
+        _compare(adcc, m, om)
+
+
+@pytest.mark.parametrize("case,n_ph,n_pphh", [("h2o_ccpvtz_cvs", 212, 179776), ("ne_ccpvtz_cvs", 100, 40000)])
+def test_c4_shapes_cvs_adc2x_sigma(case, n_ph, n_pphh):
+    """configs[3]: H2O / Ne cc-pVTZ CVS-ADC(2)-x shapes (c=2, o=8, v=106 / 50)."""
+    import adcc_b200 as adcc
+    from adc_parity_common import compare_matrices
+    data, core, om = _oracle_matrix(case, "cvs-adc2x")
+    m = adcc.AdcMatrix("cvs-adc2x", adcc.ReferenceState(data, core_orbitals=core))
+    assert m.axis_lengths == {"ph": n_ph, "pphh": n_pphh}
+    compare_matrices(m, om)

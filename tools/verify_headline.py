@@ -1,7 +1,9 @@
 """Full-size parity of the packed ADC(2)-x matvec: sampled sigma entries recomputed on the CPU in
 FP64 directly from the DEFINITION of the synthetic inputs (adcc_b200/synthetic.py hash) and the
 working equations adcc/adc_pp/matrix.py:127-133, 234-246, 270-276, 288-294.
-Independent of the device kernels' layouts: nothing here reads a staged GEMM operand.
+Independent of the device kernels' layouts: nothing here reads a staged GEMM operand or a
+device-built intermediate - the singles-singles block is rebuilt on the host from the hash
+(oovv -> t2 -> i1, i2, term_t2_eri rows; matrix.py:353-375, 933-942).
 """
 import os
 import sys
@@ -89,9 +91,43 @@ def sigma_ph_coupling_entry(seed, scale, no, nv, U, i, a):
     return s
 
 
+class PhPhFromDefinition:
+    """ph_ph_2 rows of the synthetic workload rebuilt on the host from the hash definition:
+        sigma[ia] = u[ib] i1[ab] - i2[ij] u[ja] - <ja||ib> u[jb] - 1/2 term[ikac] u[kc]
+    (adcc/adc_pp/matrix.py:353-375) with i1 / i2 (matrix.py:933-942), term_t2_eri (:363-366) and
+    t2 = <ij||ab> / (e_a + e_b - e_i - e_j) (adcc/LazyMp.py:37-54).  Host memory: two o^2 v^2 arrays."""
+
+    def __init__(self, seed, scale, no, nv):
+        self.seed, self.scale, self.no, self.nv = seed, scale, no, nv
+        e_o, e_v = synthetic_orbital_energies(no, nv)
+        self.eps_o = np.concatenate((e_o[0::2], e_o[1::2]))
+        self.eps_v = np.concatenate((e_v[0::2], e_v[1::2]))
+        a, b = np.meshgrid(np.arange(nv), np.arange(nv), indexing="ij")
+        self.oovv = np.empty((no, no, nv, nv))
+        for i in range(no):                                   # chunked: bounded temporaries
+            for j in range(no):
+                self.oovv[i, j] = synthetic_eri_value(seed, "oovv", i, j, a, b, scale)
+        den = (self.eps_v[None, None, :, None] + self.eps_v[None, None, None, :]
+               - self.eps_o[:, None, None, None] - self.eps_o[None, :, None, None])
+        self.t2 = self.oovv / den
+        x = np.tensordot(self.t2, self.oovv, axes=([0, 1, 3], [0, 1, 3]))          # [a,b]
+        self.i1 = np.diag(self.eps_v) + 0.25 * (x + x.T)
+        z = np.tensordot(self.t2, self.oovv, axes=([1, 2, 3], [1, 2, 3]))          # [i,j]
+        self.i2 = np.diag(self.eps_o) - 0.25 * (z + z.T)
+
+    def entry(self, u1, i, a):
+        no, nv = self.no, self.nv
+        s = float(np.dot(u1[i], self.i1[a])) - float(np.dot(self.i2[i], u1[:, a]))
+        jj, bb = np.meshgrid(np.arange(no), np.arange(nv), indexing="ij")
+        s -= float(np.sum(synthetic_eri_value(self.seed, "ovov", jj, a, i, bb, self.scale) * u1))
+        # term[i,k,a,c] = sum_jb t2[ijab] oovv[jkbc] + oovv[ijab] t2[jkbc]
+        term = (np.tensordot(self.t2[i, :, a, :], self.oovv, axes=([0, 1], [0, 2]))
+                + np.tensordot(self.oovv[i, :, a, :], self.t2, axes=([0, 1], [0, 2])))     # [k,c]
+        return s - 0.5 * float(np.sum(term * u1))
+
+
 def verify(matrix, v, sigma, n_pphh=24, n_ph=4, seed_samples=11):
     """Returns max relative errors of sampled sigma entries against the CPU recomputation."""
-    eng = matrix._engine
     ref = matrix.reference_state
     syn = ref.synthetic
     no, nv, seed, scale = syn["no"], syn["nv"], syn["seed"], syn["scale"]
@@ -108,13 +144,13 @@ def verify(matrix, v, sigma, n_pphh=24, n_ph=4, seed_samples=11):
         ref_val = sigma_pphh_entry(seed, scale, no, nv, u1, U, i, j, a, b)
         got = S[j * (j - 1) // 2 + i, b * (b - 1) // 2 + a]
         err2 = max(err2, abs(got - ref_val) / scale_pphh)
-    # ph: coupling part from the definition + ph_ph part from the folded singles matrix row
-    M1 = eng.M1
+    # ph: coupling part and singles-singles part, both from the definition of the inputs
+    phph = PhPhFromDefinition(seed, scale, no, nv) if n_ph > 0 else None
     scale_ph = np.max(np.abs(s1))
     err1 = 0.0
     for _ in range(n_ph):
         i, a = int(rng.integers(0, no)), int(rng.integers(0, nv))
         ref_val = sigma_ph_coupling_entry(seed, scale, no, nv, U, i, a)
-        ref_val += float(np.dot(M1[i * nv + a].cpu().numpy(), u1.ravel()))
+        ref_val += phph.entry(u1, i, a)
         err1 = max(err1, abs(s1[i, a] - ref_val) / scale_ph)
     return {"sampled_rel_err_pphh": err2, "sampled_rel_err_ph": err1, "n_pphh": n_pphh, "n_ph": n_ph}
