@@ -107,60 +107,80 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle (NumPy restatement of the reference equations) on a bounded sample
+# CPU arm: the oracle's full-size restatement (oracle/headline.py) on all host cores
 # ------------------------------------------------------------------------------------------------
 def _all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1; the CPU arm is to use every host core."""
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
     try:
         from threadpoolctl import threadpool_limits
-        threadpool_limits(limits=os.cpu_count())
+        threadpool_limits(limits=n)
     except Exception:
         pass
+    return n
 
 
-def cpu_sample(no_s=16, nv_s=96, n_matvec=3):
-    import oracle
-    _all_host_threads()
-    quick = os.environ.get("ADCCB_BENCH_QUICK") == "1"      # contract tests: tiny sample, same code path
-    if quick:
-        no_s, nv_s = 6, 10
-    from oracle.synthetic import OracleSyntheticRef
-    t0 = time.perf_counter()
-    om = oracle.OracleAdcMatrix("adc2x", OracleSyntheticRef(no_s, nv_s, seed=SEED, scale=SCALE),
-                                unique_pairs=True)
-    t_build = time.perf_counter() - t0
-    rng = np.random.default_rng(1)
-    v = {k: rng.standard_normal(s) for k, s in om.shapes.items()}
-    v["pphh"] = om.symmetrise_doubles(v["pphh"])
-    om.matvec(v)                                  # warm-up (einsum path caches, BLAS threads, pair operands)
+def workload_config(no, nv):
+    """`config` of the JSON line; identical in both arms when both run the same shape."""
+    npv = nv * (nv - 1) // 2
+    return {"workload": f"synthetic ADC(2)-x matvec nocc={no} nvirt={nv} (BASELINE configs[4]), "
+                        "random antisymmetrised FP64 ERIs from a counter-based hash",
+            "storage": f"antisymmetry-packed doubles + vvvv ({npv * npv * 8 / 1e9:.1f} GB instead of "
+                       f"{8.0 * nv ** 4 / 1e9:.1f} GB dense)",
+            "l2": "operands exceed the 126 MB L2 every step", "seed": SEED}
+
+
+def _host_mem_available():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return 0
+
+
+def cpu_shape(no, nv):
+    """The requested shape if its operands fit the host memory, else the largest nvirt that does
+    (the JSON line then names THAT shape and says so)."""
+    from oracle.headline import host_bytes_needed
+    if os.environ.get("ADCCB_BENCH_QUICK") == "1":          # contract tests: tiny, same code path
+        return 6, 10
+    avail = _host_mem_available()
+    while nv > 40 and avail and host_bytes_needed(no, nv) * 1.15 > avail:
+        nv -= 40
+    return no, nv
+
+
+def cpu_matvec_run(no, nv, n_warm, n_timed, u=None):
+    """Build the full-size CPU restatement and time `n_timed` COMPLETE matvecs (wall clock).
+    Returns (result dict, sigma of the last matvec)."""
+    cores = _all_host_threads()
+    from oracle.headline import OracleHeadline
+    oh = OracleHeadline(no, nv, seed=SEED, scale=SCALE)
+    if u is None:
+        rng = np.random.default_rng(SEED + 1)
+        u = (rng.standard_normal((no, nv)), rng.standard_normal((oh.npo, oh.npv)))
+    sig = None
+    for _ in range(n_warm):
+        sig = oh.matvec(*u)
     times = []
-    for _ in range(n_matvec):
+    for _ in range(n_timed):
         t0 = time.perf_counter()
-        om.matvec(v)
+        sig = oh.matvec(*u)
         times.append(time.perf_counter() - t0)
-    t = float(np.median(times))
-    small_gflops = pair_flops(no_s, nv_s) / t * 1e-9
-    # the two GEMMs that carry 98 % of the flops, at FULL operand extents, on column slabs
-    from oracle.adc import dominant_terms_sample
-    ab_slab, jb_slab = (16, 8) if quick else (4096, 1024)
-    fl, dt = dominant_terms_sample(NO, NV, ab_slab, jb_slab)
-    gemm_gflops = fl / dt * 1e-9
-    full = pair_flops(NO, NV)
-    return {
-        "value": gemm_gflops * 1e9 / full,          # matvec/s at nocc=40 / nvirt=400
-        "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-        "sample": (f"oracle (NumPy/OpenBLAS restatement, oooo/vvvv terms over canonical index pairs like "
-                   f"libtensor's symmetry-unique blocks). (1) column slabs of the two dominant contractions "
-                   f"at FULL operand extents (vvvv: 780 x {ab_slab} x 79800, ovov: 16000 x {jb_slab} x 16000; "
-                   f"{fl / 1e12:.2f} of {full / 1e12:.1f} TFLOP per matvec): {dt:.2f} s = {gemm_gflops:.0f} GFLOP/s "
-                   f"-> value = that rate over the whole matvec ({full / (gemm_gflops * 1e9):.0f} s/matvec; "
-                   f"favours the CPU: the bandwidth-bound parts are counted at GEMM speed). "
-                   f"(2) complete oracle matvec at nocc={no_s}, nvirt={nv_s}: {t:.3f} s = {small_gflops:.0f} GFLOP/s "
-                   f"(build {t_build:.1f} s). The full-size operands (50.9 GB packed vvvv) are not built on the "
-                   f"host; libtensor itself is not installable offline"),
-        "seconds_per_matvec_sample": t,
-        "gemm_gflops": gemm_gflops,
-    }
+    t = float(np.mean(times))
+    res = {"value": 1.0 / t, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": (f"{n_timed} complete matvec(s) at nocc={no} nvirt={nv} by the oracle's full-size "
+                      f"restatement (oracle/headline.py: canonical index pairs like libtensor's "
+                      f"symmetry-unique blocks, NumPy/OpenBLAS DGEMMs + OpenMP C index kernels, {cores} "
+                      f"threads): {t:.2f} s per matvec = {oh.flops() / t * 1e-9:.0f} GFLOP/s executed; "
+                      f"operand build {oh.build_seconds:.0f} s (not timed). libtensor itself is not "
+                      "installable offline"),
+           "seconds_per_matvec": t, "times": times, "build_s": oh.build_seconds}
+    return res, sig
 
 
 def run_reference(args):
@@ -168,17 +188,20 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    res = cpu_sample(n_matvec=max(1, args.steps))
+    no, nv = cpu_shape(args.nocc, args.nvirt)
+    res, _ = cpu_matvec_run(no, nv, args.warmup, max(1, args.steps))
+    cfg = workload_config(no, nv)
+    if (no, nv) != (args.nocc, args.nvirt):
+        cfg["note"] = (f"host memory too small for nocc={args.nocc} nvirt={args.nvirt}: timed at "
+                       f"nocc={no} nvirt={nv} instead (not extrapolated)")
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000.0 / res["value"], "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic ADC(2)-x matvec nocc={NO} nvirt={NV} (BASELINE configs[4])",
-                   "note": "CPU arm = NumPy restatement: full-extent slabs of the two dominant GEMMs, rate applied to the whole matvec"},
+        "ms_per_step": 1000.0 * res["seconds_per_matvec"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "wall_s": time.perf_counter() - t0,
+        "build_s": res["build_s"], "wall_s": time.perf_counter() - t0,
     }
     print(json.dumps(line))
 
@@ -186,6 +209,38 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def sharded_vs_single(adcc, PackedDoubles, synthetic_reference_state, rank, world, no, nv):
+    """N > 1: the complete sigma of the sharded engine against the single-GPU engine on the same
+    device-generated inputs (nocc=40 / nvirt=240: 6.6 GB of packed vvvv, fits every rank), all ranks."""
+    import torch
+    import torch.distributed as dist
+    ref = synthetic_reference_state(no, nv, seed=SEED + 7, scale=SCALE)
+    ms = adcc.AdcMatrix("adc2x", ref, doubles_storage="packed", shard=(rank, world))
+    eng = ms._engine
+    g = torch.Generator(device="cpu").manual_seed(SEED + 3)
+    u1 = torch.randn(no, nv, generator=g, dtype=torch.float64).cuda()
+    u2 = torch.randn(eng.npo, eng.npv, generator=g, dtype=torch.float64).cuda()
+    v = adcc.AmplitudeVector(ph=adcc.Tensor._wrap(ref.mospaces, ["o1", "v1"], u1),
+                             pphh=PackedDoubles._wrap(ref.mospaces, ["o1", "o1", "v1", "v1"], u2))
+    s_sh = ms.matvec(v)
+    s_sh = ms.matvec(v)                       # second call: both peer exchange buffers have been used
+    m1 = adcc.AdcMatrix("adc2x", ref, doubles_storage="packed")
+    s_1 = m1.matvec(v)
+    err = max(float((s_sh[b]._data - s_1[b]._data).abs().max() / s_1[b]._data.abs().max())
+              for b in ("ph", "pphh"))
+    t = torch.tensor([err], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    flat = torch.cat((s_sh.ph._data.reshape(-1), s_sh.pphh._data.reshape(-1)))
+    ref0 = flat.clone()
+    dist.broadcast(ref0, 0)
+    same = torch.tensor([1.0 if torch.equal(ref0, flat) else 0.0], device="cuda", dtype=torch.float64)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    del ms, m1, eng, s_sh, s_1, v
+    torch.cuda.empty_cache()
+    return {"sharded_vs_single_rel": float(t.item()), "sharded_identical_on_all_ranks": bool(same.item() == 1.0),
+            "sharded_check_shape": f"nocc={no} nvirt={nv}, complete sigma"}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -203,6 +258,10 @@ def run_gpu(args):
     from adcc_b200.packed import PackedDoubles, synthetic_reference_state
 
     no, nv = args.nocc, args.nvirt
+    sharded_check = None
+    if world > 1 and not args.no_sharded_check:
+        sharded_check = sharded_vs_single(adcc, PackedDoubles, synthetic_reference_state, rank, world,
+                                          min(no, 40), min(nv, 240))
     t0 = time.perf_counter()
     ref = synthetic_reference_state(no, nv, seed=SEED, scale=SCALE)
     matrix = adcc.AdcMatrix("adc2x", ref, doubles_storage="packed",
@@ -323,17 +382,26 @@ def run_gpu(args):
             from verify_headline import verify
             res = verify(matrix, v, sig, n_pphh=args.verify_samples, n_ph=max(1, args.verify_samples // 4))
             checks.update({k: float(x) for k, x in res.items()})
+        if sharded_check is not None:
+            checks.update(sharded_check)
 
     # ---- time to converged states ----------------------------------------------------------------
     davidson = None
-    if args.davidson and world == 1:
+    if args.davidson:
+        barrier()
         td0 = time.perf_counter()
         state = adcc.run_adc(matrix, n_states=args.n_states, kind="any", n_guesses=2 * args.n_states,
                              conv_tol=1e-6, output=None, max_iter=args.max_iter)
-        torch.cuda.synchronize()
+        barrier()
+        t_dav = time.perf_counter() - td0
+        if world > 1:
+            t = torch.tensor([t_dav], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_dav = float(t.item())
         davidson = {"n_states": args.n_states, "conv_tol": 1e-6, "converged": bool(state.converged),
                     "n_iter": int(state.n_iter), "n_applies": int(state.n_applies),
-                    "time_to_converged_s": time.perf_counter() - td0,
+                    "time_to_converged_s": t_dav,
+                    "vectors": getattr(state, "vector_distribution", "replicated" if world > 1 else "single GPU"),
                     "excitation_energies": [float(e) for e in state.excitation_energy]}
 
     if rank != 0:
@@ -342,6 +410,11 @@ def run_gpu(args):
         return
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------
+    flops_per_matvec = eng.flops_per_matvec
+    f_ovov = eng.flops["pphh_pphh/ovov"]
+    slab_exchange = ("none" if world == 1 else
+                     "GEMM epilogue -> peer memory (NVLink stores)" if eng._peer is not None
+                     else "NCCL all-gather")
     f_vvvv = eng.flops["pphh_pphh/vvvv"] / world
     t_vvvv = float(np.mean(ktimes["vvvv"])) if ktimes.get("vvvv") else None
     t_ovov = float(np.mean(ktimes["ovov"])) if ktimes.get("ovov") else None
@@ -357,29 +430,39 @@ def run_gpu(args):
         # profiles/r01_vvvv_gemm.ncu-rep (1 GPU, nocc=40/nvirt=400): 114.43 GB + 0.52 GB per launch;
         # algorithmic: W 50.9 GB once + U 0.5 GB per round of N tiles + sigma RMW 1 GB
         "traffic": 1.2325e11 if (world == 1 and no == NO and nv == NV) else None,
-        "second_kernel": {"name": "dgemm_tn_tma_kernel (ovov term)", "flops_per_launch": eng.flops["pphh_pphh/ovov"],
+        "second_kernel": {"name": "dgemm_tn_tma_kernel (ovov term)", "flops_per_launch": f_ovov / world,
                           "ms_per_launch": t_ovov,
-                          "achieved": eng.flops["pphh_pphh/ovov"] / (t_ovov * 1e-3) * 1e-12 if t_ovov else None},
+                          "achieved": f_ovov / world / (t_ovov * 1e-3) * 1e-12 if t_ovov else None},
         "share_of_step": (t_vvvv / ms_step) if t_vvvv else None,
         "section_ms": {k: float(np.mean(v)) for k, v in ktimes.items()},
     }
-    cpu = cpu_sample() if (world == 1 and not args.no_cpu_baseline) else None
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        # one COMPLETE matvec of the same workload on the host cores (bounded: one step), fed with
+        # the same trial vector; the whole sigma vector is compared with the GPU result
+        cno, cnv = cpu_shape(no, nv)
+        same = (cno, cnv) == (no, nv)
+        u_np = (u1_host.numpy(), u2_host.numpy()) if same else None
+        sig_ref = (sig.ph._data.cpu().numpy(), sig.pphh._data.cpu().numpy()) if same else None
+        del matrix, eng, sig, v
+        torch.cuda.empty_cache()
+        cpu, csig = cpu_matvec_run(cno, cnv, 0, 1, u=u_np)
+        if same:
+            checks["full_sigma_rel_err_vs_cpu_oracle"] = float(max(
+                np.max(np.abs(csig[0] - sig_ref[0])) / np.max(np.abs(sig_ref[0])),
+                np.max(np.abs(csig[1] - sig_ref[1])) / np.max(np.abs(sig_ref[1]))))
+            checks["full_sigma_elements_compared"] = int(csig[0].size + csig[1].size)
     line = {
         "metric": METRIC, "value": 1000.0 / ms_step, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"synthetic ADC(2)-x matvec nocc={no} nvirt={nv} (BASELINE configs[4]), "
-                               "random antisymmetrised FP64 ERIs from a counter-based hash",
-                   "storage": "antisymmetry-packed doubles + vvvv (50.9 GB instead of 204.8 GB dense)",
-                   "l2": "inputs (vvvv 50.9 GB, ovvv 2x10.2 GB) exceed the 126 MB L2 every step",
-                   "seed": SEED, "parallelism": f"virtual-pair slabs x{world}" if world > 1 else "single GPU",
-                   "slab_exchange": ("none" if world == 1 else
-                                     "GEMM epilogue -> peer memory (NVLink stores)" if eng._peer is not None
-                                     else "NCCL all-gather")},
-        "executed_tflop_per_step": eng.flops_per_matvec * 1e-12,
+        "config": workload_config(no, nv),
+        "parallelism": {"layout": f"virtual-pair slabs x{world}" if world > 1 else "single GPU",
+                        "slab_exchange": slab_exchange},
+        "executed_tflop_per_step": flops_per_matvec * 1e-12,
         "dense_tflop_per_step": dense_flops(no, nv) * 1e-12,
-        "achieved_tflops_executed": eng.flops_per_matvec / (ms_step * 1e-3) * 1e-12,
+        "achieved_tflops_executed": flops_per_matvec / (ms_step * 1e-3) * 1e-12,
         "e2e": {"value": 1000.0 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
         "gpu_launches": int(launches),
@@ -424,7 +507,9 @@ def main():
     ap.add_argument("--nvirt", type=int, default=NV)
     ap.add_argument("--n-states", type=int, default=5)
     ap.add_argument("--max-iter", type=int, default=40)
-    ap.add_argument("--verify-samples", type=int, default=8,
+    ap.add_argument("--no-sharded-check", action="store_true",
+                    help="N > 1: skip the sharded-vs-single-GPU full sigma comparison at nocc=40 / nvirt=240")
+    ap.add_argument("--verify-samples", type=int, default=64,
                     help="sigma entries re-derived on the CPU from the input definition (0 = off)")
     ap.add_argument("--no-davidson", dest="davidson", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -26,6 +26,7 @@ def test_reference_arm_prints_one_json_line():
     assert d["higher_is_better"] is True and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 1000.0) < 1e-6
     assert d["vs_baseline"] is None and "workload" in d["config"]
+    assert "nocc=6 nvirt=10" in d["config"]["workload"]          # the shape that was timed is the shape named
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "matvec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -102,11 +102,17 @@ class PhPhFromDefinition:
         e_o, e_v = synthetic_orbital_energies(no, nv)
         self.eps_o = np.concatenate((e_o[0::2], e_o[1::2]))
         self.eps_v = np.concatenate((e_v[0::2], e_v[1::2]))
-        a, b = np.meshgrid(np.arange(nv), np.arange(nv), indexing="ij")
         self.oovv = np.empty((no, no, nv, nv))
-        for i in range(no):                                   # chunked: bounded temporaries
-            for j in range(no):
-                self.oovv[i, j] = synthetic_eri_value(seed, "oovv", i, j, a, b, scale)
+        if no * no * nv * nv > 10 ** 7:
+            # the C restatement of the same hash (oracle/csrc, bit-identical to synthetic_eri_value:
+            # tests/test_oracle_headline_cpu.py) on all host threads; NumPy needs 35 s at 40/400
+            from oracle.headline import lib, _p
+            lib().orc_fill_dense(2, no, no, nv, nv, seed, scale, _p(self.oovv))
+        else:
+            a, b = np.meshgrid(np.arange(nv), np.arange(nv), indexing="ij")
+            for i in range(no):
+                for j in range(no):
+                    self.oovv[i, j] = synthetic_eri_value(seed, "oovv", i, j, a, b, scale)
         den = (self.eps_v[None, None, :, None] + self.eps_v[None, None, None, :]
                - self.eps_o[:, None, None, None] - self.eps_o[None, :, None, None])
         self.t2 = self.oovv / den
