@@ -66,7 +66,10 @@ def default_block_orders(method):
 
 class AdcMatrix(AdcMatrixlike):
     def __init__(self, method, hf_or_mp, block_orders=None, intermediates=None,
-                 diagonal_precomputed=None, doubles_storage="auto", shard=None):
+                 diagonal_precomputed=None, doubles_storage="auto", shard=None, vectors=None):
+        """``shard=(rank, world)``: this process holds rank's slabs of the big operands (one process
+        per GPU, torch.distributed initialised); ``vectors``: "slab" (default, doubles vectors
+        distributed by virtual-pair slabs, SlabDoubles) or "replicated"."""
         if isinstance(hf_or_mp, ReferenceState):
             hf_or_mp = LazyMp(hf_or_mp)
         elif not isinstance(hf_or_mp, LazyMp):
@@ -125,7 +128,7 @@ class AdcMatrix(AdcMatrixlike):
             self.blocks = {blk: self._make_apply(blk) for blk in self._tables}
             if self.doubles_storage == "packed":
                 from .packed import PackedAdcEngine
-                self._engine = PackedAdcEngine(self, shard=shard)
+                self._engine = PackedAdcEngine(self, shard=shard, vectors=vectors)
                 self.blocks = {blk: self._make_engine_apply(blk) for blk in self._tables
                                if self._tables[blk][0] is not None}
                 dph = adc_pp.diagonal(self._variant, "ph_ph", self.block_orders["ph_ph"], hf,
@@ -230,6 +233,14 @@ class AdcMatrix(AdcMatrixlike):
 
     def diagonal(self):
         return self._diagonal
+
+    @property
+    def vector_distribution(self):
+        """"single GPU", "replicated" or "slab" (doubles vectors distributed over the GPUs)."""
+        eng = self._engine
+        if eng is None or eng.world == 1:
+            return "single GPU"
+        return eng.vectors
 
     # ------------------------------------------------------------------ interpreter
     def _operand(self, name, ampl):
@@ -420,8 +431,10 @@ class AdcMatrix(AdcMatrixlike):
         [npo, npv]} of torch CPU tensors): the end-to-end form of ``matvec`` for callers whose
         vectors live on the host (dense store: tensors of the dense block shapes, plain upload /
         download).  Packed store: the PCIe transfers are pipelined with row slabs of the vvvv GEMM
-        (PackedAdcEngine.matvec_host).  Sharded matrices: rank 0 passes the buffers, the other
-        ranks pass None; all ranks must call."""
+        (PackedAdcEngine.matvec_host).  Sharded matrices (all ranks must call): either every rank
+        passes the SAME buffers in shared pinned host memory (``adcc_b200.shared_host_vector``) and
+        moves its own slab over its own PCIe link, or rank 0 passes private buffers and the other
+        ranks pass None (upload on rank 0 + NCCL broadcast)."""
         if self._engine is None:
             # dense store: plain upload / matvec / download (the vectors have the dense block shapes)
             from . import backend as be

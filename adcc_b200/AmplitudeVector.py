@@ -52,21 +52,41 @@ class AmplitudeVector(dict):
             t.set_random()
         return self
 
+    def _dot_plan(self):
+        """(weight per block, slab layout or None).  Packed doubles count every stored element 4
+        times (Frobenius product of the dense tensors, adcc/AmplitudeVector.py:85-95); when the
+        doubles are distributed over GPUs the replicated blocks are counted on rank 0 only and the
+        partial sums are completed by one all-reduce."""
+        layout = None
+        for t in self.values():
+            layout = getattr(t, "slab", None) or layout
+        weights = []
+        for b in self.keys():
+            w = getattr(self[b], "dot_weight", 1.0)
+            if layout is not None and getattr(self[b], "slab", None) is None and layout.rank != 0:
+                w = 0.0
+            weights.append(w)
+        return weights, layout
+
     def dot(self, other):
         """Scalar product(s) summed over the blocks on the device: one host read per call."""
-        from .Tensor import Tensor
         single = not isinstance(other, list)
         others = [other] if single else other
-        if any(type(t) is not Tensor for t in self.values()):     # packed doubles weigh their dot
-            if single:
-                return sum(self[b].dot(other[b]) for b in self.keys())
-            return sum(np.asarray(self[b].dot([av[b] for av in other])) for b in self.keys())
+        if len(others) == 0:
+            return np.zeros(0)
+        weights, layout = self._dot_plan()
         pairs = []
         for b in self.keys():
             for av in others:
                 self[b]._check_same(av[b])
             pairs.append((self[b]._contig(), [av[b]._contig() for av in others]))
-        res = be.dot_many_blocks(pairs)
+        if layout is None:
+            res = be.dot_many_blocks(pairs, scales=weights)
+        else:
+            out = be.empty((len(others),))
+            be.dot_many_blocks(pairs, scales=weights, out=out)
+            be.comm_all_reduce(out, group=layout.group)          # Gram-row all-reduce
+            res = be.to_host(out)
         return float(res[0]) if single else res
 
     def __matmul__(self, other):
@@ -122,19 +142,23 @@ class AmplitudeVector(dict):
 def dot_rows(rows):
     """[x @ ys for x, ys in rows] with a single device-to-host read: every row's batched dot writes
     its slice of one device array (used for the Davidson subspace-matrix update)."""
-    from .Tensor import Tensor
     rows = [(x, list(ys)) for x, ys in rows]
     if not rows:
         return []
-    if any(type(t) is not Tensor for x, _ in rows for t in x.values()):
-        return [np.asarray(x @ ys) for x, ys in rows]
-    out = be.empty((sum(len(ys) for _, ys in rows),))
-    pos, cuts = 0, []
+    total = sum(len(ys) for _, ys in rows)
+    if total == 0:
+        return [np.zeros(0) for _ in rows]
+    out = be.empty((total,))
+    pos, cuts, layout = 0, [], None
     for x, ys in rows:
         if ys:
+            weights, lay = x._dot_plan()
+            layout = lay or layout
             be.dot_many_blocks([(x[b]._contig(), [av[b]._contig() for av in ys]) for b in x.keys()],
-                               out=out[pos:pos + len(ys)])
+                               scales=weights, out=out[pos:pos + len(ys)])
         cuts.append((pos, pos + len(ys)))
         pos += len(ys)
+    if layout is not None:
+        be.comm_all_reduce(out, group=layout.group)              # one all-reduce per batch of Gram rows
     host = be.to_host(out)
     return [host[a:b] for a, b in cuts]

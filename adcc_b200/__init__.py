@@ -24,6 +24,7 @@ from .Intermediates import Intermediates, register_as_intermediate  # noqa: F401
 from .LazyMp import LazyMp  # noqa: F401
 from .memory_pool import memory_pool  # noqa: F401
 from .MoSpaces import MoSpaces  # noqa: F401
+from .packed import shared_host_vector  # noqa: F401
 from .projection import Projector, SubspacePartitioning  # noqa: F401
 from .ReferenceState import ReferenceState  # noqa: F401
 from .solver.davidson import jacobi_davidson  # noqa: F401

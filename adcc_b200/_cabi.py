@@ -50,6 +50,10 @@ def _declare(lib):
     lib.adccb_packed_unpack.argtypes = [c_ptr, c_int, c_int, c_ptr, c_ptr]
     lib.adccb_packed_pack.argtypes = [c_ptr, c_int, c_int, c_ptr, c_ptr]
     lib.adccb_packed_expand.argtypes = [c_ptr, c_int, c_int, c_int, c_ptr, c_ptr]
+    lib.adccb_packed_expand_slab.argtypes = [c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr]
+    lib.adccb_slab_layout.argtypes = [c_ptr, c_int, c_i64, c_i64, c_int, ctypes.POINTER(c_i64), c_i64,
+                                      c_ptr, c_ptr]
+    lib.adccb_copy2d.argtypes = [c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64]
     lib.adccb_packed_fold_virt.argtypes = [c_ptr, c_i64, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr,
                                            c_ptr, c_dbl, c_ptr]
     lib.adccb_packed_fold_occ.argtypes = [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_dbl, c_ptr]
@@ -67,7 +71,8 @@ EXPORTS = [
     "adccb_dgemm", "adccb_dgemm_peers", "adccb_peer_alloc", "adccb_peer_open", "adccb_peer_close",
     "adccb_peer_free", "adccb_strided_gather", "adccb_elementwise", "adccb_direct_sum",
     "adccb_add_columns", "adccb_lincomb", "adccb_dot_many", "adccb_spin_expand4", "adccb_spin_project", "adccb_spin_singlet",
-    "adccb_packed_unpack", "adccb_packed_pack", "adccb_packed_expand", "adccb_packed_fold_virt",
+    "adccb_packed_unpack", "adccb_packed_pack", "adccb_packed_expand", "adccb_packed_expand_slab",
+    "adccb_slab_layout", "adccb_copy2d", "adccb_packed_fold_virt",
     "adccb_packed_fold_occ", "adccb_packed_diagonal", "adccb_pair_select", "adccb_synth_fill",
 ]
 

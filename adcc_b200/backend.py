@@ -357,10 +357,11 @@ def dot_many(x, ys, scale=1.0):
     return out.cpu().numpy()
 
 
-def dot_many_blocks(pairs, scale=1.0, out=None):
+def dot_many_blocks(pairs, scale=1.0, out=None, scales=None):
     """sum over blocks b of <x_b, y_bj> for pairs = [(x_b, [y_b0 .. y_bk-1]), ...]: the partial sums
     accumulate on the device (beta = 1 from the second block on), ONE D2H copy at the end.
-    With ``out`` (device array of length k) the result stays on the device and nothing is read."""
+    With ``out`` (device array of length k) the result stays on the device and nothing is read.
+    ``scales``: one weight per block (default: ``scale`` for all)."""
     k = len(pairs[0][1])
     if k == 0:
         return np.zeros(0)
@@ -376,7 +377,8 @@ def dot_many_blocks(pairs, scale=1.0, out=None):
             if not t.is_contiguous() or t.numel() != n:
                 raise ValueError("dot_many: tensors must be contiguous and equally sized")
         ps = (ctypes.c_void_p * k)(*[t.data_ptr() for t in ys])
-        _cabi.check(_cabi.lib().adccb_dot_many(_stream(), k, _ptr(x), ps, n, float(scale),
+        _cabi.check(_cabi.lib().adccb_dot_many(_stream(), k, _ptr(x), ps, n,
+                                               float(scale if scales is None else scales[ib]),
                                                0.0 if ib == 0 else 1.0, _ptr(out), _ptr(ws),
                                                ws.numel() * 8))
     return out if keep else out.cpu().numpy()
@@ -447,6 +449,60 @@ def packed_expand(which, U, no, nv, out=None, n_pairs_o=None):
     _cabi.check(_cabi.lib().adccb_packed_expand(_stream(), which, no if n_pairs_o is None else -npo, nv,
                                                 _ptr(U), _ptr(out)))
     return out
+
+
+def packed_expand_slab(which, U, no, nv, first, count):
+    """Slab forms of packed_expand: 0: X rows (il, a), i = first + il < first + count -> [count*nv, no*nv];
+    1: Ue[i, jl, AB], j = first + jl -> [no, count*npv]; 2: Uh[a, r, b] for the `count` packed rows
+    of the row slab U -> [nv, count*nv]."""
+    shape = {0: (count * nv, no * nv), 1: (no, count * n_pairs(nv)), 2: (nv, count * nv)}[which]
+    out = empty(shape)
+    _cabi.check(_cabi.lib().adccb_packed_expand_slab(_stream(), which, no, nv, int(first), int(count),
+                                                     _ptr(U), _ptr(out)))
+    return out
+
+
+def slab_layout(direction, full, slabs, cuts, wmax):
+    """direction 0: full [nrows, npv] -> slabs [world, nrows, wmax] (zero padded); 1: slabs -> full."""
+    world = len(cuts) - 1
+    nrows, npv = full.shape
+    if tuple(slabs.shape) != (world, nrows, wmax) or not full.is_contiguous() or not slabs.is_contiguous():
+        raise ValueError("slab_layout: shape mismatch")
+    c = (ctypes.c_int64 * (world + 1))(*[int(x) for x in cuts])
+    _cabi.check(_cabi.lib().adccb_slab_layout(_stream(), int(direction), nrows, npv, world, c, int(wmax),
+                                              _ptr(full), _ptr(slabs)))
+    return slabs if direction == 0 else full
+
+
+def copy2d(dst, src, nrows, ncols):
+    """dst[:nrows, :ncols] = src[:nrows, :ncols] between 2-D FP64 views with unit column stride that
+    live in device or pinned host memory, on the current stream (one cudaMemcpy2DAsync)."""
+    if dst.stride(1) != 1 or src.stride(1) != 1:
+        raise ValueError("copy2d: unit column stride expected")
+    _cabi.check(_cabi.lib().adccb_copy2d(_stream(), ctypes.c_void_p(dst.data_ptr()), dst.stride(0) * 8,
+                                         ctypes.c_void_p(src.data_ptr()), src.stride(0) * 8,
+                                         int(ncols) * 8, int(nrows)))
+    return dst
+
+
+# --------------------------------------------------------------------------------- collectives
+# NCCL over NVLink / NVSwitch through torch.distributed (plumbing): equal-sized slabs only.
+def comm_all_gather(out, inp, group=None):
+    import torch.distributed as dist
+    dist.all_gather_into_tensor(out, inp, group=group)
+    return out
+
+
+def comm_reduce_scatter(out, inp, group=None):
+    import torch.distributed as dist
+    dist.reduce_scatter_tensor(out, inp, group=group)
+    return out
+
+
+def comm_all_reduce(t, group=None):
+    import torch.distributed as dist
+    dist.all_reduce(t, group=group)
+    return t
 
 
 def packed_fold_virt(S, nv, sa, P1, off1, P2=None, off2=None, alpha=1.0, rows=None):

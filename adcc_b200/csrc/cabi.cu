@@ -64,6 +64,10 @@ int spin_singlet(cudaStream_t st, const int* shape, const int* nalpha, double* T
 int packed_unpack(cudaStream_t st, int no, int nv, const double* U, double* out);
 int packed_pack(cudaStream_t st, int no, int nv, const double* T, double* U);
 int packed_expand(cudaStream_t st, int which, int no, int nv, const double* U, double* out);
+int packed_expand_slab(cudaStream_t st, int which, int no, int nv, int first, int count, const double* U,
+                       double* out);
+int slab_layout(cudaStream_t st, int dir, long long nrows, long long npv, int world, const long long* cut,
+                long long wmax, double* full, double* slabs);
 int packed_fold_virt(cudaStream_t st, long long nrows, int nv, long long sa, const double* P1,
                      const long long* off1, const double* P2, const long long* off2,
                      const long long* rows, double alpha, double* S);
@@ -199,6 +203,21 @@ int adccb_packed_pack(void* stream, int no, int nv, const double* T, double* U) 
 }
 int adccb_packed_expand(void* stream, int which, int no, int nv, const double* U, double* out) {
   return packed_expand((cudaStream_t)stream, which, no, nv, U, out);
+}
+int adccb_packed_expand_slab(void* stream, int which, int no, int nv, int first, int count,
+                              const double* U, double* out) {
+  return packed_expand_slab((cudaStream_t)stream, which, no, nv, first, count, U, out);
+}
+int adccb_slab_layout(void* stream, int dir, int64_t nrows, int64_t npv, int world, const int64_t* host_cut,
+                      int64_t wmax, double* full, double* slabs) {
+  return slab_layout((cudaStream_t)stream, dir, nrows, npv, world, (const long long*)host_cut, wmax, full, slabs);
+}
+int adccb_copy2d(void* stream, void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes,
+                 int64_t width_bytes, int64_t height) {
+  if (width_bytes <= 0 || height <= 0) return 0;
+  ADCCB_CUDA_OK(cudaMemcpy2DAsync(dst, (size_t)dst_pitch_bytes, src, (size_t)src_pitch_bytes, (size_t)width_bytes,
+                                  (size_t)height, cudaMemcpyDefault, (cudaStream_t)stream));
+  return 0;
 }
 int adccb_packed_fold_virt(void* stream, int64_t nrows, int nv, int64_t sa, const double* P1,
                            const int64_t* off1, const double* P2, const int64_t* off2,

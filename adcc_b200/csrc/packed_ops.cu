@@ -72,7 +72,8 @@ __global__ void pack_dense_kernel(int no, int nv, const double* __restrict__ T,
 //   mode 0: X[i,a,k,c] = u[i,k,a,c]  (ovov-term operand): r = (i,k), row = U[pair(i,k)], s = sign(k-i),
 //           base = (i*nv*no + k)*nv, sA = no*nv; r with i == k is zero-filled
 //   mode 2: Uh[a,JK,b] = u[JK,a,b]   : r = JK, row = U[JK], s = +1, base = JK*nv, sA = npo*nv
-__global__ void expand_antisym_kernel(int mode, int no, long long npo, int nv,
+//   mode 0 with an occupied slab: r = (il, k), i = i_first + il; the output holds rows (il, a) only
+__global__ void expand_antisym_kernel(int mode, int no, long long npo, int nv, int i_first,
                                       const double* __restrict__ U, double* __restrict__ out) {
   __shared__ double tile[32][33];
   const long long npv = (long long)nv * (nv - 1) / 2;
@@ -83,9 +84,9 @@ __global__ void expand_antisym_kernel(int mode, int no, long long npo, int nv,
   double sgn;
   long long base, sA;
   if (mode == 0) {
-    const int i = (int)(r / no), k = (int)(r % no);
+    const int il = (int)(r / no), k = (int)(r % no), i = i_first + il;
     sA = (long long)no * nv;
-    base = ((long long)i * nv * no + k) * nv;
+    base = ((long long)il * nv * no + k) * nv;
     if (i == k) { row = nullptr; sgn = 0.0; }
     else { row = U + pair_index(min(i, k), max(i, k)) * npv; sgn = (i < k) ? 1.0 : -1.0; }
   } else {
@@ -113,10 +114,11 @@ __global__ void expand_antisym_kernel(int mode, int no, long long npo, int nv,
   }
 }
 
-// Ue[i,j,AB] = s_ij U[pair(ij),AB]; one CTA per (i,j), 16-byte accesses when the row length is even
-__global__ void expand_occ_kernel(int no, long long npv, const double* __restrict__ U,
+// Ue[i,jl,AB] = s_ij U[pair(ij),AB], j = j_first + jl < j_first + nj; one CTA per (i,jl), 16-byte
+// accesses when the row length is even
+__global__ void expand_occ_kernel(int no, int j_first, int nj, long long npv, const double* __restrict__ U,
                                   double* __restrict__ Ue) {
-  const int i = blockIdx.x / no, j = blockIdx.x % no;
+  const int i = blockIdx.x / nj, j = j_first + blockIdx.x % nj;
   double* dst = Ue + (long long)blockIdx.x * npv;
   const double s = (i == j) ? 0.0 : ((i < j) ? 1.0 : -1.0);
   const double* row = (i == j) ? U : U + pair_index(min(i, j), max(i, j)) * npv;
@@ -343,12 +345,51 @@ __global__ void pair_select_kernel(long long L, int n, long long R, const double
   }
 }
 
+// Column slabs of a packed [nrows, npv] array: rank r owns columns [cut[r], cut[r+1]) and stores
+// them as slab r of a [world, nrows, wmax] array (zero padded up to wmax columns).
+//   dir 0: full -> slabs (input of the reduce-scatter that sums the ranks' partial sigma vectors)
+//   dir 1: slabs -> full (output of the all-gather of a trial vector's slabs)
+struct SlabCuts {
+  int world;
+  long long cut[17];
+};
+__global__ void slab_layout_kernel(int dir, long long nrows, long long npv, long long wmax, SlabCuts cuts,
+                                   double* __restrict__ full, double* __restrict__ slabs) {
+  const long long per = nrows * wmax;
+  const long long n = per * cuts.world;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / per);
+    const long long row = (idx % per) / wmax, c = idx % wmax;
+    const long long col = cuts.cut[r] + c;
+    const bool inside = col < cuts.cut[r + 1];
+    if (dir == 0) slabs[idx] = inside ? full[row * npv + col] : 0.0;
+    else if (inside) full[row * npv + col] = slabs[idx];
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // host entry points
 // ---------------------------------------------------------------------------------------
 static inline int blocks_for(long long n, int threads) {
   long long b = (n + threads - 1) / threads;
   return (int)std::max<long long>(1, std::min<long long>(b, 64LL * sm_count()));
+}
+
+int slab_layout(cudaStream_t st, int dir, long long nrows, long long npv, int world, const long long* cut,
+                long long wmax, double* full, double* slabs) {
+  if (world < 1 || world > 16) return fail("slab_layout: 1 .. 16 ranks");
+  SlabCuts c;
+  c.world = world;
+  for (int r = 0; r <= world; ++r) c.cut[r] = cut[r];
+  for (int r = 0; r < world; ++r)
+    if (cut[r + 1] < cut[r] || cut[r + 1] - cut[r] > wmax || cut[r + 1] > npv) return fail("slab_layout: bad cuts");
+  const long long n = nrows * wmax * world;
+  if (n == 0) return 0;
+  slab_layout_kernel<<<blocks_for(n, 256), 256, 0, st>>>(dir, nrows, npv, wmax, c, full, slabs);
+  ADCCB_LAUNCH_OK();
+  count_launch();
+  return 0;
 }
 
 int packed_unpack(cudaStream_t st, int no, int nv, const double* U, double* out) {
@@ -369,21 +410,29 @@ int packed_pack(cudaStream_t st, int no, int nv, const double* T, double* U) {
   return 0;
 }
 
-int packed_expand(cudaStream_t st, int which, int no, int nv, const double* U, double* out) {
-  // no < 0 (which == 2 only): U is a slab of -no rows of the packed vector
+int packed_expand_slab(cudaStream_t st, int which, int no, int nv, int first, int count, const double* U,
+                       double* out) {
+  // which 0: occupied slab i = first .. first+count-1 of X; which 1: slab of the second occupied
+  // index j of Ue; which 2: `count` rows of the packed vector starting at U (first is ignored)
   const long long npv = (long long)nv * (nv - 1) / 2;
-  const long long npo = (no < 0) ? -(long long)no : (long long)no * (no - 1) / 2;
-  if (no < 0 && which != 2) return fail("packed_expand: row slabs are supported for layout 2 only");
-  if (npv == 0 || npo == 0) return 0;
+  if (npv == 0 || count <= 0) return 0;
+  if (which != 2 && (first < 0 || first + count > no)) return fail("packed_expand: slab out of range");
+  const int t = (nv + 31) / 32;
   if (which == 0) {
-    const int t = (nv + 31) / 32;
-    expand_antisym_kernel<<<dim3(t, t, no * no), dim3(32, 8), 0, st>>>(0, no, npo, nv, U, out);
+    if ((long long)count * no > 65535) return fail("packed_expand: too many (i,k) rows");
+    expand_antisym_kernel<<<dim3(t, t, count * no), dim3(32, 8), 0, st>>>(0, no, 0, nv, first, U, out);
   } else if (which == 1) {
-    expand_occ_kernel<<<no * no, 512, 0, st>>>(no, npv, U, out);
+    expand_occ_kernel<<<no * count, 512, 0, st>>>(no, first, count, npv, U, out);
   } else if (which == 2) {
-    const int t = (nv + 31) / 32;
-    if (npo > 65535) return fail("packed_expand: too many pair rows");
-    expand_antisym_kernel<<<dim3(t, t, (unsigned)npo), dim3(32, 8), 0, st>>>(2, no, npo, nv, U, out);
+    // grid.z is limited to 65535: walk the pair rows in chunks (row r of a chunk writes out + r*nv)
+    for (long long r0 = 0; r0 < count; r0 += 65535) {
+      const long long nr = std::min<long long>(65535, count - r0);
+      expand_antisym_kernel<<<dim3(t, t, (unsigned)nr), dim3(32, 8), 0, st>>>(2, no, count, nv, 0, U + r0 * npv,
+                                                                         out + r0 * nv);
+      ADCCB_LAUNCH_OK();
+    }
+    count_launch();
+    return 0;
   } else {
     return fail("packed_expand: unknown layout");
   }
@@ -392,15 +441,30 @@ int packed_expand(cudaStream_t st, int which, int no, int nv, const double* U, d
   return 0;
 }
 
+int packed_expand(cudaStream_t st, int which, int no, int nv, const double* U, double* out) {
+  // no < 0 (which == 2 only): U is a slab of -no rows of the packed vector
+  if (no < 0 && which != 2) return fail("packed_expand: row slabs are supported for layout 2 only");
+  if (no < 0) return packed_expand_slab(st, 2, no, nv, 0, -no, U, out);
+  if (which == 2) return packed_expand_slab(st, 2, no, nv, 0, no * (no - 1) / 2, U, out);
+  return packed_expand_slab(st, which, no, nv, 0, no, U, out);
+}
+
 int packed_fold_virt(cudaStream_t st, long long nrows, int nv, long long sa, const double* P1,
                      const long long* off1, const double* P2, const long long* off2,
                      const long long* rows, double alpha, double* S) {
   if (nrows == 0 || nv < 2) return 0;
-  if (nrows > 65535) return fail("packed_fold_virt: too many rows");
   const int t = (nv + 31) / 32;
-  dim3 grid(t, t, (unsigned)nrows);
-  pack_antisym_virt_kernel<<<grid, dim3(32, 8), 0, st>>>(nv, sa, P1, off1, P2, off2, rows, alpha, S);
-  ADCCB_LAUNCH_OK();
+  // grid.z is limited to 65535 rows per launch.  Without an explicit `rows` map row r is S row r,
+  // so a chunk starting at r0 shifts S by r0 rows.
+  const long long npv = (long long)nv * (nv - 1) / 2;
+  for (long long r0 = 0; r0 < nrows; r0 += 65535) {
+    const long long nr = std::min<long long>(65535, nrows - r0);
+    dim3 grid(t, t, (unsigned)nr);
+    pack_antisym_virt_kernel<<<grid, dim3(32, 8), 0, st>>>(nv, sa, P1, off1 + r0, P2, off2 ? off2 + r0 : nullptr,
+                                                           rows ? rows + r0 : nullptr, alpha,
+                                                           rows ? S : S + r0 * npv);
+    ADCCB_LAUNCH_OK();
+  }
   count_launch();
   return 0;
 }

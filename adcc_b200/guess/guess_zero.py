@@ -13,7 +13,9 @@ def guess_zero(matrix, spin_change=0, spin_block_symmetrisation="none"):
 
     def make(block, sym):
         if packed and block == "pphh":
-            from ..packed import PackedDoubles
+            from ..packed import PackedDoubles, SlabDoubles
+            if getattr(matrix, "vector_distribution", None) == "slab":
+                return SlabDoubles.zeros(sym.mospaces, sym.subspaces, matrix._engine.layout, sym)
             return PackedDoubles.zeros(sym.mospaces, sym.subspaces, sym)
         return Tensor(sym)
     return AmplitudeVector(**{

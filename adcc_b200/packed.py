@@ -57,6 +57,8 @@ class PackedDoubles(Tensor):
 
     #: +1 for tensors that are SYMMETRIC under i<->j and a<->b (the matrix diagonal); -1 otherwise
     parity = -1
+    #: every stored element stands for 4 elements of the dense tensor in a Frobenius product
+    dot_weight = 4.0
 
     def to_dense(self):
         dense = be.packed_unpack(self._contig(), self._no, self._nv)
@@ -153,6 +155,150 @@ def torch_like_ones(t):
     return ones
 
 
+class SlabLayout:
+    """Distribution of packed doubles vectors over the GPUs of one box by virtual-pair (column)
+    slabs: rank r owns the columns [cuts[r], cuts[r+1]) of U[IJ, AB] - the slab of sigma its
+    AB-row slab of the vvvv operand produces - stored zero-padded to ``wmax`` columns so that all
+    ranks' slabs are equally sized (NCCL all-gather / reduce-scatter operate on equal chunks)."""
+
+    def __init__(self, rank, world, npo, npv, cuts, group=None):
+        self.rank, self.world, self.npo, self.npv = rank, world, npo, npv
+        self.cuts = [int(c) for c in cuts]
+        self.c0, self.c1 = self.cuts[rank], self.cuts[rank + 1]
+        self.w = self.c1 - self.c0
+        self.wmax = max(max(self.cuts[k + 1] - self.cuts[k] for k in range(world)), 1)
+        self.group = group
+
+    def gather(self, slab):
+        """Complete [npo, npv] array from every rank's slab (all-gather over NVLink + layout pass)."""
+        parts = be.empty((self.world, self.npo, self.wmax))
+        be.comm_all_gather(parts, slab, group=self.group)
+        return be.slab_layout(1, be.empty((self.npo, self.npv)), parts, self.cuts, self.wmax)
+
+    def reduce_scatter(self, full):
+        """This rank's slab of the sum over ranks of ``full`` [npo, npv] (reduce-scatter)."""
+        parts = be.slab_layout(0, full, be.empty((self.world, self.npo, self.wmax)), self.cuts, self.wmax)
+        out = be.empty((self.npo, self.wmax))
+        be.comm_reduce_scatter(out, parts, group=self.group)
+        return out
+
+    def take(self, full):
+        """This rank's zero-padded slab of a complete array (no communication)."""
+        out = be.zeros((self.npo, self.wmax))
+        if self.w > 0:
+            be.copy2d(out, full[:, self.c0:self.c1], self.npo, self.w)
+        return out
+
+
+class SlabDoubles(PackedDoubles):
+    """One rank's column slab of a packed doubles tensor (see SlabLayout).  Vector algebra acts on the
+    local slab (1/world of the work); scalar products are completed by ONE all-reduce of the
+    batched partial sums (AmplitudeVector.dot / dot_rows), which is the subspace Gram-matrix
+    all-reduce of the sharded Davidson solver."""
+
+    @classmethod
+    def _make(cls, mospaces, subspaces, data, layout, symmetry=None):
+        self = cls._wrap(mospaces, subspaces, data, symmetry)
+        self.slab = layout
+        return self
+
+    @classmethod
+    def zeros(cls, mospaces, subspaces, layout, symmetry=None):
+        return cls._make(mospaces, subspaces, be.zeros((layout.npo, layout.wmax)), layout, symmetry)
+
+    @classmethod
+    def from_full(cls, packed, layout):
+        return cls._make(packed.mospaces, packed.subspaces, layout.take(packed._contig()), layout,
+                         packed.symmetry)
+
+    def _like(self, data, keep_symmetry=True):
+        return type(self)._make(self.mospaces, self.subspaces, data, self.slab,
+                                self.symmetry if keep_symmetry else None)
+
+    def __repr__(self):
+        lay = self.slab
+        return f"SlabDoubles({self.space}, columns [{lay.c0}, {lay.c1}) of {lay.npv}, rank {lay.rank}/{lay.world})"
+
+    def to_full(self):
+        full = PackedDoubles._wrap(self.mospaces, self.subspaces, self.slab.gather(self._contig()),
+                                   self.symmetry)
+        full.parity = self.parity
+        return full
+
+    def to_dense(self):
+        return self.to_full().to_dense()
+
+    def set_from_ndarray(self, array, symmetry_tolerance=None):
+        full = PackedDoubles.zeros(self.mospaces, self.subspaces).set_from_ndarray(array, symmetry_tolerance)
+        self._data = self.slab.take(full._data)
+        return self
+
+    def set_random(self):
+        raise NotImplementedError("set_random on a distributed vector: fill a PackedDoubles and use from_full")
+
+    def _zero_pad(self):
+        lay = self.slab
+        if lay.w < lay.wmax:
+            pad = be.zeros((lay.npo, lay.wmax - lay.w))
+            be.copy2d(self._contig()[:, lay.w:], pad, lay.npo, lay.wmax - lay.w)
+        return self
+
+    def ones_like(self):
+        t = be.empty(tuple(self._data.shape))
+        be.fill(t, 1.0)
+        return self._like(t)._zero_pad()
+
+    def __add__(self, other):
+        res = super().__add__(other)
+        return res._zero_pad() if not isinstance(other, Tensor) and res is not self else res
+
+    def __truediv__(self, other):
+        if isinstance(other, Tensor):
+            raise NotImplementedError("elementwise division of distributed vectors: use div_shifted")
+        return super().__truediv__(other)
+
+    def dot(self, other):
+        single = isinstance(other, Tensor)
+        others = [other] if single else list(other)
+        for o in others:
+            self._check_same(o)
+        out = be.empty((len(others),))
+        be.dot_many_blocks([(self._contig(), [o._contig() for o in others])], scale=4.0, out=out)
+        be.comm_all_reduce(out, group=self.slab.group)
+        host = be.to_host(out)
+        return float(host[0]) if single else host
+
+    def __getitem__(self, index):
+        loc, sign = self._locate(index)
+        val = be.zeros((1,))
+        lay = self.slab
+        if loc is not None and lay.c0 <= loc[1] < lay.c1:
+            be.axpby(sign, self._contig()[loc[0], loc[1] - lay.c0].reshape(1), 0.0, val)
+        be.comm_all_reduce(val, group=lay.group)
+        return float(be.to_host(val)[0])
+
+    def __setitem__(self, index, value):
+        self._require_mutable()
+        index = self._norm_index(index)
+        orb = {index: float(value)}
+        if self.symmetry is not None and not self.symmetry.empty:
+            orb = self.symmetry.orbit(index, float(value))
+        if orb is None or self._locate(index)[0] is None:
+            raise RuntimeError(f"Setting tensor index {index} is not allowed by symmetry")
+        t, lay = self._contig(), self.slab
+        for ix, val in orb.items():
+            loc, sign = self._locate(ix)
+            if lay.c0 <= loc[1] < lay.c1:
+                t[loc[0], loc[1] - lay.c0] = sign * val
+
+    def _symm(self, perms, sign):
+        from .Tensor import _parse_perm_args
+        perms = sorted(tuple(sorted(p)) for p in _parse_perm_args(perms))
+        if (sign < 0 and perms in ([(0, 1)], [(2, 3)])) or (sign > 0 and perms == [(0, 1), (2, 3)]):
+            return self
+        return self.to_dense()._symm(perms, sign)
+
+
 class DenseSource:
     """Stages the packed / GEMM-ready operands from a ReferenceState's dense device blocks."""
 
@@ -204,9 +350,16 @@ class DenseSource:
 class PackedAdcEngine:
     """ADC(2) / ADC(2)-x / ADC(3) matvec on the packed doubles store (see module docstring)."""
 
-    def __init__(self, matrix, source=None, shard=None):
+    def __init__(self, matrix, source=None, shard=None, vectors=None):
+        """``vectors`` (sharded engines): "slab" - Davidson vectors are distributed by virtual-pair
+        slabs (SlabDoubles; default), "replicated" - every rank holds complete vectors."""
         from .functions import einsum, direct_sum
         self.rank, self.world = shard if shard is not None else (0, 1)
+        if vectors is None:
+            vectors = os.environ.get("ADCCB_VECTORS", "slab")
+        if vectors not in ("slab", "replicated"):
+            raise ValueError("vectors needs to be 'slab' or 'replicated'")
+        self.vectors = vectors if self.world > 1 else "replicated"
         hf, mp, im = matrix.reference_state, matrix.ground_state, matrix.intermediates
         self.matrix = matrix
         self.mospaces = hf.mospaces
@@ -280,7 +433,13 @@ class PackedAdcEngine:
         if self.order_dd == 1:
             self.W = src.vvvv_packed(self.ab0, self.ab1 - self.ab0)
             self.O = src.oooo_packed()
-            self.Y = src.ovov_jbkc(self.j0, self.nj)
+            if self.vectors == "slab":
+                # the ovov term runs on the occupied-i row slab of X against the complete Y, so that
+                # the expansion of X is sharded as well (2 GB replicated at nocc=40 / nvirt=400)
+                self.Yfull = src.ovov_jbkc()
+                self.Y = self.Yfull[self.j0 * nv:(self.j0 + self.nj) * nv]
+            else:
+                self.Y = src.ovov_jbkc(self.j0, self.nj)
             d_ov = (direct_sum("a-i->ia", hf.fvv.diagonal(), hf.foo.diagonal())
                     - 2.0 * einsum("iaia->ia", hf.ovov))._contig()
             d_oo = einsum("ijij->ij", hf.oooo).symmetrise()._contig()
@@ -308,7 +467,7 @@ class PackedAdcEngine:
             # W must be even - 16-byte aligned rows; nv = 2, 3 mod 4, e.g. 38, 50, 106, gives an odd
             # npv and keeps the NCCL all-gather)
             if (self.order_dd == 1 and be.peer_exchange_supported() and self.npv % 2 == 0
-                    and os.environ.get("ADCCB_P2P", "1") != "0"):
+                    and self.vectors == "replicated" and os.environ.get("ADCCB_P2P", "1") != "0"):
                 bufs = [be.PeerBuffer.create(self.npo * self.npv) for _ in range(2)]
                 if all(b is not None for b in bufs):
                     self._peer, self._peer_flip = bufs, 0
@@ -326,6 +485,25 @@ class PackedAdcEngine:
                            be.int64_tensor([row[p] for p in p_hi]))
             self._sl_lo = (be.int64_tensor([j * nv * njv + (i - self.j0) * nv for i, j in p_lo]),
                            be.int64_tensor([row[p] for p in p_lo]))
+            # distributed vectors: column slabs along the cuts of the vvvv operand
+            self.layout = SlabLayout(self.rank, self.world, self.npo, self.npv, self._cuts)
+            if self.vectors == "slab":
+                # ovov fold of an occupied-i row slab: T_r[(il,a),(j,b)], offset (il*nv + a)*(no*nv) + j*nv + b
+                ld = no * nv
+                self._si_lo = (be.int64_tensor([(i - self.j0) * nv * ld + j * nv for i, j in p_lo]),
+                               be.int64_tensor([row[p] for p in p_lo]))       # first index i: -(F - F^T)
+                self._si_hi = (be.int64_tensor([(j - self.j0) * nv * ld + i * nv for i, j in p_hi]),
+                               be.int64_tensor([row[p] for p in p_hi]))       # first index j: +(F - F^T)
+                full_diag = self.diagonal_pphh
+                self.diagonal_pphh = SlabDoubles.from_full(full_diag, self.layout)
+                self.diagonal_pphh.parity = +1
+                # padded columns of the diagonal: x / (D - shift) must stay 0 / finite there
+                lay = self.layout
+                if lay.w < lay.wmax:
+                    pad = be.empty((lay.npo, lay.wmax - lay.w))
+                    be.fill(pad, 1e300)
+                    be.copy2d(self.diagonal_pphh._data[:, lay.w:], pad, lay.npo, lay.wmax - lay.w)
+                self.diagonal_pphh.set_immutable()
         self._count_flops()
 
     def _count_flops(self):
@@ -606,6 +784,88 @@ class PackedAdcEngine:
         self._mark("step", 1)
         return AmplitudeVector(ph=self._wrap_ph(s1.view(no, nv)), pphh=self._wrap_pphh(S))
 
+    def _matvec_slab(self, u1, u2):
+        """sigma = M u on DISTRIBUTED vectors (SlabDoubles: every rank holds the virtual-pair column
+        slab its rows of the vvvv operand produce; the ph part is replicated).
+
+          1. all-gather of the trial vector's slabs (NVLink) -> complete U;
+          2. every term except vvvv as partial sums from this rank's operand slabs (ovov: occupied-i
+             row slab of X against the complete Y; ovvv: occupied j; oooo, D0, ooov: IJ pairs; ph_ph:
+             rows of M1) - all expansions and folds act on the rank's slab only;
+          3. reduce-scatter of the partial sums: each rank receives ITS column slab of their sum;
+          4. the vvvv GEMM accumulates onto that slab: the dominant term needs no exchange at all.
+        The ph part (no*nv numbers) is completed by a small all-reduce."""
+        no, nv, npo, npv = self.no, self.nv, self.npo, self.npv
+        lay = self.layout
+        if self.vectors != "slab":
+            raise ValueError("this engine was built for replicated vectors (vectors='replicated')")
+        self._mark("step", 0)
+        self._mark("gather", 0)
+        U = lay.gather(u2._contig())
+        self._mark("gather", 1)
+        P = be.zeros((npo, npv))
+        s1 = be.zeros((1, no * nv))
+        s1m = s1.view(no, nv)
+        x = u1._contig()
+        ij0, ij1 = self.ij0, self.ij1
+        nij = ij1 - ij0
+        j0, nj = self.j0, self.nj
+        # ---- ph_ph: rows (i in slab, a) of the folded singles matrix
+        r0, r1 = j0 * nv, (j0 + nj) * nv
+        if r1 > r0:
+            be.gemm(x.reshape(1, -1), self.M1[r0:r1], out=s1[:, r0:r1])
+        # ---- ph_pphh (matrix.py:270-276)
+        if nj > 0:
+            Ue = be.packed_expand_slab(1, U, no, nv, j0, nj)                      # [i,(jl,BC)]
+            be.gemm(Ue, self.V2, out=s1m, alpha=2.0, beta=1.0)
+            del Ue
+        if nij > 0:
+            Uh = be.packed_expand_slab(2, U[ij0:ij1], no, nv, 0, nij)            # [a,(JK slab,b)]
+            be.gemm(self.G1[:, ij0 * nv:ij1 * nv], Uh, out=s1m, alpha=2.0, beta=1.0)
+            del Uh
+            # ---- pphh_pphh_0 (canonical orbitals)
+            be.mul(U[ij0:ij1], self.D0[ij0:ij1], out=P[ij0:ij1])
+        if self.order_dd == 1:
+            if nij > 0:
+                Ut = be.permute(U[ij0:ij1], (1, 0))                               # [AB, KL slab]
+                be.gemm(self.O[:, ij0:ij1], Ut, out=P, alpha=1.0, beta=1.0)
+                del Ut
+            if nj > 0:
+                X = be.packed_expand_slab(0, U, no, nv, j0, nj)                   # [(il,a),(k,c)]
+                self._mark("ovov", 0)
+                T = be.gemm(X, self.Yfull)                                        # [(il,a),(j,b)]
+                self._mark("ovov", 1)
+                del X
+                ld = no * nv
+                off, rows = self._si_lo
+                be.packed_fold_virt(P, nv, ld, T, off, alpha=-1.0, rows=rows)
+                off, rows = self._si_hi
+                be.packed_fold_virt(P, nv, ld, T, off, alpha=+1.0, rows=rows)
+                del T
+        # ---- pphh_ph (matrix.py:288-294)
+        if nj > 0:
+            c1 = be.gemm(x, self.V1)                                              # [i,(jl,AB)]
+            be.packed_fold_occ(P, c1, no, nv, alpha=0.5, j_begin=j0, nj=nj)
+            del c1
+        if nij > 0:
+            c2 = be.gemm(self.G2[ij0 * nv:ij1 * nv], be.permute(x, (1, 0)))       # [(IJ slab,a),b]
+            be.packed_fold_virt(P, nv, nv, c2, self._off_rows[:nij], alpha=-0.5, rows=self._rows_ij)
+            del c2
+        # ---- sum over ranks: each rank keeps its column slab
+        self._mark("reduce", 0)
+        R = lay.reduce_scatter(P)
+        del P
+        be.comm_all_reduce(s1, group=lay.group)
+        self._mark("reduce", 1)
+        # ---- vvvv term straight onto the slab this rank owns
+        if self.order_dd == 1 and lay.w > 0:
+            self._mark("vvvv", 0)
+            be.gemm(U, self.W, out=R[:, :lay.w], alpha=1.0, beta=1.0)
+            self._mark("vvvv", 1)
+        self._mark("step", 1)
+        sig2 = SlabDoubles._make(self.mospaces, ["o1", "o1", "v1", "v1"], R, lay)
+        return AmplitudeVector(ph=self._wrap_ph(s1.view(no, nv)), pphh=sig2)
+
     def _vvvv_exchange_pipelined(self, U, buf, S, s1, pipe, host_out):
         """Tail of the pipelined sharded matvec.  The first vvvv row slab was computed before the
         other terms (peer-destination epilogue); here: all-reduce of the other terms (which is also
@@ -649,6 +909,30 @@ class PackedAdcEngine:
             finished.synchronize()
         self._mark("step", 1)
         return AmplitudeVector(ph=self._wrap_ph(s1.view(no, nv)), pphh=self._wrap_pphh(S))
+
+    def _matvec_host_slab(self, u1_host, U_host, s1_host, S_host):
+        """End-to-end form on distributed vectors: the host vectors live in pinned host memory that
+        EVERY rank has mapped (``shared_host_vector``); each rank moves only its own virtual-pair
+        column slab over its own PCIe link (strided 2-D copies), the slabs meet over NVLink inside
+        the matvec.  Collective; returns when every rank's part of sigma is in the host buffer."""
+        import torch
+        import torch.distributed as dist
+        no, nv, npo = self.no, self.nv, self.npo
+        lay = self.layout
+        x = be.empty((no, nv))
+        be.copy2d(x, u1_host, no, nv)
+        u = be.zeros((npo, lay.wmax)) if lay.w < lay.wmax else be.empty((npo, lay.wmax))
+        if lay.w > 0:
+            be.copy2d(u, U_host[:, lay.c0:lay.c1], npo, lay.w)
+        sig = self._matvec_slab(self._wrap_ph(x), SlabDoubles._make(self.mospaces, ["o1", "o1", "v1", "v1"], u, lay))
+        if lay.w > 0:
+            be.copy2d(S_host[:, lay.c0:lay.c1], sig.pphh._data, npo, lay.w)
+        if self.rank == 0:
+            be.copy2d(s1_host, sig.ph._data, no, nv)
+        if u.is_cuda:
+            torch.cuda.current_stream().synchronize()
+        dist.barrier(group=lay.group)              # every rank's slab has landed
+        return sig
 
     def _matvec_host_sharded(self, u1_host, U_host, s1_host, S_host):
         """Rank 0 holds the pinned host buffers (the other ranks pass None): the trial vector is
@@ -712,6 +996,8 @@ class PackedAdcEngine:
 
     def matvec(self, v):
         u1, u2 = v["ph"], v["pphh"]
+        if isinstance(u2, SlabDoubles):
+            return self._matvec_slab(u1, u2)
         if not isinstance(u2, PackedDoubles):
             u2 = PackedDoubles.from_dense(u2)
         U = u2._contig()
@@ -753,7 +1039,10 @@ class PackedAdcEngine:
         2 x edge_rows/npo of the vector instead of all of it.  Returns after the downloads are done."""
         import torch
         if self.world > 1:
-            self._matvec_host_sharded(u1_host, U_host, s1_host, S_host)
+            if self.vectors == "slab" and u1_host is not None and getattr(u1_host, "adccb_shared", False):
+                self._matvec_host_slab(u1_host, U_host, s1_host, S_host)
+            else:
+                self._matvec_host_sharded(u1_host, U_host, s1_host, S_host)
             return
         if self.order_dd != 1 or self.npo < 4 * edge_rows:
             v = AmplitudeVector(ph=self._wrap_ph(u1_host.to("cuda", non_blocking=True)),
@@ -951,3 +1240,44 @@ def synthetic_reference_state(no, nv, seed=20261019, scale=0.02):
     ReferenceState.__init__(ref, SyntheticHfProvider(), import_all_below_n_orbs=None)
     ref.synthetic = dict(no=no, nv=nv, seed=seed, scale=scale)
     return ref
+
+
+# ------------------------------------------------------------------------------------------------
+# host vectors shared by the ranks of one box (end-to-end form of the sharded matvec)
+# ------------------------------------------------------------------------------------------------
+_shared_counter = [0]
+
+
+def shared_host_vector(matrix, group=None):
+    """{"ph": [no, nv], "pphh": packed [npo, npv]} FP64 host tensors backed by ONE shared-memory
+    segment that every rank of the box maps and page-locks (collective call).  Whatever one rank
+    writes the others see; ``AdcMatrix.matvec_host`` on a sharded matrix lets every rank move its own
+    slab of such a vector over its own PCIe link."""
+    import torch
+    import torch.distributed as dist
+    eng = matrix._engine
+    no, nv, npo, npv = eng.no, eng.nv, eng.npo, eng.npv
+    n = no * nv + npo * npv
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    name = [None]
+    if rank == 0:
+        _shared_counter[0] += 1
+        name[0] = f"/dev/shm/adccb_{os.getpid()}_{_shared_counter[0]}"
+        with open(name[0], "wb") as f:
+            f.truncate(n * 8)
+    if dist.is_initialized():
+        dist.broadcast_object_list(name, src=0, group=group)
+    flat = torch.from_file(name[0], shared=True, size=n, dtype=torch.float64)
+    if dist.is_initialized():
+        dist.barrier(group=group)
+    if rank == 0:
+        os.unlink(name[0])                     # the mappings keep the segment alive
+    if torch.cuda.is_available():
+        err = torch.cuda.cudart().cudaHostRegister(flat.data_ptr(), n * 8, 0)
+        if int(err) != 0:
+            raise RuntimeError(f"cudaHostRegister failed ({err})")
+    out = {"ph": flat[:no * nv].view(no, nv), "pphh": flat[no * nv:].view(npo, npv)}
+    for t in out.values():
+        t.adccb_shared = True
+        t._adccb_keep = flat
+    return out

@@ -222,12 +222,19 @@ def sharded_vs_single(adcc, PackedDoubles, synthetic_reference_state, rank, worl
     u2 = torch.randn(eng.npo, eng.npv, generator=g, dtype=torch.float64).cuda()
     v = adcc.AmplitudeVector(ph=adcc.Tensor._wrap(ref.mospaces, ["o1", "v1"], u1),
                              pphh=PackedDoubles._wrap(ref.mospaces, ["o1", "o1", "v1", "v1"], u2))
-    s_sh = ms.matvec(v)
-    s_sh = ms.matvec(v)                       # second call: both peer exchange buffers have been used
+    from adcc_b200.packed import SlabDoubles
+    s_rep = ms.matvec(v)                      # complete vectors in, complete sigma out on every rank
+    errs = {}
+    if ms.vector_distribution == "slab":      # distributed vectors: slabs in, slabs out
+        vs = adcc.AmplitudeVector(ph=v.ph, pphh=SlabDoubles.from_full(v.pphh, eng.layout))
+        s_slab = ms.matvec(vs)
+        s_sh = adcc.AmplitudeVector(ph=s_slab.ph, pphh=s_slab.pphh.to_full())
+    else:
+        s_sh = ms.matvec(v)                   # second call: both peer exchange buffers have been used
     m1 = adcc.AdcMatrix("adc2x", ref, doubles_storage="packed")
     s_1 = m1.matvec(v)
-    err = max(float((s_sh[b]._data - s_1[b]._data).abs().max() / s_1[b]._data.abs().max())
-              for b in ("ph", "pphh"))
+    err = max(float((s[b]._data - s_1[b]._data).abs().max() / s_1[b]._data.abs().max())
+              for b in ("ph", "pphh") for s in (s_sh, s_rep))
     t = torch.tensor([err], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     flat = torch.cat((s_sh.ph._data.reshape(-1), s_sh.pphh._data.reshape(-1)))
@@ -235,7 +242,7 @@ def sharded_vs_single(adcc, PackedDoubles, synthetic_reference_state, rank, worl
     dist.broadcast(ref0, 0)
     same = torch.tensor([1.0 if torch.equal(ref0, flat) else 0.0], device="cuda", dtype=torch.float64)
     dist.all_reduce(same, op=dist.ReduceOp.MIN)
-    del ms, m1, eng, s_sh, s_1, v
+    del ms, m1, eng, s_sh, s_rep, s_1, v
     torch.cuda.empty_cache()
     return {"sharded_vs_single_rel": float(t.item()), "sharded_identical_on_all_ranks": bool(same.item() == 1.0),
             "sharded_check_shape": f"nocc={no} nvirt={nv}, complete sigma"}
@@ -281,8 +288,11 @@ def run_gpu(args):
     sig1_host = torch.empty_like(u1_host).pin_memory()
     sig2_host = torch.empty_like(u2_host).pin_memory()
 
+    slab = world > 1 and matrix.vector_distribution == "slab"
+
     def to_vec(h1, h2):
-        """Host (pinned) -> device.  N > 1: rank 0 uploads, NCCL broadcasts over NVLink."""
+        """Host (pinned) -> device-resident vector (outside every timed region).  N > 1: rank 0
+        uploads, NCCL broadcasts, each rank keeps its virtual-pair slab (distributed vectors)."""
         if world == 1 or rank == 0:
             d1 = h1.to("cuda", non_blocking=True)
             d2 = h2.to("cuda", non_blocking=True)
@@ -292,9 +302,15 @@ def run_gpu(args):
         if world > 1:
             dist.broadcast(d1, 0)
             dist.broadcast(d2, 0)
-        return adcc.AmplitudeVector(
-            ph=adcc.Tensor._wrap(ref.mospaces, ["o1", "v1"], d1),
-            pphh=PackedDoubles._wrap(ref.mospaces, ["o1", "o1", "v1", "v1"], d2))
+        full = PackedDoubles._wrap(ref.mospaces, ["o1", "o1", "v1", "v1"], d2)
+        if slab:
+            from adcc_b200.packed import SlabDoubles
+            full = SlabDoubles.from_full(full, eng.layout)
+        return adcc.AmplitudeVector(ph=adcc.Tensor._wrap(ref.mospaces, ["o1", "v1"], d1), pphh=full)
+
+    def full_doubles(vec):
+        """Complete packed doubles array of a (possibly distributed) vector; collective if distributed."""
+        return vec.pphh.to_full()._data if slab else vec.pphh._data
 
     def to_host(s):
         if rank == 0:                      # every rank holds the full sigma; rank 0 returns it
@@ -336,8 +352,18 @@ def run_gpu(args):
     ms_step = ms_total / args.steps
 
     # ---- end to end: host buffers in, host buffers out -------------------------------------------
-    u_host = {"ph": u1_host, "pphh": u2_host} if rank == 0 else None
-    s_host = {"ph": sig1_host, "pphh": sig2_host} if rank == 0 else None
+    if slab:
+        # host vectors in pinned memory shared by the ranks of the box: every rank moves its own
+        # slab over its own PCIe link
+        u_host, s_host = adcc.shared_host_vector(matrix), adcc.shared_host_vector(matrix)
+        if rank == 0:
+            u_host["ph"].copy_(u1_host)
+            u_host["pphh"].copy_(u2_host)
+        sig1_host, sig2_host = s_host["ph"], s_host["pphh"]
+        dist.barrier()
+    else:
+        u_host = {"ph": u1_host, "pphh": u2_host} if rank == 0 else None
+        s_host = {"ph": sig1_host, "pphh": sig2_host} if rank == 0 else None
 
     def e2e_step():                           # public API: AdcMatrix.matvec_host (pipelined PCIe);
         matrix.matvec_host(u_host, s_host)    # N > 1: rank 0 owns the host buffers
@@ -369,9 +395,10 @@ def run_gpu(args):
         again = matrix.matvec(v)
         checks["run_to_run_identical"] = bool(torch.equal(again.pphh._data, sig.pphh._data)
                                               and torch.equal(again.ph._data, sig.ph._data))
+        sig_full2, v_full2 = full_doubles(sig), full_doubles(v)
         if rank == 0:
             # the host buffers filled by the end-to-end path hold the same sigma
-            ref2 = sig.pphh._data.cpu()
+            ref2 = sig_full2.cpu()
             ref1 = sig.ph._data.cpu()
             checks["e2e_rel_diff_to_resident"] = float(max(
                 (sig2_host - ref2).abs().max() / ref2.abs().max(),
@@ -380,7 +407,10 @@ def run_gpu(args):
             # sampled sigma entries recomputed on the CPU from the definition of the inputs
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             from verify_headline import verify
-            res = verify(matrix, v, sig, n_pphh=args.verify_samples, n_ph=max(1, args.verify_samples // 4))
+            wrap2 = lambda d: PackedDoubles._wrap(ref.mospaces, ["o1", "o1", "v1", "v1"], d)   # noqa: E731
+            res = verify(matrix, adcc.AmplitudeVector(ph=v.ph, pphh=wrap2(v_full2)),
+                         adcc.AmplitudeVector(ph=sig.ph, pphh=wrap2(sig_full2)),
+                         n_pphh=args.verify_samples, n_ph=max(1, args.verify_samples // 4))
             checks.update({k: float(x) for k, x in res.items()})
         if sharded_check is not None:
             checks.update(sharded_check)
@@ -401,7 +431,7 @@ def run_gpu(args):
         davidson = {"n_states": args.n_states, "conv_tol": 1e-6, "converged": bool(state.converged),
                     "n_iter": int(state.n_iter), "n_applies": int(state.n_applies),
                     "time_to_converged_s": t_dav,
-                    "vectors": getattr(state, "vector_distribution", "replicated" if world > 1 else "single GPU"),
+                    "vectors": matrix.vector_distribution,
                     "excitation_energies": [float(e) for e in state.excitation_energy]}
 
     if rank != 0:
@@ -412,7 +442,9 @@ def run_gpu(args):
     # ---- roofline of the dominant kernel -----------------------------------------------------------
     flops_per_matvec = eng.flops_per_matvec
     f_ovov = eng.flops["pphh_pphh/ovov"]
+    vector_distribution = matrix.vector_distribution
     slab_exchange = ("none" if world == 1 else
+                     "all-gather(u) + reduce-scatter(partial sigma); vvvv slab needs no exchange" if slab else
                      "GEMM epilogue -> peer memory (NVLink stores)" if eng._peer is not None
                      else "NCCL all-gather")
     f_vvvv = eng.flops["pphh_pphh/vvvv"] / world
@@ -443,7 +475,7 @@ def run_gpu(args):
         cno, cnv = cpu_shape(no, nv)
         same = (cno, cnv) == (no, nv)
         u_np = (u1_host.numpy(), u2_host.numpy()) if same else None
-        sig_ref = (sig.ph._data.cpu().numpy(), sig.pphh._data.cpu().numpy()) if same else None
+        sig_ref = (sig.ph._data.cpu().numpy(), sig_full2.cpu().numpy()) if same else None
         del matrix, eng, sig, v
         torch.cuda.empty_cache()
         cpu, csig = cpu_matvec_run(cno, cnv, 0, 1, u=u_np)
@@ -459,7 +491,7 @@ def run_gpu(args):
         "data": "synthetic",
         "config": workload_config(no, nv),
         "parallelism": {"layout": f"virtual-pair slabs x{world}" if world > 1 else "single GPU",
-                        "slab_exchange": slab_exchange},
+                        "vectors": vector_distribution, "slab_exchange": slab_exchange},
         "executed_tflop_per_step": flops_per_matvec * 1e-12,
         "dense_tflop_per_step": dense_flops(no, nv) * 1e-12,
         "achieved_tflops_executed": flops_per_matvec / (ms_step * 1e-3) * 1e-12,

@@ -131,6 +131,25 @@ int adccb_packed_pack(void* stream, int no, int nv, const double* T, double* U);
 /* GEMM-ready expansions of packed U: which = 0: X[i,a,k,c] = u[ikac]; 1: Ue[i,j,AB] = u[ij,AB];
  * 2: Uh[a,JK,b] = u[JK,ab] (no < 0: U holds a slab of -no JK rows). */
 int adccb_packed_expand(void* stream, int which, int no, int nv, const double* U, double* out);
+/* Slab forms of adccb_packed_expand for a matvec sharded over GPUs: which = 0: rows (il, a) of X for
+ * the occupied slab i = first + il, il < count; which = 1: Ue[i, jl, AB] for the slab j = first + jl
+ * of the second occupied index; which = 2: Uh[a, r, b] for `count` packed rows starting at U. */
+int adccb_packed_expand_slab(void* stream, int which, int no, int nv, int first, int count,
+                              const double* U, double* out);
+/* Distribution of packed doubles vectors over `world` GPUs by virtual-pair (column) slabs: rank r owns
+ * columns [host_cut[r], host_cut[r+1]) of the [nrows, npv] array and keeps them as a zero-padded
+ * [nrows, wmax] slab.  dir 0: full -> [world, nrows, wmax] (the layout ncclReduceScatter sums the ranks'
+ * partial sigma vectors in); dir 1: [world, nrows, wmax] (as all-gathered) -> full.  The reference
+ * has no distributed store; this is the layout step of the sigma-vector all-gather / reduce-scatter of
+ * SURVEY 8(e). */
+int adccb_slab_layout(void* stream, int dir, int64_t nrows, int64_t npv, int world, const int64_t* host_cut,
+                      int64_t wmax, double* full, double* slabs);
+/* Stream-ordered strided 2-D copy between any two of {pinned host, device} buffers (pitches and width
+ * in bytes): a rank's column slab of a vector that lives in shared pinned host memory <-> its device
+ * slab (end-to-end form of the sharded matvec; Tensor::import_from / export_to,
+ * libadcc_src/TensorImpl.cc:1369-1441, for one slab). */
+int adccb_copy2d(void* stream, void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes,
+                 int64_t width_bytes, int64_t height);
 /* S[rows[r], AB] += alpha * (F_r[a,b] - F_r[b,a]), F_r[a,b] = P1[off1[r] + a*sa + b] - P2[off2[r] + a*sa + b]
  * (P2/off2 may be NULL; rows NULL = identity); off1/off2/rows: device int64 arrays of length nrows.  Folds the ovov-type
  * and ooov-type GEMM results into packed sigma (the antisymmetrise(2,3) of

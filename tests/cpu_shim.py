@@ -69,8 +69,8 @@ def install(monkeypatch):
 
     def dot(x, y): return float(torch.dot(x.reshape(-1), y.reshape(-1)))
 
-    def dot_many_blocks(pairs, scale=1.0, out=None):
-        res = sum(dot_many(x, ys, scale) for x, ys in pairs)
+    def dot_many_blocks(pairs, scale=1.0, out=None, scales=None):
+        res = sum(dot_many(x, ys, scale if scales is None else scales[ib]) for ib, (x, ys) in enumerate(pairs))
         if out is None:
             return res
         out.copy_(torch.from_numpy(np.asarray(res)))
@@ -146,6 +146,45 @@ def install(monkeypatch):
         po = _pairs(no)
         ii = torch.tensor([p[0] for p in po], dtype=torch.long); jj = torch.tensor([p[1] for p in po], dtype=torch.long)
         return d[ii, jj].permute(1, 0, 2).contiguous().reshape(nv, -1)
+
+    def packed_expand_slab(which, U, no, nv, first, count):
+        if which == 2:
+            return packed_expand(2, U, no, nv, n_pairs_o=count)
+        npv = nv * (nv - 1) // 2
+        full = packed_expand(which, U, no, nv)
+        if which == 0:
+            return full.reshape(no, nv, no * nv)[first:first + count].reshape(count * nv, no * nv).contiguous()
+        return full.reshape(no, no, npv)[:, first:first + count].reshape(no, count * npv).contiguous()
+
+    def slab_layout(direction, full, slabs, cuts, wmax):
+        for r in range(len(cuts) - 1):
+            w = cuts[r + 1] - cuts[r]
+            if direction == 0:
+                slabs[r].zero_()
+                slabs[r][:, :w] = full[:, cuts[r]:cuts[r + 1]]
+            else:
+                full[:, cuts[r]:cuts[r + 1]] = slabs[r][:, :w]
+        return slabs if direction == 0 else full
+
+    def copy2d(dst, src, nrows, ncols):
+        dst[:nrows, :ncols] = src[:nrows, :ncols]
+        return dst
+
+    def comm_reduce_scatter(out, inp, group=None):
+        import torch.distributed as dist          # gloo has no reduce-scatter: all-reduce + own chunk
+        tmp = inp.clone()
+        dist.all_reduce(tmp, group=group)
+        n = out.numel()
+        r = dist.get_rank(group)
+        out.copy_(tmp.reshape(-1)[r * n:(r + 1) * n].reshape(out.shape))
+        return out
+
+    def comm_all_gather(out, inp, group=None):
+        import torch.distributed as dist
+        parts = [torch.empty_like(inp) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(parts, inp.contiguous(), group=group)
+        out.copy_(torch.stack(parts).reshape(out.shape))
+        return out
 
     def packed_fold_virt(S, nv, sa, P1, off1, P2=None, off2=None, alpha=1.0, rows=None):
         pv = _pairs(nv)
@@ -261,7 +300,9 @@ def install(monkeypatch):
                          spin_singlet_=spin_singlet_, packed_unpack=packed_unpack, packed_pack=packed_pack,
                          packed_expand=packed_expand, packed_fold_virt=packed_fold_virt,
                          packed_fold_occ=packed_fold_occ, packed_diagonal=packed_diagonal,
-                         pair_select=pair_select, int64_tensor=int64_tensor, add_columns=add_columns, spin_expand4=spin_expand4, synth_fill=synth_fill).items():
+                         pair_select=pair_select, packed_expand_slab=packed_expand_slab, slab_layout=slab_layout,
+                         copy2d=copy2d, comm_reduce_scatter=comm_reduce_scatter, comm_all_gather=comm_all_gather,
+                         int64_tensor=int64_tensor, add_columns=add_columns, spin_expand4=spin_expand4, synth_fill=synth_fill).items():
         monkeypatch.setattr(be, name, fn)
     monkeypatch.setattr(be, "device", lambda: cpu)
 

@@ -47,8 +47,36 @@ def _worker(rank, world, port, no, nv, out):
     m.matvec_host(host_in, host_out)
     if rank == 0:
         same = same and torch.equal(host_out["ph"], sig.ph._data) and torch.equal(host_out["pphh"], sig.pphh._data)
-    # Davidson on the sharded matrix (replicated vectors)
+    # ---- distributed vectors (virtual-pair column slabs): matvec, scalar products, host form
+    from adcc_b200.packed import SlabDoubles, shared_host_vector
+    lay = m._engine.layout
+    assert m.vector_distribution == "slab"
+    vs = adcc.AmplitudeVector(ph=vp.ph, pphh=SlabDoubles.from_full(vp.pphh, lay))
+    ss = m.matvec(vs)
+    assert isinstance(ss.pphh, SlabDoubles) and tuple(ss.pphh._data.shape) == (lay.npo, lay.wmax)
+    full = ss.pphh.to_full()
+    err = max(err, rel_err(ss.ph.to_ndarray(), osig["ph"]), rel_err(full.to_ndarray(), osig["pphh"]))
+    assert float(ss.pphh._data[:, lay.w:].abs().sum()) == 0.0           # padding stays zero
+    d_slab, d_full = vs @ ss, vp @ sig                                   # one all-reduce vs local
+    same = same and abs(d_slab - d_full) < 1e-12 * abs(d_full)
+    d_list = vs @ [vs, ss]
+    same = same and abs(d_list[1] - d_full) < 1e-12 * abs(d_full) and abs(d_list[0] - (vp @ vp)) < 1e-12 * (vp @ vp)
+    assert abs(ss.pphh[1, 0, 2, 1] - sig.pphh[1, 0, 2, 1]) < 1e-13       # element access across ranks
+    sh_in, sh_out = shared_host_vector(m), shared_host_vector(m)
+    if rank == 0:
+        sh_in["ph"].copy_(vp.ph._data)
+        sh_in["pphh"].copy_(vp.pphh._data)
+    dist.barrier()
+    m.matvec_host(sh_in, sh_out)
+    same = same and torch.allclose(sh_out["ph"], sig.ph._data, rtol=0, atol=1e-13 * float(sig.ph._data.abs().max()))
+    same = same and torch.allclose(sh_out["pphh"], sig.pphh._data, rtol=0, atol=1e-13 * float(sig.pphh._data.abs().max()))
+    # Davidson on distributed vectors (default) and on replicated vectors: same states, same iterations
     st = adcc.run_adc(m, n_states=2, conv_tol=1e-7, output=None)
+    assert isinstance(st.excitation_vector[0].pphh, SlabDoubles)
+    mr = adcc.AdcMatrix("adc2x", ref, doubles_storage="packed", shard=(rank, world), vectors="replicated")
+    assert mr.vector_distribution == "replicated"
+    sr = adcc.run_adc(mr, n_states=2, conv_tol=1e-7, output=None)
+    same = same and st.n_iter == sr.n_iter and np.max(np.abs(st.excitation_energy - sr.excitation_energy)) < 1e-10
     if rank == 0:
         ost = oracle.run_adc(om, "adc2x", n_states=2, conv_tol=1e-7)
         np.save(out, np.array([err, float(same), np.max(np.abs(st.excitation_energy - ost.eigenvalues)),
@@ -57,7 +85,7 @@ def _worker(rank, world, port, no, nv, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,no,nv", [(2, 6, 10), (3, 6, 8)])
+@pytest.mark.parametrize("world,no,nv", [(2, 6, 10), (3, 6, 8), (3, 8, 14)])
 def test_sharded_matvec_gloo(tmp_path, world, no, nv):
     out = str(tmp_path / "res.npy")
     port = 29500 + (os.getpid() + world) % 2000

@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_sharded_matches_single_gpu():
+@pytest.mark.parametrize("no,nv", [(40, 240), (10, 38)])       # nv = 38: odd pair count (NCCL exchange)
+def test_sharded_matches_single_gpu(no, nv):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
@@ -19,7 +20,7 @@ def test_sharded_matches_single_gpu():
     world = 4 if n >= 4 else 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29571",
-           os.path.join(ROOT, "tools", "check_sharded.py"), "40", "240"]
+           os.path.join(ROOT, "tools", "check_sharded.py"), str(no), str(nv)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     rows = [json.loads(line) for line in out.stdout.splitlines() if line.startswith("{")]
@@ -29,3 +30,5 @@ def test_sharded_matches_single_gpu():
         if r["rank"] == 0:
             assert r["rel_err_ph"] < 1e-11 and r["rel_err_pphh"] < 1e-11
             assert r["host_path_rel_diff"] < 1e-13
+        assert r["slab_vs_replicated_rel"] < 1e-13 and r["slab_dot_rel"] < 1e-13
+        assert r["slab_host_path_rel_diff"] < 1e-13

@@ -58,6 +58,31 @@ for rep in range(3):
                 ((h_out["pphh"] - outs[0][1].cpu()).abs().max() / outs[0][1].abs().max()).item())
         res["host_path_rel_diff"] = max(res.get("host_path_rel_diff", 0.0), d)
         h_out["pphh"].fill_(float("nan"))
+# distributed vectors: slabs in, slabs out; end-to-end through shared pinned host vectors
+if m.vector_distribution == "slab":
+    from adcc_b200.packed import SlabDoubles, shared_host_vector
+    vs = adcc.AmplitudeVector(ph=v.ph, pphh=SlabDoubles.from_full(v.pphh, eng.layout))
+    worst = 0.0
+    for rep in range(3):
+        ss = m.matvec(vs)
+        full = ss.pphh.to_full()._data
+        worst = max(worst, ((full - outs[0][1]).abs().max() / outs[0][1].abs().max()).item(),
+                    ((ss.ph._data - outs[0][0]).abs().max() / outs[0][0].abs().max()).item())
+    res["slab_vs_replicated_rel"] = worst
+    res["slab_dot_rel"] = abs((vs @ ss) - (v @ s)) / abs(v @ s)
+    sh_in, sh_out = shared_host_vector(m), shared_host_vector(m)
+    if rank == 0:
+        sh_in["ph"].copy_(u1.cpu())
+        sh_in["pphh"].copy_(u2.cpu())
+    dist.barrier()
+    for rep in range(2):
+        sh_out["pphh"].fill_(float("nan")) if rank == 0 else None
+        dist.barrier()
+        m.matvec_host(sh_in, sh_out)
+        d = max(((sh_out["ph"] - outs[0][0].cpu()).abs().max() / outs[0][0].abs().max()).item(),
+                ((sh_out["pphh"] - outs[0][1].cpu()).abs().max() / outs[0][1].abs().max()).item())
+        res["slab_host_path_rel_diff"] = max(res.get("slab_host_path_rel_diff", 0.0), d)
+        dist.barrier()
 if os.environ.get("ADCCB_POISON"):
     res["nan"] = [[int(torch.isnan(o[0]).sum().item()), int(torch.isnan(o[1]).sum().item())] for o in outs]
     res["nan_build"] = {k: int(torch.isnan(getattr(eng, k)).sum().item())
