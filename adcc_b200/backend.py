@@ -505,6 +505,38 @@ def comm_all_reduce(t, group=None):
     return t
 
 
+def vvvv_exchange_slab(W, nv, a_begin, na):
+    """[na, nv, nv, nv] array out[al,b,c,d] = <a c||b d>, a = a_begin + al, from packed W[AB,CD]."""
+    out = empty((na, nv, nv, nv))
+    _cabi.check(_cabi.lib().adccb_vvvv_exchange_slab(_stream(), int(nv), int(a_begin), int(na), _ptr(W),
+                                                     _ptr(out)))
+    return out
+
+
+def ovvv_exchange_slab(V2, no, nv, a_begin, na):
+    """[na, nv, no, nv] array out[al,c,j,d] = <j c||a d>, a = a_begin + al, from V2[c,(j,AD)]."""
+    out = empty((na, nv, no, nv))
+    _cabi.check(_cabi.lib().adccb_ovvv_exchange_slab(_stream(), int(no), int(nv), int(a_begin), int(na),
+                                                     _ptr(V2), _ptr(out)))
+    return out
+
+
+def pair_matvec(V, nv, n_out, n_red, row_stride_out, row_stride_red, X, x_by_out, out=None, alpha=1.0, beta=0.0):
+    """out[o, a] = beta*out + alpha * sum_r sum_c A_rho[a,c] x[c] over pair-packed antisymmetric rows
+    rho = o*row_stride_out + r*row_stride_red of V; x = X[o] (x_by_out) or X[r] (see include/adccb.h)."""
+    _check_dev(V, X, out)
+    if out is None:
+        out, beta = empty((n_out, nv)), 0.0
+    if not V.is_contiguous() or X.stride(-1) != 1 or out.stride(-1) != 1:
+        raise ValueError("pair_matvec: contiguous operands expected")
+    ws = workspace()
+    _cabi.check(_cabi.lib().adccb_pair_matvec(
+        _stream(), int(nv), int(n_out), int(n_red), int(row_stride_out), int(row_stride_red), _ptr(V), _ptr(X),
+        X.stride(0), 1 if x_by_out else 0, float(alpha), float(beta), _ptr(out), out.stride(0), _ptr(ws),
+        ws.numel() * 8))
+    return out
+
+
 def packed_fold_virt(S, nv, sa, P1, off1, P2=None, off2=None, alpha=1.0, rows=None):
     """S[rows[r],AB] += alpha (F_r[a,b] - F_r[b,a]); off1/off2/rows: int64 device tensors."""
     nrows = off1.numel()
@@ -549,7 +581,7 @@ def int64_tensor(values):
 
 
 SYNTH_LAYOUTS = {"vvvv_packed": 0, "oooo_packed": 1, "ovov_jbkc": 2, "ovvv_jabc": 3, "ovvv_ajbc": 4,
-                 "ooov_ijkb": 5, "ooov_ijak": 6, "dense": 7}
+                 "ooov_ijkb": 5, "ooov_ijak": 6, "dense": 7, "vvvv_exchange": 8, "ovvv_exchange": 9}
 SYNTH_BLOCKS = {"oooo": 0, "ooov": 1, "oovv": 2, "ovov": 3, "ovvv": 4, "vvvv": 5}
 
 

@@ -68,6 +68,11 @@ int packed_expand_slab(cudaStream_t st, int which, int no, int nv, int first, in
                        double* out);
 int slab_layout(cudaStream_t st, int dir, long long nrows, long long npv, int world, const long long* cut,
                 long long wmax, double* full, double* slabs);
+int vvvv_exchange_slab(cudaStream_t st, int nv, int a_begin, int na, const double* W, double* out);
+int ovvv_exchange_slab(cudaStream_t st, int no, int nv, int a_begin, int na, const double* V2, double* out);
+int pair_matvec(cudaStream_t st, int nv, int n_out, int n_red, long long so, long long sr, const double* V,
+                const double* X, long long ldx, int x_by_out, double alpha, double beta, double* out,
+                long long ldo, double* ws, long long ws_bytes);
 int packed_fold_virt(cudaStream_t st, long long nrows, int nv, long long sa, const double* P1,
                      const long long* off1, const double* P2, const long long* off2,
                      const long long* rows, double alpha, double* S);
@@ -218,6 +223,18 @@ int adccb_copy2d(void* stream, void* dst, int64_t dst_pitch_bytes, const void* s
   ADCCB_CUDA_OK(cudaMemcpy2DAsync(dst, (size_t)dst_pitch_bytes, src, (size_t)src_pitch_bytes, (size_t)width_bytes,
                                   (size_t)height, cudaMemcpyDefault, (cudaStream_t)stream));
   return 0;
+}
+int adccb_vvvv_exchange_slab(void* stream, int nv, int a_begin, int na, const double* W, double* out) {
+  return vvvv_exchange_slab((cudaStream_t)stream, nv, a_begin, na, W, out);
+}
+int adccb_ovvv_exchange_slab(void* stream, int no, int nv, int a_begin, int na, const double* V2, double* out) {
+  return ovvv_exchange_slab((cudaStream_t)stream, no, nv, a_begin, na, V2, out);
+}
+int adccb_pair_matvec(void* stream, int nv, int n_out, int n_red, int64_t row_stride_out, int64_t row_stride_red,
+                      const double* V, const double* X, int64_t ldx, int x_by_out, double alpha, double beta,
+                      double* out, int64_t ldo, double* ws, int64_t ws_bytes) {
+  return pair_matvec((cudaStream_t)stream, nv, n_out, n_red, row_stride_out, row_stride_red, V, X, ldx, x_by_out,
+                     alpha, beta, out, ldo, ws, ws_bytes);
 }
 int adccb_packed_fold_virt(void* stream, int64_t nrows, int nv, int64_t sa, const double* P1,
                            const int64_t* off1, const double* P2, const int64_t* off2,

@@ -10,6 +10,7 @@
 // every Davidson vector operation moves 4x fewer bytes.  All kernels are HBM-bound.
 #include "common.cuh"
 #include <algorithm>
+#include <atomic>
 
 namespace adccb {
 
@@ -266,7 +267,9 @@ enum EriLayout {
   LAY_OVVV_AJBC = 4,     // V2[a,(j,BC)]  = <ja||bc>
   LAY_OOOV_IJKB = 5,     // G1[i,(JK,b)]  = <jk||ib>
   LAY_OOOV_IJAK = 6,     // G2[(IJ,a),k]  = <ij||ka>
-  LAY_DENSE = 7          // dense [p,q,r,s] of block `blk`
+  LAY_DENSE = 7,         // dense [p,q,r,s] of block `blk`
+  LAY_VVVV_EXCH = 8,     // [al,b,c,d] = <a c||b d>, a = row_begin + al   (exchange-ordered slab)
+  LAY_OVVV_EXCH = 9      // [al,c,j,d] = <j c||a d>, a = row_begin + al
 };
 
 __global__ void synth_fill_kernel(int layout, int blk, int no, int nv, unsigned long long seed,
@@ -315,6 +318,16 @@ __global__ void synth_fill_kernel(int layout, int blk, int no, int nv, unsigned 
         k = (int)(idx % no); a = (int)((idx / no) % nv);
         pair_decode(idx / ((long long)no * nv), i, j);
         v = synthetic_eri(seed, BLK_OOOV, i, j, k, a, scale);
+      } break;
+      case LAY_VVVV_EXCH: {
+        d = (int)(idx % nv); c = (int)((idx / nv) % nv); b = (int)((idx / ((long long)nv * nv)) % nv);
+        a = (int)row_begin + (int)(idx / ((long long)nv * nv * nv));
+        v = synthetic_eri(seed, BLK_VVVV, a, c, b, d, scale);
+      } break;
+      case LAY_OVVV_EXCH: {
+        d = (int)(idx % nv); j = (int)((idx / nv) % no); c = (int)((idx / ((long long)nv * no)) % nv);
+        a = (int)row_begin + (int)(idx / ((long long)nv * no * nv));
+        v = synthetic_eri(seed, BLK_OVVV, j, c, a, d, scale);
       } break;
       default: {
         const int e3 = (blk == BLK_OOOO) ? no : nv;
@@ -369,6 +382,123 @@ __global__ void slab_layout_kernel(int dir, long long nrows, long long npv, long
 }
 
 // ---------------------------------------------------------------------------------------
+// ADC(3) build / matvec helpers on pair-packed operands
+// ---------------------------------------------------------------------------------------
+// Exchange-ordered slab of the vvvv block from its pair-packed form W[AB,CD] = <ab||cd>:
+//   out[al, b, c, d] = <a c||b d>,  a = a_begin + al
+// (operand of the o^2 v^4 builds of adc3_m11: -t2sq[idjc] <ac||bd>, adcc/adc_pp/matrix.py:1033, and
+// of <ac||bd> p0[cd] in adc3_i1, :953).  One CTA per (al, c, b): the CTAs that run together share
+// the packed row pair(a,c) through L2; the output is written coalesced along d.
+__global__ void vvvv_exchange_slab_kernel(int nv, int a_begin, const double* __restrict__ W,
+                                          double* __restrict__ out) {
+  const long long npv = (long long)nv * (nv - 1) / 2;
+  const int b = blockIdx.x % nv, c = (blockIdx.x / nv) % nv, al = blockIdx.x / (nv * nv);
+  const int a = a_begin + al;
+  double* dst = out + (((long long)al * nv + b) * nv + c) * nv;
+  if (a == c) {
+    for (int d = threadIdx.x; d < nv; d += blockDim.x) dst[d] = 0.0;
+    return;
+  }
+  const double s_ac = (a < c) ? 1.0 : -1.0;
+  const double* row = W + pair_index(min(a, c), max(a, c)) * npv;
+  for (int d = threadIdx.x; d < nv; d += blockDim.x) {
+    double v = 0.0;
+    if (d != b) v = ((b < d) ? s_ac : -s_ac) * row[pair_index(min(b, d), max(b, d))];
+    dst[d] = v;
+  }
+}
+
+// Exchange-ordered slab of the ovvv block from V2[c,(j,AD)] = <jc||ad> (a<d packed):
+//   out[al, c, j, d] = <j c||a d>,  a = a_begin + al
+// (operand of pi7 = t2[ijbd] <jc||ad>, adcc/GroundState.py:239, an o^2 v^4 build).  One CTA per
+// (al, c, j); output coalesced along d.
+__global__ void ovvv_exchange_slab_kernel(int no, int nv, int a_begin, const double* __restrict__ V2,
+                                          double* __restrict__ out) {
+  const long long npv = (long long)nv * (nv - 1) / 2;
+  const int j = blockIdx.x % no, c = (blockIdx.x / no) % nv, al = blockIdx.x / (no * nv);
+  const int a = a_begin + al;
+  const double* row = V2 + ((long long)c * no + j) * npv;
+  double* dst = out + (((long long)al * nv + c) * no + j) * nv;
+  for (int d = threadIdx.x; d < nv; d += blockDim.x) {
+    double v = 0.0;
+    if (d != a) v = ((a < d) ? 1.0 : -1.0) * row[pair_index(min(a, d), max(a, d))];
+    dst[d] = v;
+  }
+}
+
+// y_rho[a] = sum_c A_rho[a,c] x_rho[c] for rows rho of an array of pair-packed ANTISYMMETRIC
+// matrices (A_rho[b,c] = V[rho*npv + pair(b,c)] for b < c), summed over a reduction index:
+//   partial[ch, o, a] = sum_{r in chunk ch} y_{rho(o,r)}[a],  rho(o,r) = o*so + r*sr,
+//   x_rho = X + (x_by_out ? o : r) * ldx.
+// Serves every contraction of ovvv (layout V2[a',(j,BC)] = <ja'||bc>) or vvvv (W) over ONE member of
+// the antisymmetric pair without unpacking it: the three-operand second-order coupling terms
+// icab,jkcd,jkbd and ijac,kbcd,kd (adcc/adc_pp/matrix.py:498-499, 525, 529) and <ia||bc> p0[ic] of
+// adc3_i1 (:951).  HBM-bound: every packed element is read once; warp w owns the columns
+// c = w, w + nwarps, ..., keeps private accumulators for y[b] += A x[c] (b < c) and reduces
+// y[c] -= sum_b A x[b] with shuffles, so the result does not depend on the launch geometry.
+constexpr int kPairWarps = 8;
+__global__ void __launch_bounds__(kPairWarps * 32)
+pair_matvec_kernel(int nv, int n_red, int chunk, long long so, long long sr, const double* __restrict__ V,
+                   const double* __restrict__ X, long long ldx, int x_by_out, double* __restrict__ partial) {
+  extern __shared__ double sm[];
+  double* xs = sm;                      // [nv]
+  double* y2 = sm + nv;                 // [nv]
+  double* yp = sm + 2 * nv;             // [kPairWarps][nv]
+  const long long npv = (long long)nv * (nv - 1) / 2;
+  const int o = blockIdx.x, ch = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int e = threadIdx.x; e < nv * (kPairWarps + 1); e += blockDim.x) y2[e] = 0.0;
+  const int r0 = ch * chunk, r1 = min(r0 + chunk, n_red);
+  for (int r = r0; r < r1; ++r) {
+    __syncthreads();                    // previous row done with xs
+    const double* x = X + (long long)(x_by_out ? o : r) * ldx;
+    for (int e = threadIdx.x; e < nv; e += blockDim.x) xs[e] = x[e];
+    __syncthreads();
+    const double* A = V + ((long long)o * so + (long long)r * sr) * npv;
+    double* ypw = yp + warp * nv;
+    for (int c = warp + 1; c < nv; c += kPairWarps) {      // column c holds pairs (b, c), b < c
+      const double* col = A + (long long)c * (c - 1) / 2;
+      const double xc = xs[c];
+      double acc = 0.0;
+      int b = lane;
+      for (; b + 96 < c; b += 128) {
+        const double a0 = col[b], a1 = col[b + 32], a2 = col[b + 64], a3 = col[b + 96];
+        ypw[b] += a0 * xc; ypw[b + 32] += a1 * xc; ypw[b + 64] += a2 * xc; ypw[b + 96] += a3 * xc;
+        acc += a0 * xs[b] + a1 * xs[b + 32] + a2 * xs[b + 64] + a3 * xs[b + 96];
+      }
+      for (; b < c; b += 32) {
+        const double a0 = col[b];
+        ypw[b] += a0 * xc;
+        acc += a0 * xs[b];
+      }
+      for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      if (lane == 0) y2[c] -= acc;
+    }
+  }
+  __syncthreads();
+  double* dst = partial + ((long long)ch * gridDim.x + o) * nv;
+  for (int a = threadIdx.x; a < nv; a += blockDim.x) {
+    double s = y2[a];
+#pragma unroll
+    for (int w = 0; w < kPairWarps; ++w) s += yp[w * nv + a];
+    dst[a] = s;
+  }
+}
+
+// out[o*ldo + a] = beta * out[o*ldo + a] + alpha * sum_ch partial[ch, o, a]   (fixed order)
+__global__ void chunk_sum_kernel(int n_out, int nv, int n_chunks, const double* __restrict__ partial,
+                                 double alpha, double beta, double* __restrict__ out, long long ldo) {
+  const long long n = (long long)n_out * nv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int ch = 0; ch < n_chunks; ++ch) s += partial[(long long)ch * n + idx];
+    double* dst = out + (idx / nv) * ldo + idx % nv;
+    *dst = (beta != 0.0 ? beta * (*dst) : 0.0) + alpha * s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // host entry points
 // ---------------------------------------------------------------------------------------
 static inline int blocks_for(long long n, int threads) {
@@ -389,6 +519,62 @@ int slab_layout(cudaStream_t st, int dir, long long nrows, long long npv, int wo
   slab_layout_kernel<<<blocks_for(n, 256), 256, 0, st>>>(dir, nrows, npv, wmax, c, full, slabs);
   ADCCB_LAUNCH_OK();
   count_launch();
+  return 0;
+}
+
+int vvvv_exchange_slab(cudaStream_t st, int nv, int a_begin, int na, const double* W, double* out) {
+  if (na <= 0 || nv < 2) return 0;
+  if (a_begin < 0 || a_begin + na > nv) return fail("vvvv_exchange_slab: slab out of range");
+  const long long blocks = (long long)na * nv * nv;
+  if (blocks > 0x7fffffffLL) return fail("vvvv_exchange_slab: slab too large");
+  vvvv_exchange_slab_kernel<<<(unsigned)blocks, 128, 0, st>>>(nv, a_begin, W, out);
+  ADCCB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+int ovvv_exchange_slab(cudaStream_t st, int no, int nv, int a_begin, int na, const double* V2, double* out) {
+  if (na <= 0 || nv < 2 || no < 1) return 0;
+  if (a_begin < 0 || a_begin + na > nv) return fail("ovvv_exchange_slab: slab out of range");
+  const long long blocks = (long long)na * nv * no;
+  if (blocks > 0x7fffffffLL) return fail("ovvv_exchange_slab: slab too large");
+  ovvv_exchange_slab_kernel<<<(unsigned)blocks, 128, 0, st>>>(no, nv, a_begin, V2, out);
+  ADCCB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+int pair_matvec(cudaStream_t st, int nv, int n_out, int n_red, long long so, long long sr, const double* V,
+                const double* X, long long ldx, int x_by_out, double alpha, double beta, double* out,
+                long long ldo, double* ws, long long ws_bytes) {
+  if (n_out <= 0 || nv < 1) return 0;
+  if (n_red <= 0) {
+    chunk_sum_kernel<<<blocks_for((long long)n_out * nv, 256), 256, 0, st>>>(n_out, nv, 0, ws, alpha, beta, out, ldo);
+    ADCCB_LAUNCH_OK();
+    count_launch();
+    return 0;
+  }
+  // enough CTAs to fill the machine: split the reduction index into chunks
+  const int want = 4 * sm_count();
+  int n_chunks = std::max(1, std::min(n_red, (want + n_out - 1) / n_out));
+  int chunk = (n_red + n_chunks - 1) / n_chunks;
+  n_chunks = (n_red + chunk - 1) / chunk;
+  if ((long long)n_chunks * n_out * nv * 8 > ws_bytes) return fail("pair_matvec: workspace too small");
+  if (n_chunks > 65535) return fail("pair_matvec: too many chunks");
+  const int smem = (kPairWarps + 2) * nv * 8;
+  if (smem > 200 * 1024) return fail("pair_matvec: nv too large for the shared-memory accumulators");
+  static std::atomic<unsigned long long> attr_devices{0};
+  const int dev = current_device();
+  if (dev >= 64 || !((attr_devices.load(std::memory_order_acquire) >> dev) & 1ULL)) {
+    ADCCB_CUDA_OK(cudaFuncSetAttribute(pair_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (dev < 64) attr_devices.fetch_or(1ULL << dev, std::memory_order_release);
+  }
+  pair_matvec_kernel<<<dim3(n_out, n_chunks), kPairWarps * 32, smem, st>>>(nv, n_red, chunk, so, sr, V, X, ldx,
+                                                                          x_by_out, ws);
+  ADCCB_LAUNCH_OK();
+  chunk_sum_kernel<<<blocks_for((long long)n_out * nv, 256), 256, 0, st>>>(n_out, nv, n_chunks, ws, alpha, beta, out, ldo);
+  ADCCB_LAUNCH_OK();
+  count_launch(2);
   return 0;
 }
 

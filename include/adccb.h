@@ -150,6 +150,24 @@ int adccb_slab_layout(void* stream, int dir, int64_t nrows, int64_t npv, int wor
  * libadcc_src/TensorImpl.cc:1369-1441, for one slab). */
 int adccb_copy2d(void* stream, void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes,
                  int64_t width_bytes, int64_t height);
+/* out[al, b, c, d] = <a c||b d> (a = a_begin + al < a_begin + na) gathered from the pair-packed vvvv
+ * block W[AB,CD]: the exchange-ordered operand slab of the o^2 v^4 builds of the ADC(3) singles block
+ * (adcc/adc_pp/matrix.py:953 "acbd,cd->ab", :1029-1033 "icjd,acbd->iajb" / "idjc,acbd->iajb"), which on
+ * the reference are libtensor contractions over the full vvvv tensor. */
+int adccb_vvvv_exchange_slab(void* stream, int nv, int a_begin, int na, const double* W, double* out);
+/* out[al, c, j, d] = <j c||a d> (a = a_begin + al) gathered from V2[c,(j,AD)] (the pair-packed ovvv
+ * layout of adccb_synth_fill layout 4): operand slab of pi7 = t2[ijbd] <jc||ad>
+ * (adcc/GroundState.py:239), which feeds adc3_pib (adcc/adc_pp/matrix.py:1087-1094). */
+int adccb_ovvv_exchange_slab(void* stream, int no, int nv, int a_begin, int na, const double* V2, double* out);
+/* Contraction of a stack of pair-packed ANTISYMMETRIC nv x nv matrices with vectors over ONE member of
+ * the packed pair:  out[o, a] = beta*out[o, a] + alpha * sum_{r < n_red} sum_c A_{rho}[a,c] x_{rho}[c],
+ * rho = o*row_stride_out + r*row_stride_red (in rows of nv(nv-1)/2 doubles of V), x_rho = X + (x_by_out ?
+ * o : r)*ldx.  With V = V2[a',(j,BC)] = <ja'||bc> it evaluates  <ic||ab> r[cb]  (adcc/adc_pp/matrix.py:498),
+ * <kb||cd> u[kd]  (:529) and  <ia||bc> p[ic]  (:951) without unpacking ovvv.  ws: scratch for the
+ * per-chunk partial sums (n_chunks * n_out * nv doubles, n_chunks <= 4*SMs/n_out + 1). */
+int adccb_pair_matvec(void* stream, int nv, int n_out, int n_red, int64_t row_stride_out, int64_t row_stride_red,
+                      const double* V, const double* X, int64_t ldx, int x_by_out, double alpha, double beta,
+                      double* out, int64_t ldo, double* ws, int64_t ws_bytes);
 /* S[rows[r], AB] += alpha * (F_r[a,b] - F_r[b,a]), F_r[a,b] = P1[off1[r] + a*sa + b] - P2[off2[r] + a*sa + b]
  * (P2/off2 may be NULL; rows NULL = identity); off1/off2/rows: device int64 arrays of length nrows.  Folds the ovov-type
  * and ooov-type GEMM results into packed sigma (the antisymmetrise(2,3) of
@@ -174,7 +192,8 @@ int adccb_pair_select(void* stream, int64_t L, int n, int64_t R, const double* i
  * hash (no host data): layout 0 W[AB,CD] (vvvv, rows row_begin..), 1 O[IJ,KL] (oooo),
  * 2 Y[(j,b),(k,c)] = <kb||jc>, 3 V1[(j,AB),c] = <jc||ab>, 4 V2[a,(j,BC)] = <ja||bc>,
  * 5 G1[i,(JK,b)] = <jk||ib>, 6 G2[(IJ,a),k] = <ij||ka>, 7 dense block blk
- * (0 oooo, 1 ooov, 2 oovv, 3 ovov, 4 ovvv, 5 vvvv).  n = number of elements written.
+ * (0 oooo, 1 ooov, 2 oovv, 3 ovov, 4 ovvv, 5 vvvv), 8 exchange-ordered vvvv slab [al,b,c,d] = <ac||bd>
+ * and 9 exchange-ordered ovvv slab [al,c,j,d] = <jc||ad> with a = row_begin + al.  n = number of elements written.
  * Stands in for ReferenceState::eri -> import_eri_* (libadcc_src/ReferenceState.cc:478-509).
  * Slabs for sharding: row_begin = first AB row of layout 0; layouts 2, 3, 4 generate the occupied
  * slab j = j_begin .. j_begin+nj-1 (nj <= 0: all). */

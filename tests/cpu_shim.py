@@ -186,6 +186,41 @@ def install(monkeypatch):
         out.copy_(torch.stack(parts).reshape(out.shape))
         return out
 
+    def _pair_dense(rows, nv):
+        """[n, npv] pair-packed antisymmetric rows -> [n, nv, nv]"""
+        pv = _pairs(nv)
+        aa = torch.tensor([p[0] for p in pv], dtype=torch.long); bb = torch.tensor([p[1] for p in pv], dtype=torch.long)
+        d = torch.zeros((rows.shape[0], nv, nv), dtype=F64)
+        d[:, aa, bb] = rows
+        d[:, bb, aa] = -rows
+        return d
+
+    def vvvv_exchange_slab(W, nv, a_begin, na):
+        npv = nv * (nv - 1) // 2
+        full = _pair_dense(_pair_dense(W.reshape(npv, npv), nv).reshape(npv, nv * nv).t().contiguous(), nv)
+        full = full.reshape(nv, nv, nv, nv)           # [c', d', a', b'] = <a'b'||c'd'> -> index as [b,d,a,c]
+        # <ac||bd> = full[b, d, a, c]
+        return full.permute(2, 0, 3, 1)[a_begin:a_begin + na].contiguous()
+
+    def ovvv_exchange_slab(V2, no, nv, a_begin, na):
+        npv = nv * (nv - 1) // 2
+        d = _pair_dense(V2.reshape(nv * no, npv), nv).reshape(nv, no, nv, nv)      # [c, j, a, d]
+        return d.permute(2, 0, 1, 3)[a_begin:a_begin + na].contiguous()
+
+    def pair_matvec(V, nv, n_out, n_red, row_stride_out, row_stride_red, X, x_by_out, out=None, alpha=1.0, beta=0.0):
+        npv = nv * (nv - 1) // 2
+        rows = V.reshape(-1, npv)
+        res = torch.zeros((n_out, nv), dtype=F64)
+        for o in range(n_out):
+            idx = torch.tensor([o * row_stride_out + r * row_stride_red for r in range(n_red)], dtype=torch.long)
+            A = _pair_dense(rows[idx], nv)
+            xs = X[o].reshape(1, nv).expand(n_red, nv) if x_by_out else X[:n_red]
+            res[o] = torch.einsum("rac,rc->a", A, xs)
+        if out is None:
+            return alpha * res
+        out.copy_(alpha * res + (beta * out if beta != 0.0 else 0.0))
+        return out
+
     def packed_fold_virt(S, nv, sa, P1, off1, P2=None, off2=None, alpha=1.0, rows=None):
         pv = _pairs(nv)
         aa = np.array([p[0] for p in pv], dtype=int); bb = np.array([p[1] for p in pv], dtype=int)
@@ -279,6 +314,12 @@ def install(monkeypatch):
         elif layout == "ooov_ijak":
             IJ, a, k = np.meshgrid(np.arange(len(po)), v, o, indexing="ij")
             arr = val(seed, "ooov", po[IJ, 0], po[IJ, 1], k, a, scale)
+        elif layout == "vvvv_exchange":
+            a, b, c, d = np.meshgrid(np.arange(row_begin, row_begin + out.shape[0]), v, v, v, indexing="ij")
+            arr = val(seed, "vvvv", a, c, b, d, scale)
+        elif layout == "ovvv_exchange":
+            a, c, j, d = np.meshgrid(np.arange(row_begin, row_begin + out.shape[0]), v, o, v, indexing="ij")
+            arr = val(seed, "ovvv", j, c, a, d, scale)
         else:
             from adcc_b200.synthetic import synthetic_eri_block
             arr = synthetic_eri_block(seed, block, no, nv, scale)
@@ -300,7 +341,8 @@ def install(monkeypatch):
                          spin_singlet_=spin_singlet_, packed_unpack=packed_unpack, packed_pack=packed_pack,
                          packed_expand=packed_expand, packed_fold_virt=packed_fold_virt,
                          packed_fold_occ=packed_fold_occ, packed_diagonal=packed_diagonal,
-                         pair_select=pair_select, packed_expand_slab=packed_expand_slab, slab_layout=slab_layout,
+                         pair_select=pair_select, vvvv_exchange_slab=vvvv_exchange_slab, ovvv_exchange_slab=ovvv_exchange_slab, pair_matvec=pair_matvec,
+                         packed_expand_slab=packed_expand_slab, slab_layout=slab_layout,
                          copy2d=copy2d, comm_reduce_scatter=comm_reduce_scatter, comm_all_gather=comm_all_gather,
                          int64_tensor=int64_tensor, add_columns=add_columns, spin_expand4=spin_expand4, synth_fill=synth_fill).items():
         monkeypatch.setattr(be, name, fn)
