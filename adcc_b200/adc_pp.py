@@ -161,15 +161,43 @@ def _i_t2sq(hf, mp, im):
     return einsum("ikac,jkbc->iajb", mp.t2oo, mp.t2oo)
 
 
+class DenseEriOps:
+    """The contractions of adc3_i1 / adc3_m11 that touch the ovvv or vvvv block
+    (adcc/adc_pp/matrix.py:951-953, 1014, 1029-1033), on dense blocks.  A reference state may carry
+    its own implementation as ``hf.big_eri_ops`` (adcc_b200/packed_adc3.py: pair-packed operands,
+    exchange-ordered slabs) for sizes at which the dense blocks cannot exist."""
+
+    def __init__(self, hf):
+        self.hf = hf
+
+    def ovvv_iabc_ic(self, p_ov):
+        return einsum("iabc,ic->ab", self.hf.ovvv, p_ov)
+
+    def vvvv_acbd_cd(self, p_vv):
+        return einsum("acbd,cd->ab", self.hf.vvvv, p_vv)
+
+    def ovvv_ibac_jc(self, x_ov):
+        return einsum("ibac,jc->iajb", self.hf.ovvv, x_ov)
+
+    def m11_v4(self, ovov, t2, t2sq):
+        return (0.5 * einsum("icjd,acbd->iajb", ovov, einsum("klac,klbd->acbd", t2, t2))
+                - einsum("idjc,acbd->iajb", t2sq, self.hf.vvvv))
+
+
+def _eri_ops(hf):
+    return getattr(hf, "big_eri_ops", None) or DenseEriOps(hf)
+
+
 def _adc3_i1(hf, mp, im):
     td2 = mp.td2(b.oovv)
     p0 = mp.second_order_dm_correction(apply_cvs=hf.has_core_occupied_space)
     t2eri_sum = (mp.t2eri(b.oovv, b.ov).transpose((1, 0, 2, 3)) - 0.25 * mp.t2eri(b.oovv, b.vv))
+    ops = _eri_ops(hf)
     return ((0.5 * einsum("ijac,ijbc->ab", mp.t2oo + td2, hf.oovv)
              - 1.0 * einsum("ijac,ijcb->ab", mp.t2oo, t2eri_sum)
-             - 2.0 * einsum("iabc,ic->ab", hf.ovvv, p0.ov)).symmetrise()
+             - 2.0 * ops.ovvv_iabc_ic(p0.ov)).symmetrise()
             + einsum("iajb,ij->ab", hf.ovov, p0.oo)
-            + einsum("acbd,cd->ab", hf.vvvv, p0.vv))
+            + ops.vvvv_acbd_cd(p0.vv))
 
 
 def _adc3_i2(hf, mp, im):
@@ -206,9 +234,10 @@ def _i_adc3_m11(hf, mp, im):
     t2eri_sum = (2.0 * mp.t2eri(b.oovv, b.ov).symmetrise((0, 1), (2, 3))
                  + 0.5 * mp.t2eri(b.oovv, b.vv) + 0.5 * mp.t2eri(b.oovv, b.oo))
     ov2 = 2.0 * p0.ov
+    ops = _eri_ops(hf)
     inner = (einsum("jkbc,ikac->iajb", hf.oovv, t2 + td2)
              - einsum("jkbc,ikac->iajb", t2, t2eri_sum)
-             - einsum("ibac,jc->iajb", hf.ovvv, ov2)
+             - ops.ovvv_ibac_jc(ov2)
              - einsum("ikja,kb->iajb", hf.ooov, ov2)
              - einsum("jaic,bc->iajb", hf.ovov, p0.vv)
              + einsum("ik,jakb->iajb", p0.oo, hf.ovov)
@@ -217,10 +246,9 @@ def _i_adc3_m11(hf, mp, im):
             - einsum("ij,ab->iajb", hf.foo - i2, d_vv)
             - einsum("jaib->iajb", hf.ovov)
             - inner.symmetrise((0, 2), (1, 3))
-            + 0.5 * einsum("icjd,acbd->iajb", hf.ovov, einsum("klac,klbd->acbd", t2, t2))
+            + ops.m11_v4(hf.ovov, t2, t2sq)
             + 0.5 * einsum("ikjl,kalb->iajb", einsum("ikcd,jlcd->ikjl", t2, t2), hf.ovov)
-            - einsum("iljk,kalb->iajb", hf.oooo, t2sq)
-            - einsum("idjc,acbd->iajb", t2sq, hf.vvvv))
+            - einsum("iljk,kalb->iajb", hf.oooo, t2sq))
 
 
 def _i_cvs_adc3_m11(hf, mp, im):

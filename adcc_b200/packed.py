@@ -346,6 +346,9 @@ class DenseSource:
         from .functions import einsum
         return einsum("abab->ab", self.hf.vvvv).symmetrise()._contig()
 
+    def ovvv_exchange_slab(self, V2e, a_begin, na):      # [al,c,j,d] = <jc||ad>
+        return be.ovvv_exchange_slab(V2e, self.no, self.nv, a_begin, na)
+
 
 class PackedAdcEngine:
     """ADC(2) / ADC(2)-x / ADC(3) matvec on the packed doubles store (see module docstring)."""
@@ -377,39 +380,9 @@ class PackedAdcEngine:
         if offdiag > 1e-12:
             raise NotImplementedError("packed engine needs canonical orbitals (diagonal Fock)")
         src = source if source is not None else getattr(hf, "packed_source", None)
-        if self.level3:
-            # ADC(3): the couplings keep their first-order structure with adc3_pia / adc3_pib in
-            # place of ooov / ovvv (matrix.py:490-532); the second-order singles block is the
-            # ov x ov matrix adc3_m11 (matrix.py:606-618).  The intermediates come from the dense
-            # builders, so the dense ERI blocks must exist.
-            if src is not None or self.world > 1:
-                raise NotImplementedError("packed ADC(3) needs dense ERI blocks for its intermediates "
-                                          "and is not sharded yet")
-            src = DenseSource(hf, mp, ooov=im.adc3_pia, ovvv=im.adc3_pib)
-        elif src is None:
+        if src is None:
             src = DenseSource(hf, mp)
         self.flops = {}
-
-        # ---- singles-singles block folded into one (ov x ov) matrix  (matrix.py:353-375)
-        if self.level3:
-            self.M1 = im.adc3_m11._contig().reshape(no * nv, no * nv)
-        else:
-            i1, i2 = im.adc2_i1, im.adc2_i2
-            m1 = einsum("ij,ab->iajb", _delta_like(hf.foo), i1) - einsum("ij,ab->iajb", i2, _delta_like(hf.fvv))
-            m1 = m1 - hf.ovov.transpose((2, 1, 0, 3))               # - <ja||ib>
-            m1 = m1 - 0.5 * im.term_t2_eri.transpose((0, 2, 1, 3))  # - 1/2 term[ikac] -> [i,a,k,c]
-            self.M1 = m1._contig().reshape(no * nv, no * nv)
-        # second-order coupling terms without a first-order counterpart (three-operand terms with
-        # t2): evaluated by the table interpreter on the unpacked doubles
-        self._extra = {"ph_pphh": [], "pphh_ph": []}
-        if self.level3:
-            for blk in self._extra:
-                for c, e in matrix._tables[blk][2]:
-                    if not _mentions(e, ("adc3_pia", "adc3_pib")):
-                        matrix._resolve_constants(e)
-                        self._extra[blk].append((c, e))
-
-        # ---- couplings (matrix.py:270-276, 288-294)
         # slabs owned by this rank (world == 1: everything)
         r, w = self.rank, self.world
         self.j0, j1 = (r * no) // w, ((r + 1) * no) // w
@@ -420,10 +393,38 @@ class PackedAdcEngine:
         self._wmax = max(cut[k + 1] - cut[k] for k in range(w))
         cut_o = [min(self.npo, ((k * self.npo // w + 1) // 2) * 2) for k in range(w)] + [self.npo]
         self.ij0, self.ij1 = cut_o[r], cut_o[r + 1]
-        self.V1 = src.ovvv_jabc(self.j0, self.nj)
-        self.V2 = src.ovvv_ajbc(self.j0, self.nj)
-        self.G1 = src.ooov_ijkb()
-        self.G2 = src.ooov_ijak()
+        self._extra3 = None
+        self.build_flops = 0.0
+
+        if self.level3:
+            # ADC(3): the couplings keep their first-order structure with adc3_pia / adc3_pib in
+            # place of ooov / ovvv (matrix.py:490-532), the singles block is the ov x ov matrix
+            # adc3_m11 (matrix.py:606-618); four three-operand second-order coupling terms come on
+            # top.  All of it is built from the pair-packed operands (packed_adc3.py), so that the
+            # dense ovvv / vvvv blocks are never needed.
+            if self.world > 1:
+                raise NotImplementedError("the packed ADC(3) engine is not sharded yet")
+            from .packed_adc3 import build_adc3_operands
+            self.W = src.vvvv_packed()
+            self.O = src.oooo_packed()
+            self.Y = src.ovov_jbkc()
+            ops3 = build_adc3_operands(hf, mp, im, src, self.W, self.O, self.Y, self.j0, self.nj)
+            self.M1 = ops3["M1"]
+            self.V1, self.V2, self.G1, self.G2 = ops3["V1"], ops3["V2"], ops3["G1"], ops3["G2"]
+            self._extra3 = ops3["extras"]
+            self.build_flops = ops3["build_flops"]
+        else:
+            # ---- singles-singles block folded into one (ov x ov) matrix  (matrix.py:353-375)
+            i1, i2 = im.adc2_i1, im.adc2_i2
+            m1 = einsum("ij,ab->iajb", _delta_like(hf.foo), i1) - einsum("ij,ab->iajb", i2, _delta_like(hf.fvv))
+            m1 = m1 - hf.ovov.transpose((2, 1, 0, 3))               # - <ja||ib>
+            m1 = m1 - 0.5 * im.term_t2_eri.transpose((0, 2, 1, 3))  # - 1/2 term[ikac] -> [i,a,k,c]
+            self.M1 = m1._contig().reshape(no * nv, no * nv)
+            # ---- couplings (matrix.py:270-276, 288-294)
+            self.V1 = src.ovvv_jabc(self.j0, self.nj)
+            self.V2 = src.ovvv_ajbc(self.j0, self.nj)
+            self.G1 = src.ooov_ijkb()
+            self.G2 = src.ooov_ijak()
 
         # ---- doubles-doubles (matrix.py:127-133, 234-246)
         eo = be.from_numpy(np.diag(foo))
@@ -431,14 +432,18 @@ class PackedAdcEngine:
         d0_ov = be.direct_sum(eo, ev, -1.0, 1.0)                 # e_a - e_i
         self.D0 = be.packed_diagonal(no, nv, d0_ov)              # e_a + e_b - e_i - e_j
         if self.order_dd == 1:
-            self.W = src.vvvv_packed(self.ab0, self.ab1 - self.ab0)
-            self.O = src.oooo_packed()
-            if self.vectors == "slab":
+            if self.level3:
+                pass                                         # W, O, Y were needed by the ADC(3) build
+            elif self.vectors == "slab":
+                self.W = src.vvvv_packed(self.ab0, self.ab1 - self.ab0)
+                self.O = src.oooo_packed()
                 # the ovov term runs on the occupied-i row slab of X against the complete Y, so that
                 # the expansion of X is sharded as well (2 GB replicated at nocc=40 / nvirt=400)
                 self.Yfull = src.ovov_jbkc()
                 self.Y = self.Yfull[self.j0 * nv:(self.j0 + self.nj) * nv]
             else:
+                self.W = src.vvvv_packed(self.ab0, self.ab1 - self.ab0)
+                self.O = src.oooo_packed()
                 self.Y = src.ovov_jbkc(self.j0, self.nj)
             d_ov = (direct_sum("a-i->ia", hf.fvv.diagonal(), hf.foo.diagonal())
                     - 2.0 * einsum("iaia->ia", hf.ovov))._contig()
@@ -515,6 +520,11 @@ class PackedAdcEngine:
             f["pphh_pphh/vvvv"] = 2.0 * npo * npv * npv
             f["pphh_pphh/oooo"] = 2.0 * npo * npo * npv
             f["pphh_pphh/ovov"] = 2.0 * (no * nv) ** 3
+        if self._extra3 is not None:
+            # three-operand second-order coupling terms: r1 / r2 GEMMs over the packed vector, the
+            # T2h x r4 GEMM and the t2eM x r3 GEMM; the two ovvv pair matvecs are HBM-bound FMAs
+            f["ph_pphh/second_order"] = 2.0 * nv * nv * npo * nv + 2.0 * no * no * no * npv + 2 * 2.0 * no * npv * nv
+            f["pphh_ph/second_order"] = 2.0 * npo * nv * nv * nv + 2.0 * no * no * no * npv + 2 * 2.0 * no * npv * nv
         self.flops = f
         self.flops_per_matvec = sum(f.values())
 
@@ -556,15 +566,35 @@ class PackedAdcEngine:
         s1 = be.gemm(Ue, self.V2, alpha=2.0)                 # sum_{j,b<c} 2 u[ij,bc] <ja||bc>
         Uh = be.packed_expand(2, U, no, nv)                 # [a,(JK,b)]
         be.gemm(self.G1, Uh, out=s1, alpha=2.0, beta=1.0)    # sum_{j<k,b} 2 <jk||ib> u[jk,ab]
+        x3 = self._extra3
+        if x3 is not None:
+            # second-order terms without a first-order counterpart (matrix.py:498-499):
+            #   + <ij||ka> r2[jk],  r2[jk] = t2[jlbc] u[klbc] = 2 sum_{l,B<C}
+            r2 = be.gemm(x3["t2e"], Ue, alpha=2.0)                                  # [j,k]
+            be.gemm(r2.reshape(1, no * no), x3["G3"], out=s1.view(1, no * nv), beta=1.0)
+            #   + <ic||ab> r1[cb],  r1[cb] = u[jkcd] t2[jkbd] = 2 sum_{J<K,d}
+            r1 = be.gemm(Uh, x3["T2uh"], alpha=2.0)                                 # [c,b]
+            be.pair_matvec(x3["V2e"], nv, n_out=no, n_red=nv, row_stride_out=1, row_stride_red=no,
+                           X=r1, x_by_out=False, out=s1, beta=1.0)
         return s1
 
     def apply_pphh_ph(self, u1, S):
         no, nv = self.no, self.nv
         x = u1._contig()
+        x3 = self._extra3
         c1 = be.gemm(x, self.V1)                             # [i,(j,AB)] = sum_c u[ic] <jc||ab>
+        if x3 is not None:
+            # + A_ij( r3[li] t2[jlab] ),  r3[li] = <lk||ic> u[kc]      (matrix.py:525)
+            r3 = be.gemm(x.reshape(1, no * nv), x3["G4"]).view(no, no)            # [l,i]
+            be.gemm(be.permute(r3, (1, 0)), x3["t2eM"], out=c1, beta=1.0)
         be.packed_fold_occ(S, c1, no, nv, alpha=0.5)         # antisymmetrise(0,1)
         xt = be.permute(x, (1, 0))                           # [b,k]
         c2 = be.gemm(self.G2, xt)                            # [(IJ,a),b] = sum_k <ij||ka> u[kb]
+        if x3 is not None:
+            # - A_ab( t2[ijac] r4[bc] ),  r4[bc] = <kb||cd> u[kd]      (matrix.py:529)
+            r4 = be.pair_matvec(x3["V2e"], nv, n_out=nv, n_red=no, row_stride_out=no, row_stride_red=1,
+                                X=x, x_by_out=False)                               # [b,c]
+            be.gemm(x3["T2h"], r4, out=c2, beta=1.0)
         be.packed_fold_virt(S, nv, nv, c2, self._off_rows, alpha=-0.5)   # - antisymmetrise(2,3)
         return S
 
@@ -1009,26 +1039,7 @@ class PackedAdcEngine:
         S = be.empty((self.npo, self.npv))
         self.apply_pphh_pphh(U, S, 0.0)
         self.apply_pphh_ph(u1, S)
-        self._extra_ph_pphh(u2, s1)
-        self._extra_pphh_ph(u1, S)
         return AmplitudeVector(ph=self._wrap_ph(s1), pphh=self._wrap_pphh(S))
-
-    def _extra_ph_pphh(self, u2, s1):
-        """s1 += table terms of ph_pphh that have no packed kernel (ADC(3) only)."""
-        if not self._extra["ph_pphh"]:
-            return
-        ampl = AmplitudeVector(pphh=u2.to_dense())
-        terms = [(c, self.matrix._eval(e, ampl)) for c, e in self._extra["ph_pphh"]]
-        be.lincomb([c for c, _ in terms], [t._contig() for _, t in terms], out=s1, beta=1.0)
-
-    def _extra_pphh_ph(self, u1, S):
-        """S += packed(table terms of pphh_ph without a packed kernel) (ADC(3) only)."""
-        if not self._extra["pphh_ph"]:
-            return
-        ampl = AmplitudeVector(ph=u1)
-        terms = [(c, self.matrix._eval(e, ampl)) for c, e in self._extra["pphh_ph"]]
-        dense = be.lincomb([c for c, _ in terms], [t._contig() for _, t in terms])
-        be.axpby(1.0, be.packed_pack(dense, self.no, self.nv), 1.0, S)
 
     def matvec_host(self, u1_host, U_host, s1_host, S_host, edge_rows=112):
         """sigma = M u for a trial vector in PINNED host buffers, result into pinned host buffers
@@ -1094,10 +1105,8 @@ class PackedAdcEngine:
         del T
         u1 = self._wrap_ph(x)
         self.apply_pphh_ph(u1, S)
-        self._extra_pphh_ph(u1, S)
         s1 = self.apply_ph_ph(u1)
         be.axpby(1.0, self.apply_ph_pphh(U), 1.0, s1)
-        self._extra_ph_pphh(self._wrap_pphh(U), s1)
         head_done = torch.cuda.Event()
         head_done.record(main)
         # rows [r2, npo): vvvv term last, while rows [0, r2) and the ph part are downloading
@@ -1120,27 +1129,15 @@ class PackedAdcEngine:
             return self._wrap_ph(self.apply_ph_ph(tensor))
         if block == "ph_pphh":
             t = tensor if isinstance(tensor, PackedDoubles) else PackedDoubles.from_dense(tensor)
-            s1 = self.apply_ph_pphh(t._contig())
-            self._extra_ph_pphh(t, s1)
-            return self._wrap_ph(s1)
+            return self._wrap_ph(self.apply_ph_pphh(t._contig()))
         S = be.zeros((self.npo, self.npv))
         if block == "pphh_ph":
             self.apply_pphh_ph(tensor, S)
-            self._extra_pphh_ph(tensor, S)
             return self._wrap_pphh(S)
         if block == "pphh_pphh":
             t = tensor if isinstance(tensor, PackedDoubles) else PackedDoubles.from_dense(tensor)
             return self._wrap_pphh(self.apply_pphh_pphh(t._contig(), S, 0.0))
         raise ValueError(block)
-
-
-def _mentions(expr, names):
-    """True if a block-table expression (adc_pp.E / A / S tuples) uses one of the operand names."""
-    if isinstance(expr, str):
-        return expr in names
-    if expr[0] == "einsum":
-        return any(_mentions(op, names) for op in expr[2])
-    return _mentions(expr[1], names)
 
 
 def _delta_like(t):
@@ -1195,6 +1192,9 @@ class SyntheticSource:
     def dense(self, block):
         shape = [self.no if c == "o" else self.nv for c in block]
         return self._fill(shape, "dense", block=block)
+
+    def ovvv_exchange_slab(self, V2e, a_begin, na):      # [al,c,j,d] = <jc||ad>
+        return be.ovvv_exchange_slab(V2e, self.no, self.nv, a_begin, na)
 
 
 def synthetic_reference_state(no, nv, seed=20261019, scale=0.02):

@@ -121,10 +121,13 @@ def _all_host_threads():
     return n
 
 
-def workload_config(no, nv):
+METHOD_LABEL = {"adc2": "ADC(2)", "adc2x": "ADC(2)-x", "adc3": "ADC(3)"}
+
+
+def workload_config(no, nv, method="adc2x"):
     """`config` of the JSON line; identical in both arms when both run the same shape."""
     npv = nv * (nv - 1) // 2
-    return {"workload": f"synthetic ADC(2)-x matvec nocc={no} nvirt={nv} (BASELINE configs[4]), "
+    return {"workload": f"synthetic {METHOD_LABEL[method]} matvec nocc={no} nvirt={nv} (BASELINE configs[4]), "
                         "random antisymmetrised FP64 ERIs from a counter-based hash",
             "storage": f"antisymmetry-packed doubles + vvvv ({npv * npv * 8 / 1e9:.1f} GB instead of "
                        f"{8.0 * nv ** 4 / 1e9:.1f} GB dense)",
@@ -271,7 +274,11 @@ def run_gpu(args):
                                           min(no, 40), min(nv, 240))
     t0 = time.perf_counter()
     ref = synthetic_reference_state(no, nv, seed=SEED, scale=SCALE)
-    matrix = adcc.AdcMatrix("adc2x", ref, doubles_storage="packed",
+    method = args.method
+    if method != "adc2x":
+        # the CPU restatement and the per-entry definition check are written for the ADC(2)-x blocks
+        args.no_cpu_baseline, args.verify_samples = True, 0
+    matrix = adcc.AdcMatrix(method, ref, doubles_storage="packed",
                             **({"shard": (rank, world)} if world > 1 else {}))
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t0
@@ -441,13 +448,14 @@ def run_gpu(args):
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------
     flops_per_matvec = eng.flops_per_matvec
-    f_ovov = eng.flops["pphh_pphh/ovov"]
+    eng_build = {"flops": eng.build_flops}
     vector_distribution = matrix.vector_distribution
     slab_exchange = ("none" if world == 1 else
                      "all-gather(u) + reduce-scatter(partial sigma); vvvv slab needs no exchange" if slab else
                      "GEMM epilogue -> peer memory (NVLink stores)" if eng._peer is not None
                      else "NCCL all-gather")
-    f_vvvv = eng.flops["pphh_pphh/vvvv"] / world
+    f_ovov = eng.flops.get("pphh_pphh/ovov", 0.0)
+    f_vvvv = eng.flops.get("pphh_pphh/vvvv", 0.0) / world
     t_vvvv = float(np.mean(ktimes["vvvv"])) if ktimes.get("vvvv") else None
     t_ovov = float(np.mean(ktimes["ovov"])) if ktimes.get("ovov") else None
     achieved = f_vvvv / (t_vvvv * 1e-3) * 1e-12 if t_vvvv else None
@@ -468,6 +476,21 @@ def run_gpu(args):
         "share_of_step": (t_vvvv / ms_step) if t_vvvv else None,
         "section_ms": {k: float(np.mean(v)) for k, v in ktimes.items()},
     }
+    if method == "adc2":
+        # no vvvv / ovov GEMM at second order: the step is the ovvv / M1 streams, HBM-bound
+        hbm_peak = 6532.2
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                hbm_peak = float(json.load(f)["hbm_gbs"])
+        except Exception:
+            pass
+        nbytes = 8.0 * (eng.V1.numel() + eng.V2.numel() + eng.M1.numel() / world + eng.G1.numel() + eng.G2.numel()
+                        + 6.0 * npo * npv)
+        roofline = {"bound": "hbm", "kernel": "whole ADC(2) step: ovvv streams (u1.V1, Ue.V2^T GEMMs), M1 GEMV, "
+                                              "expand / fold / D0 kernels",
+                    "achieved": nbytes / (ms_step * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": nbytes / (ms_step * 1e-3) * 1e-9 / hbm_peak, "traffic": None,
+                    "bytes_per_step": nbytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         # one COMPLETE matvec of the same workload on the host cores (bounded: one step), fed with
@@ -485,11 +508,11 @@ def run_gpu(args):
                 np.max(np.abs(csig[1] - sig_ref[1])) / np.max(np.abs(sig_ref[1]))))
             checks["full_sigma_elements_compared"] = int(csig[0].size + csig[1].size)
     line = {
-        "metric": METRIC, "value": 1000.0 / ms_step, "unit": UNIT, "n_gpus": world,
+        "metric": METRIC.replace("adc2x", method), "value": 1000.0 / ms_step, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": workload_config(no, nv),
+        "config": workload_config(no, nv, method),
         "parallelism": {"layout": f"virtual-pair slabs x{world}" if world > 1 else "single GPU",
                         "vectors": vector_distribution, "slab_exchange": slab_exchange},
         "executed_tflop_per_step": flops_per_matvec * 1e-12,
@@ -503,6 +526,11 @@ def run_gpu(args):
         "checks": checks,
         "build_s": t_build,
     }
+    if eng_build["flops"]:
+        line["build"] = {"seconds": t_build, "tflop": eng_build["flops"] * 1e-12,
+                         "tflops_achieved": eng_build["flops"] * 1e-12 / t_build,
+                         "note": "ADC(3) operands from pair-packed ERIs: o^2 v^4 slab GEMMs (t2sq.vvvv, ovov.(t2 t2), "
+                                 "pi7), packed pi5 / pi3, ovov-type pi4 and the (ov)^3 terms of adc3_m11"}
     if cpu is not None:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if davidson is not None:
@@ -535,6 +563,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="adcc_b200", choices=["adcc_b200", "reference"])
+    ap.add_argument("--method", default="adc2x", choices=["adc2", "adc2x", "adc3"],
+                    help="ADC(2)-x is BASELINE's metric; adc2 / adc3 print the same line for the other methods")
     ap.add_argument("--nocc", type=int, default=NO)
     ap.add_argument("--nvirt", type=int, default=NV)
     ap.add_argument("--n-states", type=int, default=5)

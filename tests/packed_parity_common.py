@@ -70,15 +70,45 @@ def check_packed_spin_kinds(method, n=3):
         np.testing.assert_allclose(st.excitation_energy, ost.eigenvalues, atol=ENERGY_ATOL, rtol=0)
 
 
-def check_synthetic(no, nv, seed=5, run=True):
+def check_synthetic(no, nv, seed=5, run=True, method="adc2x"):
     import adcc_b200 as adcc
     from adcc_b200.packed import synthetic_reference_state
     ref = synthetic_reference_state(no, nv, seed=seed, scale=0.02)
-    om = oracle.OracleAdcMatrix("adc2x", OracleSyntheticRef(no, nv, seed=seed, scale=0.02))
-    m = adcc.AdcMatrix("adc2x", ref, doubles_storage="packed")
+    om = oracle.OracleAdcMatrix(method, OracleSyntheticRef(no, nv, seed=seed, scale=0.02))
+    m = adcc.AdcMatrix(method, ref, doubles_storage="packed")
     _compare(adcc, m, om)
     if run:
         st = adcc.run_adc(m, n_states=3, conv_tol=1e-8, output=None)
-        ost = oracle.run_adc(om, "adc2x", n_states=3, conv_tol=1e-8)
+        ost = oracle.run_adc(om, method, n_states=3, conv_tol=1e-8)
         assert st.converged
         np.testing.assert_allclose(st.excitation_energy, ost.eigenvalues, atol=ENERGY_ATOL, rtol=0)
+
+
+def check_adc3_builder_vs_dense(data=None):
+    """The ADC(3) operands built from pair-packed ERIs (adcc_b200/packed_adc3.py: exchange-ordered
+    slabs, pair matvecs, packed GEMMs) against the dense intermediates of adcc_b200/adc_pp.py
+    (adc3_m11 / adc3_pia / adc3_pib evaluated with plain einsum on dense blocks)."""
+    import adcc_b200 as adcc
+    from adcc_b200 import backend as be
+    data = data if data is not None else load_h2o_sto3g()
+    ref = adcc.ReferenceState(data)
+    m = adcc.AdcMatrix("adc3", ref, doubles_storage="packed")
+    eng = m._engine
+    no, nv, npo, npv = eng.no, eng.nv, eng.npo, eng.npv
+    dense = adcc.AdcMatrix("adc3", adcc.ReferenceState(data), doubles_storage="dense")
+    im = dense.intermediates
+    m11 = im.adc3_m11.to_ndarray().reshape(no * nv, no * nv)
+    assert rel_err(eng.M1.cpu().numpy(), m11) < 1e-12
+    pia, pib = im.adc3_pia.to_ndarray(), im.adc3_pib.to_ndarray()
+    po = [(i, j) for j in range(no) for i in range(j)]
+    pv = [(a, b) for b in range(nv) for a in range(b)]
+    G2 = eng.G2.cpu().numpy().reshape(npo, nv, no)                       # [(IJ,a),k] = pia[ij,k,a]
+    want = np.stack([pia[i, j].T for i, j in po])                        # [IJ, a, k]
+    assert rel_err(G2, want) < 1e-12
+    G1 = eng.G1.cpu().numpy().reshape(no, npo, nv)                       # [i,(JK,b)] = pia[jk,i,b]
+    assert rel_err(G1, np.stack([pia[j, k] for j, k in po], axis=1)) < 1e-12
+    V2 = eng.V2.cpu().numpy().reshape(nv, no, npv)                       # [a,(j,BC)] = pib[j,a,bc]
+    want = np.stack([pib[:, :, bb, cc] for bb, cc in pv], axis=-1).transpose(1, 0, 2)
+    assert rel_err(V2, want) < 1e-12
+    V1 = eng.V1.cpu().numpy().reshape(no, npv, nv)                       # [(j,AB),c] = pib[j,c,ab]
+    assert rel_err(V1, want.transpose(1, 2, 0)) < 1e-12

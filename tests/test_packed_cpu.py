@@ -31,6 +31,18 @@ def test_synthetic_workload_small():
     check_synthetic(6, 10, seed=5)
 
 
+@pytest.mark.parametrize("no,nv", [(4, 6), (6, 10)])
+def test_synthetic_adc3_small(no, nv):
+    check_synthetic(no, nv, seed=5, method="adc3", run=(nv == 10))
+
+
+def test_adc3_packed_builder_vs_dense_intermediates():
+    from packed_parity_common import check_adc3_builder_vs_dense
+    from adcc_b200.synthetic import restricted_scf_dict
+    check_adc3_builder_vs_dense()
+    check_adc3_builder_vs_dense(restricted_scf_dict(7, 2, seed=3))
+
+
 def test_packed_tensor_semantics():
     import adcc_b200 as adcc
     from adcc_b200.packed import PackedDoubles

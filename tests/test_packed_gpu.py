@@ -103,3 +103,59 @@ def test_packed_engine_c1_shape(method):
 @pytest.mark.parametrize("no,nv", [(6, 10), (10, 38), (16, 48)])
 def test_synthetic_workload_vs_oracle(no, nv):
     check_synthetic(no, nv, seed=5, run=(nv <= 38))
+
+
+@pytest.mark.parametrize("no,nv", [(4, 6), (6, 10), (10, 38), (12, 44)])
+def test_synthetic_adc3_vs_oracle(no, nv):
+    """ADC(3) on the synthetic workload: every operand comes from the pair-packed builder
+    (exchange-ordered slabs, pair matvecs); sigma, blocks, diagonal vs the dense oracle."""
+    check_synthetic(no, nv, seed=5, method="adc3", run=(nv == 10))
+
+
+def test_adc3_packed_builder_vs_dense_intermediates():
+    from packed_parity_common import check_adc3_builder_vs_dense
+    from adcc_b200.synthetic import named_case, restricted_scf_dict
+    check_adc3_builder_vs_dense()
+    check_adc3_builder_vs_dense(restricted_scf_dict(7, 2, seed=3))
+    check_adc3_builder_vs_dense(named_case("h2o_ccpvdz")[0])
+
+
+@pytest.mark.parametrize("nv,no", [(6, 4), (38, 10), (50, 7)])
+def test_pair_matvec_and_exchange_slabs(be, nv, no):
+    """adccb_pair_matvec / adccb_vvvv_exchange_slab / adccb_ovvv_exchange_slab against NumPy."""
+    rng = np.random.default_rng(nv)
+    npv = nv * (nv - 1) // 2
+    pv = [(a, b) for b in range(nv) for a in range(b)]
+    aa, bb = np.array([p[0] for p in pv]), np.array([p[1] for p in pv])
+    V2 = rng.standard_normal((nv, no, npv))                    # [s, f, BC]
+    dense = np.zeros((nv, no, nv, nv))
+    dense[:, :, aa, bb] = V2
+    dense[:, :, bb, aa] = -V2
+    X = rng.standard_normal((no, nv))
+    V2d = be.from_numpy(V2)
+    # out[s,c] = sum_f sum_d A_(s,f)[c,d] X[f,d]
+    got = be.pair_matvec(V2d, nv, n_out=nv, n_red=no, row_stride_out=no, row_stride_red=1,
+                         X=be.from_numpy(X), x_by_out=False).cpu().numpy()
+    assert np.allclose(got, np.einsum("sfcd,fd->sc", dense, X), atol=1e-12)
+    # out[f,a] += sum_s sum_b A_(s,f)[a,b] R[s,b]
+    R = rng.standard_normal((nv, nv))
+    out0 = rng.standard_normal((no, nv))
+    out = be.from_numpy(out0)
+    be.pair_matvec(V2d, nv, n_out=no, n_red=nv, row_stride_out=1, row_stride_red=no, X=be.from_numpy(R),
+                   x_by_out=False, out=out, alpha=0.5, beta=1.0)
+    assert np.allclose(out.cpu().numpy(), out0 + 0.5 * np.einsum("sfab,sb->fa", dense, R), atol=1e-12)
+    # ovvv exchange slab: V2[c,(j,AD)] = <jc||ad> -> [al,c,j,d]
+    a0, na = 1, min(3, nv - 1)
+    got = be.ovvv_exchange_slab(V2d, no, nv, a0, na).cpu().numpy()
+    assert np.array_equal(got, dense.transpose(2, 0, 1, 3)[a0:a0 + na])
+    # vvvv exchange slab from the pair-packed block
+    W = rng.standard_normal((npv, npv))
+    full = np.zeros((nv, nv, nv, nv))
+    for (P, (a, b)) in enumerate(pv):
+        blk = np.zeros((nv, nv))
+        blk[aa, bb] = W[P]
+        blk[bb, aa] = -W[P]
+        full[a, b], full[b, a] = blk, -blk
+    got = be.vvvv_exchange_slab(be.from_numpy(W), nv, a0, na).cpu().numpy()      # [al,b,c,d] = <ac||bd>
+    assert np.array_equal(got, full.transpose(0, 2, 1, 3)[a0:a0 + na])
+
