@@ -131,8 +131,11 @@ class AdcMatrix(AdcMatrixlike):
                 self._engine = PackedAdcEngine(self, shard=shard, vectors=vectors)
                 self.blocks = {blk: self._make_engine_apply(blk) for blk in self._tables
                                if self._tables[blk][0] is not None}
-                dph = adc_pp.diagonal(self._variant, "ph_ph", self.block_orders["ph_ph"], hf,
-                                      self.ground_state, self.intermediates)
+                if getattr(self._engine, "diagonal_ph", None) is not None:
+                    dph = AmplitudeVector(ph=self._engine.diagonal_ph)
+                else:
+                    dph = adc_pp.diagonal(self._variant, "ph_ph", self.block_orders["ph_ph"], hf,
+                                          self.ground_state, self.intermediates)
                 dph.ph._contig()
                 self._diagonal = AmplitudeVector(ph=dph.ph, pphh=self._engine.diagonal_pphh)
             else:

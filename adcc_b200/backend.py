@@ -110,6 +110,12 @@ class ReplayGraph:
         return self.outputs
 
 
+def release_cached_memory():
+    """Return the allocator's cached, unused device blocks to the driver (after large builds)."""
+    if torch.cuda.is_available():
+        torch.cuda.empty_cache()
+
+
 def clone(t):
     """Device-to-device copy of a contiguous array (cudaMemcpyAsync on the current stream)."""
     return t.clone()

@@ -413,6 +413,9 @@ class PackedAdcEngine:
             self.V1, self.V2, self.G1, self.G2 = ops3["V1"], ops3["V2"], ops3["G1"], ops3["G2"]
             self._extra3 = ops3["extras"]
             self.build_flops = ops3["build_flops"]
+            # diagonal of the singles block = diagonal of adc3_m11 (matrix.py:616-618)
+            self.diagonal_ph = Tensor._wrap(self.mospaces, ["o1", "v1"],
+                                            be.gather(self.M1, [no * nv], [no * nv + 1]).reshape(no, nv))
         else:
             # ---- singles-singles block folded into one (ov x ov) matrix  (matrix.py:353-375)
             i1, i2 = im.adc2_i1, im.adc2_i2

@@ -211,4 +211,13 @@ def build_adc3_operands(hf, mp, im, src, W, Op, Y, j0=0, nj=None):
         "G3": be.permute(ooov, (0, 3, 1, 2)).reshape(no * nv, no * no),              # [(i,a),(j,k)] = <ij||ka>
         "G4": be.permute(ooov, (0, 2, 1, 3)).reshape(no * no, no * nv),              # [(l,i),(k,c)] = <lk||ic>
     }
+    if no * no * nv * nv * 8 >= (1 << 30):
+        # large problems: the o^2 v^2 intermediates of the build (pi3 / pi4 / pi5, td2, t2sq, cached GEMM
+        # layouts of the ERI blocks: ~2 GB each at nocc=40 / nvirt=400) are not needed by the matvec;
+        # give the memory back to the Davidson subspace.  They are rebuilt on demand.
+        mp._cache.clear()
+        im.cached_tensors.clear()
+        for t in list(getattr(hf, "_eri", {}).values()) + list(getattr(hf, "_fock", {}).values()):
+            t._layouts.clear()
+        be.release_cached_memory()
     return {"M1": M1, "G1": G1, "G2": G2, "V1": V1, "V2": V2, "extras": extras, "build_flops": flops}

@@ -347,6 +347,7 @@ def install(monkeypatch):
                          int64_tensor=int64_tensor, add_columns=add_columns, spin_expand4=spin_expand4, synth_fill=synth_fill).items():
         monkeypatch.setattr(be, name, fn)
     monkeypatch.setattr(be, "device", lambda: cpu)
+    monkeypatch.setattr(be, "release_cached_memory", lambda: None)
 
     class ReplayGraph:
         """Host-logic stand-in: same static-buffer protocol, the launch sequence re-runs eagerly."""
