@@ -87,13 +87,21 @@ def construct_blocks(crude_starts, length, max_block_size=MAX_BLOCK_SIZE):
 
 class MoSpaces:
     def __init__(self, hfdata, core_orbitals=None, frozen_core=None, frozen_virtual=None,
-                 max_block_size=MAX_BLOCK_SIZE):
+                 max_block_size=MAX_BLOCK_SIZE, explicit_index_lists=False):
+        """``explicit_index_lists``: the three space arguments are already lists of spin-orbital
+        indices in the host provider's convention (the form libadcc.MoSpaces takes,
+        libadcc_src/MoSpaces.hh:60-75), not the user-level numbers / ranges / pairs."""
         from .DataHfProvider import import_scf_results
         hf = import_scf_results(hfdata)
         noa = hf.n_orbs_alpha
         nf = 2 * noa
-        args = expand_spaceargs(noa, core_orbitals=core_orbitals, frozen_core=frozen_core,
-                                frozen_virtual=frozen_virtual)
+        if explicit_index_lists:
+            args = {"core_orbitals": [int(i) for i in core_orbitals or []],
+                    "frozen_core": [int(i) for i in frozen_core or []],
+                    "frozen_virtual": [int(i) for i in frozen_virtual or []]}
+        else:
+            args = expand_spaceargs(noa, core_orbitals=core_orbitals, frozen_core=frozen_core,
+                                    frozen_virtual=frozen_virtual)
         self.point_group = "C1"
         self.irreps = ["A"]
         self.irrep_totsym = "A"

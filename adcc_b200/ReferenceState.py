@@ -18,11 +18,11 @@ from .timings import Timer
 
 class ReferenceState:
     def __init__(self, hfdata, core_orbitals=None, frozen_core=None, frozen_virtual=None,
-                 symmetry_check_on_import=False, import_all_below_n_orbs=10):
+                 symmetry_check_on_import=False, import_all_below_n_orbs=10, mospaces=None):
         hf = import_scf_results(hfdata)
         self._hf = hf
-        self.mospaces = MoSpaces(hf, core_orbitals=core_orbitals, frozen_core=frozen_core,
-                                 frozen_virtual=frozen_virtual)
+        self.mospaces = mospaces if mospaces is not None else MoSpaces(
+            hf, core_orbitals=core_orbitals, frozen_core=frozen_core, frozen_virtual=frozen_virtual)
         self.timer = Timer()
         self.symmetry_check_on_import = symmetry_check_on_import
         self.restricted = hf.restricted

@@ -222,6 +222,13 @@ class Tensor:
         vals = torch.tensor(list(orb.values()), device=t.device, dtype=t.dtype)
         t[tuple(idx[:, k] for k in range(self.ndim))] = vals
 
+    #: libtensor evaluates every expression together with its symmetry, so a tensor computed on a
+    #: restricted reference carries the alpha <-> beta spin-block maps and ``select_n_*`` visits
+    #: symmetry-unique elements only (libadcc_src/TensorImpl.cc:260-282).  The dense store has no
+    #: deduced symmetry; with this switch on (the ``libadcc`` module surface turns it on) elements
+    #: that equal their global spin-flip partner are reported once, like libtensor does.
+    select_spin_unique = False
+
     def _select(self, n, key, reverse):
         arr = self.to_ndarray()
         order = np.argsort(key(arr), axis=None, kind="stable")
@@ -229,10 +236,19 @@ class Tensor:
             order = order[::-1]
         out = []
         sym = self.symmetry if (self.symmetry is not None and not self.symmetry.empty) else None
+        flip = None
+        if sym is None and Tensor.select_spin_unique and getattr(self.mospaces, "restricted", False):
+            na = [self.mospaces.n_orbs_alpha(s) for s in self.subspaces]
+            if all(2 * a == e for a, e in zip(na, arr.shape)):
+                flip = na
         for flat in order:
             idx = tuple(int(x) for x in np.unravel_index(flat, arr.shape))
             if sym is not None and not sym.is_canonical(idx):
                 continue
+            if flip is not None:
+                partner = tuple(i + a if i < a else i - a for i, a in zip(idx, flip))
+                if partner < idx and abs(arr[partner] - arr[idx]) <= 1e-12 * max(1.0, abs(arr[idx])):
+                    continue
             out.append((idx, float(arr[idx])))
             if len(out) >= n:
                 break
@@ -244,8 +260,12 @@ class Tensor:
     def select_n_absmax(self, n): return self._select(n, np.abs, True)
 
     # ------------------------------------------------------------------ arithmetic
+    #: storage kind: tensors combine only with tensors of the same storage (subclasses that keep the
+    #: dense store, like adcc.Tensor deriving from libadcc.Tensor, stay compatible)
+    _storage = "dense"
+
     def _check_same(self, other):
-        if type(self) is not type(other):
+        if self._storage != getattr(other, "_storage", None):
             raise ValueError("Cannot combine tensors with different storage "
                              f"({type(self).__name__} vs {type(other).__name__})")
         if self._data.shape != other._data.shape:

@@ -59,6 +59,7 @@ class PackedDoubles(Tensor):
     parity = -1
     #: every stored element stands for 4 elements of the dense tensor in a Frobenius product
     dot_weight = 4.0
+    _storage = "packed"
 
     def to_dense(self):
         dense = be.packed_unpack(self._contig(), self._no, self._nv)
@@ -195,6 +196,8 @@ class SlabDoubles(PackedDoubles):
     local slab (1/world of the work); scalar products are completed by ONE all-reduce of the
     batched partial sums (AmplitudeVector.dot / dot_rows), which is the subspace Gram-matrix
     all-reduce of the sharded Davidson solver."""
+
+    _storage = "slab"
 
     @classmethod
     def _make(cls, mospaces, subspaces, data, layout, symmetry=None):

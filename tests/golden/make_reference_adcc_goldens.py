@@ -1,0 +1,89 @@
+#!/usr/bin/env python3
+"""Golden sigma vectors / diagonals / block results / energies produced by the REFERENCE's own
+Python layer: the unmodified ``adcc`` package of /root/reference (workflow, AdcMatrix,
+adc_pp/matrix.py, LazyMp, solver/davidson.py, guess/*) imported in the build container and run on
+top of this repository's ``libadcc`` module surface (libadcc/__init__.py), with
+
+  * the reference's own fixture examples/water/data.py (H2O / STO-3G RHF) as input,
+  * the tensor arithmetic done by torch CPU kernels (tests/cpu_shim.py) - no CUDA here -, and
+  * tools/refshim/ standing in for the absent third-party packages opt_einsum / h5py.
+
+What this pins: the EQUATIONS and the solver control flow are the reference's, executed, not
+transcribed.  The dump mirrors the reference's own generator
+adcc/tests/generators/dump_adcc.py:192-263 (random trial vector, matvec, diagonal, per-block
+results) and is compared by tests/test_reference_goldens_*.py with the oracle, the product host
+path and the CUDA path at the tolerances of adcc/tests/AdcMatrix_test.py:213-285 or tighter.
+
+    python tests/golden/make_reference_adcc_goldens.py      # writes reference_adcc_h2o_sto3g.npz
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools", "refshim"), REF,
+                os.path.join(REF, "examples", "water")]
+
+METHODS = ["adc0", "adc1", "adc2", "adc2x", "adc3", "cvs-adc0", "cvs-adc1", "cvs-adc2", "cvs-adc2x", "cvs-adc3"]
+
+
+def main():
+    import cpu_shim
+
+    class Patch:
+        def setattr(self, obj, name, val, raising=True):
+            setattr(obj, name, val)
+    cpu_shim.install(Patch())
+    import adcc                                  # the reference package, unmodified
+    from adcc.guess import guess_zero
+    from import_data import import_data          # examples/water/import_data.py
+    assert adcc.__file__.startswith(REF), adcc.__file__
+
+    data = import_data()
+    out = {"methods": np.array(METHODS)}
+    for method in METHODS:
+        cvs = method.startswith("cvs")
+        ref = adcc.ReferenceState(data, core_orbitals=1 if cvs else None)
+        matrix = adcc.AdcMatrix(method, ref)
+        key = method.replace("-", "_")
+        rng = np.random.default_rng(sum(map(ord, key)))
+        vec = guess_zero(matrix)
+        for blk in vec.blocks:
+            arr = rng.standard_normal(vec[blk].shape)
+            if blk == "pphh":                     # antisymmetric like every doubles vector
+                arr = arr - arr.transpose(0, 1, 3, 2)
+                if not cvs:
+                    arr = arr - arr.transpose(1, 0, 2, 3)
+            vec[blk].set_from_ndarray(arr)
+            out[f"{key}/vector/{blk}"] = arr
+        sigma = adcc.evaluate(matrix @ vec)       # AdcMatrix.matvec, adcc/AdcMatrix.py:390-396
+        diag = matrix.diagonal()
+        for blk in vec.blocks:
+            out[f"{key}/matvec/{blk}"] = sigma[blk].to_ndarray()
+            out[f"{key}/diagonal/{blk}"] = diag[blk].to_ndarray()
+        for block in matrix.blocks:               # AdcMatrix.block_apply, adcc/AdcMatrix.py:375-388
+            outb, inb = block.split("_")
+            if inb not in vec.blocks or outb not in vec.blocks:
+                continue
+            res = matrix.block_apply(block, vec[inb])
+            out[f"{key}/block/{block}"] = adcc.evaluate(res).to_ndarray()
+        if not cvs:
+            mp = matrix.ground_state
+            out[f"{key}/mp2"] = np.array(mp.energy_correction(2))
+            if method == "adc3":
+                out[f"{key}/mp3"] = np.array(mp.energy_correction(3))
+        for kind, kw in (("singlet", "n_singlets"), ("triplet", "n_triplets")):
+            n = 2 if cvs else 3
+            state = adcc.run_adc(matrix, **{kw: n}, conv_tol=1e-9)
+            assert state.converged
+            out[f"{key}/{kind}/energies"] = np.array(state.excitation_energy)
+            out[f"{key}/{kind}/n_iter"] = np.array(state.n_iter)
+        print(method, out[f"{key}/singlet/energies"], out[f"{key}/singlet/n_iter"], flush=True)
+    np.savez_compressed(os.path.join(HERE, "reference_adcc_h2o_sto3g.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

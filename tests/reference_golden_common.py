@@ -1,0 +1,109 @@
+"""Comparisons against tests/golden/reference_adcc_h2o_sto3g.npz: results the REFERENCE's own,
+unmodified Python layer (adcc/adc_pp/matrix.py, LazyMp.py, solver/davidson.py ...) produced when it
+was run on this repository's ``libadcc`` surface (see tests/golden/make_reference_adcc_goldens.py)."""
+import os
+
+import numpy as np
+
+from oracle.hfdata import load_h2o_sto3g
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_adcc_h2o_sto3g.npz")
+METHODS = ["adc0", "adc1", "adc2", "adc2x", "adc3", "cvs-adc0", "cvs-adc1", "cvs-adc2", "cvs-adc2x", "cvs-adc3"]
+SIGMA_RTOL = 1e-11        # north star; the reference's own test uses rtol 1e-10 (AdcMatrix_test.py:221)
+ENERGY_ATOL = 1e-8
+
+
+def golden():
+    return np.load(GOLDEN)
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def blocks_of(g, key):
+    return sorted(k.split("/")[-1] for k in g.files if k.startswith(f"{key}/vector/"))
+
+
+def check_oracle(method):
+    import oracle
+    g = golden()
+    key = method.replace("-", "_")
+    core = 1 if method.startswith("cvs") else None
+    data = load_h2o_sto3g()
+    om = oracle.OracleAdcMatrix(method, oracle.OracleRefState(oracle.OracleHf(data), core_orbitals=core))
+    v = {b: g[f"{key}/vector/{b}"] for b in blocks_of(g, key)}
+    sig = om.matvec(v)
+    for b in v:
+        assert rel(sig[b], g[f"{key}/matvec/{b}"]) < 1e-12, (method, b)
+        assert rel(om.diagonal()[b], g[f"{key}/diagonal/{b}"]) < 1e-12, (method, "diagonal", b)
+    for blk in om.blocks:
+        if f"{key}/block/{blk}" not in g.files:
+            continue
+        outb, inb = blk.split("_")
+        res = om.blocks[blk]({inb: v[inb]})
+        want = g[f"{key}/block/{blk}"]
+        got = res[outb] if res is not None else np.zeros_like(want)
+        assert rel(got, want) < 1e-12 or np.max(np.abs(want)) == 0.0, (method, blk)
+    if f"{key}/mp2" in g.files:
+        assert abs(om.mp.energy_correction(2) - float(g[f"{key}/mp2"])) < 1e-12
+    if f"{key}/mp3" in g.files:
+        assert abs(om.mp.energy_correction(3) - float(g[f"{key}/mp3"])) < 1e-12
+    for kind in ("singlet", "triplet"):
+        want = g[f"{key}/{kind}/energies"]
+        st = oracle.run_adc(data, method, conv_tol=1e-9, core_orbitals=core,
+                            **{"n_singlets" if kind == "singlet" else "n_triplets": len(want)})
+        np.testing.assert_allclose(st.eigenvalues, want, atol=ENERGY_ATOL, rtol=0)
+
+
+def check_product(method, doubles_storage="dense"):
+    """The product path (whatever backend is active: CUDA on the GPU box, the CPU stand-in in the
+    build container) against the reference-produced goldens."""
+    import adcc_b200 as adcc
+    g = golden()
+    key = method.replace("-", "_")
+    core = 1 if method.startswith("cvs") else None
+    data = load_h2o_sto3g()
+    ref = adcc.ReferenceState(data, core_orbitals=core)
+    m = adcc.AdcMatrix(method, ref, doubles_storage=doubles_storage)
+    bl = blocks_of(g, key)
+
+    def make(b):
+        t = adcc.Tensor.from_ndarray(m.mospaces, m.axis_spaces[b], g[f"{key}/vector/{b}"])
+        if doubles_storage == "packed" and b == "pphh":
+            from adcc_b200.packed import PackedDoubles
+            t = PackedDoubles.from_dense(t)
+        return t
+    v = adcc.AmplitudeVector(**{b: make(b) for b in bl})
+    sig = m.matvec(v)
+    for b in bl:
+        assert rel(sig[b].to_ndarray(), g[f"{key}/matvec/{b}"]) < SIGMA_RTOL, (method, b)
+        d, want = m.diagonal()[b].to_ndarray(), g[f"{key}/diagonal/{b}"]
+        if doubles_storage == "packed" and b == "pphh":        # i == j / a == b entries are not stored
+            no, nv = want.shape[0], want.shape[2]
+            mask = np.ones_like(want, dtype=bool)
+            mask[np.arange(no), np.arange(no)] = False
+            mask[:, :, np.arange(nv), np.arange(nv)] = False
+            d, want = d[mask], want[mask]
+        assert rel(d, want) < SIGMA_RTOL, (method, "diagonal", b)
+    for blk in m.blocks:
+        if f"{key}/block/{blk}" not in g.files:
+            continue
+        outb, inb = blk.split("_")
+        want = g[f"{key}/block/{blk}"]
+        if np.max(np.abs(want)) == 0.0:
+            continue
+        res = m.block_apply(blk, v[inb])
+        assert rel(res.to_ndarray(), want) < SIGMA_RTOL, (method, blk)
+    if doubles_storage == "dense":
+        if f"{key}/mp2" in g.files:
+            assert abs(m.ground_state.energy_correction(2) - float(g[f"{key}/mp2"])) < 1e-12
+        if f"{key}/mp3" in g.files:
+            assert abs(m.ground_state.energy_correction(3) - float(g[f"{key}/mp3"])) < 1e-12
+    for kind in ("singlet", "triplet"):
+        want = g[f"{key}/{kind}/energies"]
+        st = adcc.run_adc(m, conv_tol=1e-9, output=None,
+                          **{"n_singlets" if kind == "singlet" else "n_triplets": len(want)})
+        assert st.converged
+        np.testing.assert_allclose(st.excitation_energy, want, atol=ENERGY_ATOL, rtol=0)
+        assert st.n_iter == int(g[f"{key}/{kind}/n_iter"]), (method, kind, st.n_iter)
