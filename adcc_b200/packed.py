@@ -352,6 +352,9 @@ class DenseSource:
     def ovvv_exchange_slab(self, V2e, a_begin, na):      # [al,c,j,d] = <jc||ad>
         return be.ovvv_exchange_slab(V2e, self.no, self.nv, a_begin, na)
 
+    def vvvv_exchange_slab(self, W, a_begin, na):        # [al,b,c,d] = <ac||bd>
+        return be.vvvv_exchange_slab(W, self.nv, a_begin, na)
+
 
 class PackedAdcEngine:
     """ADC(2) / ADC(2)-x / ADC(3) matvec on the packed doubles store (see module docstring)."""
@@ -405,13 +408,23 @@ class PackedAdcEngine:
             # adc3_m11 (matrix.py:606-618); four three-operand second-order coupling terms come on
             # top.  All of it is built from the pair-packed operands (packed_adc3.py), so that the
             # dense ovvv / vvvv blocks are never needed.
-            if self.world > 1:
-                raise NotImplementedError("the packed ADC(3) engine is not sharded yet")
             from .packed_adc3 import build_adc3_operands
-            self.W = src.vvvv_packed()
             self.O = src.oooo_packed()
-            self.Y = src.ovov_jbkc()
-            ops3 = build_adc3_operands(hf, mp, im, src, self.W, self.O, self.Y, self.j0, self.nj)
+            self.Yfull = src.ovov_jbkc()
+            self.Y = self.Yfull[self.j0 * nv:(self.j0 + self.nj) * nv]
+            if self.world == 1:
+                self.W = src.vvvv_packed()
+                ops3 = build_adc3_operands(hf, mp, im, src, self.W, self.O, self.Yfull, self.j0, self.nj)
+            else:
+                if self.vectors != "slab":
+                    raise NotImplementedError("the sharded ADC(3) engine works on distributed vectors "
+                                              "(vectors='slab')")
+                self.layout = SlabLayout(self.rank, self.world, self.npo, self.npv, self._cuts)
+                self.W = src.vvvv_packed(self.ab0, self.ab1 - self.ab0)
+                W_full = None if getattr(src, "generates_exchange_slabs", False) else src.vvvv_packed()
+                ops3 = build_adc3_operands(hf, mp, im, src, W_full, self.O, self.Yfull, self.j0, self.nj,
+                                           shard=(self.rank, self.world), layout=self.layout, W_slab=self.W)
+                del W_full
             self.M1 = ops3["M1"]
             self.V1, self.V2, self.G1, self.G2 = ops3["V1"], ops3["V2"], ops3["G1"], ops3["G2"]
             self._extra3 = ops3["extras"]
@@ -497,7 +510,8 @@ class PackedAdcEngine:
             self._sl_lo = (be.int64_tensor([j * nv * njv + (i - self.j0) * nv for i, j in p_lo]),
                            be.int64_tensor([row[p] for p in p_lo]))
             # distributed vectors: column slabs along the cuts of the vvvv operand
-            self.layout = SlabLayout(self.rank, self.world, self.npo, self.npv, self._cuts)
+            if getattr(self, "layout", None) is None:
+                self.layout = SlabLayout(self.rank, self.world, self.npo, self.npv, self._cuts)
             if self.vectors == "slab":
                 # ovov fold of an occupied-i row slab: T_r[(il,a),(j,b)], offset (il*nv + a)*(no*nv) + j*nv + b
                 ld = no * nv
@@ -649,6 +663,8 @@ class PackedAdcEngine:
         import torch.distributed as dist
         no, nv, npo, npv = self.no, self.nv, self.npo, self.npv
         world = self.world
+        if self.level3:
+            raise NotImplementedError("the sharded ADC(3) engine takes distributed vectors (SlabDoubles)")
         self._mark("step", 0)
         pipe = None
         if pipelined and self.order_dd == 1 and self._peer is not None \
@@ -820,28 +836,26 @@ class PackedAdcEngine:
         self._mark("step", 1)
         return AmplitudeVector(ph=self._wrap_ph(s1.view(no, nv)), pphh=self._wrap_pphh(S))
 
-    def _matvec_slab(self, u1, u2):
-        """sigma = M u on DISTRIBUTED vectors (SlabDoubles: every rank holds the virtual-pair column
-        slab its rows of the vvvv operand produce; the ph part is replicated).
+    def _gather_stream(self):
+        """Side stream (and its own communicator: NCCL forbids two collectives of one communicator
+        in flight on different streams) for the all-gather of the trial vector's slabs; None on the
+        host-logic path."""
+        if not self.M1.is_cuda or os.environ.get("ADCCB_GATHER_OVERLAP", "1") == "0":
+            return None
+        if getattr(self, "_gather_side", None) is None:
+            import torch
+            import torch.distributed as dist
+            self._gather_side = torch.cuda.Stream()
+            self._gather_group = dist.new_group(ranks=list(range(self.world)))
+        return self._gather_side
 
-          1. all-gather of the trial vector's slabs (NVLink) -> complete U;
-          2. every term except vvvv as partial sums from this rank's operand slabs (ovov: occupied-i
-             row slab of X against the complete Y; ovvv: occupied j; oooo, D0, ooov: IJ pairs; ph_ph:
-             rows of M1) - all expansions and folds act on the rank's slab only;
-          3. reduce-scatter of the partial sums: each rank receives ITS column slab of their sum;
-          4. the vvvv GEMM accumulates onto that slab: the dominant term needs no exchange at all.
-        The ph part (no*nv numbers) is completed by a small all-reduce."""
+    def _slab_singles_terms(self, u1):
+        """The terms that need only the (replicated) singles part of the trial vector: ph_ph and
+        pphh_ph from this rank's operand slabs.  Returns zero-initialised (P, s1) with them added;
+        runs while the doubles slabs are still being gathered."""
         no, nv, npo, npv = self.no, self.nv, self.npo, self.npv
-        lay = self.layout
-        if self.vectors != "slab":
-            raise ValueError("this engine was built for replicated vectors (vectors='replicated')")
-        self._mark("step", 0)
-        self._mark("gather", 0)
-        U = lay.gather(u2._contig())
-        self._mark("gather", 1)
         P = be.zeros((npo, npv))
         s1 = be.zeros((1, no * nv))
-        s1m = s1.view(no, nv)
         x = u1._contig()
         ij0, ij1 = self.ij0, self.ij1
         nij = ij1 - ij0
@@ -850,17 +864,71 @@ class PackedAdcEngine:
         r0, r1 = j0 * nv, (j0 + nj) * nv
         if r1 > r0:
             be.gemm(x.reshape(1, -1), self.M1[r0:r1], out=s1[:, r0:r1])
-        # ---- ph_pphh (matrix.py:270-276)
+        # ---- pphh_ph (matrix.py:288-294)
+        if nj > 0:
+            c1 = be.gemm(x, self.V1)                                              # [i,(jl,AB)]
+            if self._extra3 is not None:
+                # + A_ij( r3[li] t2[jlab] ),  r3[li] = <lk||ic> u[kc]              (matrix.py:525)
+                r3 = be.gemm(x.reshape(1, no * nv), self._extra3["G4"]).view(no, no)
+                be.gemm(be.permute(r3, (1, 0)), self._extra3["t2eM"], out=c1, beta=1.0)
+            be.packed_fold_occ(P, c1, no, nv, alpha=0.5, j_begin=j0, nj=nj)
+            del c1
+        x3 = self._extra3
+        if x3 is not None:
+            # - A_ab( t2[ijac] r4[bc] ),  r4[bc] = <kb||cd> u[kd]: partial over this rank's occupied
+            # slab of <kb||cd>, completed by a (nv x nv) all-reduce   (matrix.py:529)
+            r4 = be.zeros((nv, nv))
+            if nj > 0:
+                be.pair_matvec(x3["V2e"], nv, n_out=nv, n_red=nj, row_stride_out=nj, row_stride_red=1,
+                               X=x[j0:j0 + nj], x_by_out=False, out=r4)
+            be.comm_all_reduce(r4, group=self.layout.group)
+        if nij > 0:
+            c2 = be.gemm(self.G2[ij0 * nv:ij1 * nv], be.permute(x, (1, 0)))       # [(IJ slab,a),b]
+            if x3 is not None:
+                be.gemm(x3["T2h"][ij0 * nv:ij1 * nv], r4, out=c2, beta=1.0)
+            be.packed_fold_virt(P, nv, nv, c2, self._off_rows[:nij], alpha=-0.5, rows=self._rows_ij)
+            del c2
+        return P, s1
+
+    def _slab_partial_terms(self, u1, U, started=None):
+        """Every term except vvvv as partial sums from this rank's operand slabs: (P [npo, npv],
+        s1 [1, no*nv]); all expansions and folds act on the rank's slab only.  ``started``: the
+        (P, s1) pair of ``_slab_singles_terms`` if that part ran ahead."""
+        no, nv, npo, npv = self.no, self.nv, self.npo, self.npv
+        P, s1 = started if started is not None else self._slab_singles_terms(u1)
+        s1m = s1.view(no, nv)
+        ij0, ij1 = self.ij0, self.ij1
+        nij = ij1 - ij0
+        j0, nj = self.j0, self.nj
+        # ---- ph_pphh (matrix.py:270-276; second order: + matrix.py:498-499)
+        x3 = self._extra3
         if nj > 0:
             Ue = be.packed_expand_slab(1, U, no, nv, j0, nj)                      # [i,(jl,BC)]
             be.gemm(Ue, self.V2, out=s1m, alpha=2.0, beta=1.0)
+            if x3 is not None:
+                # + <ij||ka> r2[jk], r2[jk] = t2[jlbc] u[klbc]: partial over l in this rank's slab
+                npv_ = self.npv
+                r2 = be.gemm(x3["t2e"][:, j0 * npv_:(j0 + nj) * npv_], Ue, alpha=2.0)          # [j,k]
+                be.gemm(r2.reshape(1, no * no), x3["G3"], out=s1, beta=1.0)
             del Ue
+        r1 = be.zeros((nv, nv)) if x3 is not None else None
         if nij > 0:
             Uh = be.packed_expand_slab(2, U[ij0:ij1], no, nv, 0, nij)            # [a,(JK slab,b)]
             be.gemm(self.G1[:, ij0 * nv:ij1 * nv], Uh, out=s1m, alpha=2.0, beta=1.0)
+            if x3 is not None:
+                # r1[cb] = u[jkcd] t2[jkbd]: partial over the JK slab
+                T2uh = x3["T2uh"].view(nv, self.npo, nv)[:, ij0:ij1]
+                be.gemm(Uh, be.contiguous(T2uh).reshape(nv, nij * nv), out=r1, alpha=2.0)
             del Uh
-            # ---- pphh_pphh_0 (canonical orbitals)
-            be.mul(U[ij0:ij1], self.D0[ij0:ij1], out=P[ij0:ij1])
+        if x3 is not None:
+            # + <ic||ab> r1[cb] for i in this rank's slab of <ic||ab>
+            be.comm_all_reduce(r1, group=self.layout.group)
+            if nj > 0:
+                be.pair_matvec(x3["V2e"], nv, n_out=nj, n_red=nv, row_stride_out=1, row_stride_red=nj,
+                               X=r1, x_by_out=False, out=s1m[j0:j0 + nj], beta=1.0)
+        # ---- pphh_pphh_0 (canonical orbitals)
+        if nij > 0:
+            be.mul(U[ij0:ij1], self.D0[ij0:ij1], out=P[ij0:ij1], beta=1.0)
         if self.order_dd == 1:
             if nij > 0:
                 Ut = be.permute(U[ij0:ij1], (1, 0))                               # [AB, KL slab]
@@ -878,15 +946,49 @@ class PackedAdcEngine:
                 off, rows = self._si_hi
                 be.packed_fold_virt(P, nv, ld, T, off, alpha=+1.0, rows=rows)
                 del T
-        # ---- pphh_ph (matrix.py:288-294)
-        if nj > 0:
-            c1 = be.gemm(x, self.V1)                                              # [i,(jl,AB)]
-            be.packed_fold_occ(P, c1, no, nv, alpha=0.5, j_begin=j0, nj=nj)
-            del c1
-        if nij > 0:
-            c2 = be.gemm(self.G2[ij0 * nv:ij1 * nv], be.permute(x, (1, 0)))       # [(IJ slab,a),b]
-            be.packed_fold_virt(P, nv, nv, c2, self._off_rows[:nij], alpha=-0.5, rows=self._rows_ij)
-            del c2
+        return P, s1
+
+    def _matvec_slab(self, u1, u2):
+        """sigma = M u on DISTRIBUTED vectors (SlabDoubles: every rank holds the virtual-pair column
+        slab its rows of the vvvv operand produce; the ph part is replicated).
+
+          1. all-gather of the trial vector's slabs (NVLink) -> complete U;
+          2. every term except vvvv as partial sums from this rank's operand slabs (ovov: occupied-i
+             row slab of X against the complete Y; ovvv: occupied j; oooo, D0, ooov: IJ pairs; ph_ph:
+             rows of M1) - all expansions and folds act on the rank's slab only;
+          3. reduce-scatter of the partial sums: each rank receives ITS column slab of their sum;
+          4. the vvvv GEMM accumulates onto that slab: the dominant term needs no exchange at all.
+        The ph part (no*nv numbers) is completed by a small all-reduce."""
+        no, nv = self.no, self.nv
+        lay = self.layout
+        if self.vectors != "slab":
+            raise ValueError("this engine was built for replicated vectors (vectors='replicated')")
+        self._mark("step", 0)
+        side = self._gather_stream()
+        if side is None:
+            U = lay.gather(u2._contig())
+            started = None
+        else:
+            # the all-gather of the doubles slabs runs on a side stream while the terms that need
+            # only the singles part (ph_ph, pphh_ph: the V1 / M1 / G2 streams) are computed
+            import torch
+            main = torch.cuda.current_stream()
+            parts = be.empty((lay.world, lay.npo, lay.wmax))
+            U = be.empty((lay.npo, lay.npv))
+            ready = torch.cuda.Event()
+            ready.record(main)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                be.comm_all_gather(parts, u2._contig(), group=self._gather_group)
+                be.slab_layout(1, U, parts, lay.cuts, lay.wmax)
+                gathered = torch.cuda.Event()
+                gathered.record(side)
+            started = self._slab_singles_terms(u1)
+            main.wait_event(gathered)
+            parts.record_stream(side)
+            U.record_stream(side)
+            u2._contig().record_stream(side)
+        P, s1 = self._slab_partial_terms(u1, U, started)
         # ---- sum over ranks: each rank keeps its column slab
         self._mark("reduce", 0)
         R = lay.reduce_scatter(P)
@@ -946,29 +1048,103 @@ class PackedAdcEngine:
         self._mark("step", 1)
         return AmplitudeVector(ph=self._wrap_ph(s1.view(no, nv)), pphh=self._wrap_pphh(S))
 
-    def _matvec_host_slab(self, u1_host, U_host, s1_host, S_host):
+    def _matvec_host_slab(self, u1_host, U_host, s1_host, S_host, edge_rows=112):
         """End-to-end form on distributed vectors: the host vectors live in pinned host memory that
         EVERY rank has mapped (``shared_host_vector``); each rank moves only its own virtual-pair
         column slab over its own PCIe link (strided 2-D copies), the slabs meet over NVLink inside
-        the matvec.  Collective; returns when every rank's part of sigma is in the host buffer."""
+        the matvec.  The transfers hide behind row slabs of the vvvv GEMM: the first ``edge_rows``
+        rows are gathered and multiplied while the rest of the slab is still crossing PCIe, the last
+        rows are multiplied while everything before them is already on its way back.  Collective;
+        returns when every rank's part of sigma is in the host buffer."""
         import torch
         import torch.distributed as dist
-        no, nv, npo = self.no, self.nv, self.npo
+        no, nv, npo, npv = self.no, self.nv, self.npo, self.npv
         lay = self.layout
+        w, wmax = lay.w, lay.wmax
+        cuda = self.W.is_cuda if self.order_dd == 1 else self.M1.is_cuda
         x = be.empty((no, nv))
-        be.copy2d(x, u1_host, no, nv)
-        u = be.zeros((npo, lay.wmax)) if lay.w < lay.wmax else be.empty((npo, lay.wmax))
-        if lay.w > 0:
-            be.copy2d(u, U_host[:, lay.c0:lay.c1], npo, lay.w)
-        sig = self._matvec_slab(self._wrap_ph(x), SlabDoubles._make(self.mospaces, ["o1", "o1", "v1", "v1"], u, lay))
-        if lay.w > 0:
-            be.copy2d(S_host[:, lay.c0:lay.c1], sig.pphh._data, npo, lay.w)
-        if self.rank == 0:
-            be.copy2d(s1_host, sig.ph._data, no, nv)
-        if u.is_cuda:
-            torch.cuda.current_stream().synchronize()
-        dist.barrier(group=lay.group)              # every rank's slab has landed
-        return sig
+        u = be.zeros((npo, wmax)) if w < wmax else be.empty((npo, wmax))
+        pipelined = (cuda and self.order_dd == 1 and npo >= 4 * edge_rows
+                     and os.environ.get("ADCCB_E2E_PIPELINE", "1") != "0")
+        if not pipelined:
+            be.copy2d(x, u1_host, no, nv)
+            if w > 0:
+                be.copy2d(u, U_host[:, lay.c0:lay.c1], npo, w)
+            sig = self._matvec_slab(self._wrap_ph(x), SlabDoubles._make(self.mospaces, ["o1", "o1", "v1", "v1"], u, lay))
+            if w > 0:
+                be.copy2d(S_host[:, lay.c0:lay.c1], sig.pphh._data, npo, w)
+            if self.rank == 0:
+                be.copy2d(s1_host, sig.ph._data, no, nv)
+            if cuda:
+                torch.cuda.current_stream().synchronize()
+            dist.barrier(group=lay.group)              # every rank's slab has landed
+            return sig
+        # ---- row slabs [0, r1) | [r1, r2) | [r2, npo): sizes from a GEMM (36 TFLOP/s) vs PCIe (40 GB/s) model
+        t_gemm = 2.0 * max(lay.wmax, 1) * npv / 36e12
+        t_copy = max(lay.wmax, 1) * 8 / 40e9
+        r1 = edge_rows
+        last = int(np.ceil(npo * t_copy / (t_gemm + t_copy) / edge_rows)) * edge_rows
+        r2 = max(r1, npo - last)
+        main = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+        cs = self._copy_stream
+        start = torch.cuda.Event()
+        start.record(main)
+        cs.wait_event(start)                           # fresh buffers may recycle memory still in use on main
+        with torch.cuda.stream(cs):
+            be.copy2d(x, u1_host, no, nv)
+            if w > 0:
+                be.copy2d(u[:r1], U_host[:r1, lay.c0:lay.c1], r1, w)
+            got_a = torch.cuda.Event()
+            got_a.record(cs)
+            if w > 0:
+                be.copy2d(u[r1:], U_host[r1:, lay.c0:lay.c1], npo - r1, w)
+            got_b = torch.cuda.Event()
+            got_b.record(cs)
+        U = be.empty((npo, npv))
+
+        def gather_rows(a, b):
+            parts = be.empty((lay.world, b - a, wmax))
+            be.comm_all_gather(parts, u[a:b], group=lay.group)
+            be.slab_layout(1, U[a:b], parts, lay.cuts, wmax)
+
+        main.wait_event(got_a)
+        gather_rows(0, r1)
+        Rv = be.zeros((r1, wmax)) if w < wmax else be.empty((r1, wmax))
+        if w > 0:
+            be.gemm(U[:r1], self.W, out=Rv[:, :w])                    # while the rest of u is uploading
+        main.wait_event(got_b)
+        gather_rows(r1, npo)
+        P, s1 = self._slab_partial_terms(self._wrap_ph(x), U)
+        R = lay.reduce_scatter(P)
+        del P
+        be.comm_all_reduce(s1, group=lay.group)
+        be.axpby(1.0, Rv, 1.0, R[:r1])
+        if w > 0 and r2 > r1:
+            be.gemm(U[r1:r2], self.W, out=R[r1:r2, :w], alpha=1.0, beta=1.0)
+        head = torch.cuda.Event()
+        head.record(main)
+        if w > 0 and npo > r2:
+            be.gemm(U[r2:], self.W, out=R[r2:, :w], alpha=1.0, beta=1.0)   # while rows [0, r2) download
+        tail = torch.cuda.Event()
+        tail.record(main)
+        with torch.cuda.stream(cs):
+            cs.wait_event(head)
+            if self.rank == 0:
+                be.copy2d(s1_host, s1.view(no, nv), no, nv)
+            if w > 0:
+                be.copy2d(S_host[:r2, lay.c0:lay.c1], R[:r2], r2, w)
+            cs.wait_event(tail)
+            if w > 0 and npo > r2:
+                be.copy2d(S_host[r2:, lay.c0:lay.c1], R[r2:], npo - r2, w)
+            finished = torch.cuda.Event()
+            finished.record(cs)
+        main.wait_event(finished)
+        finished.synchronize()
+        dist.barrier(group=lay.group)                  # every rank's slab has landed
+        sig2 = SlabDoubles._make(self.mospaces, ["o1", "o1", "v1", "v1"], R, lay)
+        return AmplitudeVector(ph=self._wrap_ph(s1.view(no, nv)), pphh=sig2)
 
     def _matvec_host_sharded(self, u1_host, U_host, s1_host, S_host):
         """Rank 0 holds the pinned host buffers (the other ranks pass None): the trial vector is
@@ -1199,8 +1375,19 @@ class SyntheticSource:
         shape = [self.no if c == "o" else self.nv for c in block]
         return self._fill(shape, "dense", block=block)
 
+    #: exchange-ordered slabs come straight from the hash: a sharded build needs neither the complete
+    #: pair-packed vvvv block nor the complete ovvv operand on any rank
+    generates_exchange_slabs = True
+
     def ovvv_exchange_slab(self, V2e, a_begin, na):      # [al,c,j,d] = <jc||ad>
-        return be.ovvv_exchange_slab(V2e, self.no, self.nv, a_begin, na)
+        if V2e is not None:
+            return be.ovvv_exchange_slab(V2e, self.no, self.nv, a_begin, na)
+        return self._fill((na, self.nv, self.no, self.nv), "ovvv_exchange", row_begin=a_begin)
+
+    def vvvv_exchange_slab(self, W, a_begin, na):        # [al,b,c,d] = <ac||bd>
+        if W is not None:
+            return be.vvvv_exchange_slab(W, self.nv, a_begin, na)
+        return self._fill((na, self.nv, self.nv, self.nv), "vvvv_exchange", row_begin=a_begin)
 
 
 def synthetic_reference_state(no, nv, seed=20261019, scale=0.02):

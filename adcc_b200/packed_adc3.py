@@ -44,45 +44,65 @@ def _slab(n_total, bytes_per_index, budget=8 << 30):
 class PackedEriOps:
     """hf.big_eri_ops on pair-packed operands (see adc_pp.DenseEriOps for the dense statement)."""
 
-    def __init__(self, mospaces, no, nv, W, V2e, T2p):
+    def __init__(self, mospaces, no, nv, src, W, V2e, T2p, j0=0, nj=None, shard=(0, 1), group=None):
+        """``V2e``: [a,(jl,BC)] for the occupied slab j0 .. j0+nj-1 this rank owns; ``W``: whatever
+        ``src.vvvv_exchange_slab`` needs (the complete pair-packed block, or None for a generating
+        source).  With shard = (rank, world) the virtual-index slab loops are dealt out round-robin
+        and every result is completed by an all-reduce over NVLink."""
         self.ms, self.no, self.nv = mospaces, no, nv
         self.npo, self.npv = be.n_pairs(no), be.n_pairs(nv)
-        self.W, self.V2e, self.T2p = W, V2e, T2p
+        self.src, self.W, self.V2e, self.T2p = src, W, V2e, T2p
+        self.j0, self.nj = j0, (no if nj is None else nj)
+        self.rank, self.world = shard
+        self.group = group
         self.flops = 0.0
 
     def _t(self, data, spaces):
         return Tensor._wrap(self.ms, spaces, data)
 
+    def _sum(self, data):
+        if self.world > 1:
+            be.comm_all_reduce(data, group=self.group)
+        return data
+
+    def _my_slabs(self, n_total, na):
+        return [a0 for k, a0 in enumerate(range(0, n_total, na)) if k % self.world == self.rank]
+
     # <ia||bc> p[ic] -> [a,b]        (matrix.py:951)
     def ovvv_iabc_ic(self, p_ov):
-        no, nv = self.no, self.nv
-        out = be.pair_matvec(self.V2e, nv, n_out=nv, n_red=no, row_stride_out=no, row_stride_red=1,
-                             X=p_ov._contig(), x_by_out=False)
-        return self._t(out, [V, V])
+        nv, nj = self.nv, self.nj
+        out = be.zeros((nv, nv))
+        if nj > 0:
+            be.pair_matvec(self.V2e, nv, n_out=nv, n_red=nj, row_stride_out=nj, row_stride_red=1,
+                           X=p_ov._contig()[self.j0:self.j0 + nj], x_by_out=False, out=out)
+        return self._t(self._sum(out), [V, V])
 
     # <ib||ac> x[jc] -> [i,a,j,b]    (matrix.py:1014)
     def ovvv_ibac_jc(self, x_ov):
-        no, nv = self.no, self.nv
+        no, nv, nj, j0 = self.no, self.nv, self.nj, self.j0
         x = x_ov._contig()
-        res = be.empty((no, nv, no, nv))                       # [j, b, i, a]
-        for j in range(no):
-            xj = x[j].reshape(1, nv).expand(nv * no, nv)       # the same vector for every row (b, i)
-            be.pair_matvec(self.V2e, nv, n_out=nv * no, n_red=1, row_stride_out=1, row_stride_red=0,
-                           X=xj, x_by_out=True, out=res[j].view(nv * no, nv))
-        return self._t(res, [O, V, O, V]).transpose((2, 3, 0, 1))
+        res = be.zeros((no, nv, no, nv))                       # [j, b, i, a]; this rank fills i in its slab
+        if nj > 0:
+            tmp = be.empty((nv * nj, nv))
+            for j in range(no):
+                xj = x[j].reshape(1, nv).expand(nv * nj, nv)   # the same vector for every row (b, il)
+                be.pair_matvec(self.V2e, nv, n_out=nv * nj, n_red=1, row_stride_out=1, row_stride_red=0,
+                               X=xj, x_by_out=True, out=tmp)
+                be.copy2d(res[j].view(nv, no * nv)[:, j0 * nv:(j0 + nj) * nv], tmp.view(nv, nj * nv), nv, nj * nv)
+        return self._t(self._sum(res), [O, V, O, V]).transpose((2, 3, 0, 1))
 
     # <ac||bd> p[cd] -> [a,b]        (matrix.py:953)
     def vvvv_acbd_cd(self, p_vv):
         nv = self.nv
         p = p_vv._contig().reshape(1, nv * nv)
-        out = be.empty((nv, nv))
+        out = be.zeros((nv, nv))
         na = _slab(nv, 8 * nv ** 3)
-        for a0 in range(0, nv, na):
+        for a0 in self._my_slabs(nv, na):
             n = min(na, nv - a0)
-            Z = be.vvvv_exchange_slab(self.W, nv, a0, n).view(n * nv, nv * nv)
+            Z = self.src.vvvv_exchange_slab(self.W, a0, n).view(n * nv, nv * nv)
             be.gemm(Z, p, out=out[a0:a0 + n].view(n * nv, 1))
             self.flops += 2.0 * n * nv * nv * nv
-        return self._t(out, [V, V])
+        return self._t(self._sum(out), [V, V])
 
     # 1/2 <ic||jd> (t2[klac] t2[klbd]) - t2sq[idjc] <ac||bd> -> [i,a,j,b]   (matrix.py:1029-1033)
     def m11_v4(self, ovov, t2, t2sq):
@@ -93,12 +113,14 @@ class PackedEriOps:
         Uh = be.packed_expand(2, self.T2p, no, nv).view(nv, npo, nv)                    # [a, KL, c]
         T2ac = be.contiguous(Uh.permute(0, 2, 1)).view(nv * nv, npo)
         del Uh
-        res = be.empty((no * no, nv * nv))                                              # [(i,j),(a,b)]
+        res = be.zeros((no * no, nv * nv))                                              # [(i,j),(a,b)]
         na = _slab(nv, 3 * 8 * nv ** 3, budget=24 << 30)
-        for a0 in range(0, nv, na):
+        if self.world > 1:
+            na = max(1, min(na, -(-nv // (4 * self.world))))      # enough slabs to balance the ranks
+        for a0 in self._my_slabs(nv, na):
             n = min(na, nv - a0)
             cols = res[:, a0 * nv:(a0 + n) * nv]
-            Z = be.vvvv_exchange_slab(self.W, nv, a0, n).view(n * nv, nv * nv)         # [(a,b),(c,d)] = <ac||bd>
+            Z = self.src.vvvv_exchange_slab(self.W, a0, n).view(n * nv, nv * nv)       # [(a,b),(c,d)] = <ac||bd>
             be.gemm(B1, Z, out=cols, alpha=-1.0)
             del Z
             Q = be.gemm(T2ac[a0 * nv:(a0 + n) * nv], T2ac, alpha=2.0)                  # [(a,c),(b,d)]
@@ -107,18 +129,25 @@ class PackedEriOps:
             be.gemm(B2, Qx, out=cols, alpha=0.5, beta=1.0)
             del Qx
             self.flops += 2 * 2.0 * no * no * n * nv ** 3 + 2.0 * n * nv * nv * nv * npo
-        return self._t(res.view(no, no, nv, nv), [O, O, V, V]).transpose((0, 2, 1, 3))
+        return self._t(self._sum(res).view(no, no, nv, nv), [O, O, V, V]).transpose((0, 2, 1, 3))
 
 
-def build_adc3_operands(hf, mp, im, src, W, Op, Y, j0=0, nj=None):
+def build_adc3_operands(hf, mp, im, src, W, Op, Y, j0=0, nj=None, shard=(0, 1), layout=None, W_slab=None):
     """Returns the dict of operands the packed engine needs at third order.
 
-    ``W``, ``Op``, ``Y``: pair-packed vvvv / oooo and the [(j,b),(k,c)] ovov operand (complete).
-    ``j0``, ``nj``: occupied slab of the coupling operands V1 / V2 to keep (sharded engines)."""
+    ``Op``, ``Y``: pair-packed oooo and the complete [(j,b),(k,c)] ovov operand.  ``W``: the complete
+    pair-packed vvvv block (single GPU / dense sources) or None when ``src`` generates exchange-ordered
+    slabs itself.  ``j0``, ``nj``: occupied slab of the ovvv-type operands this rank owns.
+    Sharded build (shard = (rank, world), ``layout`` = SlabLayout, ``W_slab`` = this rank's AB rows of
+    W): pi5 is assembled from the ranks' column slabs, the ovvv contractions run on the rank's
+    occupied slab, the o^2 v^4 slab loops are dealt out over the ranks; partial results are summed by
+    all-reduces, the pib operands are produced for the rank's own slab only (no communication)."""
     ms = hf.mospaces
     no, nv = ms.n_orbs(O), ms.n_orbs(V)
     npo, npv = be.n_pairs(no), be.n_pairs(nv)
     nj = no if nj is None else nj
+    rank, world = shard
+    group = layout.group if layout is not None else None
     flops = 0.0
 
     def T(data, spaces):
@@ -130,14 +159,29 @@ def build_adc3_operands(hf, mp, im, src, W, Op, Y, j0=0, nj=None):
         cache[key] = tensor
         return tensor
 
-    V2e = src.ovvv_ajbc()                     # [a,(j,BC)] = <ja||bc>
+    def allsum(data):
+        if world > 1:
+            be.comm_all_reduce(data, group=group)
+        return data
+
+    V2e = src.ovvv_ajbc(j0, nj)               # [a,(jl,BC)] = <ja||bc>, occupied slab of this rank
     G1e = src.ooov_ijkb()                     # [i,(JK,b)] = <jk||ib>
     G2e = src.ooov_ijak()                     # [(IJ,a),k] = <ij||ka>
+    V2x = V2e if world == 1 else None         # operand of src.ovvv_exchange_slab (complete, or generated)
+    if world > 1 and not getattr(src, "generates_exchange_slabs", False):
+        V2x = src.ovvv_ajbc()
     t2 = mp.t2oo
     T2p = be.packed_pack(t2._contig(), no, nv)
 
     # ---- t2eri pi5 / pi3 / pi4 (GroundState.py:219-241) into LazyMp's cache
-    p5 = be.gemm(T2p, W, alpha=2.0)
+    if world == 1:
+        p5 = be.gemm(T2p, W, alpha=2.0)
+    else:
+        slab = be.zeros((npo, layout.wmax))
+        if layout.w > 0:
+            be.gemm(T2p, W_slab, out=slab[:, :layout.w], alpha=2.0)
+        p5 = layout.gather(slab)
+        del slab
     seed(mp._cache, ("t2eri", b.oovv + b.vv), T(be.packed_unpack(p5, no, nv), [O, O, V, V]))
     del p5
     p3 = be.gemm(Op, be.permute(T2p, (1, 0)), alpha=2.0)
@@ -148,16 +192,19 @@ def build_adc3_operands(hf, mp, im, src, W, Op, Y, j0=0, nj=None):
     seed(mp._cache, ("t2eri", b.oovv + b.ov),
          T(be.contiguous(T4.view(no, nv, no, nv).permute(2, 0, 1, 3)), [O, O, V, V]))
     del T4
-    flops += 2.0 * npo * npv * npv + 2.0 * npo * npo * npv + 2.0 * (no * nv) ** 3
+    flops += 2.0 * npo * npv * npv / world + 2.0 * npo * npo * npv + 2.0 * (no * nv) ** 3
     # ---- ts2_ov = 1/2 ph_pphh_1(t2) / (-df)   (LazyMp.py:72-104)
     Ue = be.packed_expand(1, T2p, no, nv)                                   # [i,(j,BC)]
-    s = be.gemm(Ue, V2e, alpha=2.0)                                         # t2[ijbc] <ja||bc>
+    s = be.zeros((no, nv))
+    if nj > 0:
+        be.gemm(Ue[:, j0 * npv:(j0 + nj) * npv], V2e, out=s, alpha=2.0)     # t2[ijbc] <ja||bc>, j in slab
+    allsum(s)
     Uh = be.packed_expand(2, T2p, no, nv)                                   # [a,(JK,b)]
     be.gemm(G1e, Uh, out=s, alpha=2.0, beta=1.0)                            # <jk||ib> t2[jkab]
     seed(mp._cache, ("ts2_ov", False), (0.5 * T(s, [O, V])) / (-1.0 * mp.df(b.ov)))
 
     # ---- singles block: the generic equations with the ovvv / vvvv contractions injected
-    ops = PackedEriOps(ms, no, nv, W, V2e, T2p)
+    ops = PackedEriOps(ms, no, nv, src, W, V2e, T2p, j0, nj, shard, group)
     hf.big_eri_ops = ops
     try:
         M1 = im.adc3_m11._contig().reshape(no * nv, no * nv)
@@ -169,43 +216,48 @@ def build_adc3_operands(hf, mp, im, src, W, Op, Y, j0=0, nj=None):
     pi2 = mp.t2eri(b.ooov, b.ov)                                            # t2[ilab] <lk||jb> -> [i,j,k,a]
     base = hf.ooov - 2.0 * pi2.antisymmetrise(0, 1)
     piaP = be.permute(be.pair_select(base._contig(), 0), (0, 2, 1))         # [IJ,a,k]
-    pi1 = be.gemm(T2p, V2e.view(nv * no, npv), alpha=2.0)                   # [IJ,(a,k)] = t2[ijbc] <ka||bc>
+    pi1 = be.zeros((npo, nv, no))                                           # [IJ,a,k] = t2[ijbc] <ka||bc>
+    if nj > 0:
+        part = be.gemm(T2p, V2e.view(nv * nj, npv), alpha=2.0)              # [IJ,(a,kl)], k in slab
+        be.copy2d(pi1.view(npo * nv, no)[:, j0:j0 + nj], part.view(npo * nv, nj), npo * nv, nj)
+        del part
+    allsum(pi1)
     be.axpby(-0.5, pi1, 1.0, piaP)
     del pi1, base
     G2 = piaP.view(npo * nv, no)                                            # [(IJ,a),k]
     G1 = be.permute(piaP.view(npo, nv, no), (2, 0, 1)).reshape(no, npo * nv)   # [i,(JK,b)]
-    flops += 2.0 * npo * npv * no * nv
+    flops += 2.0 * npo * npv * nj * nv
 
-    # ---- adc3_pib in the V2 layout [a,(i,BC)]  (matrix.py:1087-1094)
+    # ---- adc3_pib of the rank's occupied slab in the V2 layout [a,(il,BC)]  (matrix.py:1087-1094)
     pibV2 = be.clone(V2e)
-    Gt2 = be.permute(G2e.view(npo, nv, no), (1, 2, 0)).reshape(nv * no, npo)     # [(a,i),JK] = <jk||ia>
-    be.gemm(Gt2, be.permute(T2p, (1, 0)), out=pibV2.view(nv * no, npv), alpha=-1.0, beta=1.0)   # -1/2 pi6
+    Gt2 = be.contiguous(be.permute(G2e.view(npo, nv, no), (1, 2, 0))[:, j0:j0 + nj]).reshape(nv * nj, npo)
+    S2 = pibV2.view(nv * nj, npv)                                           # rows (a, il)
+    if nj > 0:
+        be.gemm(Gt2, be.permute(T2p, (1, 0)), out=S2, alpha=-1.0, beta=1.0)  # -1/2 pi6, [(a,il),JK] = <jk||ia>
     del Gt2
-    S2 = pibV2.view(nv * no, npv)
+    X2s = X2[j0 * nv:(j0 + nj) * nv]                                        # rows (il, b) of X(t2)
     na = _slab(nv, 2 * 8 * nv * no * nv, budget=4 << 30)
-    for a0 in range(0, nv, na):                                             # + 2 A_bc pi7, pi7 = t2[ijbd] <jc||ad>
+    for a0 in (range(0, nv, na) if nj > 0 else ()):                         # + 2 A_bc pi7, pi7 = t2[ijbd] <jc||ad>
         n = min(na, nv - a0)
-        Vx = src.ovvv_exchange_slab(V2e, a0, n).view(n * nv, no * nv)      # [(a,c),(j,d)]
-        P7 = be.gemm(Vx, X2)                                                # [(a,c),(i,b)] = pi7[i,a,b,c]
+        Vx = src.ovvv_exchange_slab(V2x, a0, n).view(n * nv, no * nv)      # [(a,c),(j,d)]
+        P7 = be.gemm(Vx, X2s)                                               # [(a,c),(il,b)] = pi7[i,a,b,c]
         del Vx
-        off = be.int64_tensor([al * nv * no * nv + i * nv for al in range(n) for i in range(no)])
-        rows = be.int64_tensor([(a0 + al) * no + i for al in range(n) for i in range(no)])
-        be.packed_fold_virt(S2, nv, no * nv, P7, off, alpha=-1.0, rows=rows)
+        off = be.int64_tensor([al * nv * nj * nv + il * nv for al in range(n) for il in range(nj)])
+        rows = be.int64_tensor([(a0 + al) * nj + il for al in range(n) for il in range(nj)])
+        be.packed_fold_virt(S2, nv, nj * nv, P7, off, alpha=-1.0, rows=rows)
         del P7
-    flops += 2.0 * nv * nv * (no * nv) ** 2 + 2.0 * nv * no * npo * npv
-    del X2
-    # coupling operands of this rank's occupied slab
-    sl = pibV2.view(nv, no, npv)[:, j0:j0 + nj]
-    V2 = be.contiguous(sl).reshape(nv, nj * npv)                            # [a,(jl,BC)]
-    V1 = be.permute(sl, (1, 2, 0)).reshape(nj * npv, nv)                    # [(jl,AB),c]
-    del pibV2, S2, sl
+    flops += 2.0 * nv * nv * (no * nv) * (nj * nv) + 2.0 * nv * nj * npo * npv
+    del X2, X2s, V2x
+    V2 = pibV2.view(nv, nj * npv)                                           # [a,(jl,BC)]
+    V1 = be.permute(pibV2.view(nv, nj, npv), (1, 2, 0)).reshape(nj * npv, nv)   # [(jl,AB),c]
+    del S2
 
     # ---- operands of the three-operand second-order coupling terms (matrix.py:498-499, 525, 529)
     ooov = hf.ooov._contig()                                                # [i,j,k,a]
     extras = {
-        "V2e": V2e,
+        "V2e": V2e,                                                                  # [a,(jl,BC)], slab
         "t2e": Ue,                                                                   # [j,(l,BC)] = t2[jl,BC]
-        "t2eM": be.permute(Ue.view(no, no, npv), (0, 2, 1)).reshape(no * npv, no),   # [(j,AB),l]
+        "t2eM": be.permute(Ue.view(no, no, npv)[j0:j0 + nj], (0, 2, 1)).reshape(nj * npv, no),   # [(jl,AB),l]
         "T2uh": Uh,                                                                  # [b,(JK,d)] = t2[JK,b,d]
         "T2h": be.permute(Uh.view(nv, npo, nv), (1, 0, 2)).reshape(npo * nv, nv),    # [(IJ,a),c]
         "G3": be.permute(ooov, (0, 3, 1, 2)).reshape(no * nv, no * no),              # [(i,a),(j,k)] = <ij||ka>

@@ -32,3 +32,24 @@ def test_sharded_matches_single_gpu(no, nv):
             assert r["host_path_rel_diff"] < 1e-13
         assert r["slab_vs_replicated_rel"] < 1e-13 and r["slab_dot_rel"] < 1e-13
         assert r["slab_host_path_rel_diff"] < 1e-13
+
+
+def test_sharded_adc2_adc3_match_single_gpu():
+    """Sharded ADC(2) / ADC(3) (build dealt out over the ranks, distributed vectors) vs one GPU."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 4 if n >= 4 else 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29573",
+           os.path.join(ROOT, "tools", "check_sharded_methods.py"), "16", "60"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rows = [json.loads(line) for line in out.stdout.splitlines() if line.startswith("{")]
+    assert len(rows) == world
+    for r in rows:
+        for method in ("adc2", "adc3"):
+            assert r[f"{method}_run_to_run_identical"]
+            assert r[f"{method}_rel_err_ph"] < 1e-11 and r[f"{method}_rel_err_pphh"] < 1e-11
+            assert r[f"{method}_diag_err"] < 1e-11
