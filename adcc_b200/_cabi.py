@@ -54,6 +54,8 @@ def _declare(lib):
     lib.adccb_slab_layout.argtypes = [c_ptr, c_int, c_i64, c_i64, c_int, ctypes.POINTER(c_i64), c_i64,
                                       c_ptr, c_ptr]
     lib.adccb_copy2d.argtypes = [c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64]
+    lib.adccb_block_gather.argtypes = [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]
+    lib.adccb_block_scatter_add.argtypes = [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_i64]
     lib.adccb_vvvv_exchange_slab.argtypes = [c_ptr, c_int, c_int, c_int, c_ptr, c_ptr]
     lib.adccb_ovvv_exchange_slab.argtypes = [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr]
     lib.adccb_pair_matvec.argtypes = [c_ptr, c_int, c_int, c_int, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_int,
@@ -76,7 +78,7 @@ EXPORTS = [
     "adccb_peer_free", "adccb_strided_gather", "adccb_elementwise", "adccb_direct_sum",
     "adccb_add_columns", "adccb_lincomb", "adccb_dot_many", "adccb_spin_expand4", "adccb_spin_project", "adccb_spin_singlet",
     "adccb_packed_unpack", "adccb_packed_pack", "adccb_packed_expand", "adccb_packed_expand_slab",
-    "adccb_slab_layout", "adccb_copy2d", "adccb_vvvv_exchange_slab", "adccb_ovvv_exchange_slab", "adccb_pair_matvec", "adccb_packed_fold_virt",
+    "adccb_slab_layout", "adccb_copy2d", "adccb_block_gather", "adccb_block_scatter_add", "adccb_vvvv_exchange_slab", "adccb_ovvv_exchange_slab", "adccb_pair_matvec", "adccb_packed_fold_virt",
     "adccb_packed_fold_occ", "adccb_packed_diagonal", "adccb_pair_select", "adccb_synth_fill",
 ]
 

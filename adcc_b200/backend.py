@@ -511,6 +511,32 @@ def comm_all_reduce(t, group=None):
     return t
 
 
+def _idx_ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def block_gather(inp, rows=None, cols=None):
+    """Compact copy inp[rows][:, cols] of a row-major 2-D array (rows / cols: device int64 lists)."""
+    if inp.stride(1) != 1:
+        raise ValueError("block_gather: unit column stride expected")
+    nr = rows.numel() if rows is not None else inp.shape[0]
+    nc = cols.numel() if cols is not None else inp.shape[1]
+    out = empty((nr, nc))
+    _cabi.check(_cabi.lib().adccb_block_gather(_stream(), nr, nc, _idx_ptr(rows), _idx_ptr(cols), _ptr(inp),
+                                               inp.stride(0), _ptr(out)))
+    return out
+
+
+def block_scatter_add(out, blk, rows=None, cols=None, alpha=1.0):
+    """out[rows][:, cols] += alpha * blk."""
+    if out.stride(1) != 1 or not blk.is_contiguous():
+        raise ValueError("block_scatter_add: unit column stride expected")
+    nr, nc = blk.shape
+    _cabi.check(_cabi.lib().adccb_block_scatter_add(_stream(), nr, nc, _idx_ptr(rows), _idx_ptr(cols), float(alpha),
+                                                    _ptr(blk), _ptr(out), out.stride(0)))
+    return out
+
+
 def vvvv_exchange_slab(W, nv, a_begin, na):
     """[na, nv, nv, nv] array out[al,b,c,d] = <a c||b d>, a = a_begin + al, from packed W[AB,CD]."""
     out = empty((na, nv, nv, nv))

@@ -68,6 +68,8 @@ int packed_expand_slab(cudaStream_t st, int which, int no, int nv, int first, in
                        double* out);
 int slab_layout(cudaStream_t st, int dir, long long nrows, long long npv, int world, const long long* cut,
                 long long wmax, double* full, double* slabs);
+int block_select(cudaStream_t st, int mode, long long nr, long long nc, const long long* rows,
+                 const long long* cols, long long ld, double alpha, double* big, double* blk);
 int vvvv_exchange_slab(cudaStream_t st, int nv, int a_begin, int na, const double* W, double* out);
 int ovvv_exchange_slab(cudaStream_t st, int no, int nv, int a_begin, int na, const double* V2, double* out);
 int pair_matvec(cudaStream_t st, int nv, int n_out, int n_red, long long so, long long sr, const double* V,
@@ -223,6 +225,16 @@ int adccb_copy2d(void* stream, void* dst, int64_t dst_pitch_bytes, const void* s
   ADCCB_CUDA_OK(cudaMemcpy2DAsync(dst, (size_t)dst_pitch_bytes, src, (size_t)src_pitch_bytes, (size_t)width_bytes,
                                   (size_t)height, cudaMemcpyDefault, (cudaStream_t)stream));
   return 0;
+}
+int adccb_block_gather(void* stream, int64_t n_rows, int64_t n_cols, const int64_t* rows, const int64_t* cols,
+                       const double* in, int64_t ld, double* out) {
+  return block_select((cudaStream_t)stream, 0, n_rows, n_cols, (const long long*)rows, (const long long*)cols, ld,
+                      1.0, const_cast<double*>(in), out);
+}
+int adccb_block_scatter_add(void* stream, int64_t n_rows, int64_t n_cols, const int64_t* rows, const int64_t* cols,
+                            double alpha, const double* blk, double* out, int64_t ld) {
+  return block_select((cudaStream_t)stream, 1, n_rows, n_cols, (const long long*)rows, (const long long*)cols, ld,
+                      alpha, out, const_cast<double*>(blk));
 }
 int adccb_vvvv_exchange_slab(void* stream, int nv, int a_begin, int na, const double* W, double* out) {
   return vvvv_exchange_slab((cudaStream_t)stream, nv, a_begin, na, W, out);

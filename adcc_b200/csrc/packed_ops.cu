@@ -382,6 +382,30 @@ __global__ void slab_layout_kernel(int dir, long long nrows, long long npv, long
 }
 
 // ---------------------------------------------------------------------------------------
+// spin-block selection: compact copies of the rows / columns of one spin class
+// ---------------------------------------------------------------------------------------
+// mode 0: out[r, c] = in[rows[r] * ld + cols[c]]                  (gather a block)
+// mode 1: in[rows[r] * ld + cols[c]] += alpha * out[r, c]         (scatter-add a block back)
+// rows == nullptr / cols == nullptr: identity.  <pq||rs> vanishes unless the spin projections of bra
+// and ket agree, so for a restricted reference the pair-packed vvvv / oooo operands and the ovov
+// operand are block diagonal once their composite indices are ordered by spin class
+// (libtensor keeps this structure in its spin-block symmetry elements,
+// libadcc_src/TensorImpl/as_lt_symmetry.cc:100-172); these kernels move the classes in and out of
+// the dense GEMM operands.
+__global__ void block_select_kernel(int mode, long long nr, long long nc, const long long* __restrict__ rows,
+                                    const long long* __restrict__ cols, long long ld, double alpha,
+                                    double* __restrict__ big, double* __restrict__ blk) {
+  const long long n = nr * nc;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / nc, c = idx % nc;
+    const long long src = (rows ? rows[r] : r) * ld + (cols ? cols[c] : c);
+    if (mode == 0) blk[idx] = big[src];
+    else big[src] += alpha * blk[idx];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // ADC(3) build / matvec helpers on pair-packed operands
 // ---------------------------------------------------------------------------------------
 // Exchange-ordered slab of the vvvv block from its pair-packed form W[AB,CD] = <ab||cd>:
@@ -517,6 +541,15 @@ int slab_layout(cudaStream_t st, int dir, long long nrows, long long npv, int wo
   const long long n = nrows * wmax * world;
   if (n == 0) return 0;
   slab_layout_kernel<<<blocks_for(n, 256), 256, 0, st>>>(dir, nrows, npv, wmax, c, full, slabs);
+  ADCCB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+int block_select(cudaStream_t st, int mode, long long nr, long long nc, const long long* rows,
+                 const long long* cols, long long ld, double alpha, double* big, double* blk) {
+  if (nr <= 0 || nc <= 0) return 0;
+  block_select_kernel<<<blocks_for(nr * nc, 256), 256, 0, st>>>(mode, nr, nc, rows, cols, ld, alpha, big, blk);
   ADCCB_LAUNCH_OK();
   count_launch();
   return 0;

@@ -529,14 +529,104 @@ class PackedAdcEngine:
                     be.fill(pad, 1e300)
                     be.copy2d(self.diagonal_pphh._data[:, lay.w:], pad, lay.npo, lay.wmax - lay.w)
                 self.diagonal_pphh.set_immutable()
+        self._spin = None
+        if (self.order_dd == 1 and self.world == 1 and getattr(hf, "restricted", False)
+                and os.environ.get("ADCCB_SPIN_BLOCKS", "1") != "0"):
+            self._spin = self._build_spin_blocks()
         self._count_flops()
+
+    # ------------------------------------------------------------------ spin-blocked operands
+    def _build_spin_blocks(self):
+        """Restricted references: <pq||rs> vanishes unless bra and ket have the same spin projection,
+        so W[AB,CD], O[IJ,KL] are block diagonal over the pair classes (alpha-alpha, alpha-beta,
+        beta-beta) and Y[(j,b),(k,c)] over the classes s_j - s_b of its composite indices.  Only the
+        diagonal blocks are kept (37.5 % of the elements and of the GEMM flops of the three
+        first-order doubles terms; the beta-beta block equals the alpha-alpha one and is stored once).
+        libtensor holds the same structure as spin-block symmetry elements
+        (libadcc_src/TensorImpl/as_lt_symmetry.cc:100-172).  Exact for ANY trial vector: the
+        structure belongs to the integrals.  Returns None (dense operands stay) if the staged
+        operands do not have the structure to 1e-12."""
+        import torch
+        no, nv = self.no, self.nv
+        ms = self.mospaces
+        na_o, na_v = ms.n_orbs_alpha("o1"), ms.n_orbs_alpha("v1")
+        if 2 * na_o != no or 2 * na_v != nv:
+            return None
+
+        def pair_classes(n, na):
+            q = np.repeat(np.arange(n), np.arange(n))
+            p = np.concatenate([np.arange(k) for k in range(n)]) if n > 1 else np.zeros(0, dtype=int)
+            cls = (p >= na).astype(int) + (q >= na).astype(int)
+            return [np.nonzero(cls == c)[0] for c in range(3)]
+
+        def dev(ix):
+            return torch.as_tensor(ix, dtype=torch.int64, device=self.D0.device)
+
+        vcls = [dev(ix) for ix in pair_classes(nv, na_v)]
+        ocls = [dev(ix) for ix in pair_classes(no, na_o)]
+        jj, bb = np.meshgrid(np.arange(no), np.arange(nv), indexing="ij")
+        delta = ((jj >= na_o).astype(int) - (bb >= na_v).astype(int)).reshape(-1)
+        ycls = [dev(np.nonzero(delta == d)[0]) for d in (0, 1, -1)]
+
+        def blocks(M, classes, same_first_last):
+            total = float(be.dot(be.contiguous(M).reshape(-1), be.contiguous(M).reshape(-1)))
+            out, kept = [], 0.0
+            for ix in classes:
+                blk = be.block_gather(M, ix, ix) if ix.numel() else None
+                out.append(blk)
+                if blk is not None:
+                    kept += float(be.dot(blk.reshape(-1), blk.reshape(-1)))
+            if abs(total - kept) > 1e-12 * max(total, 1e-300):
+                return None                              # not spin-block diagonal
+            if same_first_last and out[0] is not None and out[2] is not None and out[0].shape == out[2].shape:
+                d = be.lincomb([1.0, -1.0], [out[0], out[2]])
+                if float(be.dot(d.reshape(-1), d.reshape(-1))) <= 1e-24 * max(kept, 1e-300):
+                    out[2] = out[0]                      # beta-beta == alpha-alpha: stored once
+            return out
+
+        Wb = blocks(self.W, vcls, True)
+        Ob = blocks(self.O, ocls, True)
+        Yb = blocks(self.Y, ycls, False)
+        if Wb is None or Ob is None or Yb is None:
+            return None
+        self.W = self.O = self.Y = None                  # the dense operands are no longer needed
+        be.release_cached_memory()
+        return {"v": vcls, "o": ocls, "y": ycls, "W": Wb, "O": Ob, "Y": Yb}
+
+    def _spin_vvvv(self, U, S):
+        """S += sum over pair classes of U[:, class] W_class^T, scattered to the class columns."""
+        sp = self._spin
+        for ix, Wc in zip(sp["v"], sp["W"]):
+            if Wc is not None:
+                be.block_scatter_add(S, be.gemm(be.block_gather(U, None, ix), Wc), None, ix)
+
+    def _spin_oooo(self, U, S):
+        sp = self._spin
+        for ix, Oc in zip(sp["o"], sp["O"]):
+            if Oc is not None:
+                Uc = be.block_gather(U, ix, None)                                   # [KL in class, AB]
+                be.block_scatter_add(S, be.gemm(Oc, be.permute(Uc, (1, 0))), ix, None)
+
+    def _spin_ovov(self, X):
+        """T[(i,a),(j,b)] = sum_kc X[(i,a),(k,c)] <kb||jc> from the three diagonal blocks of Y."""
+        sp = self._spin
+        T = be.zeros((X.shape[0], self.no * self.nv))
+        for ix, Yc in zip(sp["y"], sp["Y"]):
+            if Yc is not None:
+                be.block_scatter_add(T, be.gemm(be.block_gather(X, None, ix), Yc), None, ix)
+        return T
 
     def _count_flops(self):
         no, nv, npo, npv = self.no, self.nv, self.npo, self.npv
         f = {"ph_ph": 2.0 * (no * nv) ** 2,
              "ph_pphh": 2.0 * no * nv * (no * npv) + 2.0 * no * nv * (npo * nv),
              "pphh_ph": 2.0 * no * (no * npv) * nv + 2.0 * (npo * nv) * nv * no}
-        if self.order_dd == 1:
+        if self.order_dd == 1 and getattr(self, "_spin", None) is not None:
+            sp = self._spin
+            f["pphh_pphh/vvvv"] = sum(2.0 * npo * ix.numel() ** 2 for ix in sp["v"])
+            f["pphh_pphh/oooo"] = sum(2.0 * npv * ix.numel() ** 2 for ix in sp["o"])
+            f["pphh_pphh/ovov"] = sum(2.0 * no * nv * ix.numel() ** 2 for ix in sp["y"])
+        elif self.order_dd == 1:
             f["pphh_pphh/vvvv"] = 2.0 * npo * npv * npv
             f["pphh_pphh/oooo"] = 2.0 * npo * npo * npv
             f["pphh_pphh/ovov"] = 2.0 * (no * nv) ** 3
@@ -624,6 +714,19 @@ class PackedAdcEngine:
         # 0th order: 2 A_ab(u f_vv) - 2 A_ij(f_oo u) = (e_a + e_b - e_i - e_j) u for canonical orbitals
         be.mul(U, self.D0, out=S, beta=beta)
         if self.order_dd == 0:
+            return S
+        if self._spin is not None:
+            # restricted reference: only the spin-conserving diagonal blocks of W / O / Y exist
+            self._mark("vvvv", 0)
+            self._spin_vvvv(U, S)
+            self._mark("vvvv", 1)
+            self._spin_oooo(U, S)
+            X = be.packed_expand(0, U, no, nv)
+            self._mark("ovov", 0)
+            T = self._spin_ovov(X)
+            self._mark("ovov", 1)
+            del X
+            be.packed_fold_virt(S, nv, no * nv, T, self._off_ovov_1, T, self._off_ovov_2, alpha=-1.0)
             return S
         self._mark("vvvv", 0)
         be.gemm(U, self.W, out=S, alpha=1.0, beta=1.0)       # 1/2 u[ijcd] <ab||cd> = sum_{c<d}
@@ -1237,7 +1340,7 @@ class PackedAdcEngine:
             else:
                 self._matvec_host_sharded(u1_host, U_host, s1_host, S_host)
             return
-        if self.order_dd != 1 or self.npo < 4 * edge_rows:
+        if self.order_dd != 1 or self.npo < 4 * edge_rows or self._spin is not None:
             v = AmplitudeVector(ph=self._wrap_ph(u1_host.to("cuda", non_blocking=True)),
                                 pphh=self._wrap_pphh(U_host.to("cuda", non_blocking=True)))
             s = self.matvec(v)

@@ -150,6 +150,17 @@ int adccb_slab_layout(void* stream, int dir, int64_t nrows, int64_t npv, int wor
  * libadcc_src/TensorImpl.cc:1369-1441, for one slab). */
 int adccb_copy2d(void* stream, void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes,
                  int64_t width_bytes, int64_t height);
+/* Spin-blocked operands for restricted references.  out[r, c] = in[rows[r]*ld + cols[c]] (gather) and
+ * out[rows[r]*ld + cols[c]] += alpha * blk[r, c] (scatter-add); rows / cols: device int64 index lists,
+ * NULL = identity.  <pq||rs> vanishes unless bra and ket carry the same spin projection, so the
+ * pair-packed vvvv / oooo operands and the ovov operand are block diagonal over spin classes of their
+ * composite indices; libtensor holds that structure as spin-block symmetry elements
+ * (libadcc_src/TensorImpl/as_lt_symmetry.cc:100-172, adcc/guess/guess_zero.py:143-161), here the classes
+ * are gathered into compact GEMM operands and the results scattered back. */
+int adccb_block_gather(void* stream, int64_t n_rows, int64_t n_cols, const int64_t* rows, const int64_t* cols,
+                       const double* in, int64_t ld, double* out);
+int adccb_block_scatter_add(void* stream, int64_t n_rows, int64_t n_cols, const int64_t* rows, const int64_t* cols,
+                            double alpha, const double* blk, double* out, int64_t ld);
 /* out[al, b, c, d] = <a c||b d> (a = a_begin + al < a_begin + na) gathered from the pair-packed vvvv
  * block W[AB,CD]: the exchange-ordered operand slab of the o^2 v^4 builds of the ADC(3) singles block
  * (adcc/adc_pp/matrix.py:953 "acbd,cd->ab", :1029-1033 "icjd,acbd->iajb" / "idjc,acbd->iajb"), which on

@@ -186,6 +186,16 @@ def install(monkeypatch):
         out.copy_(torch.stack(parts).reshape(out.shape))
         return out
 
+    def block_gather(inp, rows=None, cols=None):
+        res = inp if rows is None else inp[rows]
+        return (res if cols is None else res[:, cols]).contiguous()
+
+    def block_scatter_add(out, blk, rows=None, cols=None, alpha=1.0):
+        r = torch.arange(out.shape[0]) if rows is None else rows
+        c = torch.arange(out.shape[1]) if cols is None else cols
+        out[r[:, None], c[None, :]] += alpha * blk
+        return out
+
     def _pair_dense(rows, nv):
         """[n, npv] pair-packed antisymmetric rows -> [n, nv, nv]"""
         pv = _pairs(nv)
@@ -341,7 +351,7 @@ def install(monkeypatch):
                          spin_singlet_=spin_singlet_, packed_unpack=packed_unpack, packed_pack=packed_pack,
                          packed_expand=packed_expand, packed_fold_virt=packed_fold_virt,
                          packed_fold_occ=packed_fold_occ, packed_diagonal=packed_diagonal,
-                         pair_select=pair_select, vvvv_exchange_slab=vvvv_exchange_slab, ovvv_exchange_slab=ovvv_exchange_slab, pair_matvec=pair_matvec,
+                         pair_select=pair_select, block_gather=block_gather, block_scatter_add=block_scatter_add, vvvv_exchange_slab=vvvv_exchange_slab, ovvv_exchange_slab=ovvv_exchange_slab, pair_matvec=pair_matvec,
                          packed_expand_slab=packed_expand_slab, slab_layout=slab_layout,
                          copy2d=copy2d, comm_reduce_scatter=comm_reduce_scatter, comm_all_gather=comm_all_gather,
                          int64_tensor=int64_tensor, add_columns=add_columns, spin_expand4=spin_expand4, synth_fill=synth_fill).items():

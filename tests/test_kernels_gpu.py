@@ -220,3 +220,27 @@ def test_gather_randomised_permutations(be):
 def test_tensor_symmetrise_reference_goldens_device(be):
     from tensor_golden_common import check_tensor_goldens
     check_tensor_goldens()
+
+
+@pytest.mark.parametrize("M,N,K,hint", [(780, 4096, 9600, 0), (2048, 2048, 2048, 128), (2048, 2048, 2048, 112),
+                                        (40, 240, 96000, 0), (2000, 1600, 1600, 0)])
+def test_gemm_pipeline_stress_bitwise(be, M, N, K, hint):
+    """Regression guard for the shared-memory WAR race the TMA pipeline once had (a refill
+    overtaking delayed fragment reads, about once per 1e4 tiles with L2-resident operands): many
+    back-to-back launches on operands that stay in L2, every result compared BITWISE with the first
+    one, and the first one with the generic (non-TMA) kernel path."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g, dtype=torch.float64).cuda()
+    B = torch.randn(N, K, generator=g, dtype=torch.float64).cuda()
+    C0 = be.gemm(A, B, tile_hint=hint).clone()
+    # generic kernel: odd leading dimension defeats the TMA alignment rule
+    Ap = torch.zeros(M, K + 1, dtype=torch.float64, device="cuda")
+    Ap[:, :K] = A
+    Cg = be.gemm(Ap[:, :K], B)
+    assert float((Cg - C0).abs().max() / C0.abs().max()) < 1e-13
+    bad = torch.zeros((), dtype=torch.int64, device="cuda")
+    for _ in range(60):
+        C = be.gemm(A, B, tile_hint=hint)
+        bad += (C != C0).any()
+    assert int(bad.item()) == 0
