@@ -47,6 +47,8 @@ def _declare(lib):
     lib.adccb_spin_singlet.argtypes = [c_ptr, ctypes.POINTER(ctypes.c_int),
                                        ctypes.POINTER(ctypes.c_int), c_ptr]
     c_int = ctypes.c_int
+    lib.adccb_precond_apply.argtypes = [c_ptr, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_ptr, c_ptr,
+                                        c_dbl, c_int, c_dbl, c_int, c_ptr]
     lib.adccb_packed_unpack.argtypes = [c_ptr, c_int, c_int, c_ptr, c_ptr]
     lib.adccb_packed_pack.argtypes = [c_ptr, c_int, c_int, c_ptr, c_ptr]
     lib.adccb_packed_expand.argtypes = [c_ptr, c_int, c_int, c_int, c_ptr, c_ptr]
@@ -56,6 +58,7 @@ def _declare(lib):
     lib.adccb_copy2d.argtypes = [c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64]
     lib.adccb_block_gather.argtypes = [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]
     lib.adccb_block_scatter_add.argtypes = [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_i64]
+    lib.adccb_block_scatter.argtypes = [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_i64]
     lib.adccb_vvvv_exchange_slab.argtypes = [c_ptr, c_int, c_int, c_int, c_ptr, c_ptr]
     lib.adccb_ovvv_exchange_slab.argtypes = [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr]
     lib.adccb_pair_matvec.argtypes = [c_ptr, c_int, c_int, c_int, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_int,
@@ -76,9 +79,9 @@ EXPORTS = [
     "adccb_version", "adccb_last_error", "adccb_launch_count", "adccb_device_info",
     "adccb_dgemm", "adccb_dgemm_peers", "adccb_peer_alloc", "adccb_peer_open", "adccb_peer_close",
     "adccb_peer_free", "adccb_strided_gather", "adccb_elementwise", "adccb_direct_sum",
-    "adccb_add_columns", "adccb_lincomb", "adccb_dot_many", "adccb_spin_expand4", "adccb_spin_project", "adccb_spin_singlet",
+    "adccb_add_columns", "adccb_lincomb", "adccb_dot_many", "adccb_spin_expand4", "adccb_spin_project", "adccb_spin_singlet", "adccb_precond_apply",
     "adccb_packed_unpack", "adccb_packed_pack", "adccb_packed_expand", "adccb_packed_expand_slab",
-    "adccb_slab_layout", "adccb_copy2d", "adccb_block_gather", "adccb_block_scatter_add", "adccb_vvvv_exchange_slab", "adccb_ovvv_exchange_slab", "adccb_pair_matvec", "adccb_packed_fold_virt",
+    "adccb_slab_layout", "adccb_copy2d", "adccb_block_gather", "adccb_block_scatter_add", "adccb_block_scatter", "adccb_vvvv_exchange_slab", "adccb_ovvv_exchange_slab", "adccb_pair_matvec", "adccb_packed_fold_virt",
     "adccb_packed_fold_occ", "adccb_packed_diagonal", "adccb_pair_select", "adccb_synth_fill",
 ]
 

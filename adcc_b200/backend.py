@@ -427,6 +427,20 @@ def spin_singlet_(t, n_alpha):
     return t
 
 
+def precond_apply(x, D, shift, n_alpha, sym_mode=0, spin_fac=0.0, purify=False):
+    """Purify(Sym(SpinProject(x / (D - shift)))) in one launch (see include/adccb.h); x, D: contiguous
+    dense blocks of rank 2 or 4 (D may be None)."""
+    if not x.is_contiguous() or (D is not None and not D.is_contiguous()):
+        raise ValueError("precond_apply: contiguous blocks expected")
+    nd = x.dim()
+    sh = (ctypes.c_int * nd)(*[int(s) for s in x.shape])
+    na = (ctypes.c_int * nd)(*[int(s) for s in n_alpha])
+    out = torch.empty_like(x)
+    _cabi.check(_cabi.lib().adccb_precond_apply(_stream(), nd, sh, na, _ptr(x), _ptr(D), float(shift),
+                                                int(sym_mode), float(spin_fac), 1 if purify else 0, _ptr(out)))
+    return out
+
+
 # --------------------------------------------------------------------------------- packed doubles
 def n_pairs(n):
     return n * (n - 1) // 2
@@ -527,13 +541,14 @@ def block_gather(inp, rows=None, cols=None):
     return out
 
 
-def block_scatter_add(out, blk, rows=None, cols=None, alpha=1.0):
-    """out[rows][:, cols] += alpha * blk."""
+def block_scatter_add(out, blk, rows=None, cols=None, alpha=1.0, assign=False):
+    """out[rows][:, cols] += alpha * blk  (assign: = instead of +=)."""
     if out.stride(1) != 1 or not blk.is_contiguous():
         raise ValueError("block_scatter_add: unit column stride expected")
     nr, nc = blk.shape
-    _cabi.check(_cabi.lib().adccb_block_scatter_add(_stream(), nr, nc, _idx_ptr(rows), _idx_ptr(cols), float(alpha),
-                                                    _ptr(blk), _ptr(out), out.stride(0)))
+    fn = _cabi.lib().adccb_block_scatter if assign else _cabi.lib().adccb_block_scatter_add
+    _cabi.check(fn(_stream(), nr, nc, _idx_ptr(rows), _idx_ptr(cols), float(alpha), _ptr(blk), _ptr(out),
+                   out.stride(0)))
     return out
 
 

@@ -60,6 +60,8 @@ int spin_expand4(cudaStream_t st, const int* n, const double* T, double* out);
 int spin_project(cudaStream_t st, int nd, const int* shape, const int* nalpha, double fac,
                  const double* in, double* out);
 int spin_singlet(cudaStream_t st, const int* shape, const int* nalpha, double* T);
+int precond_apply(cudaStream_t st, int nd, const int* shape, const int* nalpha, const double* x, const double* D,
+                  double shift, int sym_mode, double spin_fac, int purify, double* out);
 
 int packed_unpack(cudaStream_t st, int no, int nv, const double* U, double* out);
 int packed_pack(cudaStream_t st, int no, int nv, const double* T, double* U);
@@ -202,6 +204,11 @@ int adccb_spin_singlet(void* stream, const int* shape, const int* n_alpha, doubl
   return spin_singlet((cudaStream_t)stream, shape, n_alpha, T);
 }
 
+int adccb_precond_apply(void* stream, int ndim, const int* shape, const int* n_alpha, const double* x,
+                        const double* D, double shift, int sym_mode, double spin_fac, int purify, double* out) {
+  return precond_apply((cudaStream_t)stream, ndim, shape, n_alpha, x, D, shift, sym_mode, spin_fac, purify, out);
+}
+
 int adccb_packed_unpack(void* stream, int no, int nv, const double* U, double* out) {
   return packed_unpack((cudaStream_t)stream, no, nv, U, out);
 }
@@ -230,6 +237,11 @@ int adccb_block_gather(void* stream, int64_t n_rows, int64_t n_cols, const int64
                        const double* in, int64_t ld, double* out) {
   return block_select((cudaStream_t)stream, 0, n_rows, n_cols, (const long long*)rows, (const long long*)cols, ld,
                       1.0, const_cast<double*>(in), out);
+}
+int adccb_block_scatter(void* stream, int64_t n_rows, int64_t n_cols, const int64_t* rows, const int64_t* cols,
+                        double alpha, const double* blk, double* out, int64_t ld) {
+  return block_select((cudaStream_t)stream, 2, n_rows, n_cols, (const long long*)rows, (const long long*)cols, ld,
+                      alpha, out, const_cast<double*>(blk));
 }
 int adccb_block_scatter_add(void* stream, int64_t n_rows, int64_t n_cols, const int64_t* rows, const int64_t* cols,
                             double alpha, const double* blk, double* out, int64_t ld) {

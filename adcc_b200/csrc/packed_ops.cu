@@ -392,16 +392,21 @@ __global__ void slab_layout_kernel(int dir, long long nrows, long long npv, long
 // (libtensor keeps this structure in its spin-block symmetry elements,
 // libadcc_src/TensorImpl/as_lt_symmetry.cc:100-172); these kernels move the classes in and out of
 // the dense GEMM operands.
+// mode 2: in[rows[r] * ld + cols[c]]  = alpha * out[r, c]         (scatter a block back, no accumulation)
+// One thread per column (its column index is read once, coalesced), blockIdx.y strides over the rows:
+// no per-element integer division, contiguous accesses on the compact side.
 __global__ void block_select_kernel(int mode, long long nr, long long nc, const long long* __restrict__ rows,
                                     const long long* __restrict__ cols, long long ld, double alpha,
                                     double* __restrict__ big, double* __restrict__ blk) {
-  const long long n = nr * nc;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const long long r = idx / nc, c = idx % nc;
-    const long long src = (rows ? rows[r] : r) * ld + (cols ? cols[c] : c);
-    if (mode == 0) blk[idx] = big[src];
-    else big[src] += alpha * blk[idx];
+  const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const long long col = cols ? cols[c] : c;
+  for (long long r = blockIdx.y; r < nr; r += gridDim.y) {
+    double* b = big + (rows ? rows[r] : r) * ld + col;
+    double* k = blk + r * nc + c;
+    if (mode == 0) *k = *b;
+    else if (mode == 1) *b += alpha * (*k);
+    else *b = alpha * (*k);
   }
 }
 
@@ -549,7 +554,9 @@ int slab_layout(cudaStream_t st, int dir, long long nrows, long long npv, int wo
 int block_select(cudaStream_t st, int mode, long long nr, long long nc, const long long* rows,
                  const long long* cols, long long ld, double alpha, double* big, double* blk) {
   if (nr <= 0 || nc <= 0) return 0;
-  block_select_kernel<<<blocks_for(nr * nc, 256), 256, 0, st>>>(mode, nr, nc, rows, cols, ld, alpha, big, blk);
+  const unsigned gx = (unsigned)((nc + 255) / 256);
+  const unsigned gy = (unsigned)std::min<long long>(nr, std::max<long long>(1, (32LL * sm_count()) / gx));
+  block_select_kernel<<<dim3(gx, gy), 256, 0, st>>>(mode, nr, nc, rows, cols, ld, alpha, big, blk);
   ADCCB_LAUNCH_OK();
   count_launch();
   return 0;

@@ -585,6 +585,73 @@ __global__ void spin_singlet_kernel(SpinDesc d, double* __restrict__ T) {
   }
 }
 
+// Fused Davidson correction step on the dense store (SURVEY K5 + K2 + K8): for a residual block x,
+//   p = x / (D - shift)                                  Jacobi preconditioner (preconditioner.py:65-82)
+//   q = spin projection of p (fac = +1 singlet, -1 triplet, 0 none: q = p)
+//   r = index symmetrisation of q: sym_mode 0 none, 1 doubles A_ij A_ab S_(ij)(ab) (AdcMatrix.py:449-455),
+//       2 CVS doubles A_ab (AdcMatrix.py:445-447)
+//   out = r, and for singlets (purify) the aaaa / bbbb blocks = r[abab] + r[abba]
+//         (amplitude_vector_enforce_spin_kind.cc:119-167)
+// evaluated per output element from gathered inputs: one launch, one write pass, instead of
+// div / project / antisymmetrise x2 / symmetrise / purify passes.
+struct PrecondDesc {
+  int nd, sym_mode, purify;
+  int shape[4], nalpha[4];
+  double shift, fac;
+};
+__device__ __forceinline__ double precond_q(const PrecondDesc& d, const double* __restrict__ x,
+                                            const double* __restrict__ D, const int (&c)[4]) {
+  long long idx = 0, fidx = 0;
+  int nbeta_h = 0, nbeta_p = 0;
+  for (int k = 0; k < d.nd; ++k) {
+    const bool beta = c[k] >= d.nalpha[k];
+    if (k < d.nd / 2) nbeta_h += beta; else nbeta_p += beta;
+    idx = idx * d.shape[k] + c[k];
+    fidx = fidx * d.shape[k] + (beta ? c[k] - d.nalpha[k] : c[k] + d.nalpha[k]);
+  }
+  const double p = D ? x[idx] / (D[idx] - d.shift) : x[idx];
+  if (d.fac == 0.0) return p;
+  if (nbeta_h != nbeta_p) return 0.0;
+  const double pf = D ? x[fidx] / (D[fidx] - d.shift) : x[fidx];
+  return 0.5 * (p + d.fac * pf);
+}
+__device__ __forceinline__ double precond_r(const PrecondDesc& d, const double* __restrict__ x,
+                                            const double* __restrict__ D, int i, int j, int a, int b) {
+  const int c0[4] = {i, j, a, b};
+  if (d.nd != 4 || d.sym_mode == 0) return precond_q(d, x, D, c0);
+  const int c1[4] = {i, j, b, a};
+  if (d.sym_mode == 2) return 0.5 * (precond_q(d, x, D, c0) - precond_q(d, x, D, c1));
+  const int c2[4] = {j, i, a, b}, c3[4] = {j, i, b, a};
+  return 0.25 * (precond_q(d, x, D, c0) - precond_q(d, x, D, c2) - precond_q(d, x, D, c1) + precond_q(d, x, D, c3));
+}
+__global__ void precond_fused_kernel(PrecondDesc d, long long n, const double* __restrict__ x,
+                                     const double* __restrict__ D, double* __restrict__ out) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int c[4] = {0, 0, 0, 0};
+    long long rem = idx;
+    for (int k = d.nd - 1; k >= 0; --k) {
+      c[k] = (int)(rem % d.shape[k]);
+      rem /= d.shape[k];
+    }
+    if (d.nd == 2) {
+      out[idx] = precond_q(d, x, D, c);
+      continue;
+    }
+    double v;
+    const bool b0 = c[0] >= d.nalpha[0], b1 = c[1] >= d.nalpha[1], b2 = c[2] >= d.nalpha[2], b3 = c[3] >= d.nalpha[3];
+    if (d.purify && b0 == b1 && b1 == b2 && b2 == b3) {
+      const int i = b0 ? c[0] - d.nalpha[0] : c[0], j = b0 ? c[1] - d.nalpha[1] : c[1];
+      const int a = b0 ? c[2] - d.nalpha[2] : c[2], b = b0 ? c[3] - d.nalpha[3] : c[3];
+      v = precond_r(d, x, D, i, j + d.nalpha[1], a, b + d.nalpha[3]) +
+          precond_r(d, x, D, i, j + d.nalpha[1], a + d.nalpha[2], b);
+    } else {
+      v = precond_r(d, x, D, c[0], c[1], c[2], c[3]);
+    }
+    out[idx] = v;
+  }
+}
+
 // Spin expansion of a restricted (spatial) two-electron block in chemists' order:
 // out[p,q,r,s] = T[p',q',r',s'] if spin(p)==spin(q) and spin(r)==spin(s), else 0, where every output
 // axis is [alpha | beta] over the same n[k] spatial orbitals (adcc/backends/EriBuilder.py:117-119).
@@ -631,6 +698,32 @@ int spin_project(cudaStream_t st, int nd, const int* shape, const int* nalpha, d
   }
   if (n == 0) return 0;
   spin_project_kernel<<<grid_for(n, 256, 2), 256, 0, st>>>(d, n, fac, in, out);
+  ADCCB_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+int precond_apply(cudaStream_t st, int nd, const int* shape, const int* nalpha, const double* x, const double* D,
+                  double shift, int sym_mode, double spin_fac, int purify, double* out) {
+  if (nd != 2 && nd != 4) return fail("precond_apply: rank 2 or 4 blocks");
+  if (sym_mode < 0 || sym_mode > 2) return fail("precond_apply: unknown symmetrisation mode");
+  PrecondDesc d;
+  d.nd = nd; d.sym_mode = (nd == 4) ? sym_mode : 0; d.purify = (nd == 4) ? purify : 0;
+  d.shift = shift; d.fac = spin_fac;
+  long long n = 1;
+  for (int k = 0; k < 4; ++k) {
+    d.shape[k] = k < nd ? shape[k] : 1;
+    d.nalpha[k] = k < nd ? nalpha[k] : 1;
+    if (k < nd) n *= shape[k];
+    if (k < nd && (spin_fac != 0.0 || purify) && 2 * nalpha[k] != shape[k])
+      return fail("precond_apply: spin kinds need equal alpha/beta halves");
+  }
+  if (nd == 4 && sym_mode == 1 && (shape[0] != shape[1] || shape[2] != shape[3]))
+    return fail("precond_apply: antisymmetrised index pairs need equal extents");
+  if (nd == 4 && sym_mode == 2 && shape[2] != shape[3])
+    return fail("precond_apply: antisymmetrised index pairs need equal extents");
+  if (n == 0) return 0;
+  precond_fused_kernel<<<grid_for(n, 256, 2), 256, 0, st>>>(d, n, x, D, out);
   ADCCB_LAUNCH_OK();
   count_launch();
   return 0;

@@ -531,7 +531,8 @@ class PackedAdcEngine:
                 self.diagonal_pphh.set_immutable()
         self._spin = None
         if (self.order_dd == 1 and self.world == 1 and getattr(hf, "restricted", False)
-                and os.environ.get("ADCCB_SPIN_BLOCKS", "1") != "0"):
+                and os.environ.get("ADCCB_SPIN_BLOCKS", "1") != "0"
+                and (nv >= 64 or os.environ.get("ADCCB_SPIN_BLOCKS") == "1")):
             self._spin = self._build_spin_blocks()
         self._count_flops()
 
@@ -610,10 +611,10 @@ class PackedAdcEngine:
     def _spin_ovov(self, X):
         """T[(i,a),(j,b)] = sum_kc X[(i,a),(k,c)] <kb||jc> from the three diagonal blocks of Y."""
         sp = self._spin
-        T = be.zeros((X.shape[0], self.no * self.nv))
+        T = be.empty((X.shape[0], self.no * self.nv))       # the three classes cover every column once
         for ix, Yc in zip(sp["y"], sp["Y"]):
             if Yc is not None:
-                be.block_scatter_add(T, be.gemm(be.block_gather(X, None, ix), Yc), None, ix)
+                be.block_scatter_add(T, be.gemm(be.block_gather(X, None, ix), Yc), None, ix, assign=True)
         return T
 
     def _count_flops(self):

@@ -173,15 +173,18 @@ def davidson_iterations(matrix, state, max_subspace, max_iter, n_ep, n_block, is
                 _project(Ass, SS, Ax, range(n_ss_vec), upper=True)
 
         with state.timer.record("preconditioner"):
-            if preconditioner:
-                if hasattr(preconditioner, "update_shifts"):
-                    rvals_eps = 1e-6
-                    preconditioner.update_shifts(rvals - rvals_eps)
-                preconds = evaluate(preconditioner @ residuals)
-            else:
-                preconds = residuals
-            if explicit_symmetrisation:
-                explicit_symmetrisation.symmetrise(preconds)
+            preconds = None
+            if preconditioner and hasattr(preconditioner, "update_shifts"):
+                rvals_eps = 1e-6
+                preconditioner.update_shifts(rvals - rvals_eps)
+            fused = getattr(explicit_symmetrisation, "precondition_and_symmetrise", None)
+            if preconditioner and fused is not None:
+                # device mapping: preconditioner + explicit symmetrisation in one kernel per block
+                preconds = fused(preconditioner, residuals)
+            if preconds is None:
+                preconds = evaluate(preconditioner @ residuals) if preconditioner else residuals
+                if explicit_symmetrisation:
+                    explicit_symmetrisation.symmetrise(preconds)
 
         with state.timer.record("orthogonalisation"):
             n_ss_added = 0

@@ -25,8 +25,46 @@ def amplitude_vector_enforce_spin_kind(tensor, block, spin_kind):
 
 
 class IndexSymmetrisation:
+    #: spin projection of the fused correction step: 0 none, +1 singlet, -1 triplet
+    _spin_fac = 0.0
+
     def __init__(self, matrix):
         self.symmetrisation_functions = matrix.construct_symmetrisation_for_blocks()
+        # the fused kernel implements AdcMatrix's own recipes (AdcMatrix.py:431-472) only
+        from ..AdcMatrix import AdcMatrix
+        standard = getattr(type(matrix), "construct_symmetrisation_for_blocks", None) \
+            is AdcMatrix.construct_symmetrisation_for_blocks
+        self._sym_mode = None
+        if standard and type(self) in (IndexSymmetrisation, IndexSpinSymmetrisation):
+            self._sym_mode = {"pphh": 2 if matrix.is_core_valence_separated else 1}
+
+    def precondition_and_symmetrise(self, preconditioner, vectors):
+        """[Purify(Sym(SpinProject(v_k / (D - shift_k))))] in ONE kernel launch per block
+        (adccb_precond_apply) instead of the preconditioner launch followed by the projector, the
+        three index (anti)symmetrisations and the purification.  Returns None when the fused
+        kernel does not apply (packed / distributed stores, custom symmetrisation functions,
+        non-Jacobi preconditioners); the caller then takes the separate steps."""
+        from .preconditioner import JacobiPreconditioner
+        if self._sym_mode is None or type(preconditioner) is not JacobiPreconditioner:
+            return None
+        shifts = preconditioner.shifts
+        if not hasattr(shifts, "__len__") or len(shifts) != len(vectors):
+            return None
+        for vec in vectors:
+            for b, t in vec.items():
+                if type(t) is not Tensor or t.ndim not in (2, 4) or b not in preconditioner.diagonal.blocks:
+                    return None
+        out = []
+        for vec, shift in zip(vectors, shifts):
+            blocks = {}
+            for b, t in vec.items():
+                n_alpha = [t.mospaces.n_orbs_alpha(s) for s in t.subspaces]
+                data = be.precond_apply(t._contig(), preconditioner.diagonal[b]._contig(), float(shift), n_alpha,
+                                        sym_mode=self._sym_mode.get(b, 0), spin_fac=self._spin_fac,
+                                        purify=(self._spin_fac > 0 and b == "pphh"))
+                blocks[b] = Tensor._wrap(t.mospaces, t.subspaces, data, t.symmetry)
+            out.append(AmplitudeVector(**blocks))
+        return out
 
     def symmetrise(self, new_vectors):
         if isinstance(new_vectors, AmplitudeVector):
@@ -49,6 +87,7 @@ class IndexSpinSymmetrisation(IndexSymmetrisation):
         if enforce_spin_kind not in ("singlet", "triplet"):
             raise ValueError("enforce_spin_kind needs to be 'singlet' or 'triplet'")
         self.enforce_spin_kind = enforce_spin_kind
+        self._spin_fac = 1.0 if enforce_spin_kind == "singlet" else -1.0
 
     def symmetrise(self, new_vectors):
         if isinstance(new_vectors, AmplitudeVector):

@@ -117,6 +117,18 @@ int adccb_spin_project(void* stream, int ndim, const int* shape, const int* n_al
  * libadcc_src/amplitude_vector_enforce_spin_kind.cc:33-170. */
 int adccb_spin_singlet(void* stream, const int* shape, const int* n_alpha, double* T);
 
+/* Fused Davidson correction step on a dense rank-2 (ph) or rank-4 (pphh) block:
+ *   out = Purify( Sym( SpinProject( x / (D - shift) ) ) )
+ * D may be NULL (no preconditioning); spin_fac +1 singlet / -1 triplet / 0 none (adcc/guess/guess_zero.py:
+ * 121-161 spin-block maps, as adccb_spin_project); sym_mode 0 none, 1 antisymmetrise(0,1), antisymmetrise(2,3),
+ * symmetrise((0,1),(2,3)) (adcc/AdcMatrix.py:449-455), 2 antisymmetrise(2,3) (CVS, AdcMatrix.py:445-447);
+ * purify != 0: singlet purification of the aaaa / bbbb blocks (libadcc_src/
+ * amplitude_vector_enforce_spin_kind.cc:33-170).  Replaces, in one launch, the chain
+ * adcc/solver/preconditioner.py:65-82 -> adcc/solver/explicit_symmetrisation.py:49-98 the reference runs as
+ * separate libtensor evaluations per new subspace vector (davidson.py:255-272). */
+int adccb_precond_apply(void* stream, int ndim, const int* shape, const int* n_alpha, const double* x,
+                        const double* D, double shift, int sym_mode, double spin_fac, int purify, double* out);
+
 /* ---- antisymmetry-packed doubles store: U[IJ,AB], IJ = j(j-1)/2+i (i<j), AB = b(b-1)/2+a (a<b).
  * The doubles part of every ADC vector is antisymmetric in (i,j) and (a,b)
  * (adcc/guess/guess_zero.py:163-171); libtensor stores canonical blocks only, this store keeps
@@ -161,6 +173,9 @@ int adccb_block_gather(void* stream, int64_t n_rows, int64_t n_cols, const int64
                        const double* in, int64_t ld, double* out);
 int adccb_block_scatter_add(void* stream, int64_t n_rows, int64_t n_cols, const int64_t* rows, const int64_t* cols,
                             double alpha, const double* blk, double* out, int64_t ld);
+/* same, assigning instead of accumulating: out[rows[r]*ld + cols[c]] = alpha * blk[r, c] */
+int adccb_block_scatter(void* stream, int64_t n_rows, int64_t n_cols, const int64_t* rows, const int64_t* cols,
+                        double alpha, const double* blk, double* out, int64_t ld);
 /* out[al, b, c, d] = <a c||b d> (a = a_begin + al < a_begin + na) gathered from the pair-packed vvvv
  * block W[AB,CD]: the exchange-ordered operand slab of the o^2 v^4 builds of the ADC(3) singles block
  * (adcc/adc_pp/matrix.py:953 "acbd,cd->ab", :1029-1033 "icjd,acbd->iajb" / "idjc,acbd->iajb"), which on

@@ -102,6 +102,21 @@ def install(monkeypatch):
         return t
 
 
+    def precond_apply(x, D, shift, n_alpha, sym_mode=0, spin_fac=0.0, purify=False):
+        p = x / (D - shift) if D is not None else x.clone()
+        if spin_fac != 0.0:
+            p = spin_project(p, n_alpha, spin_fac)
+        if x.dim() == 4 and sym_mode == 1:
+            p = 0.5 * (p - p.permute(1, 0, 2, 3))
+            p = 0.5 * (p - p.permute(0, 1, 3, 2))
+            p = 0.5 * (p + p.permute(1, 0, 3, 2))
+        elif x.dim() == 4 and sym_mode == 2:
+            p = 0.5 * (p - p.permute(0, 1, 3, 2))
+        p = p.contiguous()
+        if x.dim() == 4 and purify:
+            spin_singlet_(p, n_alpha)
+        return p
+
     # ---- packed doubles primitives (numpy restatements of csrc/packed_ops.cu)
     def _pairs(n):
         return [(p, q) for q in range(n) for p in range(q)]
@@ -190,10 +205,13 @@ def install(monkeypatch):
         res = inp if rows is None else inp[rows]
         return (res if cols is None else res[:, cols]).contiguous()
 
-    def block_scatter_add(out, blk, rows=None, cols=None, alpha=1.0):
+    def block_scatter_add(out, blk, rows=None, cols=None, alpha=1.0, assign=False):
         r = torch.arange(out.shape[0]) if rows is None else rows
         c = torch.arange(out.shape[1]) if cols is None else cols
-        out[r[:, None], c[None, :]] += alpha * blk
+        if assign:
+            out[r[:, None], c[None, :]] = alpha * blk
+        else:
+            out[r[:, None], c[None, :]] += alpha * blk
         return out
 
     def _pair_dense(rows, nv):
@@ -348,7 +366,7 @@ def install(monkeypatch):
                          scaled_copy=scaled_copy, mul=mul, div=div, div_shift=div_shift,
                          add_scalar=add_scalar, direct_sum=direct_sum, lincomb=lincomb,
                          dot_many=dot_many, dot=dot, dot_many_blocks=dot_many_blocks, to_host=to_host, upload=upload, download=download, spin_project=spin_project,
-                         spin_singlet_=spin_singlet_, packed_unpack=packed_unpack, packed_pack=packed_pack,
+                         spin_singlet_=spin_singlet_, precond_apply=precond_apply, packed_unpack=packed_unpack, packed_pack=packed_pack,
                          packed_expand=packed_expand, packed_fold_virt=packed_fold_virt,
                          packed_fold_occ=packed_fold_occ, packed_diagonal=packed_diagonal,
                          pair_select=pair_select, block_gather=block_gather, block_scatter_add=block_scatter_add, vvvv_exchange_slab=vvvv_exchange_slab, ovvv_exchange_slab=ovvv_exchange_slab, pair_matvec=pair_matvec,

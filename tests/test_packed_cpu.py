@@ -82,3 +82,20 @@ def test_synthetic_definition_symmetries():
         if swap:
             assert np.array_equal(v, v.transpose(2, 3, 0, 1))
         assert 0.015 < v[v != 0].std() < 0.025
+
+
+@pytest.mark.parametrize("method", ["adc2x", "adc3"])
+def test_spin_blocked_operands_restricted_reference(method, monkeypatch):
+    """Restricted references keep only the spin-conserving diagonal blocks of W / O / Y (forced on
+    here; by default from 64 virtual spin orbitals up): same sigma, blocks, diagonal and states."""
+    import adcc_b200 as adcc
+    from oracle.hfdata import load_h2o_sto3g
+    from adcc_b200.synthetic import restricted_scf_dict
+    monkeypatch.setenv("ADCCB_SPIN_BLOCKS", "1")
+    for data in (load_h2o_sto3g(), restricted_scf_dict(9, 3, seed=11)):
+        m = adcc.AdcMatrix(method, adcc.ReferenceState(data), doubles_storage="packed")
+        assert m._engine._spin is not None and m._engine.W is None
+        sp = m._engine._spin
+        assert sp["W"][2] is sp["W"][0] and sp["O"][2] is sp["O"][0]        # beta-beta stored once
+        check_packed_matrix(method, data)
+    check_packed_run(method)

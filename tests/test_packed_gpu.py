@@ -159,3 +159,20 @@ def test_pair_matvec_and_exchange_slabs(be, nv, no):
     got = be.vvvv_exchange_slab(be.from_numpy(W), nv, a0, na).cpu().numpy()      # [al,b,c,d] = <ac||bd>
     assert np.array_equal(got, full.transpose(0, 2, 1, 3)[a0:a0 + na])
 
+
+
+@pytest.mark.parametrize("method", ["adc2x", "adc3"])
+def test_spin_blocked_operands_restricted_reference(method, monkeypatch):
+    """Restricted references keep only the spin-conserving diagonal blocks of W / O / Y (forced on
+    here; by default from 64 virtual spin orbitals up): same sigma, blocks, diagonal and states."""
+    import adcc_b200 as adcc
+    from oracle.hfdata import load_h2o_sto3g
+    from adcc_b200.synthetic import restricted_scf_dict
+    monkeypatch.setenv("ADCCB_SPIN_BLOCKS", "1")
+    for data in (load_h2o_sto3g(), restricted_scf_dict(9, 3, seed=11)):
+        m = adcc.AdcMatrix(method, adcc.ReferenceState(data), doubles_storage="packed")
+        assert m._engine._spin is not None and m._engine.W is None
+        sp = m._engine._spin
+        assert sp["W"][2] is sp["W"][0] and sp["O"][2] is sp["O"][0]        # beta-beta stored once
+        check_packed_matrix(method, data)
+    check_packed_run(method)
