@@ -244,3 +244,63 @@ def test_gemm_pipeline_stress_bitwise(be, M, N, K, hint):
         C = be.gemm(A, B, tile_hint=hint)
         bad += (C != C0).any()
     assert int(bad.item()) == 0
+
+
+@pytest.mark.parametrize("shape,sym_mode,fac,purify", [((6, 6, 8, 8), 1, 1.0, True), ((6, 6, 8, 8), 1, -1.0, False),
+                                                       ((6, 6, 8, 8), 1, 0.0, False), ((6, 4, 8, 8), 2, 1.0, True),
+                                                       ((10, 14), 0, 1.0, False), ((10, 14), 0, 0.0, False)])
+def test_fused_precondition_symmetrise_spin(be, shape, sym_mode, fac, purify):
+    """adccb_precond_apply against the chain of separate steps in NumPy."""
+    rng = np.random.default_rng(len(shape) + sym_mode)
+    x = rng.standard_normal(shape)
+    D = rng.uniform(1.0, 3.0, shape)
+    shift = 0.37
+    na = [s // 2 for s in shape]
+    got = be.precond_apply(be.from_numpy(x), be.from_numpy(D), shift, na, sym_mode=sym_mode, spin_fac=fac,
+                           purify=purify).cpu().numpy()
+    p = x / (D - shift)
+    if fac != 0.0:
+        f = p
+        for ax, n in enumerate(na):
+            f = np.concatenate((np.take(f, range(n, 2 * n), axis=ax), np.take(f, range(n), axis=ax)), axis=ax)
+        spin = [np.array([0] * n + [1] * n) for n in na]
+        if len(shape) == 2:
+            keep = spin[0][:, None] == spin[1][None, :]
+        else:
+            keep = (spin[0][:, None, None, None] + spin[1][None, :, None, None]
+                    == spin[2][None, None, :, None] + spin[3][None, None, None, :])
+        p = 0.5 * (p + fac * f) * keep
+    if sym_mode == 1:
+        p = 0.5 * (p - p.transpose(1, 0, 2, 3))
+        p = 0.5 * (p - p.transpose(0, 1, 3, 2))
+        p = 0.5 * (p + p.transpose(1, 0, 3, 2))
+    elif sym_mode == 2:
+        p = 0.5 * (p - p.transpose(0, 1, 3, 2))
+    if purify:
+        ni, nj, a_, b_ = na
+        new = p[:ni, nj:, :a_, b_:] + p[:ni, nj:, a_:, :b_]
+        p = p.copy()
+        p[:ni, :nj, :a_, :b_] = new
+        p[ni:, nj:, a_:, b_:] = new
+    assert np.max(np.abs(got - p)) < 1e-14 * max(1.0, np.max(np.abs(p)))
+
+
+def test_block_gather_scatter(be):
+    import torch
+    rng = np.random.default_rng(3)
+    M = rng.standard_normal((37, 300))
+    rows = np.array([3, 0, 36, 17, 5])
+    cols = np.sort(rng.choice(300, 70, replace=False))
+    d = be.from_numpy(M)
+    r, c = (torch.as_tensor(v, dtype=torch.int64, device=d.device) for v in (rows, cols))
+    assert np.array_equal(be.block_gather(d, r, c).cpu().numpy(), M[np.ix_(rows, cols)])
+    assert np.array_equal(be.block_gather(d, None, c).cpu().numpy(), M[:, cols])
+    assert np.array_equal(be.block_gather(d[:, 10:], r, None).cpu().numpy(), M[rows][:, 10:])
+    blk = rng.standard_normal((5, 70))
+    ref = M.copy()
+    ref[np.ix_(rows, cols)] += -0.5 * blk
+    be.block_scatter_add(d, be.from_numpy(blk), r, c, alpha=-0.5)
+    assert np.allclose(d.cpu().numpy(), ref, atol=1e-15)
+    ref[np.ix_(rows, cols)] = 2.0 * blk
+    be.block_scatter_add(d, be.from_numpy(blk), r, c, alpha=2.0, assign=True)
+    assert np.array_equal(d.cpu().numpy(), ref)
