@@ -13,7 +13,13 @@
 #include <stdint.h>
 #include <stddef.h>
 
+#include <omp.h>
+
 typedef long long i64;
+
+/* torchrun exports OMP_NUM_THREADS=1; the CPU arm is to use every host core */
+void orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int orc_get_threads(void) { return omp_get_max_threads(); }
 
 static inline i64 pidx(i64 p, i64 q) { return q * (q - 1) / 2 + p; } /* p < q */
 

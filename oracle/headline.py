@@ -58,8 +58,9 @@ def lib():
             getattr(L, name).argtypes = [it, it, dp, dp]
         for name in ("orc_fold_iajb", "orc_fold_ij", "orc_fold_ab"):
             getattr(L, name).argtypes = [it, it, dp, dbl, dp]
-        for f in dir(L):
-            pass
+        L.orc_set_threads.argtypes = [it]
+        L.orc_get_threads.restype = it
+        L.orc_set_threads(os.cpu_count() or 1)
         _lib = L
     return _lib
 
