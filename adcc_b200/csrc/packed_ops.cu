@@ -26,6 +26,15 @@ __device__ __forceinline__ void pair_decode(long long P, int& p, int& q) {
   p = (int)(P - qq * (qq - 1) / 2);
 }
 
+// cheap exact decode for pair indices below 2^23 (single-precision sqrt + one correction step each way)
+__device__ __forceinline__ void pair_decode32(int P, int& p, int& q) {
+  int qq = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)P)) * 0.5f);
+  while (qq * (qq - 1) / 2 > P) --qq;
+  while ((qq + 1) * qq / 2 <= P) ++qq;
+  q = qq;
+  p = P - qq * (qq - 1) / 2;
+}
+
 // ---------------------------------------------------------------------------------------
 // dense <-> packed
 // ---------------------------------------------------------------------------------------
@@ -78,8 +87,12 @@ __global__ void expand_antisym_kernel(int mode, int no, long long npo, int nv, i
                                       const double* __restrict__ U, double* __restrict__ out) {
   __shared__ double tile[32][33];
   const long long npv = (long long)nv * (nv - 1) / 2;
-  const int a0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  if (a0 > c0) return;                          // tiles below the diagonal are produced as mirrors
+  // blockIdx.x enumerates the tiles on and above the diagonal (ta <= tc); the tiles below it are
+  // produced as mirrors, so no block is launched for them
+  int tc = (int)((sqrtf(8.0f * (float)blockIdx.x + 1.0f) - 1.0f) * 0.5f);
+  while (tc * (tc + 1) / 2 > (int)blockIdx.x) --tc;
+  while ((tc + 1) * (tc + 2) / 2 <= (int)blockIdx.x) ++tc;
+  const int a0 = ((int)blockIdx.x - tc * (tc + 1) / 2) * 32, c0 = tc * 32;
   const long long r = blockIdx.z;
   const double* row;
   double sgn;
@@ -151,8 +164,11 @@ __global__ void pack_antisym_virt_kernel(int nv, long long sa, const double* __r
   __shared__ double tile[32][33];
   const long long npv = (long long)nv * (nv - 1) / 2;
   const long long r = blockIdx.z;
-  const int a0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
-  if (a0 > b0 + 31) return;   // tile entirely below the diagonal (a > b everywhere)
+  // blockIdx.x enumerates the tiles with ta <= tb only (the others hold a > b everywhere)
+  int tb = (int)((sqrtf(8.0f * (float)blockIdx.x + 1.0f) - 1.0f) * 0.5f);
+  while (tb * (tb + 1) / 2 > (int)blockIdx.x) --tb;
+  while ((tb + 1) * (tb + 2) / 2 <= (int)blockIdx.x) ++tb;
+  const int a0 = ((int)blockIdx.x - tb * (tb + 1) / 2) * 32, b0 = tb * 32;
   const double* F1 = P1 + off1[r];
   const double* F2 = P2 ? P2 + off2[r] : nullptr;
   // tile[bb][aa] = F[a0+aa, b0+bb] read coalesced along b
@@ -204,20 +220,27 @@ __global__ void pack_antisym_occ_slab_kernel(int no, int j_begin, int nj, long l
 
 // D[IJ,AB] = 1/2 (dov[i,a] + dov[j,b] + dov[i,b] + dov[j,a]) + doo[i,j] + dvv[a,b]
 // (packed form of adcc/adc_pp/matrix.py:109-124 (doo = dvv = 0, dov = e_a - e_i) and :212-231)
+// grid (column chunks, rows): the occupied pair is decoded once per block, the virtual pair with a
+// single-precision sqrt; no 64-bit division per element (the first version spent its time there:
+// 0.15 of the copy peak)
 __global__ void packed_diagonal_kernel(int no, int nv, const double* __restrict__ dov,
                                        const double* __restrict__ doo, const double* __restrict__ dvv,
                                        double* __restrict__ D) {
-  const long long npv = (long long)nv * (nv - 1) / 2, npo = (long long)no * (no - 1) / 2;
-  const long long n = npo * npv;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
-       idx += (long long)gridDim.x * blockDim.x) {
-    int i, j, a, b;
-    pair_decode(idx / npv, i, j);
-    pair_decode(idx % npv, a, b);
-    double v = 0.5 * (dov[i * nv + a] + dov[j * nv + b] + dov[i * nv + b] + dov[j * nv + a]);
-    if (doo) v += doo[i * no + j];
-    if (dvv) v += dvv[(long long)a * nv + b];
-    D[idx] = v;
+  const int npv = nv * (nv - 1) / 2, npo = no * (no - 1) / 2;
+  for (int row = blockIdx.y; row < npo; row += gridDim.y) {
+    int i, j;
+    pair_decode32(row, i, j);
+    const double* di = dov + (long long)i * nv;
+    const double* dj = dov + (long long)j * nv;
+    const double oo = doo ? doo[i * no + j] : 0.0;
+    double* Drow = D + (long long)row * npv;
+    for (int P = blockIdx.x * blockDim.x + threadIdx.x; P < npv; P += gridDim.x * blockDim.x) {
+      int a, b;
+      pair_decode32(P, a, b);
+      double v = 0.5 * (di[a] + dj[b] + di[b] + dj[a]) + oo;
+      if (dvv) v += dvv[(long long)a * nv + b];
+      Drow[P] = v;
+    }
   }
 }
 
@@ -271,6 +294,24 @@ enum EriLayout {
   LAY_VVVV_EXCH = 8,     // [al,b,c,d] = <a c||b d>, a = row_begin + al   (exchange-ordered slab)
   LAY_OVVV_EXCH = 9      // [al,c,j,d] = <j c||a d>, a = row_begin + al
 };
+
+// W[AB,CD] rows of the pair-packed vvvv block: grid (column chunks, rows), row pair decoded once per
+// block, column pair with a single-precision sqrt (the generic kernel below pays two 64-bit divisions
+// and two double-precision sqrt decodes per element: 0.12 of the write peak)
+__global__ void synth_vvvv_rows_kernel(int nv, unsigned long long seed, double scale, long long row_begin,
+                                       long long n_rows, double* __restrict__ out) {
+  const int npv = nv * (nv - 1) / 2;
+  for (long long r = blockIdx.y; r < n_rows; r += gridDim.y) {
+    int a, b;
+    pair_decode32((int)(row_begin + r), a, b);
+    double* row = out + r * npv;
+    for (int P = blockIdx.x * blockDim.x + threadIdx.x; P < npv; P += gridDim.x * blockDim.x) {
+      int c, d;
+      pair_decode32(P, c, d);
+      row[P] = synthetic_eri(seed, BLK_VVVV, a, b, c, d, scale);
+    }
+  }
+}
 
 __global__ void synth_fill_kernel(int layout, int blk, int no, int nv, unsigned long long seed,
                                   double scale, long long n, long long row_begin, int j_begin,
@@ -646,15 +687,15 @@ int packed_expand_slab(cudaStream_t st, int which, int no, int nv, int first, in
   const int t = (nv + 31) / 32;
   if (which == 0) {
     if ((long long)count * no > 65535) return fail("packed_expand: too many (i,k) rows");
-    expand_antisym_kernel<<<dim3(t, t, count * no), dim3(32, 8), 0, st>>>(0, no, 0, nv, first, U, out);
+    expand_antisym_kernel<<<dim3(t * (t + 1) / 2, 1, count * no), dim3(32, 8), 0, st>>>(0, no, 0, nv, first, U, out);
   } else if (which == 1) {
     expand_occ_kernel<<<no * count, 512, 0, st>>>(no, first, count, npv, U, out);
   } else if (which == 2) {
     // grid.z is limited to 65535: walk the pair rows in chunks (row r of a chunk writes out + r*nv)
     for (long long r0 = 0; r0 < count; r0 += 65535) {
       const long long nr = std::min<long long>(65535, count - r0);
-      expand_antisym_kernel<<<dim3(t, t, (unsigned)nr), dim3(32, 8), 0, st>>>(2, no, count, nv, 0, U + r0 * npv,
-                                                                         out + r0 * nv);
+      expand_antisym_kernel<<<dim3(t * (t + 1) / 2, 1, (unsigned)nr), dim3(32, 8), 0, st>>>(2, no, count, nv, 0,
+                                                                                       U + r0 * npv, out + r0 * nv);
       ADCCB_LAUNCH_OK();
     }
     count_launch();
@@ -685,7 +726,7 @@ int packed_fold_virt(cudaStream_t st, long long nrows, int nv, long long sa, con
   const long long npv = (long long)nv * (nv - 1) / 2;
   for (long long r0 = 0; r0 < nrows; r0 += 65535) {
     const long long nr = std::min<long long>(65535, nrows - r0);
-    dim3 grid(t, t, (unsigned)nr);
+    dim3 grid(t * (t + 1) / 2, 1, (unsigned)nr);
     pack_antisym_virt_kernel<<<grid, dim3(32, 8), 0, st>>>(nv, sa, P1, off1 + r0, P2, off2 ? off2 + r0 : nullptr,
                                                            rows ? rows + r0 : nullptr, alpha,
                                                            rows ? S : S + r0 * npv);
@@ -718,7 +759,11 @@ int packed_diagonal(cudaStream_t st, int no, int nv, const double* dov, const do
                     const double* dvv, double* D) {
   const long long n = (long long)no * (no - 1) / 2 * ((long long)nv * (nv - 1) / 2);
   if (n == 0) return 0;
-  packed_diagonal_kernel<<<blocks_for(n, 256), 256, 0, st>>>(no, nv, dov, doo, dvv, D);
+  if (nv >= 4096 || no >= 4096) return fail("packed_diagonal: extents must be < 4096");
+  const long long npv_ = (long long)nv * (nv - 1) / 2, npo_ = (long long)no * (no - 1) / 2;
+  const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((npv_ + 255) / 256, 64));
+  const unsigned gy = (unsigned)std::min<long long>(npo_, 65535);
+  packed_diagonal_kernel<<<dim3(gx, gy), 256, 0, st>>>(no, nv, dov, doo, dvv, D);
   ADCCB_LAUNCH_OK();
   count_launch();
   return 0;
@@ -729,6 +774,16 @@ int synth_fill(cudaStream_t st, int layout, int blk, int no, int nv, unsigned lo
   if (n <= 0) return 0;
   if (no >= 1024 || nv >= 1024) return fail("synth_fill: extents must be < 1024");
   if (nj <= 0) nj = no;
+  const long long npv_ = (long long)nv * (nv - 1) / 2;
+  if (layout == LAY_VVVV_PACKED && npv_ > 0 && n % npv_ == 0) {
+    const long long n_rows = n / npv_;
+    const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((npv_ + 255) / 256, 64));
+    synth_vvvv_rows_kernel<<<dim3(gx, (unsigned)std::min<long long>(n_rows, 65535)), 256, 0, st>>>(
+        nv, seed, scale, row_begin, n_rows, out);
+    ADCCB_LAUNCH_OK();
+    count_launch();
+    return 0;
+  }
   synth_fill_kernel<<<blocks_for(n, 256), 256, 0, st>>>(layout, blk, no, nv, seed, scale, n, row_begin,
                                                         j_begin, nj, out);
   ADCCB_LAUNCH_OK();

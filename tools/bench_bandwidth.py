@@ -73,6 +73,46 @@ report("packed_unpack (to_ndarray path)", 8 * (n + no * no * nv * nv), lambda: b
 report("packed_pack (dense -> packed)", 8 * (n + no * no * nv * nv), lambda: be.packed_pack(dense, no, nv))
 W = torch.empty(2048, npv, device="cuda", dtype=torch.float64)
 report("synth_fill vvvv rows (hash generator)", 8 * W.numel(), lambda: be.synth_fill(W, "vvvv_packed", no, nv, 1, 0.02))
+# ---- round 2: ADC(3) build / matvec helpers, spin blocks, distributed-vector layout, fused correction step
+del vecs[4:], X, Ue, Uh, dense, W
+torch.cuda.empty_cache()
+V2 = torch.randn(nv, no * npv, device="cuda", dtype=torch.float64)            # [a,(j,BC)], 10.2 GB
+r1 = torch.randn(nv, nv, device="cuda", dtype=torch.float64)
+u1 = torch.randn(no, nv, device="cuda", dtype=torch.float64)
+s1 = torch.zeros(no, nv, device="cuda", dtype=torch.float64)
+report("pair_matvec <ic||ab> r1[cb] (sum over c, out i)", 8 * V2.numel(),
+       lambda: be.pair_matvec(V2, nv, n_out=no, n_red=nv, row_stride_out=1, row_stride_red=no, X=r1, x_by_out=False,
+                              out=s1, beta=1.0))
+report("pair_matvec r4[bc] = <kb||cd> u[kd] (sum over k)", 8 * V2.numel(),
+       lambda: be.pair_matvec(V2, nv, n_out=nv, n_red=no, row_stride_out=no, row_stride_red=1, X=u1, x_by_out=False))
+report("ovvv_exchange_slab (40 a: [a,c,j,d] from V2)", 8 * 40 * nv * no * nv,
+       lambda: be.ovvv_exchange_slab(V2, no, nv, 100, 40))
+del V2
+torch.cuda.empty_cache()
+Wn = 8000                                                                     # rows pair(a,c) up to a,c < 127
+nvs = 120
+npvs = nvs * (nvs - 1) // 2
+Ws = torch.randn(npvs, npvs, device="cuda", dtype=torch.float64)
+report(f"vvvv_exchange_slab (nv={nvs}, 60 a: [a,b,c,d] from packed W)", 8 * 60 * nvs ** 3,
+       lambda: be.vvvv_exchange_slab(Ws, nvs, 30, 60))
+del Ws
+big = torch.empty(16, nv, nv, nv, device="cuda", dtype=torch.float64)
+report("synth_fill exchange-ordered vvvv slab (16 a, hash)", 8 * big.numel(),
+       lambda: be.synth_fill(big, "vvvv_exchange", no, nv, 1, 0.02, row_begin=100))
+del big
+cuts = [min(npv, ((k * npv // 8 + 127) // 128) * 128) for k in range(8)] + [npv]
+wmax = max(cuts[k + 1] - cuts[k] for k in range(8))
+slabs = torch.empty(8, npo, wmax, device="cuda", dtype=torch.float64)
+report("slab_layout full -> 8 padded column slabs", 8 * 2 * n, lambda: be.slab_layout(0, vecs[0], slabs, cuts, wmax))
+report("slab_layout 8 slabs -> full", 8 * 2 * n, lambda: be.slab_layout(1, vecs[1], slabs, cuts, wmax))
+cols = torch.arange(0, npv, 3, device="cuda", dtype=torch.int64)
+blk = torch.empty(npo, cols.numel(), device="cuda", dtype=torch.float64)
+report("block_gather U[:, every 3rd column]", 8 * 2 * blk.numel(), lambda: be.block_gather(vecs[0], None, cols))
+report("block_scatter_add S[:, cols] += blk", 8 * 3 * blk.numel(), lambda: be.block_scatter_add(vecs[1], blk, None, cols))
+xd = torch.randn(24, 24, 140, 140, device="cuda", dtype=torch.float64)
+dd = torch.rand(24, 24, 140, 140, device="cuda", dtype=torch.float64) + 1.0
+report("precond_apply fused (dense 24x24x140x140, singlet)", 8 * 3 * xd.numel(),
+       lambda: be.precond_apply(xd, dd, 0.3, [12, 12, 70, 70], sym_mode=1, spin_fac=1.0, purify=True))
 os.makedirs("gpurun_out", exist_ok=True)
 with open("gpurun_out/bandwidth_kernels.txt", "w") as f:
     f.write(f"# achieved HBM bandwidth, L2 flushed between repetitions, peak = {PEAK} GB/s (MEASURED_PEAKS.json copy)\n")
