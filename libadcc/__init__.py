@@ -10,9 +10,10 @@ CUDA kernels:
     PYTHONPATH=<this repo>:<adcc source tree> python -c "import adcc; adcc.adc2(data, n_singlets=3)"
 
 Scope: everything the ADC matvec + Jacobi-Davidson path touches (libadcc.pyi:34-66, 67-178,
-180-279, 281-388, 390-539, 541-631, 633-793, 795-936).  Property infrastructure that needs tensors
-with an AO-basis axis (``orbital_coefficients`` as Tensor, ``make_symmetry_operator_basis``) is
-outside the path and raises NotImplementedError.
+180-279, 281-388, 390-539, 541-631, 633-793, 795-936), plus the tensors with an AO-basis axis
+(``orbital_coefficients*``, ``make_symmetry_operator_basis``) the reference's operator-integral
+import needs, so that its transition dipole moments / oscillator strengths run too.  Triples
+symmetries raise NotImplementedError.
 
 adcc additionally needs ``opt_einsum`` (pairwise contraction paths); where that third-party
 package is not installed, tools/refshim/ holds a minimal stand-in.
@@ -115,6 +116,22 @@ class MoIndexTranslation(_ProductMoIndexTranslation):
     """libadcc.pyi:180-279."""
 
 
+class _AxisSymmetry(Symmetry):
+    """Symmetry of tensors that carry the AO-basis axis "b" (libadcc_src/make_symmetry.cc:275-342,
+    428-463): the axis is not an MO subspace, so the extents are given explicitly; no permutational
+    symmetry is recorded (the dense store does not need it)."""
+
+    def __init__(self, mospaces, subspaces, shape):
+        self.mospaces = mospaces
+        self.subspaces = list(subspaces)
+        self.space = "".join(self.subspaces)
+        self.ndim = len(self.subspaces)
+        self.shape = tuple(int(x) for x in shape)
+        self.irreps_allowed = ["A"]
+        self._perms, self._perm_strings = [], []
+        self.spin_block_maps, self.spin_blocks_forbidden = [], []
+
+
 # ------------------------------------------------------------------------------ reference state
 class ReferenceState:
     """libadcc.pyi:390-539 / libadcc_src/ReferenceState.hh: lazy, cached Fock / ERI import."""
@@ -130,13 +147,30 @@ class ReferenceState:
     def import_all(self): return self._impl.import_all()
     def flush_hf_cache(self): return self._impl.flush_hf_cache()
 
-    def _coeff(self, *a):
-        raise NotImplementedError("orbital coefficients as tensors with an AO-basis axis are outside the "
-                                  "ADC matvec / Davidson path this backend replaces")
+    def _coeff(self, space, keep):
+        """MO coefficients of a subspace as a tensor with an AO-basis axis "b"
+        (libadcc_src/ReferenceState.cc:101-334): keep "ab" -> [n_space, 2 n_bas], block diagonal
+        (alpha rows [C, 0], beta rows [0, C]); "a" / "b" -> [n_space, n_bas] with the rows of the
+        other spin zeroed."""
+        impl = self._impl
+        if not (isinstance(space, str) and space.endswith("b") and len(space) == 3):
+            raise ValueError(f"Invalid space string {space}: an object orbital_coefficients({space}) is not known.")
+        sub = space[:2]
+        c = _np.asarray(impl._coefficients(space, keep))              # rows of the other spin already zero
+        n_bas = c.shape[1]
+        if keep == "ab":
+            is_alpha = _np.asarray(impl._host_index(sub)) < impl.hf_provider.n_orbs_alpha
+            full = _np.zeros((c.shape[0], 2 * n_bas))
+            full[is_alpha, :n_bas] = c[is_alpha]
+            full[~is_alpha, n_bas:] = c[~is_alpha]
+            c = full
+        t = Tensor.from_ndarray(impl.mospaces, [sub, "b"], c, _AxisSymmetry(impl.mospaces, [sub, "b"], c.shape))
+        t.set_immutable()
+        return t
 
-    def orbital_coefficients(self, space): return self._coeff(space)
-    def orbital_coefficients_alpha(self, space): return self._coeff(space)
-    def orbital_coefficients_beta(self, space): return self._coeff(space)
+    def orbital_coefficients(self, space): return self._coeff(space, "ab")
+    def orbital_coefficients_alpha(self, space): return self._coeff(space, "a")
+    def orbital_coefficients_beta(self, space): return self._coeff(space, "b")
 
     def gauge_origin_to_xyz(self, gauge_origin):
         return self._impl.hf_provider.transform_gauge_origin_to_xyz(gauge_origin)
@@ -264,8 +298,21 @@ def _not_on_path(name):
     return fail
 
 
-make_symmetry_operator_basis = _not_on_path("make_symmetry_operator_basis")
-make_symmetry_orbital_coefficients = _not_on_path("make_symmetry_orbital_coefficients")
+def make_symmetry_operator_basis(mospaces, n_bas, symmetry="nosymmetry", n_particle_op=1, blocks="ab"):
+    """Operator in the AO basis, block diagonal over (alpha | beta) copies of the n_bas functions
+    (libadcc_src/make_symmetry.cc:428-463)."""
+    n = 2 * n_bas if blocks == "ab" else n_bas
+    rank = 2 * int(n_particle_op)
+    return _AxisSymmetry(mospaces, ["b"] * rank, (n,) * rank)
+
+
+def make_symmetry_orbital_coefficients(mospaces, space, n_bas, blocks="ab"):
+    if not space.endswith("b") or len(space) != 3:
+        raise ValueError(f"Expect exactly a two-dimensional space string like 'o1b', not {space}.")
+    n = 2 * n_bas if blocks == "ab" else n_bas
+    return _AxisSymmetry(mospaces, [space[:2], "b"], (mospaces.n_orbs(space[:2]), n))
+
+
 make_symmetry_triples = _not_on_path("make_symmetry_triples")
 
 

@@ -81,6 +81,11 @@ def main():
             assert state.converged
             out[f"{key}/{kind}/energies"] = np.array(state.excitation_energy)
             out[f"{key}/{kind}/n_iter"] = np.array(state.n_iter)
+            if kind == "singlet" and method not in ("adc0", "cvs-adc0"):
+                # the reference's own property code: adc_pp/transition_dm.py, OperatorIntegrals.py,
+                # ElectronicTransition._oscillator_strength (2/3 |mu|^2 omega)
+                out[f"{key}/singlet/oscillator_strength"] = np.array(state.oscillator_strength)
+                out[f"{key}/singlet/transition_dipole_moment"] = np.array(state.transition_dipole_moment)
         print(method, out[f"{key}/singlet/energies"], out[f"{key}/singlet/n_iter"], flush=True)
     np.savez_compressed(os.path.join(HERE, "reference_adcc_h2o_sto3g.npz"), **out)
 
