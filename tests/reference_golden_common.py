@@ -11,6 +11,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref
 METHODS = ["adc0", "adc1", "adc2", "adc2x", "adc3", "cvs-adc0", "cvs-adc1", "cvs-adc2", "cvs-adc2x", "cvs-adc3"]
 SIGMA_RTOL = 1e-11        # north star; the reference's own test uses rtol 1e-10 (AdcMatrix_test.py:221)
 ENERGY_ATOL = 1e-8
+OSC_RTOL, OSC_ATOL = 1e-6, 1e-10    # "matching oscillator strengths": 1e-6 relative
 
 
 def golden():
@@ -54,6 +55,13 @@ def check_oracle(method):
         st = oracle.run_adc(data, method, conv_tol=1e-9, core_orbitals=core,
                             **{"n_singlets" if kind == "singlet" else "n_triplets": len(want)})
         np.testing.assert_allclose(st.eigenvalues, want, atol=ENERGY_ATOL, rtol=0)
+        if kind == "singlet" and f"{key}/singlet/oscillator_strength" in g.files:
+            # the reference's own property code (adc_pp/transition_dm.py, OperatorIntegrals.py) produced these
+            from oracle.properties import oscillator_strengths
+            f, mu = oscillator_strengths(om, st)
+            np.testing.assert_allclose(f, g[f"{key}/singlet/oscillator_strength"], rtol=OSC_RTOL, atol=OSC_ATOL)
+            np.testing.assert_allclose(np.abs(mu), np.abs(g[f"{key}/singlet/transition_dipole_moment"]),
+                                       rtol=0, atol=1e-6)
 
 
 def check_product(method, doubles_storage="dense"):
@@ -107,3 +115,8 @@ def check_product(method, doubles_storage="dense"):
         assert st.converged
         np.testing.assert_allclose(st.excitation_energy, want, atol=ENERGY_ATOL, rtol=0)
         assert st.n_iter == int(g[f"{key}/{kind}/n_iter"]), (method, kind, st.n_iter)
+        if kind == "singlet" and f"{key}/singlet/oscillator_strength" in g.files:
+            np.testing.assert_allclose(st.oscillator_strength, g[f"{key}/singlet/oscillator_strength"],
+                                       rtol=OSC_RTOL, atol=OSC_ATOL)
+            np.testing.assert_allclose(np.abs(st.transition_dipole_moment),
+                                       np.abs(g[f"{key}/singlet/transition_dipole_moment"]), rtol=0, atol=1e-6)

@@ -70,6 +70,8 @@ def test_unmodified_reference_adcc_runs_on_this_backend():
         "data = import_data()\n"
         "s = adcc.adc2(data, n_singlets=3, conv_tol=1e-8, output=None)\n"
         "assert np.max(np.abs(s.excitation_energy - [0.47051314, 0.57255495, 0.59367339])) < 1e-6\n"   # smoke_test.py:32-58
+        "f = s.oscillator_strength\n"                     # the reference's property code on AO-basis tensors
+        "assert f.shape == (3,) and abs(f[2] - 0.0598777655) < 1e-7 and f[1] < 1e-6\n"
         "t = adcc.adc3(s.matrix.ground_state, n_triplets=3, conv_tol=1e-8, output=None)\n"
         "assert np.max(np.abs(t.excitation_energy - [0.39246043, 0.48770981, 0.51755248])) < 1e-6\n"
         "c = adcc.cvs_adc2x(data, n_singlets=2, core_orbitals=1, conv_tol=1e-8, output=None)\n"
