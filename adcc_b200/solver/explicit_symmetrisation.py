@@ -106,6 +106,9 @@ class IndexSpinSymmetrisation(IndexSymmetrisation):
                     if self.enforce_spin_kind == "singlet":
                         be.spin_singlet_(dense, n_alpha)
                     new = PackedDoubles.from_dense(Tensor._wrap(t.mospaces, t.subspaces, dense))
+                    if getattr(t, "slab", None) is not None:      # distributed vector: keep this rank's slab
+                        from ..packed import SlabDoubles
+                        new = SlabDoubles.from_full(new, t.slab)
                     new.symmetry = t.symmetry
                     vec[b] = new
                     packed_done.append(id(vec))

@@ -134,6 +134,16 @@ def _worker_methods(rank, world, port, no, nv, out):
             ost = oracle.run_adc(om, method, n_states=2, conv_tol=1e-7)
             res.append(float(np.max(np.abs(st.excitation_energy - ost.eigenvalues))))
             res.append(float(st.converged))
+    # restricted molecule (H2O / STO-3G), sharded, singlets and triplets on distributed vectors:
+    # spin projection + purification act on the gathered vector, each rank keeps its slab
+    from oracle.hfdata import load_h2o_sto3g
+    data = load_h2o_sto3g()
+    mh = adcc.AdcMatrix("adc2x", adcc.ReferenceState(data), doubles_storage="packed", shard=(rank, world))
+    for kw in (dict(n_singlets=3), dict(n_triplets=3)):
+        st = adcc.run_adc(mh, conv_tol=1e-8, output=None, **kw)
+        ost = oracle.run_adc(data, "adc2x", conv_tol=1e-8, **kw)
+        res.append(float(np.max(np.abs(st.excitation_energy - ost.eigenvalues))))
+        res.append(float(st.converged and st.n_iter == ost.n_iter))
     if rank == 0:
         np.save(out, np.array(res))
     dist.barrier()
@@ -145,6 +155,7 @@ def test_sharded_adc2_adc3_gloo(tmp_path, world, no, nv):
     out = str(tmp_path / "res.npy")
     port = 31500 + (os.getpid() + world) % 2000
     mp.spawn(_worker_methods, args=(world, port, no, nv, out), nprocs=world, join=True)
-    e2, d2, e3, d3, de, conv = np.load(out)
+    e2, d2, e3, d3, de, conv, des, oks, det, okt = np.load(out)
     assert max(e2, e3) < 1e-11 and max(d2, d3) < 1e-11
     assert conv == 1.0 and de < 1e-8
+    assert des < 1e-8 and det < 1e-8 and oks == 1.0 and okt == 1.0
