@@ -39,11 +39,14 @@ class IndexSymmetrisation:
             self._sym_mode = {"pphh": 2 if matrix.is_core_valence_separated else 1}
 
     def precondition_and_symmetrise(self, preconditioner, vectors):
-        """[Purify(Sym(SpinProject(v_k / (D - shift_k))))] in ONE kernel launch per block
-        (adccb_precond_apply) instead of the preconditioner launch followed by the projector, the
-        three index (anti)symmetrisations and the purification.  Returns None when the fused
-        kernel does not apply (packed / distributed stores, custom symmetrisation functions,
-        non-Jacobi preconditioners); the caller then takes the separate steps."""
+        """[Purify(Sym(SpinProject(v_k / (D - shift_k))))]: the division as one coalesced launch, then
+        ONE gather kernel (adccb_precond_apply without a diagonal) for the projector, the three index
+        (anti)symmetrisations and the purification together - two launches per block instead of
+        six.  (Measured: dividing inside the gather kernel, 16 FP64 divisions per doubles element,
+        made the single-launch form slower than the chain it replaced.)  Blocks that need neither
+        projection nor symmetrisation take the division only.  Returns None when the fused kernel
+        does not apply (packed / distributed stores, custom symmetrisation functions, non-Jacobi
+        preconditioners); the caller then takes the separate steps."""
         from .preconditioner import JacobiPreconditioner
         if self._sym_mode is None or type(preconditioner) is not JacobiPreconditioner:
             return None
@@ -59,9 +62,11 @@ class IndexSymmetrisation:
             blocks = {}
             for b, t in vec.items():
                 n_alpha = [t.mospaces.n_orbs_alpha(s) for s in t.subspaces]
-                data = be.precond_apply(t._contig(), preconditioner.diagonal[b]._contig(), float(shift), n_alpha,
-                                        sym_mode=self._sym_mode.get(b, 0), spin_fac=self._spin_fac,
-                                        purify=(self._spin_fac > 0 and b == "pphh"))
+                data = be.div_shift(t._contig(), preconditioner.diagonal[b]._contig(), float(shift))
+                sym_mode = self._sym_mode.get(b, 0)
+                if sym_mode != 0 or self._spin_fac != 0.0:
+                    data = be.precond_apply(data, None, 0.0, n_alpha, sym_mode=sym_mode, spin_fac=self._spin_fac,
+                                            purify=(self._spin_fac > 0 and b == "pphh"))
                 blocks[b] = Tensor._wrap(t.mospaces, t.subspaces, data, t.symmetry)
             out.append(AmplitudeVector(**blocks))
         return out

@@ -113,6 +113,9 @@ xd = torch.randn(24, 24, 140, 140, device="cuda", dtype=torch.float64)
 dd = torch.rand(24, 24, 140, 140, device="cuda", dtype=torch.float64) + 1.0
 report("precond_apply fused (dense 24x24x140x140, singlet)", 8 * 3 * xd.numel(),
        lambda: be.precond_apply(xd, dd, 0.3, [12, 12, 70, 70], sym_mode=1, spin_fac=1.0, purify=True))
+report("correction step as shipped: div_shift, then gather kernel", 8 * 5 * xd.numel(),
+       lambda: be.precond_apply(be.div_shift(xd, dd, 0.3), None, 0.0, [12, 12, 70, 70], sym_mode=1, spin_fac=1.0,
+                                purify=True))
 os.makedirs("gpurun_out", exist_ok=True)
 with open("gpurun_out/bandwidth_kernels.txt", "w") as f:
     f.write(f"# achieved HBM bandwidth, L2 flushed between repetitions, peak = {PEAK} GB/s (MEASURED_PEAKS.json copy)\n")
