@@ -12,6 +12,12 @@
 //     sm_100a has natively; every larger mma.sync f64 shape lowers to it);
 //   * accumulators stay in registers; the epilogue applies alpha/beta or writes split-K
 //     partials that a second kernel reduces in a fixed order (deterministic).
+// N-major B (template flag BNM): the same kernel with B given as B[k][n] (n contiguous), i.e.
+//   C = A . B without a transposed copy of B.  The B slab of a stage is then BN/16 TMA boxes of
+//   16 k-rows x 16 n-columns; the k <-> (h, t, slot) relabelling of the A fragments puts the four
+//   k-rows of one DMMA on rows 2t (+1) of an 8-row swizzle period, so the 64-bit fragment loads
+//   of a half warp fall into 8 distinct 16-byte chunks (conflict-free).  Used for the ovvv
+//   couplings: u1 . V2 and Ue . V2^T both read the ONE stored layout V2[a,(j,BC)].
 // Fallback path (dgemm_generic_kernel): arbitrary element strides, used when the TMA
 // alignment rules do not hold (odd leading dimension) - same DMMA core, plain loads.
 #include "common.cuh"
@@ -59,6 +65,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ double lds64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ double2 lds128(uint32_t addr) {
   double2 v;
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
@@ -94,7 +105,9 @@ struct PeerDests {
 
 // epilogue shared by the main kernel and the stream-K fix-up: thread (warp, lane) holds
 // C[row pg][cols t, t+4] of each 8x8 block of its warp tile
-template <int WARPS_N, int MB, int NB, int BM, int BN, bool PEERS>
+// NAT: the B fragments were read with lane g <-> tile column g (N-major B), so the thread holds
+// columns 2t, 2t+1 of each 8x8 block instead of t, t+4
+template <int WARPS_N, int MB, int NB, int BM, int BN, bool PEERS, bool NAT = false>
 __device__ __forceinline__ void store_tile(const double (&acc)[MB][NB][2], int warp, int lane,
                                            int tile_m, int tile_n, double* __restrict__ C,
                                            long long ldc, int M, int N, double alpha, double beta,
@@ -126,7 +139,8 @@ __device__ __forceinline__ void store_tile(const double (&acc)[MB][NB][2], int w
   const int g = lane >> 2, t = lane & 3;
   const int pg = (g >> 1) | ((g & 1) << 2);
   const int row0 = tile_m * BM + wm * MB * 8 + pg;
-  const int col0 = tile_n * BN + wn * NB * 8 + t;
+  const int col0 = tile_n * BN + wn * NB * 8 + (NAT ? 2 * t : t);
+  constexpr int kSecond = NAT ? 1 : 4;
 #pragma unroll
   for (int i = 0; i < MB; ++i) {
     const int r = row0 + i * 8;
@@ -136,8 +150,9 @@ __device__ __forceinline__ void store_tile(const double (&acc)[MB][NB][2], int w
     for (int j = 0; j < NB; ++j) {
       const int c = col0 + j * 8;
       if (c < N) Crow[c] = (beta == 0.0) ? alpha * acc[i][j][0] : alpha * acc[i][j][0] + beta * Crow[c];
-      if (c + 4 < N)
-        Crow[c + 4] = (beta == 0.0) ? alpha * acc[i][j][1] : alpha * acc[i][j][1] + beta * Crow[c + 4];
+      if (c + kSecond < N)
+        Crow[c + kSecond] =
+            (beta == 0.0) ? alpha * acc[i][j][1] : alpha * acc[i][j][1] + beta * Crow[c + kSecond];
     }
   }
 }
@@ -188,7 +203,7 @@ struct SegIter {
   }
 };
 
-template <int WARPS_M, int WARPS_N, int MB, int NB, int STAGES, bool PEERS>
+template <int WARPS_M, int WARPS_N, int MB, int NB, int STAGES, bool PEERS, bool BNM = false>
 __global__ void __launch_bounds__((WARPS_M * WARPS_N + 1) * 32, 1)
 dgemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA,
                     const __grid_constant__ CUtensorMap tmB, double* __restrict__ C,
@@ -233,7 +248,13 @@ dgemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA,
           mbar_expect_tx(full, Cfg::STAGE_BYTES);
           const uint32_t dst = smem_base + s * Cfg::STAGE_BYTES;
           tma_load_2d(dst, &tmA, full, (k_start + n) * kBK, tm * Cfg::BM);
-          tma_load_2d(dst + Cfg::A_BYTES, &tmB, full, (k_start + n) * kBK, tn * Cfg::BN);
+          if constexpr (BNM) {
+            static_assert(!BNM || Cfg::BN % 16 == 0, "N-major B needs whole 16-column boxes");
+            for (int b = 0; b < Cfg::BN / 16; ++b)
+              tma_load_2d(dst + Cfg::A_BYTES + b * 2048, &tmB, full, tn * Cfg::BN + 16 * b, (k_start + n) * kBK);
+          } else {
+            tma_load_2d(dst + Cfg::A_BYTES, &tmB, full, (k_start + n) * kBK, tn * Cfg::BN);
+          }
         }
       }
     }
@@ -248,6 +269,14 @@ dgemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA,
   const int pg = (g >> 1) | ((g & 1) << 2);
   const uint32_t a_off = (uint32_t)((wm * MB * 8 + pg) * 128 + ((t ^ pg) << 4));
   const uint32_t b_off = (uint32_t)(Cfg::A_BYTES + (wn * NB * 8 + pg) * 128 + ((t ^ pg) << 4));
+  // N-major B: column (wn*NB*8 + 8j + g) of the tile = box col>>4, 16-byte chunk (col&15)>>1, half col&1;
+  // k-row 8h + 2t + q of the slab sits at chunk ^ (2t + q)
+  uint32_t bn_off[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const int col = wn * NB * 8 + 8 * j + g;
+    bn_off[j] = (uint32_t)(Cfg::A_BYTES + (col >> 4) * 2048 + (2 * t) * 128 + ((col & 1) << 3));
+  }
 
   double acc[MB][NB][2];
   // A stage is handed back to the producer ONE iteration late, after the wait for the next
@@ -281,8 +310,22 @@ dgemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA,
         double2 af[MB], bf[NB];
 #pragma unroll
         for (int i = 0; i < MB; ++i) af[i] = lds128((sa + i * 1024) ^ (h << 6));
+        if constexpr (BNM) {
+          const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES + h * 1024;   // rows 8h ..
 #pragma unroll
-        for (int j = 0; j < NB; ++j) bf[j] = lds128((sb + j * 1024) ^ (h << 6));
+          for (int j = 0; j < NB; ++j) {
+            // (col & 15) >> 1 = 4 * (j & 1) + (g >> 1) when the warp's first column is a multiple of 16,
+            // else shifted by 4: computed from the column itself
+            const int col = wn * NB * 8 + 8 * j + g;
+            const uint32_t c = (uint32_t)((col & 15) >> 1);
+            const uint32_t base = stage + bn_off[j];
+            bf[j].x = lds64(base + ((c ^ (uint32_t)(2 * t)) << 4));
+            bf[j].y = lds64(base + 128 + ((c ^ (uint32_t)(2 * t + 1)) << 4));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NB; ++j) bf[j] = lds128((sb + j * 1024) ^ (h << 6));
+        }
 #pragma unroll
         for (int i = 0; i < MB; ++i)
 #pragma unroll
@@ -295,7 +338,7 @@ dgemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA,
     }
 
     if (slot < 0) {
-      store_tile<WARPS_N, MB, NB, Cfg::BM, Cfg::BN, PEERS>(acc, warp, lane, tm, tn, C, ldc, M, N, alpha, beta, peers);
+      store_tile<WARPS_N, MB, NB, Cfg::BM, Cfg::BN, PEERS, BNM>(acc, warp, lane, tm, tn, C, ldc, M, N, alpha, beta, peers);
     } else {
       // fragment-ordered partial: element (reg, consumer thread) -> coalesced
       constexpr int kCT = Cfg::kConsumerWarps * 32;
@@ -313,7 +356,7 @@ dgemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA,
 }
 
 // sums the partial segments of every stream-K tile that no single CTA covered, in CTA order
-template <int WARPS_M, int WARPS_N, int MB, int NB, int STAGES, bool PEERS>
+template <int WARPS_M, int WARPS_N, int MB, int NB, int STAGES, bool PEERS, bool BNM = false>
 __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32)
 dgemm_fixup_kernel(double* __restrict__ C, long long ldc, int M, int N, int tiles_m, int k_iters,
                    long long sk_tile0, long long sk_tiles, long long ipc, double alpha, double beta,
@@ -341,7 +384,7 @@ dgemm_fixup_kernel(double* __restrict__ C, long long ldc, int M, int N, int tile
         }
     }
     const long long tile = sk_tile0 + tl;
-    store_tile<WARPS_N, MB, NB, Cfg::BM, Cfg::BN, PEERS>(acc, threadIdx.x >> 5, threadIdx.x & 31,
+    store_tile<WARPS_N, MB, NB, Cfg::BM, Cfg::BN, PEERS, BNM>(acc, threadIdx.x >> 5, threadIdx.x & 31,
                                                  (int)(tile % tiles_m), (int)(tile / tiles_m), C, ldc,
                                                  M, N, alpha, beta, peers);
   }
@@ -450,12 +493,26 @@ static bool make_map_2d(CUtensorMap* tm, const double* base, long long rows, lon
   return r == CUDA_SUCCESS;
 }
 
-template <int WARPS_M, int WARPS_N, int MB, int NB, int STAGES, bool PEERS>
+// B[k][n], n contiguous: boxes of 16 n-columns (one 128-byte swizzle row) x 16 k-rows
+static bool make_map_nmajor(CUtensorMap* tm, const double* base, long long k_rows, long long n_cols, long long ld) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)n_cols, (cuuint64_t)k_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 8};
+  cuuint32_t box[2] = {16, (cuuint32_t)kBK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int WARPS_M, int WARPS_N, int MB, int NB, int STAGES, bool PEERS, bool BNM = false>
 static int launch_tma(cudaStream_t st, int M, int N, int K, double alpha, const double* A,
                       long long lda, const double* B, long long ldb, double beta, double* C,
                       long long ldc, double* ws, long long ws_bytes, const PeerDests& peers) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, MB, NB, STAGES>;
-  auto kern = dgemm_tn_tma_kernel<WARPS_M, WARPS_N, MB, NB, STAGES, PEERS>;
+  auto kern = dgemm_tn_tma_kernel<WARPS_M, WARPS_N, MB, NB, STAGES, PEERS, BNM>;
   // the attribute belongs to the (function, device) pair: set it once per device
   // (one-process-many-GPU hosts launch the same instantiation on several devices)
   static std::atomic<unsigned long long> attr_devices{0};
@@ -465,7 +522,9 @@ static int launch_tma(cudaStream_t st, int M, int N, int K, double alpha, const 
     if (dev < 64) attr_devices.fetch_or(1ULL << dev, std::memory_order_release);
   }
   CUtensorMap tmA, tmB;
-  if (!make_map_2d(&tmA, A, M, K, lda, Cfg::BM) || !make_map_2d(&tmB, B, N, K, ldb, Cfg::BN))
+  // BNM: ldb is the stride between k-rows of B[k][n]
+  if (!make_map_2d(&tmA, A, M, K, lda, Cfg::BM) ||
+      !(BNM ? make_map_nmajor(&tmB, B, K, N, ldb) : make_map_2d(&tmB, B, N, K, ldb, Cfg::BN)))
     return fail("cuTensorMapEncodeTiled failed");
   const int tm = (M + Cfg::BM - 1) / Cfg::BM, tn = (N + Cfg::BN - 1) / Cfg::BN;
   const long long tiles = (long long)tm * tn;
@@ -500,7 +559,7 @@ static int launch_tma(cudaStream_t st, int M, int N, int K, double alpha, const 
   count_launch();
   if (has_partials) {
     const int blocks = (int)std::min<long long>(sk_tiles, 4LL * nsm);
-    dgemm_fixup_kernel<WARPS_M, WARPS_N, MB, NB, STAGES, PEERS><<<blocks, Cfg::kConsumerWarps * 32, 0, st>>>(
+    dgemm_fixup_kernel<WARPS_M, WARPS_N, MB, NB, STAGES, PEERS, BNM><<<blocks, Cfg::kConsumerWarps * 32, 0, st>>>(
         C, ldc, M, N, tm, k_iters, sk_tile0, sk_tiles, ipc, alpha, beta, ws, peers);
     ADCCB_LAUNCH_OK();
     count_launch();
@@ -527,6 +586,21 @@ static int dgemm_impl(cudaStream_t st, long long M, long long N, long long K, do
                       ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && get_encode_fn() != nullptr &&
                       (peers.n > 0 || (long long)M * N * K >= 32LL * 32 * 32);
+  // C = A . B with B[k][n] stored n-contiguous (no transposed copy): same tiles, N-major B loads
+  const bool tma_nn_ok = peers.n == 0 && acs == 1 && brs == 1 && N > 1 && (ars % 2 == 0) && (bcs % 2 == 0) &&
+                         ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && get_encode_fn() != nullptr &&
+                         (long long)M * N * K >= 32LL * 32 * 32;
+  if (tma_nn_ok && !(bcs == 1)) {
+#define ADCCB_TMA_NN(WM, WN, MB, NB)                                                                       \
+  return launch_tma<WM, WN, MB, NB, 6, false, true>(st, (int)M, (int)N, (int)K, alpha, A, ars, B, bcs, beta, C, \
+                                                    ldc, ws, ws_bytes, peers)
+    if (tile_hint == 16 || (tile_hint == 0 && M <= 16)) ADCCB_TMA_NN(1, 8, 2, 2);
+    if (tile_hint == 40 || (tile_hint == 0 && M <= 40)) ADCCB_TMA_NN(1, 8, 5, 2);
+    if (tile_hint == 64 || (tile_hint == 0 && M <= 64)) ADCCB_TMA_NN(1, 8, 8, 2);
+    ADCCB_TMA_NN(2, 4, 8, 4);
+#undef ADCCB_TMA_NN
+  }
   if (tma_ok) {
     // row-tile height: the smallest tile that covers M for skinny outputs (these are HBM-bound
     // streams over the big operand, so DMMA rows spent on zero padding would make them

@@ -426,7 +426,7 @@ class PackedAdcEngine:
                                            shard=(self.rank, self.world), layout=self.layout, W_slab=self.W)
                 del W_full
             self.M1 = ops3["M1"]
-            self.V1, self.V2, self.G1, self.G2 = ops3["V1"], ops3["V2"], ops3["G1"], ops3["G2"]
+            self.V2, self.G1, self.G2 = ops3["V2"], ops3["G1"], ops3["G2"]
             self._extra3 = ops3["extras"]
             self.build_flops = ops3["build_flops"]
             # diagonal of the singles block = diagonal of adc3_m11 (matrix.py:616-618)
@@ -440,7 +440,6 @@ class PackedAdcEngine:
             m1 = m1 - 0.5 * im.term_t2_eri.transpose((0, 2, 1, 3))  # - 1/2 term[ikac] -> [i,a,k,c]
             self.M1 = m1._contig().reshape(no * nv, no * nv)
             # ---- couplings (matrix.py:270-276, 288-294)
-            self.V1 = src.ovvv_jabc(self.j0, self.nj)
             self.V2 = src.ovvv_ajbc(self.j0, self.nj)
             self.G1 = src.ooov_ijkb()
             self.G2 = src.ooov_ijak()
@@ -537,6 +536,13 @@ class PackedAdcEngine:
         self._count_flops()
 
     # ------------------------------------------------------------------ spin-blocked operands
+    @property
+    def V1(self):
+        """<jc||ab> as the GEMM operand [(j,AB),c] of pphh_ph: a VIEW of V2[c,(j,AB)] - both ovvv
+        couplings read the one stored layout (adccb_dgemm takes B n-contiguous, SURVEY 8(b)
+        "a10 + a11 from one ovvv pass" - here one copy, two DMMA-bound launches)."""
+        return self.V2.t()
+
     def _build_spin_blocks(self):
         """Restricted references: <pq||rs> vanishes unless bra and ket have the same spin projection,
         so W[AB,CD], O[IJ,KL] are block diagonal over the pair classes (alpha-alpha, alpha-beta,
@@ -693,7 +699,7 @@ class PackedAdcEngine:
         no, nv = self.no, self.nv
         x = u1._contig()
         x3 = self._extra3
-        c1 = be.gemm(x, self.V1)                             # [i,(j,AB)] = sum_c u[ic] <jc||ab>
+        c1 = be.gemm(x, self.V1)                             # [i,(j,AB)] = sum_c u[ic] <jc||ab> (N-major B)
         if x3 is not None:
             # + A_ij( r3[li] t2[jlab] ),  r3[li] = <lk||ic> u[kc]      (matrix.py:525)
             r3 = be.gemm(x.reshape(1, no * nv), x3["G4"]).view(no, no)            # [l,i]

@@ -249,7 +249,6 @@ def build_adc3_operands(hf, mp, im, src, W, Op, Y, j0=0, nj=None, shard=(0, 1), 
     flops += 2.0 * nv * nv * (no * nv) * (nj * nv) + 2.0 * nv * nj * npo * npv
     del X2, X2s, V2x
     V2 = pibV2.view(nv, nj * npv)                                           # [a,(jl,BC)]
-    V1 = be.permute(pibV2.view(nv, nj, npv), (1, 2, 0)).reshape(nj * npv, nv)   # [(jl,AB),c]
     del S2
 
     # ---- operands of the three-operand second-order coupling terms (matrix.py:498-499, 525, 529)
@@ -272,4 +271,4 @@ def build_adc3_operands(hf, mp, im, src, W, Op, Y, j0=0, nj=None, shard=(0, 1), 
         for t in list(getattr(hf, "_eri", {}).values()) + list(getattr(hf, "_fock", {}).values()):
             t._layouts.clear()
         be.release_cached_memory()
-    return {"M1": M1, "G1": G1, "G2": G2, "V1": V1, "V2": V2, "extras": extras, "build_flops": flops}
+    return {"M1": M1, "G1": G1, "G2": G2, "V2": V2, "extras": extras, "build_flops": flops}

@@ -110,5 +110,5 @@ def check_adc3_builder_vs_dense(data=None):
     V2 = eng.V2.cpu().numpy().reshape(nv, no, npv)                       # [a,(j,BC)] = pib[j,a,bc]
     want = np.stack([pib[:, :, bb, cc] for bb, cc in pv], axis=-1).transpose(1, 0, 2)
     assert rel_err(V2, want) < 1e-12
-    V1 = eng.V1.cpu().numpy().reshape(no, npv, nv)                       # [(j,AB),c] = pib[j,c,ab]
+    V1 = eng.V1.contiguous().cpu().numpy().reshape(no, npv, nv)          # [(j,AB),c] = pib[j,c,ab] (view of V2)
     assert rel_err(V1, want.transpose(1, 2, 0)) < 1e-12

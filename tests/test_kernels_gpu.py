@@ -69,6 +69,32 @@ def test_gemm_peer_destinations(be, M, N, K, hint, ndest):
         be.gemm_peers(A, B, bufs[0][:, c0:c0 + N], [bufs[0].data_ptr()] * 8, col_offset=c0, ldc=ld)
 
 
+@pytest.mark.parametrize("M,N,K,hint", [(40, 3000, 400, 0), (8, 130, 37, 0), (64, 1000, 512, 0), (200, 258, 1000, 0),
+                                        (40, 100000, 400, 0), (300, 334, 514, 16), (300, 334, 514, 40),
+                                        (300, 334, 514, 64), (16, 48, 40000, 0), (2, 79800, 400, 0)])
+def test_gemm_n_major_b(be, M, N, K, hint):
+    """C = A . B with B stored [K][N] (N contiguous): the TMA kernel's N-major B loads, no transposed
+    copy.  Same sums in the same order as the K-contiguous kernel on B^T -> bit-identical to it."""
+    import torch
+    rng = np.random.default_rng(M + N + K + hint)
+    A = rng.standard_normal((M, K))
+    Bkn = rng.standard_normal((K, N))
+    dA, dB = be.from_numpy(A), be.from_numpy(Bkn)
+    C = be.gemm(dA, dB.t(), tile_hint=hint)
+    assert _rel(C.cpu().numpy(), A @ Bkn) < 1e-13
+    ref = be.gemm(dA, dB.t().contiguous(), tile_hint=hint)          # K-contiguous copy of B
+    assert torch.equal(C, ref)
+    C0 = rng.standard_normal((M, N))
+    out = be.from_numpy(C0)
+    be.gemm(dA, dB.t(), out=out, alpha=-0.5, beta=2.0, tile_hint=hint)
+    assert _rel(out.cpu().numpy(), -0.5 * (A @ Bkn) + 2.0 * C0) < 1e-13
+    # column window of a wider buffer (the j-slab view of V2[a,(j,BC)])
+    if N >= 64:
+        view = dB[:, 16:16 + N // 2 * 2 - 16]
+        Cv = be.gemm(dA, view.t(), tile_hint=hint)
+        assert _rel(Cv.cpu().numpy(), A @ Bkn[:, 16:16 + N // 2 * 2 - 16]) < 1e-13
+
+
 def test_gemm_generic_strides(be):
     rng = np.random.default_rng(7)
     # odd leading dimension -> generic path; transposed operands

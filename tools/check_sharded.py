@@ -86,7 +86,7 @@ if m.vector_distribution == "slab":
 if os.environ.get("ADCCB_POISON"):
     res["nan"] = [[int(torch.isnan(o[0]).sum().item()), int(torch.isnan(o[1]).sum().item())] for o in outs]
     res["nan_build"] = {k: int(torch.isnan(getattr(eng, k)).sum().item())
-                        for k in ("M1", "V1", "V2", "G1", "G2", "D0", "W", "O", "Y")}
+                        for k in ("M1", "V2", "G1", "G2", "D0", "W", "O", "Y")}
 if rank == 0:
     m1 = adcc.AdcMatrix("adc2x", ref, doubles_storage="packed")
     s1 = m1.matvec(v)

@@ -37,7 +37,7 @@ ref = synthetic_reference_state(no, nv, seed=7, scale=5e-4)
 m = adcc.AdcMatrix("adc2x", ref, doubles_storage="packed")
 eng = m._engine
 torch.cuda.synchronize()
-res["build"] = {k: nans(getattr(eng, k)) for k in ("M1", "V1", "V2", "G1", "G2", "D0", "W", "O", "Y")}
+res["build"] = {k: nans(getattr(eng, k)) for k in ("M1", "V2", "G1", "G2", "D0", "W", "O", "Y")}
 res["diag"] = nans(eng.diagonal_pphh._data)
 g = torch.Generator(device="cpu").manual_seed(3)
 u1 = torch.randn(no, nv, generator=g, dtype=torch.float64).cuda()
