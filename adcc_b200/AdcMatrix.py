@@ -127,8 +127,12 @@ class AdcMatrix(AdcMatrixlike):
                 self._tables[blk] = adc_pp.BLOCKS[key]
             self.blocks = {blk: self._make_apply(blk) for blk in self._tables}
             if self.doubles_storage == "packed":
-                from .packed import PackedAdcEngine
-                self._engine = PackedAdcEngine(self, shard=shard, vectors=vectors)
+                if self.is_core_valence_separated:
+                    from .packed_cvs import PackedCvsEngine
+                    self._engine = PackedCvsEngine(self, shard=shard, vectors=vectors)
+                else:
+                    from .packed import PackedAdcEngine
+                    self._engine = PackedAdcEngine(self, shard=shard, vectors=vectors)
                 self.blocks = {blk: self._make_engine_apply(blk) for blk in self._tables
                                if self._tables[blk][0] is not None}
                 if getattr(self._engine, "diagonal_ph", None) is not None:
@@ -169,23 +173,29 @@ class AdcMatrix(AdcMatrixlike):
         if requested not in ("auto", "dense", "packed"):
             raise ValueError("doubles_storage needs to be 'auto', 'dense' or 'packed'")
         orders = tuple(self.block_orders.get(b) for b in ("ph_ph", "ph_pphh", "pphh_ph", "pphh_pphh"))
-        packable = (not self.is_core_valence_separated
-                    and orders in ((2, 1, 1, 0), (2, 1, 1, 1), (3, 2, 2, 1)))
+        if self.is_core_valence_separated:
+            packable = orders in ((2, 1, 1, 0), (2, 1, 1, 1))       # packed_cvs.py: virtual pairs only
+        else:
+            packable = orders in ((2, 1, 1, 0), (2, 1, 1, 1), (3, 2, 2, 1))
         if requested == "packed" and not packable:
-            raise NotImplementedError("packed doubles storage is implemented for ADC(2), ADC(2)-x "
-                                      "and ADC(3)")
+            raise NotImplementedError("packed doubles storage is implemented for ADC(2), ADC(2)-x, "
+                                      "ADC(3), CVS-ADC(2) and CVS-ADC(2)-x")
         if requested == "auto":
             # packed: 4x less doubles / vvvv storage and 4x fewer vvvv flops; it pays once the
             # vector is large or the vvvv term dominates (measured: methyloxirane cc-pVDZ ADC(3),
             # nv = 140: 3.1 -> 1.4-2.1 s for 8 singlets, 56 -> 27 GB)
             no, nv = self.mospaces.n_orbs("o1"), self.mospaces.n_orbs("v1")
-            big = no * no * nv * nv * 8 >= (1 << 30)
+            n2 = self.mospaces.n_orbs("o2") if self.is_core_valence_separated else no
+            big = no * n2 * nv * nv * 8 >= (1 << 30)
             vvvv_bound = self.block_orders.get("pphh_pphh") == 1 and nv >= 96
             if not (packable and (big or vvvv_bound)):
                 return "dense"
             hf = self.reference_state
             if getattr(hf, "packed_source", None) is None:
-                for f in (hf.foo.to_ndarray(), hf.fvv.to_ndarray()):     # packed needs canonical orbitals
+                focks = [hf.foo.to_ndarray(), hf.fvv.to_ndarray()]
+                if self.is_core_valence_separated:
+                    focks.append(hf.fcc.to_ndarray())
+                for f in focks:                                          # packed needs canonical orbitals
                     if np.max(np.abs(f - np.diag(np.diag(f)))) > 1e-12:
                         return "dense"
             return "packed"

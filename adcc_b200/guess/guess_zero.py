@@ -14,6 +14,9 @@ def guess_zero(matrix, spin_change=0, spin_block_symmetrisation="none"):
     def make(block, sym):
         if packed and block == "pphh":
             from ..packed import PackedDoubles, SlabDoubles
+            if matrix.is_core_valence_separated:
+                from ..packed_cvs import CvsPackedDoubles
+                return CvsPackedDoubles.zeros(sym.mospaces, sym.subspaces, sym)
             if getattr(matrix, "vector_distribution", None) == "slab":
                 return SlabDoubles.zeros(sym.mospaces, sym.subspaces, matrix._engine.layout, sym)
             return PackedDoubles.zeros(sym.mospaces, sym.subspaces, sym)

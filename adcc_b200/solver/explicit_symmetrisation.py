@@ -110,7 +110,8 @@ class IndexSpinSymmetrisation(IndexSymmetrisation):
                     dense = be.spin_project(t.to_dense()._contig(), n_alpha, fac)
                     if self.enforce_spin_kind == "singlet":
                         be.spin_singlet_(dense, n_alpha)
-                    new = PackedDoubles.from_dense(Tensor._wrap(t.mospaces, t.subspaces, dense))
+                    store = PackedDoubles if t._storage in ("packed", "slab") else type(t)   # CVS: virtual pairs
+                    new = store.from_dense(Tensor._wrap(t.mospaces, t.subspaces, dense))
                     if getattr(t, "slab", None) is not None:      # distributed vector: keep this rank's slab
                         from ..packed import SlabDoubles
                         new = SlabDoubles.from_full(new, t.slab)

@@ -70,6 +70,65 @@ def check_packed_spin_kinds(method, n=3):
         np.testing.assert_allclose(st.excitation_energy, ost.eigenvalues, atol=ENERGY_ATOL, rtol=0)
 
 
+def check_packed_cvs_matrix(method, data=None, core=1, seed=11):
+    """CVS-ADC(2) / CVS-ADC(2)-x on the virtual-pair-packed store (adcc_b200/packed_cvs.py) against
+    the oracle: sigma, every block, both diagonals, hermiticity, dense round trip of the vector."""
+    import adcc_b200 as adcc
+    from adcc_b200.packed_cvs import CvsPackedDoubles, PackedCvsEngine
+    data = data if data is not None else load_h2o_sto3g()
+    m = adcc.AdcMatrix(method, adcc.ReferenceState(data, core_orbitals=core), doubles_storage="packed")
+    assert isinstance(m._engine, PackedCvsEngine)
+    om = oracle.OracleAdcMatrix(method, oracle.OracleRefState(oracle.OracleHf(data), core_orbitals=core))
+    _compare_cvs(adcc, m, om, seed)
+    return m, om
+
+
+def _compare_cvs(adcc, m, om, seed=11, against_dense=True):
+    from adcc_b200.packed_cvs import CvsPackedDoubles
+    method = m.method.name
+    v, ov = random_vector(m, om, seed)
+    vp = adcc.AmplitudeVector(ph=v.ph, pphh=CvsPackedDoubles.from_dense(v.pphh))
+    assert rel_err(vp.pphh.to_ndarray(), ov["pphh"]) < 1e-14
+    assert abs(vp @ vp - v @ v) < 1e-11 * abs(v @ v)                       # every stored element counts twice
+    sig, osig = m.matvec(vp), om.matvec(ov)
+    assert isinstance(sig.pphh, CvsPackedDoubles)
+    assert rel_err(sig.ph.to_ndarray(), osig["ph"]) < SIGMA_RTOL
+    assert rel_err(sig.pphh.to_ndarray(), osig["pphh"]) < SIGMA_RTOL
+    for blk in ("ph_ph", "ph_pphh", "pphh_ph", "pphh_pphh"):
+        outb, inb = blk.split("_")
+        res = m.block_apply(blk, vp[inb])
+        ores = om.blocks[blk]({inb: ov[inb]})[outb]
+        assert rel_err(res.to_ndarray(), ores) < SIGMA_RTOL, blk
+    assert rel_err(m.diagonal().ph.to_ndarray(), om.diagonal()["ph"]) < SIGMA_RTOL
+    dd, od = m.diagonal().pphh.to_ndarray(), om.diagonal()["pphh"]
+    mask = np.ones_like(od, dtype=bool)
+    n_v = od.shape[2]
+    mask[:, :, np.arange(n_v), np.arange(n_v)] = False                     # a == b is not stored
+    assert rel_err(dd[mask], od[mask]) < SIGMA_RTOL
+    w, _ = random_vector(m, om, seed + 1)
+    wp = adcc.AmplitudeVector(ph=w.ph, pphh=CvsPackedDoubles.from_dense(w.pphh))
+    lhs, rhs = vp @ m.matvec(wp), sig @ wp
+    assert abs(lhs - rhs) < 1e-11 * max(1.0, abs(lhs))
+    if against_dense:      # the dense table interpreter gives the same sigma from the same (unpacked) vector
+        md = adcc.AdcMatrix(method, m.reference_state, doubles_storage="dense")
+        sd = md.matvec(v)
+        assert rel_err(sig.pphh.to_ndarray(), sd.pphh.to_ndarray()) < SIGMA_RTOL
+
+
+def check_packed_cvs_run(method, data=None, core=1, n=2, kinds=("singlet", "triplet", "any")):
+    """Davidson on the packed CVS store: energies and iteration counts of the oracle's solver."""
+    import adcc_b200 as adcc
+    data = data if data is not None else load_h2o_sto3g()
+    for kind in kinds:
+        kw = {"singlet": {"n_singlets": n}, "triplet": {"n_triplets": n}, "any": {"n_states": n}}[kind]
+        m = adcc.AdcMatrix(method, adcc.ReferenceState(data, core_orbitals=core), doubles_storage="packed")
+        st = adcc.run_adc(m, conv_tol=1e-8, output=None, **kw)
+        ost = oracle.run_adc(data, method, conv_tol=1e-8, core_orbitals=core, kind=kind, **kw)
+        assert st.converged and st.n_iter == ost.n_iter, (kind, st.n_iter, ost.n_iter)
+        np.testing.assert_allclose(st.excitation_energy, ost.eigenvalues, atol=ENERGY_ATOL, rtol=0)
+    return st
+
+
 def check_synthetic(no, nv, seed=5, run=True, method="adc2x"):
     import adcc_b200 as adcc
     from adcc_b200.packed import synthetic_reference_state

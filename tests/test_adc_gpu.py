@@ -196,12 +196,18 @@ def test_c3_shape_adc3_sigma(storage):
         _compare(adcc, m, om)
 
 
+@pytest.mark.parametrize("storage", ["dense", "packed"])
 @pytest.mark.parametrize("case,n_ph,n_pphh", [("h2o_ccpvtz_cvs", 212, 179776), ("ne_ccpvtz_cvs", 100, 40000)])
-def test_c4_shapes_cvs_adc2x_sigma(case, n_ph, n_pphh):
-    """configs[3]: H2O / Ne cc-pVTZ CVS-ADC(2)-x shapes (c=2, o=8, v=106 / 50)."""
+def test_c4_shapes_cvs_adc2x_sigma(case, n_ph, n_pphh, storage):
+    """configs[3]: H2O / Ne cc-pVTZ CVS-ADC(2)-x shapes (c=2, o=8, v=106 / 50), on the dense store and
+    on the virtual-pair-packed store (adcc_b200/packed_cvs.py)."""
     import adcc_b200 as adcc
     from adc_parity_common import compare_matrices
     data, core, om = _oracle_matrix(case, "cvs-adc2x")
-    m = adcc.AdcMatrix("cvs-adc2x", adcc.ReferenceState(data, core_orbitals=core))
+    m = adcc.AdcMatrix("cvs-adc2x", adcc.ReferenceState(data, core_orbitals=core), doubles_storage=storage)
     assert m.axis_lengths == {"ph": n_ph, "pphh": n_pphh}
-    compare_matrices(m, om)
+    if storage == "dense":
+        compare_matrices(m, om)
+    else:
+        from packed_parity_common import _compare_cvs
+        _compare_cvs(adcc, m, om, against_dense=False)

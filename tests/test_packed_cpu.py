@@ -27,6 +27,16 @@ def test_packed_singlets_triplets_h2o(method):
     check_packed_spin_kinds(method)
 
 
+@pytest.mark.parametrize("method", ["cvs-adc2", "cvs-adc2x"])
+def test_packed_cvs_matvec_and_davidson(method):
+    """SURVEY 8(a) rows a8/a10/a11/a13/a14 (+CVS) on the virtual-pair-packed store."""
+    from packed_parity_common import check_packed_cvs_matrix, check_packed_cvs_run
+    from adcc_b200.synthetic import restricted_scf_dict
+    check_packed_cvs_matrix(method)
+    check_packed_cvs_matrix(method, restricted_scf_dict(9, 4, seed=2), core=2)       # two core orbitals
+    check_packed_cvs_run(method)
+
+
 def test_synthetic_workload_small():
     check_synthetic(6, 10, seed=5)
 
@@ -67,6 +77,38 @@ def test_packed_tensor_semantics():
     assert q[1, 0, 3, 2] == 2.0 and q[0, 1, 3, 2] == -2.0
     with pytest.raises(ValueError):
         PackedDoubles.zeros(ref.mospaces, ["o1", "o1", "v1", "v1"]).set_from_ndarray(np.ones((10, 10, 4, 4)))
+
+
+def test_cvs_packed_tensor_semantics():
+    import adcc_b200 as adcc
+    from adcc_b200.packed_cvs import CvsPackedDoubles
+    from oracle.hfdata import load_h2o_sto3g
+    ref = adcc.ReferenceState(load_h2o_sto3g(), core_orbitals=1)
+    rng = np.random.default_rng(0)
+    d = rng.standard_normal((8, 2, 4, 4))
+    d = d - d.transpose(0, 1, 3, 2)
+    t = adcc.Tensor.from_ndarray(ref.mospaces, "o1o2v1v1", d)
+    p = CvsPackedDoubles.from_dense(t)
+    assert p.shape == (8, 2, 4, 4) and p.packed_shape == (16, 6) and p.size == 256
+    np.testing.assert_allclose(p.to_ndarray(), d, atol=1e-15)
+    assert abs(p.dot(p) - np.vdot(d, d)) < 1e-11          # dense Frobenius weight (2x)
+    np.testing.assert_allclose(p.dot([p, 2.0 * p]), [np.vdot(d, d), 2 * np.vdot(d, d)], rtol=1e-13)
+    np.testing.assert_allclose((2.0 * p - p / 4.0).to_ndarray(), 1.75 * d, atol=1e-14)
+    assert p.antisymmetrise(2, 3) is p
+    assert p[3, 1, 2, 3] == -p[3, 1, 3, 2] == d[3, 1, 2, 3] and p[0, 0, 1, 1] == 0.0
+    with pytest.raises(ValueError):
+        p + t                                              # mixed storage
+    q = p.zeros_like()
+    q[5, 1, 3, 2] = 2.0
+    assert q[5, 1, 2, 3] == -2.0 and type(q) is CvsPackedDoubles
+    with pytest.raises(ValueError):
+        CvsPackedDoubles.zeros(ref.mospaces, ["o1", "o2", "v1", "v1"]).set_from_ndarray(np.ones((8, 2, 4, 4)))
+    # a non-antisymmetric dense tensor is antisymmetrised on the way in
+    e = rng.standard_normal((8, 2, 4, 4))
+    pe = CvsPackedDoubles.from_dense(adcc.Tensor.from_ndarray(ref.mospaces, "o1o2v1v1", e))
+    np.testing.assert_allclose(pe.to_ndarray(), 0.5 * (e - e.transpose(0, 1, 3, 2)), atol=1e-15)
+    with pytest.raises(NotImplementedError):
+        adcc.AdcMatrix("cvs-adc3", ref, doubles_storage="packed")
 
 
 def test_synthetic_definition_symmetries():

@@ -88,6 +88,18 @@ def test_packed_engine_h2o(method):
     check_packed_run(method)
 
 
+@pytest.mark.parametrize("method", ["cvs-adc2", "cvs-adc2x"])
+def test_packed_cvs_engine(method):
+    """CVS variants on the virtual-pair-packed store: sigma / blocks / diagonal vs the oracle, Davidson
+    singlets, triplets and "any" with the oracle's iteration counts."""
+    from packed_parity_common import check_packed_cvs_matrix, check_packed_cvs_run
+    from adcc_b200.synthetic import restricted_scf_dict
+    check_packed_cvs_matrix(method)
+    check_packed_cvs_matrix(method, restricted_scf_dict(9, 4, seed=2), core=2)
+    check_packed_cvs_matrix(method, restricted_scf_dict(24, 5, seed=4), core=1)      # nv = 38: TMA GEMM paths
+    check_packed_cvs_run(method)
+
+
 @pytest.mark.parametrize("method", ["adc2x", "adc3"])
 def test_packed_singlets_triplets_h2o(method):
     check_packed_spin_kinds(method)

@@ -1,5 +1,6 @@
 """Time-to-converged states for the molecular-shape configs of BASELINE.json (synthetic restricted
-SCF data of the same shapes); dense engine, through run_adc."""
+SCF data of the same shapes), through run_adc.  ADCCB_STORAGE / ADCCB_CVS_STORAGE
+(auto | dense | packed) choose the doubles store of the generic / CVS cases."""
 import json
 import os
 import sys
@@ -17,16 +18,24 @@ CASES = [("h2o_ccpvdz", "adc2", dict(n_singlets=3, conv_tol=1e-6)),
          ("methyloxirane_ccpvdz", "adc3", dict(n_singlets=8)),
          ("ne_ccpvtz_cvs", "cvs-adc2x", dict(n_singlets=4, conv_tol=1e-8)),
          ("h2o_ccpvtz_cvs", "cvs-adc2x", dict(n_singlets=7, conv_tol=1e-8))]
+# beyond BASELINE: a CVS shape where the doubles store matters (c=2, o=22, v=196; only when named)
+EXTRA = {"cvs_large": ("cvs-adc2x", dict(n_singlets=5, conv_tol=1e-8), (110, 12, 1))}
 only = sys.argv[1:]
+CASES += [(k, v[0], v[1]) for k, v in EXTRA.items() if k in only]
 res = []
 for name, method, kw in CASES:
     if only and name not in only:
         continue
-    data, core = named_case(name)
+    if name in EXTRA:
+        from adcc_b200.synthetic import restricted_scf_dict
+        n_orb, n_occ, core = EXTRA[name][2]
+        data = restricted_scf_dict(n_orb, n_occ, seed=77)
+    else:
+        data, core = named_case(name)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     ref = adcc.ReferenceState(data, core_orbitals=core or None)
-    storage = STORAGE if not method.startswith("cvs") else "auto"
+    storage = os.environ.get("ADCCB_CVS_STORAGE", "auto") if method.startswith("cvs") else STORAGE
     matrix = adcc.AdcMatrix(method, ref, doubles_storage=storage)
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t0
