@@ -187,7 +187,11 @@ class AdcMatrix(AdcMatrixlike):
             no, nv = self.mospaces.n_orbs("o1"), self.mospaces.n_orbs("v1")
             n2 = self.mospaces.n_orbs("o2") if self.is_core_valence_separated else no
             big = no * n2 * nv * nv * 8 >= (1 << 30)
-            vvvv_bound = self.block_orders.get("pphh_pphh") == 1 and nv >= 96
+            # CVS (packed_cvs.py, virtual pairs only): measured on one B200, c=2 / o=8 / v=106 is still
+            # launch-bound (dense 0.09 s, packed 0.15 s for 7 singlets), c=2 / o=22 / v=196 runs 0.29 s
+            # dense, 0.19 s packed
+            vvvv_bound = (self.block_orders.get("pphh_pphh") == 1
+                          and nv >= (160 if self.is_core_valence_separated else 96))
             if not (packable and (big or vvvv_bound)):
                 return "dense"
             hf = self.reference_state

@@ -171,7 +171,7 @@ class PackedCvsEngine:
         self.flops = {"ph_pphh": 2.0 * nc * nv * (self.R * nv + no * self.npv),
                       "pphh_ph": 2.0 * nc * nv * (self.R * nv + no * self.npv)}
         if self.order_dd == 1:
-            self.W = be.packed_pack(hf.vvvv._contig(), nv, nv)                          # [AB,CD]
+            self.W = be.even_pitch(be.packed_pack(hf.vvvv._contig(), nv, nv))           # [AB,CD], TMA-ready rows
             self.O = be.contiguous(hf.ococ._contig().reshape(self.R, self.R))            # [(iJ),(lK)]
             self.Ycv = be.permute(hf.cvcv._contig(), (2, 1, 0, 3)).reshape(nc * nv, nc * nv)   # [(J,b),(K,c)]
             self.Yov = be.permute(hf.ovov._contig(), (0, 3, 2, 1)).reshape(no * nv, no * nv)   # [(i,a),(k,c)]
