@@ -505,6 +505,10 @@ class AdcMatrix(AdcMatrixlike):
         if n == 0:
             return []
         blocks = vectors[0].blocks
+        if (self._engine is not None and not self.extra_terms and hasattr(self._engine, "matvec_batch")
+                and type(self).matvec is AdcMatrix.matvec and all(v.blocks == blocks for v in vectors)):
+            with self.timer.record("matvec_batch"):
+                return self._engine.matvec_batch(vectors)
         if (n == 1 or self.extra_terms or self._engine is not None
                 or os.environ.get("ADCCB_NO_BATCH", "0") == "1"
                 or any(v.blocks != blocks for v in vectors)

@@ -116,6 +116,12 @@ def release_cached_memory():
         torch.cuda.empty_cache()
 
 
+def free_memory():
+    """Bytes the device can still hand out: free device memory plus the allocator's cached blocks."""
+    free, _ = torch.cuda.mem_get_info()
+    return free + torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
+
+
 def clone(t):
     """Device-to-device copy of a contiguous array (cudaMemcpyAsync on the current stream)."""
     return t.clone()

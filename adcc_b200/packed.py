@@ -1333,6 +1333,73 @@ class PackedAdcEngine:
         self.apply_pphh_ph(u1, S)
         return AmplitudeVector(ph=self._wrap_ph(s1), pphh=self._wrap_pphh(S))
 
+    def matvec_batch(self, vectors):
+        """[M v for v in vectors] with ONE pass over the big constant operands (adcc/AdcMatrix.py:402-408
+        loops over the list): the packed vectors are stacked along the GEMM row dimension, so W, Y,
+        V2 and M1 are streamed once per batch instead of once per vector -
+            vvvv   [nb*IJ, AB]   = Us . W^T          ovov  [nb*(ia), (jb)] = X_all . Y^T
+            ph_pphh [nb*i, a]    = Ue_all . V2^T     pphh_ph [nb*i, (j,AB)] = u1s . V2
+            ph_ph  [nb, (ia)]    = u1s . M1^T
+        - while the expansions / folds and the small oooo / ooov terms run per vector.  Batches are
+        cut so that the stacked temporaries stay inside half of the free device memory.  Engines
+        with distributed vectors, spin-blocked operands or the ADC(3) second-order terms take the
+        per-vector path."""
+        n = len(vectors)
+        if (n <= 1 or self.world > 1 or self._spin is not None or self._extra3 is not None
+                or os.environ.get("ADCCB_NO_BATCH", "0") == "1"
+                or any(isinstance(v["pphh"], SlabDoubles) for v in vectors)):
+            return [self.matvec(v) for v in vectors]
+        no, nv, npo, npv = self.no, self.nv, self.npo, self.npv
+        ov = no * nv
+        per_vector = 8.0 * (2.0 * ov * ov * (self.order_dd == 1) + 2.0 * no * no * npv + 3.0 * npo * npv)
+        chunk = int(max(1, min(n, 0.5 * be.free_memory() // per_vector)))
+        if chunk < n:
+            return sum((self.matvec_batch(vectors[k:k + chunk]) for k in range(0, n, chunk)), [])
+        u1s, Us = be.empty((n, no, nv)), be.empty((n, npo, npv))
+        for k, v in enumerate(vectors):
+            u2 = v["pphh"] if isinstance(v["pphh"], PackedDoubles) else PackedDoubles.from_dense(v["pphh"])
+            be.axpby(1.0, v["ph"]._contig(), 0.0, u1s[k])
+            be.axpby(1.0, u2._contig(), 0.0, Us[k])
+        # ---- singles row of the matrix
+        s1s = be.gemm(u1s.view(n, ov), self.M1).view(n * no, nv)                      # ph_ph
+        Ue = be.empty((n * no, no * npv))
+        for k in range(n):
+            be.packed_expand(1, Us[k], no, nv, out=Ue[k * no:(k + 1) * no])
+        be.gemm(Ue, self.V2, out=s1s, alpha=2.0, beta=1.0)                             # ph_pphh, ovvv part
+        del Ue
+        for k in range(n):
+            Uh = be.packed_expand(2, Us[k], no, nv)
+            be.gemm(self.G1, Uh, out=s1s[k * no:(k + 1) * no], alpha=2.0, beta=1.0)    # ph_pphh, ooov part
+        del Uh
+        # ---- doubles row
+        Ss = be.empty((n, npo, npv))
+        for k in range(n):
+            be.mul(Us[k], self.D0, out=Ss[k], beta=0.0)
+        if self.order_dd == 1:
+            self._mark("vvvv", 0)
+            be.gemm(Us.view(n * npo, npv), self.W, out=Ss.view(n * npo, npv), beta=1.0)
+            self._mark("vvvv", 1)
+            X = be.empty((n * ov, ov))
+            for k in range(n):
+                be.gemm(self.O, be.permute(Us[k], (1, 0)), out=Ss[k], beta=1.0)
+                be.packed_expand(0, Us[k], no, nv, out=X[k * ov:(k + 1) * ov])
+            self._mark("ovov", 0)
+            T = be.gemm(X, self.Y)
+            self._mark("ovov", 1)
+            del X
+            for k in range(n):
+                be.packed_fold_virt(Ss[k], nv, ov, T[k * ov:(k + 1) * ov], self._off_ovov_1,
+                                    T[k * ov:(k + 1) * ov], self._off_ovov_2, alpha=-1.0)
+            del T
+        c1 = be.gemm(u1s.view(n * no, nv), self.V1)                                   # pphh_ph, ovvv part
+        for k in range(n):
+            be.packed_fold_occ(Ss[k], c1[k * no:(k + 1) * no], no, nv, alpha=0.5)
+            c2 = be.gemm(self.G2, be.permute(u1s[k], (1, 0)))
+            be.packed_fold_virt(Ss[k], nv, nv, c2, self._off_rows, alpha=-0.5)
+        del c1
+        s1s = s1s.view(n, no, nv)
+        return [AmplitudeVector(ph=self._wrap_ph(s1s[k]), pphh=self._wrap_pphh(Ss[k])) for k in range(n)]
+
     def matvec_host(self, u1_host, U_host, s1_host, S_host, edge_rows=112):
         """sigma = M u for a trial vector in PINNED host buffers, result into pinned host buffers
         (ph: [no, nv]; pphh: packed [npo, npv]).  Same kernels as ``matvec``; the vvvv GEMM is cut

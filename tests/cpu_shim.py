@@ -143,6 +143,13 @@ def install(monkeypatch):
         return from_numpy(t[ii[:, None], jj[:, None], aa[None, :], bb[None, :]])
 
     def packed_expand(which, U, no, nv, out=None, n_pairs_o=None):
+        res = _packed_expand(which, U, no, nv, n_pairs_o)
+        if out is not None:
+            out.copy_(res.reshape(out.shape))
+            return out
+        return res
+
+    def _packed_expand(which, U, no, nv, n_pairs_o=None):
         if n_pairs_o is not None:
             assert which == 2
             pv = _pairs(nv)
@@ -376,6 +383,7 @@ def install(monkeypatch):
         monkeypatch.setattr(be, name, fn)
     monkeypatch.setattr(be, "device", lambda: cpu)
     monkeypatch.setattr(be, "release_cached_memory", lambda: None)
+    monkeypatch.setattr(be, "free_memory", lambda: 8 << 30)
 
     class ReplayGraph:
         """Host-logic stand-in: same static-buffer protocol, the launch sequence re-runs eagerly."""

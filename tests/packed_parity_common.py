@@ -70,6 +70,35 @@ def check_packed_spin_kinds(method, n=3):
         np.testing.assert_allclose(st.excitation_energy, ost.eigenvalues, atol=ENERGY_ATOL, rtol=0)
 
 
+def check_packed_batched(method, data=None, n=3, tiny_memory=False):
+    """AdcMatrix @ [vectors] on the packed store (PackedAdcEngine.matvec_batch: the big operands are
+    streamed once per batch) equals the per-vector matvec and the oracle; Davidson on top of it
+    keeps the oracle's iteration counts.  tiny_memory: force the batch to be cut into chunks."""
+    import adcc_b200 as adcc
+    from adcc_b200 import backend as be
+    data = data if data is not None else load_h2o_sto3g()
+    m = adcc.AdcMatrix(method, adcc.ReferenceState(data), doubles_storage="packed")
+    om = oracle.OracleAdcMatrix(method, oracle.OracleRefState(oracle.OracleHf(data)))
+    vecs = [random_vector(m, om, 20 + k) for k in range(n)]
+    packed = [_packed_vector(adcc, v) for v, _ in vecs]
+    keep = be.free_memory
+    if tiny_memory:
+        be.free_memory = lambda: 1
+    try:
+        batched = m @ packed
+    finally:
+        be.free_memory = keep
+    assert len(batched) == n
+    for (v, ov), vp, res in zip(vecs, packed, batched):
+        osig = om.matvec(ov)
+        single = m.matvec(vp)
+        for k in osig:
+            assert rel_err(res[k].to_ndarray(), osig[k]) < SIGMA_RTOL, k
+            assert rel_err(res[k].to_ndarray(), single[k].to_ndarray()) < 1e-13, k
+    assert m @ [] == []
+    return m
+
+
 def check_packed_cvs_matrix(method, data=None, core=1, seed=11):
     """CVS-ADC(2) / CVS-ADC(2)-x on the virtual-pair-packed store (adcc_b200/packed_cvs.py) against
     the oracle: sigma, every block, both diagonals, hermiticity, dense round trip of the vector."""

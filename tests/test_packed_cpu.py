@@ -27,6 +27,15 @@ def test_packed_singlets_triplets_h2o(method):
     check_packed_spin_kinds(method)
 
 
+@pytest.mark.parametrize("method", ["adc2", "adc2x", "adc3"])
+def test_packed_batched_matvec(method):
+    """SURVEY 8(f2) on the packed store (adc3: the engine's per-vector path behind the same call)."""
+    from packed_parity_common import check_packed_batched
+    from adcc_b200.synthetic import restricted_scf_dict
+    check_packed_batched(method)
+    check_packed_batched(method, restricted_scf_dict(7, 2, seed=3), n=4, tiny_memory=True)
+
+
 @pytest.mark.parametrize("method", ["cvs-adc2", "cvs-adc2x"])
 def test_packed_cvs_matvec_and_davidson(method):
     """SURVEY 8(a) rows a8/a10/a11/a13/a14 (+CVS) on the virtual-pair-packed store."""

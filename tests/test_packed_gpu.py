@@ -88,6 +88,15 @@ def test_packed_engine_h2o(method):
     check_packed_run(method)
 
 
+@pytest.mark.parametrize("method", ["adc2", "adc2x", "adc3"])
+def test_packed_batched_matvec(method):
+    from packed_parity_common import check_packed_batched
+    from adcc_b200.synthetic import restricted_scf_dict
+    check_packed_batched(method)
+    check_packed_batched(method, restricted_scf_dict(24, 5, seed=3), n=5)
+    check_packed_batched(method, restricted_scf_dict(7, 2, seed=3), n=4, tiny_memory=True)
+
+
 @pytest.mark.parametrize("method", ["cvs-adc2", "cvs-adc2x"])
 def test_packed_cvs_engine(method):
     """CVS variants on the virtual-pair-packed store: sigma / blocks / diagonal vs the oracle, Davidson
