@@ -1345,7 +1345,10 @@ class PackedAdcEngine:
         with distributed vectors, spin-blocked operands or the ADC(3) second-order terms take the
         per-vector path."""
         n = len(vectors)
+        # (measured at nocc=40 / nvirt=400: ADC(2) Davidson 2.73 -> 2.42 s; ADC(2)-x, whose per-vector
+        # GEMMs already have 780 rows and run at 0.97 of the DMMA peak, 43.8 -> 44.2 s: not batched)
         if (n <= 1 or self.world > 1 or self._spin is not None or self._extra3 is not None
+                or (self.order_dd == 1 and self.npo >= 448)
                 or os.environ.get("ADCCB_NO_BATCH", "0") == "1"
                 or any(isinstance(v["pphh"], SlabDoubles) for v in vectors)):
             return [self.matvec(v) for v in vectors]
