@@ -29,7 +29,10 @@ int adccb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* K1 contraction core.  C[m,n] = alpha * sum_k A(m,k) * B(n,k) + beta * C[m,n],
  * A(m,k) = A[m*a_rs + k*a_cs], B(n,k) = B[n*b_rs + k*b_cs], C row-major with leading dim ldc.
- * K-contiguous, 16-byte aligned operands take the TMA + DMMA path, everything else the
+ * K-contiguous, 16-byte aligned operands (a_cs == b_cs == 1, even row strides) take the TMA + DMMA
+ * path; so does an N-major B (b_rs == 1, even b_cs: B stored as B[k][n], i.e. C = A . B without a
+ * transposed copy - both ovvv couplings of adcc/adc_pp/matrix.py:270-276, 288-294 read ONE stored
+ * <ja||bc> layout this way, the "a10 + a11 from one ovvv layout" of SURVEY 8(b)); everything else the
  * generic DMMA path.  `ws` is scratch for split-K partials (may be NULL: no split-K).
  * tile_hint: 0 = automatic, 112 / 128 = force the row-tile height.
  * Replaces libadcc::TensorImpl<N>::tensordot -> libtensor::expr::contract + eval
@@ -123,7 +126,8 @@ int adccb_spin_singlet(void* stream, const int* shape, const int* n_alpha, doubl
  * 121-161 spin-block maps, as adccb_spin_project); sym_mode 0 none, 1 antisymmetrise(0,1), antisymmetrise(2,3),
  * symmetrise((0,1),(2,3)) (adcc/AdcMatrix.py:449-455), 2 antisymmetrise(2,3) (CVS, AdcMatrix.py:445-447);
  * purify != 0: singlet purification of the aaaa / bbbb blocks (libadcc_src/
- * amplitude_vector_enforce_spin_kind.cc:33-170).  Replaces, in one launch, the chain
+ * amplitude_vector_enforce_spin_kind.cc:33-170).  The Python host divides first (adccb_elementwise op 4,
+ * coalesced) and calls this with D == NULL: the gathered form of the division measured slower.  Replaces the chain
  * adcc/solver/preconditioner.py:65-82 -> adcc/solver/explicit_symmetrisation.py:49-98 the reference runs as
  * separate libtensor evaluations per new subspace vector (davidson.py:255-272). */
 int adccb_precond_apply(void* stream, int ndim, const int* shape, const int* n_alpha, const double* x,
