@@ -39,6 +39,8 @@ def _declare(lib):
     lib.adccb_add_columns.argtypes = [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64]
     lib.adccb_lincomb.argtypes = [c_ptr, ctypes.c_int, ctypes.POINTER(c_dbl),
                                   ctypes.POINTER(c_ptr), c_i64, c_dbl, c_ptr]
+    lib.adccb_lincomb_multi.argtypes = [c_ptr, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_dbl),
+                                        ctypes.POINTER(c_ptr), c_i64, c_dbl, ctypes.POINTER(c_ptr)]
     lib.adccb_dot_many.argtypes = [c_ptr, ctypes.c_int, c_ptr, ctypes.POINTER(c_ptr), c_i64,
                                    c_dbl, c_dbl, c_ptr, c_ptr, c_i64]
     lib.adccb_spin_expand4.argtypes = [c_ptr, ctypes.POINTER(ctypes.c_int), c_ptr, c_ptr]
@@ -79,7 +81,7 @@ EXPORTS = [
     "adccb_version", "adccb_last_error", "adccb_launch_count", "adccb_device_info",
     "adccb_dgemm", "adccb_dgemm_peers", "adccb_peer_alloc", "adccb_peer_open", "adccb_peer_close",
     "adccb_peer_free", "adccb_strided_gather", "adccb_elementwise", "adccb_direct_sum",
-    "adccb_add_columns", "adccb_lincomb", "adccb_dot_many", "adccb_spin_expand4", "adccb_spin_project", "adccb_spin_singlet", "adccb_precond_apply",
+    "adccb_add_columns", "adccb_lincomb", "adccb_lincomb_multi", "adccb_dot_many", "adccb_spin_expand4", "adccb_spin_project", "adccb_spin_singlet", "adccb_precond_apply",
     "adccb_packed_unpack", "adccb_packed_pack", "adccb_packed_expand", "adccb_packed_expand_slab",
     "adccb_slab_layout", "adccb_copy2d", "adccb_block_gather", "adccb_block_scatter_add", "adccb_block_scatter", "adccb_vvvv_exchange_slab", "adccb_ovvv_exchange_slab", "adccb_pair_matvec", "adccb_packed_fold_virt",
     "adccb_packed_fold_occ", "adccb_packed_diagonal", "adccb_pair_select", "adccb_synth_fill",

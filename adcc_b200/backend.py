@@ -382,6 +382,24 @@ def lincomb(coeffs, tensors, out=None, beta=0.0):
     return out
 
 
+def lincomb_multi(coeff_rows, tensors):
+    """[sum_k coeff_rows[j][k] * tensors[k] for j]: all outputs from ONE pass over the inputs."""
+    n = tensors[0].numel()
+    for t in tensors:
+        if not t.is_contiguous() or t.numel() != n:
+            raise ValueError("lincomb_multi: tensors must be contiguous and equally sized")
+    C = np.ascontiguousarray(coeff_rows, dtype=np.float64)
+    m, k = C.shape
+    if k != len(tensors):
+        raise ValueError("lincomb_multi: one coefficient per tensor and output expected")
+    outs = [torch.empty_like(tensors[0]) for _ in range(m)]
+    cs = C.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    ps = (ctypes.c_void_p * k)(*[t.data_ptr() for t in tensors])
+    os_ = (ctypes.c_void_p * m)(*[o.data_ptr() for o in outs])
+    _cabi.check(_cabi.lib().adccb_lincomb_multi(_stream(), k, m, cs, ps, n, 0.0, os_))
+    return outs
+
+
 def dot_many(x, ys, scale=1.0):
     """numpy array of <x, y_j>; one pass over x and all y_j; one D2H copy."""
     n = x.numel()
@@ -539,6 +557,13 @@ def copy2d(dst, src, nrows, ncols):
                                          ctypes.c_void_p(src.data_ptr()), src.stride(0) * 8,
                                          int(ncols) * 8, int(nrows)))
     return dst
+
+
+def copy2d_raw(dst_ptr, dst_pitch, src_ptr, src_pitch, nrows, ncols):
+    """copy2d between raw device addresses (pitches in elements): pulls from peer-mapped memory."""
+    _cabi.check(_cabi.lib().adccb_copy2d(_stream(), ctypes.c_void_p(int(dst_ptr)), int(dst_pitch) * 8,
+                                         ctypes.c_void_p(int(src_ptr)), int(src_pitch) * 8,
+                                         int(ncols) * 8, int(nrows)))
 
 
 # --------------------------------------------------------------------------------- collectives

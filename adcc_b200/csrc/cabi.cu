@@ -54,6 +54,8 @@ int add_columns(cudaStream_t st, long long nrows, long long ncols, double* S, lo
                 long long col0, const double* G, long long ldg);
 int lincomb(cudaStream_t st, int nvec, const double* coeff, const double* const* ptrs, long long n,
             double beta, double* out);
+int lincomb_multi(cudaStream_t st, int nvec, int nout, const double* coeff, const double* const* ptrs,
+                  long long n, double beta, double* const* outs);
 int dot_many(cudaStream_t st, int nvec, const double* x, const double* const* ys, long long n,
              double scale, double beta, double* out_dev, double* ws, long long ws_bytes);
 int spin_expand4(cudaStream_t st, const int* n, const double* T, double* out);
@@ -184,6 +186,11 @@ int adccb_add_columns(void* stream, int64_t nrows, int64_t ncols, double* S, int
 int adccb_lincomb(void* stream, int nvec, const double* host_coeff, const double* const* host_ptrs,
                   int64_t n, double beta, double* out) {
   return lincomb((cudaStream_t)stream, nvec, host_coeff, host_ptrs, n, beta, out);
+}
+
+int adccb_lincomb_multi(void* stream, int nvec, int nout, const double* host_coeff,
+                        const double* const* host_ptrs, int64_t n, double beta, double* const* host_outs) {
+  return lincomb_multi((cudaStream_t)stream, nvec, nout, host_coeff, host_ptrs, n, beta, host_outs);
 }
 
 int adccb_dot_many(void* stream, int nvec, const double* x, const double* const* host_ys, int64_t n,

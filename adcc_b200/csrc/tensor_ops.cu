@@ -273,6 +273,78 @@ int lincomb(cudaStream_t st, int nvec, const double* coeff, const double* const*
 }
 
 // ---------------------------------------------------------------------------------------
+// lincomb_multi:  out_j = sum_k C[j][k] * x[k], j < nout: ONE pass over the inputs for all outputs
+// (residuals / Ritz vectors / subspace collapse of the Davidson loop, adcc/solver/davidson.py:
+// 139-140, 151, 168-170: nout combinations of the same 2 n_ss vectors).  Every output is summed
+// in the order and with the instructions of lincomb_kernel: bit-identical to nout separate calls.
+// ---------------------------------------------------------------------------------------
+constexpr int kMaxOut = 8;
+struct MultiList {
+  int n, m;
+  const double* ptr[kMaxVec];
+  double* out[kMaxOut];
+  double coeff[kMaxOut][kMaxVec];
+};
+
+template <int M>
+__global__ void lincomb_multi_kernel(const __grid_constant__ MultiList v, long long n, double beta) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    double s[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) s[j] = (beta != 0.0) ? beta * v.out[j][i] : 0.0;
+#pragma unroll 4
+    for (int k = 0; k < v.n; ++k) {
+      const double x = v.ptr[k][i];
+#pragma unroll
+      for (int j = 0; j < M; ++j) s[j] += v.coeff[j][k] * x;
+    }
+#pragma unroll
+    for (int j = 0; j < M; ++j) v.out[j][i] = s[j];
+  }
+}
+
+int lincomb_multi(cudaStream_t st, int nvec, int nout, const double* coeff, const double* const* ptrs,
+                  long long n, double beta, double* const* outs) {
+  if (n <= 0 || nout <= 0) return 0;
+  if (nvec == 0) {
+    for (int j = 0; j < nout; ++j) {
+      const int rc = elementwise(st, EW_FILL, n, beta == 0.0 ? 1.0 : 0.0, nullptr, nullptr, 0.0, beta, outs[j]);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  for (int j0 = 0; j0 < nout; j0 += kMaxOut) {
+    const int m = std::min(kMaxOut, nout - j0);
+    for (int k0 = 0; k0 < nvec; k0 += kMaxVec) {
+      MultiList v;
+      v.n = std::min(kMaxVec, nvec - k0);
+      v.m = m;
+      for (int k = 0; k < v.n; ++k) v.ptr[k] = ptrs[k0 + k];
+      for (int j = 0; j < m; ++j) {
+        v.out[j] = outs[j0 + j];
+        for (int k = 0; k < v.n; ++k) v.coeff[j][k] = coeff[(size_t)(j0 + j) * nvec + k0 + k];
+      }
+      const double b = k0 == 0 ? beta : 1.0;
+      const int grid = grid_for(n, 256, 2);
+      switch (m) {
+        case 1: lincomb_multi_kernel<1><<<grid, 256, 0, st>>>(v, n, b); break;
+        case 2: lincomb_multi_kernel<2><<<grid, 256, 0, st>>>(v, n, b); break;
+        case 3: lincomb_multi_kernel<3><<<grid, 256, 0, st>>>(v, n, b); break;
+        case 4: lincomb_multi_kernel<4><<<grid, 256, 0, st>>>(v, n, b); break;
+        case 5: lincomb_multi_kernel<5><<<grid, 256, 0, st>>>(v, n, b); break;
+        case 6: lincomb_multi_kernel<6><<<grid, 256, 0, st>>>(v, n, b); break;
+        case 7: lincomb_multi_kernel<7><<<grid, 256, 0, st>>>(v, n, b); break;
+        default: lincomb_multi_kernel<8><<<grid, 256, 0, st>>>(v, n, b); break;
+      }
+      ADCCB_LAUNCH_OK();
+      count_launch();
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
 // dot_many: out[j] = scale * <x, y_j>, j < nvec (<= kMaxVec per launch).  Stage 1 writes one
 // partial per block and vector, stage 2 sums the partials in block order (deterministic).
 // ---------------------------------------------------------------------------------------

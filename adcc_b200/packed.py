@@ -498,6 +498,21 @@ class PackedAdcEngine:
                     for b in bufs:
                         if b is not None:
                             b.close()
+            # distributed vectors: the partial sigma of the non-vvvv terms lives in peer-mapped memory,
+            # every rank PULLS its column slab from the peers with copy-engine 2-D copies while its
+            # vvvv GEMM runs (no SMs, unlike an NCCL reduce-scatter, which cannot share an SM with
+            # the persistent GEMM CTAs), then sums the slabs in rank order.  Two buffers, alternating
+            # per matvec (see _matvec_slab for why that is enough).
+            self._pull = None
+            if (self.vectors == "slab" and be.peer_exchange_supported()
+                    and os.environ.get("ADCCB_CE_EXCHANGE", "1") != "0"):
+                bufs = [be.PeerBuffer.create(self.npo * self.npv) for _ in range(2)]
+                if all(b is not None for b in bufs):
+                    self._pull, self._pull_flip, self._pull_stage = bufs, 0, None
+                else:
+                    for b in bufs:
+                        if b is not None:
+                            b.close()
             # ovov fold of a j-slab: T_r[(i,a),(jl,b)], offset (i*nv + a)*(nj*nv) + jl*nv + b
             njv = self.nj * nv
             own = range(self.j0, self.j0 + self.nj)
@@ -964,7 +979,12 @@ class PackedAdcEngine:
         pphh_ph from this rank's operand slabs.  Returns zero-initialised (P, s1) with them added;
         runs while the doubles slabs are still being gathered."""
         no, nv, npo, npv = self.no, self.nv, self.npo, self.npv
-        P = be.zeros((npo, npv))
+        if getattr(self, "_pull", None) is not None:
+            self._pull_flip ^= 1
+            P = self._pull[self._pull_flip].local.view(npo, npv)
+            be.fill(P, 0.0)
+        else:
+            P = be.zeros((npo, npv))
         s1 = be.zeros((1, no * nv))
         x = u1._contig()
         ij0, ij1 = self.ij0, self.ij1
@@ -1101,18 +1121,70 @@ class PackedAdcEngine:
         P, s1 = self._slab_partial_terms(u1, U, started)
         # ---- sum over ranks: each rank keeps its column slab
         self._mark("reduce", 0)
-        R = lay.reduce_scatter(P)
-        del P
-        be.comm_all_reduce(s1, group=lay.group)
-        self._mark("reduce", 1)
-        # ---- vvvv term straight onto the slab this rank owns
-        if self.order_dd == 1 and lay.w > 0:
-            self._mark("vvvv", 0)
-            be.gemm(U, self.W, out=R[:, :lay.w], alpha=1.0, beta=1.0)
-            self._mark("vvvv", 1)
+        if getattr(self, "_pull", None) is not None and self.order_dd == 1:
+            R = self._pull_exchange(P, s1, U)
+        else:
+            R = lay.reduce_scatter(P)
+            del P
+            be.comm_all_reduce(s1, group=lay.group)
+            self._mark("reduce", 1)
+            # ---- vvvv term straight onto the slab this rank owns
+            if self.order_dd == 1 and lay.w > 0:
+                self._mark("vvvv", 0)
+                be.gemm(U, self.W, out=R[:, :lay.w], alpha=1.0, beta=1.0)
+                self._mark("vvvv", 1)
         self._mark("step", 1)
         sig2 = SlabDoubles._make(self.mospaces, ["o1", "o1", "v1", "v1"], R, lay)
         return AmplitudeVector(ph=self._wrap_ph(s1.view(no, nv)), pphh=sig2)
+
+    def _pull_exchange(self, P, s1, U):
+        """Steps 3 + 4 of _matvec_slab without an SM-side collective on the doubles: ``P`` (this
+        rank's partial sums, complete) is the ``local`` array of a peer-mapped buffer.
+
+          * the small all-reduce of the ph part doubles as the barrier "every rank's P is complete"
+            (a rank contributes to it only after its own P kernels, in stream order);
+          * side stream: one pitched copy per peer, the peer's columns [cut_r, cut_r + w) of P ->
+            a local stage slab (copy engines over NVLink);
+          * main stream, meanwhile: R = own columns of P, R += U W^T (the vvvv GEMM);
+          * join: R += stage slabs, in rank order (deterministic).
+
+        Buffer reuse: matvec k + 2 writes the buffer that peers read during matvec k.  A rank passes
+        the ph all-reduce of matvec k + 1 only after every rank has entered it, i.e. after every
+        rank's pulls of matvec k have been waited for on its main stream - so two buffers suffice."""
+        import torch
+        lay = self.layout
+        npo, npv, wmax, w = lay.npo, lay.npv, lay.wmax, lay.w
+        buf = self._pull[self._pull_flip]
+        be.comm_all_reduce(s1, group=lay.group)
+        main = torch.cuda.current_stream()
+        side = self._gather_stream() or main
+        if self._pull_stage is None:
+            self._pull_stage = be.zeros((max(lay.world - 1, 1), npo, wmax))     # pad columns stay zero
+        stage = self._pull_stage
+        c0 = lay.cuts[lay.rank]
+        if w > 0:
+            ready = torch.cuda.Event()
+            ready.record(main)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                k = 0
+                for r in range(lay.world):
+                    if r == lay.rank:
+                        continue
+                    be.copy2d_raw(stage[k].data_ptr(), wmax, int(buf.peer_ptrs[r]) + 8 * c0, npv, npo, w)
+                    k += 1
+                pulled = torch.cuda.Event()
+                pulled.record(side)
+        self._mark("reduce", 1)
+        R = be.zeros((npo, wmax)) if w < wmax else be.empty((npo, wmax))
+        if w > 0:
+            be.copy2d(R, P[:, c0:c0 + w], npo, w)
+            self._mark("vvvv", 0)
+            be.gemm(U, self.W, out=R[:, :w], alpha=1.0, beta=1.0)
+            self._mark("vvvv", 1)
+            main.wait_event(pulled)
+            be.lincomb([1.0] * (lay.world - 1), [stage[k] for k in range(lay.world - 1)], out=R, beta=1.0)
+        return R
 
     def _vvvv_exchange_pipelined(self, U, buf, S, s1, pipe, host_out):
         """Tail of the pipelined sharded matvec.  The first vvvv row slab was computed before the

@@ -42,7 +42,7 @@ import scipy.linalg as la
 
 from ..AdcMatrix import AdcMatrixlike
 from ..AmplitudeVector import AmplitudeVector, dot_rows
-from ..functions import evaluate, lincomb
+from ..functions import evaluate, lincomb, lincomb_many
 from ..timings import strtime, strtime_short
 from .common import select_eigenpairs
 from .explicit_symmetrisation import IndexSymmetrisation
@@ -120,8 +120,8 @@ def davidson_iterations(matrix, state, max_subspace, max_iter, n_ep, n_block, is
         _project(Ass, SS, Ax, range(n_ss_vec), upper=True)
 
     def ritz_vectors(rvecs, mask):
-        return [lincomb(v, SS, evaluate=True)
-                for i, v in enumerate(np.transpose(rvecs)) if i in mask]
+        rows = [v for i, v in enumerate(np.transpose(rvecs)) if i in mask]
+        return lincomb_many(rows, SS) if rows else []
 
     while state.n_iter < max_iter:
         state.n_iter += 1
@@ -136,8 +136,9 @@ def davidson_iterations(matrix, state, max_subspace, max_iter, n_ep, n_block, is
                 rvals, rvecs = evals[sel], evecs[:, sel]
 
         with state.timer.record("residuals"):
-            residuals = [lincomb(np.hstack((v, -rvals[i] * v)), Ax + SS, evaluate=True)
-                         for i, v in enumerate(np.transpose(rvecs))]
+            # device mapping: all n_block combinations from ONE pass over Ax + SS
+            residuals = lincomb_many([np.hstack((v, -rvals[i] * v))
+                                      for i, v in enumerate(np.transpose(rvecs))], Ax + SS)
             assert len(residuals) == n_block
             epair_mask = select_eigenpairs(rvals, n_ep, which)
             state.eigenvalues = rvals[epair_mask]
@@ -165,9 +166,9 @@ def davidson_iterations(matrix, state, max_subspace, max_iter, n_ep, n_block, is
         if n_ss_vec + n_block > max_subspace:
             callback(state, "restart")
             with state.timer.record("projection"):
-                SS = [lincomb(v, SS, evaluate=True) for v in np.transpose(rvecs)]
+                SS = lincomb_many(np.transpose(rvecs), SS)
                 state.subspace_vectors = SS
-                Ax = [lincomb(v, Ax, evaluate=True) for v in np.transpose(rvecs)]
+                Ax = lincomb_many(np.transpose(rvecs), Ax)
                 n_ss_vec = len(SS)
                 Ass = Ass_cont[:n_ss_vec, :n_ss_vec]
                 _project(Ass, SS, Ax, range(n_ss_vec), upper=True)

@@ -451,6 +451,8 @@ def run_gpu(args):
     eng_build = {"flops": eng.build_flops}
     vector_distribution = matrix.vector_distribution
     slab_exchange = ("none" if world == 1 else
+                     "all-gather(u) + copy-engine pull of the partial-sigma slabs from peer memory under the "
+                     "vvvv GEMM; vvvv slab needs no exchange" if slab and getattr(eng, "_pull", None) is not None else
                      "all-gather(u) + reduce-scatter(partial sigma); vvvv slab needs no exchange" if slab else
                      "GEMM epilogue -> peer memory (NVLink stores)" if eng._peer is not None
                      else "NCCL all-gather")

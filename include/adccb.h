@@ -96,6 +96,14 @@ int adccb_add_columns(void* stream, int64_t nrows, int64_t ncols, double* S, int
 int adccb_lincomb(void* stream, int nvec, const double* host_coeff, const double* const* host_ptrs,
                   int64_t n, double beta, double* out);
 
+/* host_outs[j][:] = beta * host_outs[j][:] + sum_k host_coeff[j*nvec + k] * host_ptrs[k][:], j < nout:
+ * nout linear combinations of the SAME nvec inputs in one pass over the inputs (each output summed
+ * exactly as adccb_lincomb would).  The Davidson loop forms its n_block residuals, Ritz vectors and the
+ * collapsed subspace this way (adcc/solver/davidson.py:139-140, 151, 168-170, where the reference
+ * evaluates one libtensor linear combination per output). */
+int adccb_lincomb_multi(void* stream, int nvec, int nout, const double* host_coeff,
+                        const double* const* host_ptrs, int64_t n, double beta, double* const* host_outs);
+
 /* out_dev[j] = beta * out_dev[j] + scale * <x, y_j>, j < nvec, in one pass over x and every
  * y_j with a fixed-order two-stage reduction.  ws: >= 32*4736*8 bytes of device scratch.
  * libadcc_src/TensorImpl.cc:1120-1144 (dot with a list), libadcc_src/Tensor.hh:198-206. */

@@ -64,6 +64,9 @@ def install(monkeypatch):
             return out
         return res.contiguous()
 
+    def lincomb_multi(coeff_rows, tensors):
+        return [lincomb(row, tensors) for row in np.asarray(coeff_rows, dtype=float)]
+
     def dot_many(x, ys, scale=1.0):
         return np.array([scale * float(torch.dot(x.reshape(-1), y.reshape(-1))) for y in ys])
 
@@ -371,7 +374,7 @@ def install(monkeypatch):
     for name, fn in dict(empty=empty, zeros=zeros, from_numpy=from_numpy, gemm=gemm, gather=gather,
                          permute=permute, contiguous=contiguous, fill=fill, axpby=axpby,
                          scaled_copy=scaled_copy, mul=mul, div=div, div_shift=div_shift,
-                         add_scalar=add_scalar, direct_sum=direct_sum, lincomb=lincomb,
+                         add_scalar=add_scalar, direct_sum=direct_sum, lincomb=lincomb, lincomb_multi=lincomb_multi,
                          dot_many=dot_many, dot=dot, dot_many_blocks=dot_many_blocks, to_host=to_host, upload=upload, download=download, spin_project=spin_project,
                          spin_singlet_=spin_singlet_, precond_apply=precond_apply, packed_unpack=packed_unpack, packed_pack=packed_pack,
                          packed_expand=packed_expand, packed_fold_virt=packed_fold_virt,

@@ -85,6 +85,24 @@ def test_api_surface_and_errors(h2o):
     assert state.converged
 
 
+def test_lincomb_many(h2o):
+    """lincomb_many = several lincomb calls on the same inputs (blocks of AmplitudeVectors included)."""
+    import adcc_b200 as adcc
+    from adcc_b200.functions import lincomb, lincomb_many
+    m = adcc.AdcMatrix("adc2", adcc.ReferenceState(h2o))
+    vecs = [adcc.guess_zero(m).set_random() for _ in range(4)]
+    C = np.random.default_rng(1).standard_normal((3, 4))
+    outs = lincomb_many(C, vecs)
+    assert len(outs) == 3
+    for row, o in zip(C, outs):
+        want = lincomb(row, vecs, evaluate=True)
+        for b in want.blocks:
+            np.testing.assert_allclose(o[b].to_ndarray(), want[b].to_ndarray(), rtol=0, atol=1e-14)
+    assert lincomb_many(np.zeros((0, 4)), vecs) == []
+    with pytest.raises(ValueError):
+        lincomb_many(np.ones((2, 3)), vecs)
+
+
 def test_tensor_algebra_semantics(h2o):
     """Closed-form expectations in the style of libadcc_src/tests/TensorTest.cc:99-970 and
     adcc/tests/einsum_test.py (numpy.einsum as the reference, rtol 1e-10 / atol 1e-14)."""

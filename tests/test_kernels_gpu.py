@@ -169,6 +169,22 @@ def test_lincomb_and_dots(be):
     assert be.dot(e, e) == 4.0
 
 
+@pytest.mark.parametrize("k,m,n", [(3, 2, 1000), (70, 11, 4099), (32, 8, 262144), (1, 1, 5), (40, 5, 100003)])
+def test_lincomb_multi(be, k, m, n):
+    """adccb_lincomb_multi: m combinations of the same k inputs in one pass, each bit-identical to
+    adccb_lincomb on the same coefficients (the Davidson loop relies on that)."""
+    import torch
+    rng = np.random.default_rng(k + m + n)
+    xs = [be.from_numpy(rng.standard_normal(n)) for _ in range(k)]
+    C = rng.standard_normal((m, k))
+    outs = be.lincomb_multi(C, xs)
+    assert len(outs) == m
+    for j in range(m):
+        assert torch.equal(outs[j], be.lincomb(C[j], xs))
+    ref = C @ np.stack([x.cpu().numpy() for x in xs])
+    assert _rel(np.stack([o.cpu().numpy() for o in outs]), ref) < 1e-13
+
+
 def test_spin_kernels(be):
     from oracle.davidson import enforce_spin_maps, enforce_spin_kind
     rng = np.random.default_rng(9)

@@ -11,8 +11,10 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("no,nv", [(40, 240), (10, 38)])       # nv = 38: odd pair count (NCCL exchange)
-def test_sharded_matches_single_gpu(no, nv):
+@pytest.mark.parametrize("no,nv,pull", [(40, 240, "1"), (10, 38, "1"), (40, 240, "0")])    # nv = 38: odd pair count
+def test_sharded_matches_single_gpu(no, nv, pull):
+    """pull = "1": partial sigma exchanged by copy-engine pulls from peer-mapped memory under the vvvv
+    GEMM (PackedAdcEngine._pull_exchange); "0": NCCL reduce-scatter."""
     import torch
     n = torch.cuda.device_count()
     if n < 2:
@@ -21,11 +23,13 @@ def test_sharded_matches_single_gpu(no, nv):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29571",
            os.path.join(ROOT, "tools", "check_sharded.py"), str(no), str(nv)]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT,
+                         env=dict(os.environ, ADCCB_CE_EXCHANGE=pull))
     assert out.returncode == 0, out.stderr[-2000:]
     rows = [json.loads(line) for line in out.stdout.splitlines() if line.startswith("{")]
     assert len(rows) == world
     for r in rows:
+        assert r["slab_exchange"] == ("copy-engine pull" if pull == "1" else "nccl reduce-scatter")
         assert r["run_to_run_identical"] and r["identical_to_rank0"]
         if r["rank"] == 0:
             assert r["rel_err_ph"] < 1e-11 and r["rel_err_pphh"] < 1e-11

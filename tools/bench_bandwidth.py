@@ -47,6 +47,8 @@ out = torch.empty_like(vecs[0])
 D = torch.rand(npo, npv, device="cuda", dtype=torch.float64) + 1.0
 for k in (2, 10, 20):
     report(f"lincomb k={k} (residual / CGS / collapse)", 8 * n * (k + 1), lambda k=k: be.lincomb(np.ones(k), vecs[:k], out=out))
+C5 = np.ones((5, 20))
+report("lincomb_multi m=5 k=20 (5 residuals, one pass)", 8 * n * (20 + 5), lambda: be.lincomb_multi(C5, vecs[:20]))
 for m in (1, 10, 20):
     report(f"dot_many m={m} (p @ SS, subspace rows)", 8 * n * (m + 1), lambda m=m: be.dot_many(vecs[20], vecs[:m]))
 report("div_shift r/(D-s) (Jacobi preconditioner)", 8 * n * 3, lambda: be.div_shift(vecs[0], D, 0.3))

@@ -69,6 +69,7 @@ if m.vector_distribution == "slab":
         worst = max(worst, ((full - outs[0][1]).abs().max() / outs[0][1].abs().max()).item(),
                     ((ss.ph._data - outs[0][0]).abs().max() / outs[0][0].abs().max()).item())
     res["slab_vs_replicated_rel"] = worst
+    res["slab_exchange"] = "copy-engine pull" if getattr(eng, "_pull", None) is not None else "nccl reduce-scatter"
     res["slab_dot_rel"] = abs((vs @ ss) - (v @ s)) / abs(v @ s)
     sh_in, sh_out = shared_host_vector(m), shared_host_vector(m)
     if rank == 0:
