@@ -1137,6 +1137,52 @@ class PackedAdcEngine:
         sig2 = SlabDoubles._make(self.mospaces, ["o1", "o1", "v1", "v1"], R, lay)
         return AmplitudeVector(ph=self._wrap_ph(s1.view(no, nv)), pphh=sig2)
 
+    def _pull_start(self, P, s1):
+        """First half of the copy-engine exchange of the partial sigma (see _pull_exchange): the ph
+        all-reduce (= barrier "every rank's P is complete"), the pulls of this rank's column slab
+        from every peer on the side stream, and R = this rank's own columns of P on the main stream.
+        Returns (R [npo, wmax], token for _pull_finish)."""
+        import torch
+        lay = self.layout
+        npo, npv, wmax, w = lay.npo, lay.npv, lay.wmax, lay.w
+        buf = self._pull[self._pull_flip]
+        be.comm_all_reduce(s1, group=lay.group)
+        main = torch.cuda.current_stream()
+        side = self._gather_stream() or main
+        if self._pull_stage is None:
+            self._pull_stage = be.zeros((max(lay.world - 1, 1), npo, wmax))     # pad columns stay zero
+        stage = self._pull_stage
+        c0 = lay.cuts[lay.rank]
+        pulled = None
+        if w > 0:
+            ready = torch.cuda.Event()
+            ready.record(main)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                k = 0
+                for r in range(lay.world):
+                    if r == lay.rank:
+                        continue
+                    be.copy2d_raw(stage[k].data_ptr(), wmax, int(buf.peer_ptrs[r]) + 8 * c0, npv, npo, w)
+                    k += 1
+                pulled = torch.cuda.Event()
+                pulled.record(side)
+        R = be.zeros((npo, wmax)) if w < wmax else be.empty((npo, wmax))
+        if w > 0:
+            be.copy2d(R, P[:, c0:c0 + w], npo, w)
+        return R, pulled
+
+    def _pull_finish(self, R, pulled):
+        """R += the slabs pulled from the peers, in rank order (deterministic)."""
+        import torch
+        lay = self.layout
+        if pulled is None:
+            return R
+        torch.cuda.current_stream().wait_event(pulled)
+        stage = self._pull_stage
+        be.lincomb([1.0] * (lay.world - 1), [stage[k] for k in range(lay.world - 1)], out=R, beta=1.0)
+        return R
+
     def _pull_exchange(self, P, s1, U):
         """Steps 3 + 4 of _matvec_slab without an SM-side collective on the doubles: ``P`` (this
         rank's partial sums, complete) is the ``local`` array of a peer-mapped buffer.
@@ -1151,40 +1197,14 @@ class PackedAdcEngine:
         Buffer reuse: matvec k + 2 writes the buffer that peers read during matvec k.  A rank passes
         the ph all-reduce of matvec k + 1 only after every rank has entered it, i.e. after every
         rank's pulls of matvec k have been waited for on its main stream - so two buffers suffice."""
-        import torch
         lay = self.layout
-        npo, npv, wmax, w = lay.npo, lay.npv, lay.wmax, lay.w
-        buf = self._pull[self._pull_flip]
-        be.comm_all_reduce(s1, group=lay.group)
-        main = torch.cuda.current_stream()
-        side = self._gather_stream() or main
-        if self._pull_stage is None:
-            self._pull_stage = be.zeros((max(lay.world - 1, 1), npo, wmax))     # pad columns stay zero
-        stage = self._pull_stage
-        c0 = lay.cuts[lay.rank]
-        if w > 0:
-            ready = torch.cuda.Event()
-            ready.record(main)
-            side.wait_event(ready)
-            with torch.cuda.stream(side):
-                k = 0
-                for r in range(lay.world):
-                    if r == lay.rank:
-                        continue
-                    be.copy2d_raw(stage[k].data_ptr(), wmax, int(buf.peer_ptrs[r]) + 8 * c0, npv, npo, w)
-                    k += 1
-                pulled = torch.cuda.Event()
-                pulled.record(side)
+        R, pulled = self._pull_start(P, s1)
         self._mark("reduce", 1)
-        R = be.zeros((npo, wmax)) if w < wmax else be.empty((npo, wmax))
-        if w > 0:
-            be.copy2d(R, P[:, c0:c0 + w], npo, w)
+        if lay.w > 0:
             self._mark("vvvv", 0)
-            be.gemm(U, self.W, out=R[:, :w], alpha=1.0, beta=1.0)
+            be.gemm(U, self.W, out=R[:, :lay.w], alpha=1.0, beta=1.0)
             self._mark("vvvv", 1)
-            main.wait_event(pulled)
-            be.lincomb([1.0] * (lay.world - 1), [stage[k] for k in range(lay.world - 1)], out=R, beta=1.0)
-        return R
+        return self._pull_finish(R, pulled)
 
     def _vvvv_exchange_pipelined(self, U, buf, S, s1, pipe, host_out):
         """Tail of the pipelined sharded matvec.  The first vvvv row slab was computed before the
@@ -1299,12 +1319,17 @@ class PackedAdcEngine:
         main.wait_event(got_b)
         gather_rows(r1, npo)
         P, s1 = self._slab_partial_terms(self._wrap_ph(x), U)
-        R = lay.reduce_scatter(P)
-        del P
-        be.comm_all_reduce(s1, group=lay.group)
+        pulled = None
+        if getattr(self, "_pull", None) is not None:
+            R, pulled = self._pull_start(P, s1)            # peers' slabs arrive under the middle GEMM
+        else:
+            R = lay.reduce_scatter(P)
+            del P
+            be.comm_all_reduce(s1, group=lay.group)
         be.axpby(1.0, Rv, 1.0, R[:r1])
         if w > 0 and r2 > r1:
             be.gemm(U[r1:r2], self.W, out=R[r1:r2, :w], alpha=1.0, beta=1.0)
+        self._pull_finish(R, pulled)
         head = torch.cuda.Event()
         head.record(main)
         if w > 0 and npo > r2:

@@ -88,6 +88,24 @@ def test_packed_tensor_semantics():
         PackedDoubles.zeros(ref.mospaces, ["o1", "o1", "v1", "v1"]).set_from_ndarray(np.ones((10, 10, 4, 4)))
 
 
+def test_doubles_guesses_on_packed_stores():
+    """Doubles guesses (adcc/guess/guesses_from_diagonal.py:233-305, fill_pp_doubles_guesses) written
+    through element access into the packed stores equal the dense-store guesses."""
+    import adcc_b200 as adcc
+    from oracle.hfdata import load_h2o_sto3g
+    data = load_h2o_sto3g()
+    for core, method in ((None, "adc2x"), (1, "cvs-adc2x")):
+        ref = adcc.ReferenceState(data, core_orbitals=core)
+        packed = adcc.AdcMatrix(method, ref, doubles_storage="packed")
+        dense = adcc.AdcMatrix(method, ref, doubles_storage="dense")
+        for fn in (adcc.guesses_singlet, adcc.guesses_triplet, adcc.guesses_any):
+            gp, gd = fn(packed, 4, block="pphh"), fn(dense, 4, block="pphh")
+            assert len(gp) == len(gd) == 4
+            for a, b in zip(gp, gd):
+                np.testing.assert_allclose(a.pphh.to_ndarray(), b.pphh.to_ndarray(), atol=1e-15)
+                assert abs(a @ a - 1.0) < 1e-13
+
+
 def test_cvs_packed_tensor_semantics():
     import adcc_b200 as adcc
     from adcc_b200.packed_cvs import CvsPackedDoubles
