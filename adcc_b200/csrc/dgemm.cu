@@ -90,6 +90,12 @@ struct TileCfg {
   static constexpr int A_BYTES = BM * kBK * 8;
   static constexpr int B_BYTES = BN * kBK * 8;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  // a TMA box holds at most 256 rows: wider B tiles arrive as two boxes (each a multiple of the
+  // 8-row swizzle period, so the second one lands 1024-byte aligned behind the first)
+  static constexpr int B_BOXES = BN <= 256 ? 1 : 2;
+  static constexpr int B_BOX_ROWS = BN / B_BOXES;
+  static_assert(BN % B_BOXES == 0 && B_BOX_ROWS % 8 == 0 && B_BOX_ROWS <= 256, "B tile does not split into TMA boxes");
+  static_assert(A_BYTES % 1024 == 0 && STAGE_BYTES % 1024 == 0, "stages must keep the 1024-byte swizzle alignment");
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;
 };
 
@@ -253,7 +259,10 @@ dgemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA,
             for (int b = 0; b < Cfg::BN / 16; ++b)
               tma_load_2d(dst + Cfg::A_BYTES + b * 2048, &tmB, full, tn * Cfg::BN + 16 * b, (k_start + n) * kBK);
           } else {
-            tma_load_2d(dst + Cfg::A_BYTES, &tmB, full, (k_start + n) * kBK, tn * Cfg::BN);
+#pragma unroll
+            for (int b = 0; b < Cfg::B_BOXES; ++b)
+              tma_load_2d(dst + Cfg::A_BYTES + b * Cfg::B_BOX_ROWS * 128, &tmB, full, (k_start + n) * kBK,
+                          tn * Cfg::BN + b * Cfg::B_BOX_ROWS);
           }
         }
       }
@@ -529,7 +538,7 @@ static int launch_tma(cudaStream_t st, int M, int N, int K, double alpha, const 
   CUtensorMap tmA, tmB;
   // BNM: ldb is the stride between k-rows of B[k][n]
   if (!make_map_2d(&tmA, A, M, K, lda, Cfg::BM) ||
-      !(BNM ? make_map_nmajor(&tmB, B, K, N, ldb) : make_map_2d(&tmB, B, N, K, ldb, Cfg::BN)))
+      !(BNM ? make_map_nmajor(&tmB, B, K, N, ldb) : make_map_2d(&tmB, B, N, K, ldb, Cfg::B_BOX_ROWS)))
     return fail("cuTensorMapEncodeTiled failed");
   const int tm = (M + Cfg::BM - 1) / Cfg::BM, tn = (N + Cfg::BN - 1) / Cfg::BN;
   const long long tiles = (long long)tm * tn;
@@ -545,7 +554,12 @@ static int launch_tma(cudaStream_t st, int M, int N, int K, double alpha, const 
   } else if (tiles >= nsm) {
     const long long q = tiles / nsm, r = tiles % nsm;
     n_ctas = nsm;
-    dp_waves = (int)((r == 0) ? q : q - 1);
+    // The ragged last round alone goes to stream-K when it gives every CTA at least half a tile;
+    // otherwise the last full round joins it ("two-tile" stream-K: spans of 1 - 1.5 tiles).  Stream-K
+    // spans start at unrelated k offsets, so nothing they read is shared through L2: with the
+    // two-tile rule everywhere the vvvv GEMM (29.5 rounds) read 100.6 GB per launch, with this rule
+    // 77.7 GB, same duration (profiles/r02_gemm_pacing_and_streamk_tail_ab.txt).
+    dp_waves = (int)((r == 0 || 2 * r >= nsm) ? q : q - 1);
     sk_tile0 = (long long)dp_waves * nsm;
     sk_tiles = tiles - sk_tile0;
     ipc = (sk_tiles * k_iters + n_ctas - 1) / n_ctas;
@@ -616,6 +630,12 @@ static int dgemm_impl(cudaStream_t st, long long M, long long N, long long K, do
                                                            brs, beta, C, ldc, ws, ws_bytes, peers)      \
                      : launch_tma<WM, WN, MB, NB, 6, false>(st, (int)M, (int)N, (int)K, alpha, A, ars, B, \
                                                             brs, beta, C, ldc, ws, ws_bytes, peers)
+    // skinny split-K stream against a B operand of up to 400 rows (Ue . V2^T of the ovvv coupling at
+    // nvirt = 400: M = nocc, K = nocc * npv): ONE 40 x 400 tile, 10 consumer warps of 5 x 5 fragment
+    // blocks, instead of four 128-column tiles of which the last is 88 % padding
+    if (peers.n == 0 && ((tile_hint == 0 && M <= 40 && N > 256 && N <= 400) || tile_hint == 400))
+      return launch_tma<1, 10, 5, 5, 4, false>(st, (int)M, (int)N, (int)K, alpha, A, ars, B, brs, beta, C, ldc, ws,
+                                               ws_bytes, peers);
     if (tile_hint == 0 || tile_hint == 16 || tile_hint == 40 || tile_hint == 64) {
       if (tile_hint == 16 || (tile_hint == 0 && M <= 16)) ADCCB_TMA(1, 8, 2, 2);
       if (tile_hint == 40 || (tile_hint == 0 && M <= 40)) ADCCB_TMA(1, 8, 5, 2);

@@ -34,7 +34,7 @@ def test_gemm_tn_tma(be, M, N, K):
     assert _rel(out.cpu().numpy(), -0.5 * ref + 2.0 * C0) < 1e-13
 
 
-@pytest.mark.parametrize("hint", [16, 40, 64, 112, 128])
+@pytest.mark.parametrize("hint", [16, 40, 64, 112, 128, 400])
 def test_gemm_tile_variants(be, hint):
     rng = np.random.default_rng(5)
     A = rng.standard_normal((300, 514))
@@ -265,7 +265,9 @@ def test_tensor_symmetrise_reference_goldens_device(be):
 
 
 @pytest.mark.parametrize("M,N,K,hint", [(780, 4096, 9600, 0), (2048, 2048, 2048, 128), (2048, 2048, 2048, 112),
-                                        (40, 240, 96000, 0), (2000, 1600, 1600, 0)])
+                                        (40, 240, 96000, 0), (2000, 1600, 1600, 0),
+                                        (780, 8192, 12800, 0),        # 2 data-parallel rounds + two-tile stream-K tail
+                                        (40, 400, 96000, 0), (37, 390, 50000, 0)])   # one 40 x 400 tile, two B boxes
 def test_gemm_pipeline_stress_bitwise(be, M, N, K, hint):
     """Regression guard for the shared-memory WAR race the TMA pipeline once had (a refill
     overtaking delayed fragment reads, about once per 1e4 tiles with L2-resident operands): many
