@@ -7,6 +7,7 @@ diagonal_precomputed)``, ``matvec`` / ``@`` / ``rmatvec``, ``block_apply``, ``di
 :74-130.  The blocks are the contraction tables of adcc_b200/adc_pp.py; ``matvec`` evaluates
 all terms of all blocks and merges the terms of each output block in one fused lincomb launch.
 """
+import contextlib
 import os
 from collections import namedtuple
 
@@ -331,6 +332,25 @@ class AdcMatrix(AdcMatrixlike):
             outblock, inblock = block.split("_")
             ret = self.blocks[block](AmplitudeVector(**{inblock: tensor}))
             return getattr(ret, outblock)
+
+    @contextlib.contextmanager
+    def spin_conserving_vectors(self):
+        """Promise, for the duration of the block, that every vector handed to ``matvec`` is zero in
+        the spin blocks that change M_s - true for the Davidson iterations started from this package's
+        singlet / triplet / any guesses (adcc/guess/guess_zero.py:121-161 forbids those blocks, and
+        lincomb / preconditioner / matvec keep them zero).  The spin-blocked packed engine then
+        multiplies only the matching row class of the vector with each operand block.  No effect on
+        other engines; a matvec outside the block makes no assumption."""
+        eng = self._engine
+        if eng is None or not hasattr(eng, "ms_conserving"):
+            yield
+            return
+        previous = eng.ms_conserving
+        eng.ms_conserving = True
+        try:
+            yield
+        finally:
+            eng.ms_conserving = previous
 
     def _matvec_terms(self, v):
         collected = {}

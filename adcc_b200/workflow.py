@@ -27,6 +27,7 @@ Same call signature, validation, defaults and guess heuristics as adcc/workflow.
 ``estimate_n_guesses``, ``obtain_guesses_by_inspection``); only the Davidson eigensolver of the
 hot path is available (eigensolver="davidson").
 """
+import contextlib
 import sys
 import warnings
 
@@ -181,7 +182,10 @@ def diagonalise_adcmatrix(matrix, n_states, kind, eigensolver="davidson", guesse
     else:
         raise InputError(f"Solver {eigensolver} unknown, try 'davidson'.")
 
+    structure = contextlib.nullcontext()
     if guesses is None:
+        if kind in ("singlet", "triplet", "any") and hasattr(matrix, "spin_conserving_vectors"):
+            structure = matrix.spin_conserving_vectors()      # the guesses made below conserve M_s
         if n_guesses is None:
             n_guesses = estimate_n_guesses(matrix=matrix, n_states=n_states,
                                            singles_only=("pphh" not in matrix.axis_blocks),
@@ -196,8 +200,9 @@ def diagonalise_adcmatrix(matrix, n_states, kind, eigensolver="davidson", guesse
         if n_guesses_doubles is not None:
             warnings.warn("Ignoring n_guesses_doubles parameter, since guesses are explicitly provided.")
     solverargs.setdefault("which", "SA")
-    return run_eigensolver(matrix, guesses, n_ep=n_states, conv_tol=conv_tol, callback=callback,
-                           explicit_symmetrisation=explicit_symmetrisation, **solverargs)
+    with structure:
+        return run_eigensolver(matrix, guesses, n_ep=n_states, conv_tol=conv_tol, callback=callback,
+                               explicit_symmetrisation=explicit_symmetrisation, **solverargs)
 
 
 def estimate_n_guesses(matrix, n_states, singles_only=True, n_guesses_per_state=2):

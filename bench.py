@@ -13,8 +13,10 @@ One "step" = one sigma = M u through the public API (AdcMatrix.matvec).  Prints 
   roofline   dominant kernel (packed vvvv DMMA GEMM): executed flops / CUDA-event time against the
              DMMA.8x8x4 issue peak measured on this pool (profiles/r01_fp64_peak_microbench.txt;
              MEASURED_PEAKS.json carries no FP64 figure)
-  cpu_baseline  oracle timed on the host cores on a bounded reduced-size sample, extrapolated by
-             the dense flop count (labelled as such)
+  cpu_baseline  ONE complete matvec of the same workload by the oracle's full-size restatement
+             (oracle/headline.py) on all host cores, fed with the same trial vector; its sigma is
+             compared element by element with the GPU's (checks.full_sigma_rel_err_vs_cpu_oracle)
+  --impl reference   times `steps` such complete CPU matvecs and prints the same line
 """
 import argparse
 import json

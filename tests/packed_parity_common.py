@@ -70,6 +70,34 @@ def check_packed_spin_kinds(method, n=3):
         np.testing.assert_allclose(st.excitation_energy, ost.eigenvalues, atol=ENERGY_ATOL, rtol=0)
 
 
+def check_spin_conserving_rows(method, data):
+    """The spin-blocked engine under AdcMatrix.spin_conserving_vectors(): for vectors that are zero in
+    the M_s-changing spin blocks (the guesses of every spin kind and what Davidson makes of them) the
+    row-restricted class GEMMs give the same sigma as the all-rows path; outside the block nothing is
+    assumed (random vectors are covered by check_packed_matrix)."""
+    import adcc_b200 as adcc
+    from adcc_b200.guess import guesses_any, guesses_singlet, guesses_triplet
+    m = adcc.AdcMatrix(method, adcc.ReferenceState(data), doubles_storage="packed")
+    eng = m._engine
+    assert eng._spin is not None and eng.ms_conserving is False
+    vecs = []
+    for make in (guesses_any, guesses_singlet, guesses_triplet):
+        g = make(m, 3, block="ph") + make(m, 2, block="pphh")
+        vecs += g
+        vecs.append(m @ g[0] + 0.3 * (m @ g[-1]))          # a Krylov-type vector: still M_s-conserving
+    for v in vecs:
+        full = m @ v
+        with m.spin_conserving_vectors():
+            assert eng.ms_conserving is True
+            fast = m @ v
+        assert eng.ms_conserving is False
+        for b in ("ph", "pphh"):
+            ref = full[b]._data
+            assert float((fast[b]._data - ref).abs().max()) <= 1e-13 * max(float(ref.abs().max()), 1e-300)
+    flops_all = eng.flops["pphh_pphh/vvvv"]
+    assert flops_all > 0
+
+
 def check_packed_batched(method, data=None, n=3, tiny_memory=False):
     """AdcMatrix @ [vectors] on the packed store (PackedAdcEngine.matvec_batch: the big operands are
     streamed once per batch) equals the per-vector matvec and the oracle; Davidson on top of it

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import cpu_shim
-from packed_parity_common import check_packed_matrix, check_packed_run, check_packed_spin_kinds, check_synthetic
+from packed_parity_common import check_packed_matrix, check_packed_run, check_packed_spin_kinds, check_spin_conserving_rows, check_synthetic
 
 
 @pytest.fixture(autouse=True)
@@ -167,4 +167,6 @@ def test_spin_blocked_operands_restricted_reference(method, monkeypatch):
         sp = m._engine._spin
         assert sp["W"][2] is sp["W"][0] and sp["O"][2] is sp["O"][0]        # beta-beta stored once
         check_packed_matrix(method, data)
-    check_packed_run(method)
+        check_spin_conserving_rows(method, data)
+    check_packed_run(method)                 # through run_adc: row-restricted class GEMMs
+    check_packed_spin_kinds(method)
