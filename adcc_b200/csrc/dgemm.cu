@@ -384,12 +384,31 @@ dgemm_fixup_kernel(double* __restrict__ C, long long ldc, int M, int N, int tile
     const long long t0 = tl * (long long)k_iters, t1 = t0 + k_iters;
     const long long b_first = t0 / ipc, b_last = (t1 - 1) / ipc;
     if (b_first == b_last && b_first * ipc <= t0 && (b_first + 1) * ipc >= t1) continue;  // stored directly
+    // CTA b's span starts inside this tile (its first segment, slot 0) or before it (then the tile holds
+    // its last segment, slot 1).  Four independent loads per step: a skinny split-K GEMM sums up to
+    // one segment per SM here, and a dependent chain of 148 x 2 loads took 0.09 ms
+    // (profiles/r02_bench_launches.csv); the order of the additions stays fixed (deterministic).
     double a0 = 0.0, a1 = 0.0;
-    for (long long b = b_first; b <= b_last; ++b) {
-      const int slot = ((b * ipc) / k_iters == tl) ? 0 : 1;   // first or last segment of CTA b
-      const double* P = partial + ((size_t)2 * b + slot) * (size_t)(MB * NB * 2) * kThreads;
-      a0 += P[(size_t)((bi * NB + bj) * 2 + 0) * kThreads + threadIdx.x];
-      a1 += P[(size_t)((bi * NB + bj) * 2 + 1) * kThreads + threadIdx.x];
+    const size_t seg = (size_t)(MB * NB * 2) * kThreads;
+    const double* P0 = partial + (size_t)((bi * NB + bj) * 2) * kThreads + threadIdx.x;
+    long long b = b_first;
+    for (; b + 3 <= b_last; b += 4) {
+      double x[4], y[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int slot = ((b + q) * ipc >= t0) ? 0 : 1;
+        const double* P = P0 + ((size_t)2 * (b + q) + slot) * seg;
+        x[q] = P[0];
+        y[q] = P[kThreads];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { a0 += x[q]; a1 += y[q]; }
+    }
+    for (; b <= b_last; ++b) {
+      const int slot = (b * ipc >= t0) ? 0 : 1;
+      const double* P = P0 + ((size_t)2 * b + slot) * seg;
+      a0 += P[0];
+      a1 += P[kThreads];
     }
     const long long tile = sk_tile0 + tl;
     const int r = (int)(tile % tiles_m) * Cfg::BM + wm * MB * 8 + pg + bi * 8;

@@ -471,10 +471,11 @@ def run_gpu(args):
                        "MEASURED_PEAKS.json has no FP64 entry; cuBLAS DGEMM reaches 36.2-36.5 here",
         "flops_per_launch": f_vvvv, "ms_per_launch": t_vvvv,
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture
-        # profiles/r02_vvvv_gemm.ncu-rep (1 GPU, nocc=40/nvirt=400): 145.25 GB + 0.59 GB per launch
-        # (round 1 capture: 122.7 + 0.5); algorithmic: W 50.9 GB once + U 0.5 GB per wave of tiles
-        # (30 waves) + sigma RMW 1 GB = 67 GB: the 7 CTAs that share a W slab drift apart in L2
-        "traffic": 1.4584e11 if (world == 1 and no == NO and nv == NV) else None,
+        # profiles/r02_vvvv_gemm.ncu-rep (1 GPU, nocc=40/nvirt=400): 89.44 GB + 0.53 GB per launch
+        # (145.8 GB before the stream-K tail was shortened to the ragged round, 123.2 GB in round 1);
+        # algorithmic: W 50.9 GB once + U 0.5 GB per round of tiles (29.5 rounds) + sigma RMW 1 GB =
+        # 66.6 GB - the rest is the stream-K tail, whose spans share nothing through L2
+        "traffic": 8.9967e10 if (world == 1 and no == NO and nv == NV) else None,
         "second_kernel": {"name": "dgemm_tn_tma_kernel (ovov term)", "flops_per_launch": f_ovov / world,
                           "ms_per_launch": t_ovov,
                           "achieved": f_ovov / world / (t_ovov * 1e-3) * 1e-12 if t_ovov else None},
