@@ -651,8 +651,9 @@ static int dgemm_impl(cudaStream_t st, long long M, long long N, long long K, do
                                                             brs, beta, C, ldc, ws, ws_bytes, peers)
     // skinny split-K stream against a B operand of up to 400 rows (Ue . V2^T of the ovvv coupling at
     // nvirt = 400: M = nocc, K = nocc * npv): ONE 40 x 400 tile, 10 consumer warps of 5 x 5 fragment
-    // blocks, instead of four 128-column tiles of which the last is 88 % padding
-    if (peers.n == 0 && ((tile_hint == 0 && M <= 40 && N > 256 && N <= 400) || tile_hint == 400))
+    // blocks, instead of four 128-column tiles of which the last is 88 % padding (up to 16 rows the
+    // 16-row tiles stay: these streams are HBM-bound only while few DMMA rows are spent on padding)
+    if (peers.n == 0 && ((tile_hint == 0 && M > 16 && M <= 40 && N > 256 && N <= 400) || tile_hint == 400))
       return launch_tma<1, 10, 5, 5, 4, false>(st, (int)M, (int)N, (int)K, alpha, A, ars, B, brs, beta, C, ldc, ws,
                                                ws_bytes, peers);
     if (tile_hint == 0 || tile_hint == 16 || tile_hint == 40 || tile_hint == 64) {
