@@ -11,9 +11,15 @@ answers for H2O/STO-3G (adcc/tests/smoke_test.py:32-58: adc0..adc3 and cvs-adc0.
 again from its second, PySCF-generated fixture (examples/0_basics/h2o_sto3g_hfdata.hdf5 ->
 tests/golden/h2o_sto3g_pyscf_hfdata.npz, full 14^4 eri_ffff), see tests/test_hdf5_cpu.py; the
 (anti)symmetrisers are checked against the reference's vendored tensor goldens.
-Sigma vectors are not dumped anywhere in the reference tree, so per-entry sigma parity
-between the reference and this oracle is pinned only through those eigenvalues and
-through hermiticity / symmetry invariants.
+Round 2 adds per-entry pins: the reference's own, unmodified Python layer (adcc/workflow.py,
+AdcMatrix.py, adc_pp/matrix.py, LazyMp.py, guess/*, solver/davidson.py, adc_pp/transition_dm.py)
+was imported from /root/reference and run on the libadcc/ module surface of this repository; the
+sigma vectors, diagonals, per-block results, MP energies, states, Davidson iteration counts and
+oscillator strengths it produced for ten methods are committed as
+tests/golden/reference_adcc_h2o_sto3g.npz (generator beside it) and this oracle agrees with them
+to 1e-12 (tests/test_reference_goldens_cpu.py).  libadcc itself (libtensor arithmetic) cannot be
+built offline, so there is no oracle/_ref; its floating-point results are pinned only through the
+known answers above.
 
 Everything works on dense spin-orbital arrays in adcc's index convention
 (libadcc_src/MoSpaces.cc:379-405: alpha block then beta block per axis, each sorted by
