@@ -83,12 +83,25 @@ class ExcitedStates:
         return 2.0 / 3.0 * np.array([np.linalg.norm(t) ** 2 * e
                                      for t, e in zip(tdm, self.excitation_energy)])
 
+    # -- state densities (adcc/ElectronicStates.py:205-264)
+    @property
+    def state_diffdm(self):
+        """Difference densities (state minus ground state) as {block: Tensor}, upper blocks of a
+        Hermitian block matrix."""
+        from .properties import state_diffdm
+        return [state_diffdm(self.property_method, self.ground_state, v) for v in self.excitation_vector]
+
+    @property
+    def state_dipole_moment(self):
+        from .properties import state_dipole_moments
+        return state_dipole_moments(self)
+
     def describe(self, oscillator_strengths=True, rotatory_strengths=False, state_dipole_moments=False,
                  transition_dipole_moments=False, block_norms=True, ssq=False):
         """Human-readable table of the states (adcc/ExcitedStates.py:50-166): one column group per
         requested quantity, each column as wide as its widest entry plus one, header line
-        ``method (property method)    kind, converged``.  Rotatory strengths, state dipole
-        moments and <S^2> belong to subsystems outside this path and are not shown."""
+        ``method (property method)    kind, converged``.  Rotatory strengths and <S^2> belong to
+        subsystems outside this path and are not shown."""
         eV = 27.211386245988
         has_dipole = hasattr(self.reference_state.operator_integral_provider, "electric_dipole")
         columns = [_column("#", [str(i) for i in range(self.size)])]
@@ -105,6 +118,10 @@ class ExcitedStates:
                 if block in self.matrix.axis_blocks:
                     columns.append(_column(label, [f"{v[block].dot(v[block]):^9.4f}"
                                                    for v in self.excitation_vector]))
+        if state_dipole_moments and has_dipole:
+            vals = [f"{d[0]:^8.4f} {d[1]:^8.4f} {d[2]:^8.4f}{np.linalg.norm(d):^8.4f}"
+                    for d in self.state_dipole_moment]
+            columns.append(_column("state dipole moment", vals, unit="x(au)    y(au)    z(au)    abs(au)"))
         width = sum(c["width"] for c in columns)
         method = self.method.name
         if self.property_method != self.method.name:

@@ -182,6 +182,12 @@ class LazyMp:
             raise NotImplementedError("Only the second-order difference density is on the hot path.")
         return self.second_order_dm_correction(apply_cvs=apply_cvs)
 
+    def dipole_moment(self, level=2):
+        """Ground-state dipole moment with the density corrected up to ``level``
+        (adcc/GroundState.py:178-189)."""
+        from .properties import ground_state_dipole_moment
+        return self._cached(("dipole_moment", level), lambda: ground_state_dipole_moment(self, level))
+
     # LazyMp.py:245-296
     def energy_correction(self, level=2):
         assert level >= 0

@@ -211,4 +211,5 @@ class ReferenceState:
 
     @property
     def nuclear_dipole(self):
-        return np.asarray(self._hf.get_nuclear_multipole(1))
+        # (order, gauge_origin): libadcc_src/ReferenceState.cc:353-358; the dipole does not depend on the origin argument
+        return np.asarray(self._hf.get_nuclear_multipole(1, "origin"))

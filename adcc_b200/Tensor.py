@@ -320,33 +320,34 @@ class Tensor:
             return self._like(be.div(self._contig(), other._contig()))
         return NotImplemented
 
-    def __iadd__(self, other):
+    # ``a += b`` REBINDS ``a`` to a new tensor; the object ``a`` named before - and every other
+    # reference to it - keeps its values (libadcc_src/pyiface/export_Tensor.cc:352-410:
+    # ``return self = self->add(other)`` assigns to the by-value shared_ptr argument).  The
+    # reference's own code relies on it, e.g. ``p1_oo = dm.oo.evaluate(); dm.oo += ...`` in
+    # adcc/adc_pp/state_diffdm.py:70-86 keeps the first-order block in ``p1_oo``.  Immutable
+    # operands are therefore fine.
+    def _scale_inplace(self, factor):
+        """Scale the stored values of THIS object (native routines that fill caller-owned tensors,
+        e.g. fill_pp_doubles_guesses, libadcc_src/fill_pp_doubles_guesses.cc:26-71)."""
         self._require_mutable()
-        if isinstance(other, Tensor):
-            self._check_same(other)
-            be.axpby(1.0, other._contig(), 1.0, self._contig())
-            return self
-        return NotImplemented
+        t = self._contig()
+        be.axpby(float(factor), t, 0.0, t)
+        return self
+
+    def __iadd__(self, other):
+        return self.__add__(other)
 
     def __isub__(self, other):
-        self._require_mutable()
-        if isinstance(other, Tensor):
-            self._check_same(other)
-            be.axpby(-1.0, other._contig(), 1.0, self._contig())
-            return self
-        return NotImplemented
+        return self.__sub__(other)
 
     def __imul__(self, other):
-        self._require_mutable()
         if isinstance(other, numbers.Number):
-            t = self._contig()
-            be.axpby(float(other), t, 0.0, t)
-            return self
+            return self.__mul__(other)
         return NotImplemented
 
     def __itruediv__(self, other):
         if isinstance(other, numbers.Number):
-            return self.__imul__(1.0 / float(other))
+            return self.__mul__(1.0 / float(other))
         return NotImplemented
 
     def div_shifted(self, diagonal, shift):

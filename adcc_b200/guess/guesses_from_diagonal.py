@@ -291,7 +291,7 @@ def _fill_pp_doubles_guesses(guesses_d, mospaces, df02, df13, spin_change_twice,
             if norm == 0.0:
                 continue
             if norm != 1.0:
-                t *= 1.0 / np.sqrt(norm)
+                t._scale_inplace(1.0 / np.sqrt(norm))     # the caller's tensor object is filled (t *= c would rebind)
             n_built += 1
     return n_built
 

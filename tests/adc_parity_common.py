@@ -104,6 +104,21 @@ def check_oscillator_strengths(data, method, core, n=3, conv_tol=1e-9):
     assert f.shape == of.shape
     np.testing.assert_allclose(f, of, rtol=1e-6, atol=1e-10)
     assert np.all(f >= 0)
+    # state difference densities / state dipole moments (adcc/adc_pp/state_diffdm.py, ElectronicStates.py:247-264)
+    from oracle.properties import state_diffdm, state_dipole_moments
+    om = oracle.OracleAdcMatrix(method, oref)
+    tol = max(1e-7, 100.0 * conv_tol)                 # first order in the eigenvector error
+    np.testing.assert_allclose(state.state_dipole_moment, state_dipole_moments(om, ostate), rtol=0, atol=tol)
+    for dm, ovec in zip(state.state_diffdm, ostate.eigenvectors):
+        odm = state_diffdm(om, ovec)
+        assert sorted(dm) == sorted(odm)
+        for blk in dm:
+            assert np.max(np.abs(dm[blk].to_ndarray() - odm[blk])) < tol, (method, blk)
+        # a difference density moves no charge: tr(diffdm) = 0 (second order: to the order of the method)
+        tr = sum(float(np.trace(dm[blk].to_ndarray())) for blk in dm if blk[0] == blk[1])
+        assert abs(tr) < (1e-10 if method in ("adc0", "adc1", "cvs-adc0", "cvs-adc1") else 0.2)
+    text = state.describe(state_dipole_moments=True)
+    assert "state dipole moment" in text
     return f
 
 

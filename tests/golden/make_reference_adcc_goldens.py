@@ -86,6 +86,17 @@ def main():
                 # ElectronicTransition._oscillator_strength (2/3 |mu|^2 omega)
                 out[f"{key}/singlet/oscillator_strength"] = np.array(state.oscillator_strength)
                 out[f"{key}/singlet/transition_dipole_moment"] = np.array(state.transition_dipole_moment)
+            if kind == "singlet":
+                # the reference's state densities: adc_pp/state_diffdm.py, ElectronicStates.state_dipole_moment,
+                # GroundState.dipole_moment (the dense matrix is in the order of the full orbital axis:
+                # OneParticleDensity.to_ndarray, adcc/NParticleOperator.py)
+                out[f"{key}/singlet/state_dipole_moment"] = np.array(state.state_dipole_moment)
+                level = state.property_method.level.to_int()
+                gs = state.reference_state.dipole_moment if level == 0 else state.ground_state.dipole_moment(level)
+                out[f"{key}/ground_state_dipole_moment"] = np.array(gs)
+                for n, ddm in enumerate(state.state_diffdm):
+                    for blk in ddm.blocks_nonzero:
+                        out[f"{key}/singlet/state_diffdm/{n}/{blk}"] = ddm[blk].to_ndarray()
         print(method, out[f"{key}/singlet/energies"], out[f"{key}/singlet/n_iter"], flush=True)
     np.savez_compressed(os.path.join(HERE, "reference_adcc_h2o_sto3g.npz"), **out)
 

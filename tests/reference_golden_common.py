@@ -12,6 +12,9 @@ METHODS = ["adc0", "adc1", "adc2", "adc2x", "adc3", "cvs-adc0", "cvs-adc1", "cvs
 SIGMA_RTOL = 1e-11        # north star; the reference's own test uses rtol 1e-10 (AdcMatrix_test.py:221)
 ENERGY_ATOL = 1e-8
 OSC_RTOL, OSC_ATOL = 1e-6, 1e-10    # "matching oscillator strengths": 1e-6 relative
+# state densities are quadratic in eigenvectors converged to a residual norm of 1e-9
+DIPOLE_ATOL, DENSITY_ATOL = 1e-7, 1e-7
+_SPACES = {"o": "o1", "v": "v1", "c": "o2"}
 
 
 def golden():
@@ -62,6 +65,24 @@ def check_oracle(method):
             np.testing.assert_allclose(f, g[f"{key}/singlet/oscillator_strength"], rtol=OSC_RTOL, atol=OSC_ATOL)
             np.testing.assert_allclose(np.abs(mu), np.abs(g[f"{key}/singlet/transition_dipole_moment"]),
                                        rtol=0, atol=1e-6)
+        if kind == "singlet":
+            # state densities of the reference's own property code (adc_pp/state_diffdm.py,
+            # ElectronicStates.state_dipole_moment, GroundState.dipole_moment); quadratic in the
+            # eigenvector, so its sign does not matter
+            from oracle.properties import ground_state_dipole_moment, state_diffdm, state_dipole_moments
+            level = min(int((method[4:] if core else method)[3]), 2)
+            np.testing.assert_allclose(ground_state_dipole_moment(om, level), g[f"{key}/ground_state_dipole_moment"],
+                                       rtol=0, atol=1e-10)
+            np.testing.assert_allclose(state_dipole_moments(om, st), g[f"{key}/singlet/state_dipole_moment"],
+                                       rtol=0, atol=DIPOLE_ATOL)
+            for n, vec in enumerate(st.eigenvectors):
+                dm = state_diffdm(om, vec)
+                for blk, rho in dm.items():
+                    gk = f"{key}/singlet/state_diffdm/{n}/{_SPACES[blk[0]]}{_SPACES[blk[1]]}"
+                    if gk in g.files:
+                        assert np.max(np.abs(rho - g[gk])) < DENSITY_ATOL, (method, n, blk)
+                    else:                                   # the reference dropped it as a zero block
+                        assert np.max(np.abs(rho)) < DENSITY_ATOL, (method, n, blk)
 
 
 def check_product(method, doubles_storage="dense"):
@@ -120,3 +141,19 @@ def check_product(method, doubles_storage="dense"):
                                        rtol=OSC_RTOL, atol=OSC_ATOL)
             np.testing.assert_allclose(np.abs(st.transition_dipole_moment),
                                        np.abs(g[f"{key}/singlet/transition_dipole_moment"]), rtol=0, atol=1e-6)
+        if kind == "singlet" and doubles_storage == "dense":
+            level = min(int((method[4:] if core else method)[3]), 2)
+            np.testing.assert_allclose(m.ground_state.dipole_moment(level), g[f"{key}/ground_state_dipole_moment"],
+                                       rtol=0, atol=1e-10)
+            np.testing.assert_allclose(st.state_dipole_moment, g[f"{key}/singlet/state_dipole_moment"],
+                                       rtol=0, atol=DIPOLE_ATOL)
+            for n, dm in enumerate(st.state_diffdm):
+                for blk, rho in dm.items():
+                    gk = f"{key}/singlet/state_diffdm/{n}/{_SPACES[blk[0]]}{_SPACES[blk[1]]}"
+                    if gk in g.files:
+                        assert np.max(np.abs(rho.to_ndarray() - g[gk])) < DENSITY_ATOL, (method, n, blk)
+                    else:
+                        assert np.max(np.abs(rho.to_ndarray())) < DENSITY_ATOL, (method, n, blk)
+        elif kind == "singlet":                              # packed doubles: same numbers through to_dense()
+            np.testing.assert_allclose(st.state_dipole_moment, g[f"{key}/singlet/state_dipole_moment"],
+                                       rtol=0, atol=DIPOLE_ATOL)

@@ -241,6 +241,18 @@ def test_tensor_ops_closed_form(h2o):
     C -= B
     C /= 4.0
     np.testing.assert_allclose(C.to_ndarray(), (3.0 * a - a.T) / 4.0, atol=1e-15)
+    # augmented assignment rebinds, it does not touch the object named before (export_Tensor.cc:352-410:
+    # "return self = self->add(other)"); the reference's state_diffdm.py:70-86 depends on it
+    D = A.copy()
+    alias = D
+    D += A
+    D *= 3.0
+    np.testing.assert_allclose(alias.to_ndarray(), a, atol=0)
+    np.testing.assert_allclose(D.to_ndarray(), 6.0 * a, atol=1e-15)
+    frozen = A.copy()
+    frozen.set_immutable()
+    frozen += A                                  # fine: a new tensor
+    np.testing.assert_allclose(frozen.to_ndarray(), 2.0 * a, atol=1e-15)
     assert np.all(A.ones_like().to_ndarray() == 1.0) and np.all(A.empty_like().to_ndarray() == 0.0)
     assert A.nosym_like().symmetry is None
     r = adcc.Tensor(adcc.Symmetry(ms, "o1o1v1v1", permutations=["ijab", "-jiab", "-ijba"])).set_random()

@@ -74,6 +74,8 @@ def test_unmodified_reference_adcc_runs_on_this_backend():
         "assert f.shape == (3,) and abs(f[2] - 0.0598777655) < 1e-7 and f[1] < 1e-6\n"
         "t = adcc.adc3(s.matrix.ground_state, n_triplets=3, conv_tol=1e-8, output=None)\n"
         "assert np.max(np.abs(t.excitation_energy - [0.39246043, 0.48770981, 0.51755248])) < 1e-6\n"
+        "d = s.state_dipole_moment\n"                    # adc_pp/state_diffdm.py + GroundState.dipole_moment
+        "assert d.shape == (3, 3) and abs(d[0][0] - 3.47507848) < 1e-6 and abs(d[0][2] - 2.44979355) < 1e-6\n"
         "c = adcc.cvs_adc2x(data, n_singlets=2, core_orbitals=1, conv_tol=1e-8, output=None)\n"
         "assert np.max(np.abs(c.excitation_energy - [19.90528006, 19.9990468])) < 1e-6\n"
         "print('ok')\n")
