@@ -145,3 +145,55 @@ class ExcitedStates:
             lines.append("| " + "".join(row) + " |")
         lines.append(hline)
         return "\n".join(lines)
+
+
+class State2States:
+    """Transition properties from the excited state ``initial`` to all higher-lying states of an
+    ExcitedStates object (adcc/State2States.py:33-140): excitation energies, state-to-state
+    transition densities, transition dipole moments and oscillator strengths."""
+
+    def __init__(self, data, method=None, property_method=None, initial=0):
+        self.parent = data if isinstance(data, ExcitedStates) else ExcitedStates(data, method, property_method)
+        if not 0 <= initial < self.parent.size:
+            raise ValueError(f"initial = {initial} is not one of the {self.parent.size} states")
+        self.initial = int(initial)
+        self.method = self.parent.method
+        self.property_method = self.parent.property_method
+        self.reference_state = self.parent.reference_state
+        self.ground_state = self.parent.ground_state
+        if self.method.is_core_valence_separated:
+            raise NotImplementedError("State2States is not implemented for CVS methods.")
+
+    @property
+    def size(self):
+        return self.parent.size - self.initial - 1
+
+    @property
+    def excitation_energy(self):
+        e = self.parent.excitation_energy
+        return np.array([e[f] - e[self.initial] for f in range(self.initial + 1, self.parent.size)])
+
+    excitation_energy_uncorrected = excitation_energy
+
+    @property
+    def excitation_vector(self):
+        return self.parent.excitation_vector[self.initial + 1:]
+
+    @property
+    def transition_dm(self):
+        from .properties import state2state_transition_dm
+        start = self.parent.excitation_vector[self.initial]
+        return [state2state_transition_dm(self.property_method, self.ground_state, start, final)
+                for final in self.excitation_vector]
+
+    @property
+    def transition_dipole_moment(self):
+        from .properties import _dipole_of_density
+        cache = {}
+        return np.array([_dipole_of_density(self.reference_state, dm, cache, hermitian=False)
+                         for dm in self.transition_dm]).reshape(self.size, 3)
+
+    @property
+    def oscillator_strength(self):
+        return 2.0 / 3.0 * np.array([np.linalg.norm(t) ** 2 * abs(e)
+                                     for t, e in zip(self.transition_dipole_moment, self.excitation_energy)])

@@ -14,7 +14,7 @@ from .AmplitudeVector import AmplitudeVector  # noqa: F401
 from .AoEriProvider import AoDataHfProvider  # noqa: F401
 from .DataHfProvider import DataHfProvider, HartreeFockProvider  # noqa: F401
 from .exceptions import InputError  # noqa: F401
-from .ExcitedStates import ExcitedStates  # noqa: F401
+from .ExcitedStates import ExcitedStates, State2States  # noqa: F401
 from .functions import (contract, copy, direct_sum, dot, einsum, empty_like, evaluate,  # noqa: F401
                         lincomb, linear_combination, nosym_like, ones_like, tensordot, trace,
                         transpose, zeros_like)

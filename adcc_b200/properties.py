@@ -7,7 +7,8 @@ transition density matrices), the AO -> MO dipole transform of adcc/OperatorInte
 (mu = tr(D rho), f = 2/3 |mu|^2 omega).  State difference densities follow
 adcc/adc_pp/state_diffdm.py:37-160 (ISR(0), ISR(1), ISR(2), CVS-ISR(1), CVS-ISR(2)), the state dipole
 moment adcc/ElectronicStates.py:247-264 and the ground-state part adcc/GroundState.py:137-146,
-178-189.  All contractions run through the device einsum.
+178-189, state-to-state transition densities adcc/adc_pp/state2state_transition_dm.py:35-118.  All
+contractions run through the device einsum.
 """
 from math import sqrt
 
@@ -219,3 +220,64 @@ def state_dipole_moments(states):
     return np.array([gs + _dipole_of_density(states.reference_state,
                                              state_diffdm(states.property_method, states.ground_state, v), cache)
                      for v in states.excitation_vector])
+
+
+# ------------------------------------------------------------------------------------------------
+# transition densities between excited states
+# ------------------------------------------------------------------------------------------------
+def state2state_transition_dm(method, ground_state, amplitude_from, amplitude_to):
+    """Transition density between two excited states as {block: Tensor} with the blocks "oo", "vv"
+    and - from first order with doubles - "ov", "vo" (no symmetry between them).  The final state is
+    the bra side (adcc/adc_pp/state2state_transition_dm.py:35-118, 161-165)."""
+    level, cvs = _isr_level(method)
+    if cvs:
+        raise NotImplementedError("state2state_transition_dm is not implemented for CVS methods.")
+    mp = ground_state
+    left, right = amplitude_to, amplitude_from
+    ul1, ur1 = left.ph, right.ph
+    dm = {"oo": -1.0 * einsum("ja,ia->ij", ul1, ur1), "vv": einsum("ia,ib->ab", ul1, ur1)}
+    has_doubles = "pphh" in left.blocks and "pphh" in right.blocks
+    if level < 1:
+        return dm
+    if has_doubles:
+        ul2, ur2 = _dense_doubles(left), _dense_doubles(right)
+        dm["ov"] = -2.0 * einsum("jb,ijab->ia", ul1, ur2)
+        dm["vo"] = -2.0 * einsum("ijab,jb->ai", ul2, ur1)
+    if level < 2:
+        return dm
+    if not has_doubles:
+        raise ValueError("The second-order state-to-state density needs the doubles parts of both vectors.")
+    t2 = mp.t2(b.oovv)
+    p0 = mp.mp2_diffdm
+    p1_oo, p1_vv, p1_ov, p1_vo = dm["oo"], dm["vv"], dm["ov"], dm["vo"]
+    rul1 = einsum("ijab,jb->ia", t2, ul1)
+    rur1 = einsum("ijab,jb->ia", t2, ur1)
+    dm["oo"] = p1_oo + (
+        -2.0 * einsum("ikab,jkab->ij", ur2, ul2)
+        + 0.5 * einsum("ik,kj->ij", p1_oo, p0.oo) + 0.5 * einsum("ik,kj->ij", p0.oo, p1_oo)
+        - 0.5 * einsum("ikcd,lk,jlcd->ij", t2, p1_oo, t2)
+        + 1.0 * einsum("ikcd,jkcb,db->ij", t2, t2, p1_vv)
+        - 0.5 * einsum("ia,jkac,kc->ij", ur1, t2, rul1)
+        - 0.5 * einsum("ikac,kc,ja->ij", t2, rur1, ul1)
+        - 1.0 * einsum("ia,ja->ij", rul1, rur1))
+    dm["vv"] = p1_vv + (
+        2.0 * einsum("ijac,ijbc->ab", ul2, ur2)
+        - 0.5 * einsum("ac,cb->ab", p1_vv, p0.vv) - 0.5 * einsum("ac,cb->ab", p0.vv, p1_vv)
+        - 0.5 * einsum("klbc,klad,cd->ab", t2, t2, p1_vv)
+        + 1.0 * einsum("klbc,jk,jlac->ab", t2, p1_oo, t2)
+        + 0.5 * einsum("ikac,kc,ib->ab", t2, rul1, ur1)
+        + 0.5 * einsum("ia,ikbc,kc->ab", ul1, t2, rur1)
+        + 1.0 * einsum("ia,ib->ab", rur1, rul1))
+    dm["ov"] = p1_ov + (
+        -1.0 * einsum("ijab,bj->ia", t2, p1_vo)
+        - einsum("ib,ba->ia", p0.ov, p1_vv)
+        + einsum("ij,ja->ia", p1_oo, p0.ov)
+        - einsum("ib,klca,klcb->ia", ur1, t2, ul2)
+        - einsum("ikcd,jkcd,ja->ia", t2, ul2, ur1))
+    dm["vo"] = p1_vo + (
+        -1.0 * einsum("ijab,jb->ai", t2, p1_ov)
+        - einsum("ib,ab->ai", p0.ov, p1_vv)
+        + einsum("ji,ja->ai", p1_oo, p0.ov)
+        - einsum("ib,klca,klcb->ai", ul1, t2, ur2)
+        - einsum("ikcd,jkcd,ja->ai", t2, ur2, ul1))
+    return dm

@@ -5,7 +5,8 @@ Restates adcc/adc_pp/transition_dm.py:36-97 (tdm_isr0/1/2, tdm_cvs_isr2),
 adcc/OperatorIntegrals.py:37-76 (AO->MO, spin-block-diagonal) and
 adcc/ElectronicTransition.py:178-183 (f = 2/3 |mu|^2 omega) on dense arrays.  State difference densities and
 state dipole moments restate adcc/adc_pp/state_diffdm.py:37-160, adcc/ElectronicStates.py:247-264 and
-adcc/GroundState.py:137-146, 178-189.  Pinned by the goldens the reference's own property code
+adcc/GroundState.py:137-146, 178-189; state-to-state transition densities restate
+adcc/adc_pp/state2state_transition_dm.py:35-118 and adcc/State2States.py:79-140.  Pinned by the goldens the reference's own property code
 produced (tests/golden/reference_adcc_h2o_sto3g.npz, tests/reference_golden_common.py).
 """
 from math import sqrt
@@ -160,3 +161,66 @@ def state_dipole_moments(matrix, state, level=None):
     gs = ground_state_dipole_moment(matrix, level)
     return np.array([gs + _dipole_of_density(matrix.hf, state_diffdm(matrix, vec, level))
                      for vec in state.eigenvectors])
+
+
+def state2state_transition_dm(matrix, vec_from, vec_to, level=None):
+    """adcc/adc_pp/state2state_transition_dm.py:35-118 (the final state is the bra side, :161-165)."""
+    mp = matrix.mp
+    if matrix.cvs:
+        raise NotImplementedError("no CVS state-to-state densities in the reference")
+    if level is None:
+        level = min(int(matrix.method[3]), 2)
+    ul1, ur1 = vec_to["ph"], vec_from["ph"]
+    ul2, ur2 = vec_to.get("pphh"), vec_from.get("pphh")
+    dm = {"oo": -es("ja,ia->ij", ul1, ur1), "vv": es("ia,ib->ab", ul1, ur1)}
+    if level < 1:
+        return dm
+    if ul2 is not None and ur2 is not None:
+        dm["ov"] = -2.0 * es("jb,ijab->ia", ul1, ur2)
+        dm["vo"] = -2.0 * es("ijab,jb->ai", ul2, ur1)
+    if level < 2:
+        return dm
+    t2 = mp.t2oo
+    p0 = mp.mp2_diffdm()
+    p1_oo, p1_vv, p1_ov, p1_vo = dm["oo"], dm["vv"], dm["ov"], dm["vo"]
+    rul1 = es("ijab,jb->ia", t2, ul1)
+    rur1 = es("ijab,jb->ia", t2, ur1)
+    dm["oo"] = p1_oo + (
+        -2.0 * es("ikab,jkab->ij", ur2, ul2)
+        + 0.5 * es("ik,kj->ij", p1_oo, p0["oo"]) + 0.5 * es("ik,kj->ij", p0["oo"], p1_oo)
+        - 0.5 * es("ikcd,lk,jlcd->ij", t2, p1_oo, t2) + es("ikcd,jkcb,db->ij", t2, t2, p1_vv)
+        - 0.5 * es("ia,jkac,kc->ij", ur1, t2, rul1) - 0.5 * es("ikac,kc,ja->ij", t2, rur1, ul1)
+        - es("ia,ja->ij", rul1, rur1))
+    dm["vv"] = p1_vv + (
+        2.0 * es("ijac,ijbc->ab", ul2, ur2)
+        - 0.5 * es("ac,cb->ab", p1_vv, p0["vv"]) - 0.5 * es("ac,cb->ab", p0["vv"], p1_vv)
+        - 0.5 * es("klbc,klad,cd->ab", t2, t2, p1_vv) + es("klbc,jk,jlac->ab", t2, p1_oo, t2)
+        + 0.5 * es("ikac,kc,ib->ab", t2, rul1, ur1) + 0.5 * es("ia,ikbc,kc->ab", ul1, t2, rur1)
+        + es("ia,ib->ab", rur1, rul1))
+    dm["ov"] = p1_ov + (
+        -es("ijab,bj->ia", t2, p1_vo) - es("ib,ba->ia", p0["ov"], p1_vv) + es("ij,ja->ia", p1_oo, p0["ov"])
+        - es("ib,klca,klcb->ia", ur1, t2, ul2) - es("ikcd,jkcd,ja->ia", t2, ul2, ur1))
+    dm["vo"] = p1_vo + (
+        -es("ijab,jb->ai", t2, p1_ov) - es("ib,ab->ai", p0["ov"], p1_vv) + es("ji,ja->ai", p1_oo, p0["ov"])
+        - es("ib,klca,klcb->ai", ul1, t2, ur2) - es("ikcd,jkcd,ja->ai", t2, ur2, ul1))
+    return dm
+
+
+def state2state(matrix, state, initial=0, level=None):
+    """(excitation energies, transition dipole moments, oscillator strengths, densities) from state
+    ``initial`` to every higher one (adcc/State2States.py:79-140)."""
+    hf = matrix.hf
+    e0, v0 = state.eigenvalues[initial], state.eigenvectors[initial]
+    ene, mus, dms = [], [], []
+    for e, v in zip(state.eigenvalues[initial + 1:], state.eigenvectors[initial + 1:]):
+        dm = state2state_transition_dm(matrix, v0, v, level)
+        mu = np.zeros(3)
+        for blk, rho in dm.items():
+            for comp in range(3):
+                mu[comp] += float(np.vdot(_dipole_block(hf, blk, comp), rho))
+        ene.append(e - e0)
+        mus.append(mu)
+        dms.append(dm)
+    ene, mus = np.array(ene), np.array(mus).reshape(len(ene), 3)
+    f = 2.0 / 3.0 * np.array([np.linalg.norm(m) ** 2 * abs(w) for m, w in zip(mus, ene)])
+    return ene, mus, f, dms

@@ -117,6 +117,15 @@ def check_oscillator_strengths(data, method, core, n=3, conv_tol=1e-9):
         # a difference density moves no charge: tr(diffdm) = 0 (second order: to the order of the method)
         tr = sum(float(np.trace(dm[blk].to_ndarray())) for blk in dm if blk[0] == blk[1])
         assert abs(tr) < (1e-10 if method in ("adc0", "adc1", "cvs-adc0", "cvs-adc1") else 0.2)
+    if not method.startswith("cvs") and state.size > 1:
+        # transitions between excited states (adcc/State2States.py, adc_pp/state2state_transition_dm.py)
+        from oracle.properties import state2state
+        s2s = adcc.State2States(state, initial=0)
+        oene, omus, of2, _ = state2state(om, ostate, initial=0)
+        np.testing.assert_allclose(s2s.excitation_energy, oene, rtol=0, atol=1e-8)
+        np.testing.assert_allclose(np.abs(s2s.transition_dipole_moment), np.abs(omus), rtol=0, atol=tol)
+        np.testing.assert_allclose(s2s.oscillator_strength, of2, rtol=1e-4, atol=10 * tol)
+        assert s2s.size == state.size - 1 and len(s2s.transition_dm) == s2s.size
     text = state.describe(state_dipole_moments=True)
     assert "state dipole moment" in text
     return f

@@ -97,6 +97,15 @@ def main():
                 for n, ddm in enumerate(state.state_diffdm):
                     for blk in ddm.blocks_nonzero:
                         out[f"{key}/singlet/state_diffdm/{n}/{blk}"] = ddm[blk].to_ndarray()
+                if not cvs:
+                    # transitions between excited states: adcc/State2States.py, adc_pp/state2state_transition_dm.py
+                    s2s = adcc.State2States(state, initial=0)
+                    out[f"{key}/singlet/s2s/excitation_energy"] = np.array(s2s.excitation_energy)
+                    out[f"{key}/singlet/s2s/transition_dipole_moment"] = np.array(s2s.transition_dipole_moment)
+                    out[f"{key}/singlet/s2s/oscillator_strength"] = np.array(s2s.oscillator_strength)
+                    for n, tdm in enumerate(s2s.transition_dm):
+                        for blk in tdm.blocks_nonzero:
+                            out[f"{key}/singlet/s2s/transition_dm/{n}/{blk}"] = tdm[blk].to_ndarray()
         print(method, out[f"{key}/singlet/energies"], out[f"{key}/singlet/n_iter"], flush=True)
     np.savez_compressed(os.path.join(HERE, "reference_adcc_h2o_sto3g.npz"), **out)
 

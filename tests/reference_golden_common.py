@@ -83,6 +83,29 @@ def check_oracle(method):
                         assert np.max(np.abs(rho - g[gk])) < DENSITY_ATOL, (method, n, blk)
                     else:                                   # the reference dropped it as a zero block
                         assert np.max(np.abs(rho)) < DENSITY_ATOL, (method, n, blk)
+            if f"{key}/singlet/s2s/excitation_energy" in g.files:
+                from oracle.properties import state2state
+                _compare_s2s(g, key, *state2state(om, st, initial=0), to_array=lambda a: a)
+
+
+def _compare_s2s(g, key, ene, mus, f, dms, to_array):
+    """State-to-state quantities against the reference's State2States output; the density and the
+    dipole carry the product of two eigenvector signs, so they are compared up to one sign each."""
+    np.testing.assert_allclose(ene, g[f"{key}/singlet/s2s/excitation_energy"], rtol=0, atol=ENERGY_ATOL)
+    np.testing.assert_allclose(f, g[f"{key}/singlet/s2s/oscillator_strength"], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(np.abs(mus), np.abs(g[f"{key}/singlet/s2s/transition_dipole_moment"]),
+                               rtol=0, atol=DIPOLE_ATOL)
+    for n, dm in enumerate(dms):
+        got, want = {}, {}
+        for blk, rho in dm.items():
+            got[blk] = to_array(rho)
+            gk = f"{key}/singlet/s2s/transition_dm/{n}/{_SPACES[blk[0]]}{_SPACES[blk[1]]}"
+            want[blk] = g[gk] if gk in g.files else np.zeros_like(got[blk])      # dropped as a zero block
+        big = max(want, key=lambda blk: np.max(np.abs(want[blk])))              # the sign from the largest element
+        k = np.unravel_index(np.argmax(np.abs(want[big])), want[big].shape)
+        sign = 1.0 if got[big][k] * want[big][k] >= 0 else -1.0
+        for blk in got:
+            assert np.max(np.abs(sign * got[blk] - want[blk])) < DENSITY_ATOL, (key, n, blk)
 
 
 def check_product(method, doubles_storage="dense"):
@@ -154,6 +177,10 @@ def check_product(method, doubles_storage="dense"):
                         assert np.max(np.abs(rho.to_ndarray() - g[gk])) < DENSITY_ATOL, (method, n, blk)
                     else:
                         assert np.max(np.abs(rho.to_ndarray())) < DENSITY_ATOL, (method, n, blk)
+            if f"{key}/singlet/s2s/excitation_energy" in g.files:
+                s2s = adcc.State2States(st, initial=0)
+                _compare_s2s(g, key, s2s.excitation_energy, s2s.transition_dipole_moment, s2s.oscillator_strength,
+                             s2s.transition_dm, to_array=lambda t: t.to_ndarray())
         elif kind == "singlet":                              # packed doubles: same numbers through to_dense()
             np.testing.assert_allclose(st.state_dipole_moment, g[f"{key}/singlet/state_dipole_moment"],
                                        rtol=0, atol=DIPOLE_ATOL)
