@@ -690,8 +690,17 @@ int packed_expand_slab(cudaStream_t st, int which, int no, int nv, int first, in
   if (which != 2 && (first < 0 || first + count > no)) return fail("packed_expand: slab out of range");
   const int t = (nv + 31) / 32;
   if (which == 0) {
-    if ((long long)count * no > 65535) return fail("packed_expand: too many (i,k) rows");
-    expand_antisym_kernel<<<dim3(t * (t + 1) / 2, 1, count * no), dim3(32, 8), 0, st>>>(0, no, 0, nv, first, U, out);
+    // grid.z is limited to 65535 (i,k) rows: walk the occupied slab in chunks of whole i
+    if (no > 65535) return fail("packed_expand: more than 65535 occupied spin orbitals");
+    const int ci = std::max(1, 65535 / no);
+    for (int i0 = 0; i0 < count; i0 += ci) {
+      const int ni = std::min(ci, count - i0);
+      expand_antisym_kernel<<<dim3(t * (t + 1) / 2, 1, (unsigned)(ni * no)), dim3(32, 8), 0, st>>>(
+          0, no, 0, nv, first + i0, U, out + (long long)i0 * nv * no * nv);
+      ADCCB_LAUNCH_OK();
+    }
+    count_launch();
+    return 0;
   } else if (which == 1) {
     expand_occ_kernel<<<no * count, 512, 0, st>>>(no, first, count, npv, U, out);
   } else if (which == 2) {
