@@ -24,8 +24,8 @@
 
 Same call signature, validation, defaults and guess heuristics as adcc/workflow.py:45-520
 (``construct_adcmatrix``, ``validate_state_parameters``, ``diagonalise_adcmatrix``,
-``estimate_n_guesses``, ``obtain_guesses_by_inspection``); only the Davidson eigensolver of the
-hot path is available (eigensolver="davidson").
+``estimate_n_guesses``, ``obtain_guesses_by_inspection``); the Jacobi-Davidson eigensolver of the
+hot path (eigensolver="davidson", default) and the block Lanczos solver (eigensolver="lanczos").
 """
 import contextlib
 import sys
@@ -40,6 +40,8 @@ from .LazyMp import LazyMp
 from .ReferenceState import ReferenceState
 from .solver.davidson import default_print as davidson_default_print
 from .solver.davidson import jacobi_davidson
+from .solver.lanczos import default_print as lanczos_default_print
+from .solver.lanczos import lanczos
 from .solver.explicit_symmetrisation import IndexSpinSymmetrisation, IndexSymmetrisation
 
 __all__ = ["run_adc"]
@@ -179,6 +181,10 @@ def diagonalise_adcmatrix(matrix, n_states, kind, eigensolver="davidson", guesse
         callback = setup_solver_printing("Jacobi-Davidson", matrix, kind,
                                          davidson_default_print, output=output)
         run_eigensolver = jacobi_davidson
+    elif eigensolver == "lanczos":
+        n_guesses_per_state = 1
+        callback = setup_solver_printing("Lanczos", matrix, kind, lanczos_default_print, output=output)
+        run_eigensolver = lanczos
     else:
         raise InputError(f"Solver {eigensolver} unknown, try 'davidson'.")
 

@@ -184,3 +184,33 @@ def check_product(method, doubles_storage="dense"):
         elif kind == "singlet":                              # packed doubles: same numbers through to_dense()
             np.testing.assert_allclose(st.state_dipole_moment, g[f"{key}/singlet/state_dipole_moment"],
                                        rtol=0, atol=DIPOLE_ATOL)
+
+
+LANCZOS_METHODS = ["adc2", "adc2x", "cvs-adc2"]
+
+
+def check_lanczos(method, doubles_storage="dense", iter_slack=0):
+    """run_adc(..., eigensolver="lanczos") of the product against what the reference's own Lanczos
+    solver (adcc/solver/lanczos.py, LanczosIterator.py, orthogonaliser.py) produced on the libadcc
+    surface: energies to 1e-8 and identical iteration counts."""
+    import warnings
+    import adcc_b200 as adcc
+    g = golden()
+    key = method.replace("-", "_")
+    core = 1 if method.startswith("cvs") else None
+    ref = adcc.ReferenceState(load_h2o_sto3g(), core_orbitals=core)
+    m = adcc.AdcMatrix(method, ref, doubles_storage=doubles_storage)
+    for kind in ("singlet", "triplet"):
+        want = g[f"{key}/lanczos/{kind}/energies"]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            st = adcc.run_adc(m, conv_tol=1e-8, output=None, eigensolver="lanczos",
+                              **{"n_singlets" if kind == "singlet" else "n_triplets": len(want)})
+        assert st.converged
+        np.testing.assert_allclose(st.excitation_energy, want, atol=ENERGY_ATOL, rtol=0)
+        # 30 - 70 steps whose last one is decided by |r| |b^T y| against 1e-8 |theta|: device rounding may
+        # move it by a step (iter_slack), the host path reproduces the count
+        assert abs(st.n_iter - int(g[f"{key}/lanczos/{kind}/n_iter"])) <= iter_slack, (method, kind, st.n_iter)
+        # the same states as the Jacobi-Davidson solver finds
+        np.testing.assert_allclose(st.excitation_energy, g[f"{key}/{kind}/energies"], atol=1e-7, rtol=0)
+        assert np.all(st.solver_state.residual_norms < 1e-5)

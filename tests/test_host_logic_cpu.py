@@ -409,3 +409,42 @@ def test_matvec_between_host_buffers_dense_store(h2o, method):
     osig = omatrix.matvec(ov)
     for b in osig:
         assert rel_err(s_host[b].numpy(), osig[b]) < SIGMA_RTOL
+
+
+def test_lanczos_solver_api(h2o):
+    """The second eigensolver behind run_adc (adcc/solver/lanczos.py:255-311): both ends of the
+    spectrum against the dense export of the matrix, thick restarts, the true residuals, the
+    reference's warnings and argument checks."""
+    import warnings
+    import scipy.linalg as la
+    import adcc_b200 as adcc
+    from adcc_b200.guess import guesses_any
+    from adcc_b200.solver.lanczos import lanczos, LanczosIterator
+    matrix = adcc.AdcMatrix("adc2", adcc.ReferenceState(h2o))
+    spectrum = np.linalg.eigvalsh(matrix.to_ndarray())
+    guesses = guesses_any(matrix, 3, block="ph")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        low = lanczos(matrix, guesses, n_ep=2, which="SA", conv_tol=1e-8, debug_checks=True)
+        high = lanczos(matrix, guesses, n_ep=2, which="LA", conv_tol=1e-8)
+    assert low.converged and high.converged and low.algorithm == "lanczos"
+    assert low.n_restart > 0                                   # max_subspace = 24 with blocks of 3
+    assert low.subspace_orthogonality < 1e-9
+    for val in low.eigenvalues:
+        assert np.min(np.abs(spectrum - val)) < 1e-7
+    np.testing.assert_allclose(high.eigenvalues, spectrum[-2:], atol=1e-7)
+    # true residuals A x - theta x of the returned vectors
+    for val, vec, rn in zip(low.eigenvalues, low.eigenvectors, low.residual_norms):
+        r = matrix @ vec - val * vec
+        assert abs(np.sqrt(r @ r) - rn) < 1e-7 and rn < 1e-5
+        assert abs(vec @ vec - 1.0) < 1e-8
+    with pytest.warns(la.LinAlgWarning, match="Maximum number of iterations"):
+        short = lanczos(matrix, guesses, n_ep=2, which="SA", max_iter=2)
+    assert not short.converged and short.n_iter == 2 and short.n_applies == 6
+    with pytest.raises(TypeError):
+        LanczosIterator(matrix, ["not a vector"])
+    with pytest.raises(ValueError):
+        LanczosIterator(matrix, guesses, ritz_vectors=guesses[:1], ritz_values=np.zeros(2),
+                        ritz_overlaps=np.zeros((2, 3)))
+    with pytest.raises(adcc.InputError):
+        adcc.run_adc(matrix, n_singlets=2, eigensolver="arnoldi", output=None)

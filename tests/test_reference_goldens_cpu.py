@@ -29,6 +29,14 @@ def test_packed_host_path_vs_reference_produced_goldens(method, monkeypatch):
     check_product(method, doubles_storage="packed")
 
 
+@pytest.mark.parametrize("method,storage", [("adc2", "dense"), ("adc2", "packed"), ("adc2x", "dense"),
+                                            ("adc2x", "packed"), ("cvs-adc2", "dense")])
+def test_lanczos_vs_reference_produced_goldens(method, storage, monkeypatch):
+    from reference_golden_common import check_lanczos
+    cpu_shim.install(monkeypatch)
+    check_lanczos(method, storage)
+
+
 def test_libadcc_module_surface():
     """Every name the reference's Python layer looks up in ``libadcc`` (libadcc.pyi) exists; runs in a
     subprocess because importing libadcc switches select_n_* to libtensor's symmetry-unique mode."""

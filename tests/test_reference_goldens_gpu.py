@@ -17,3 +17,10 @@ def test_cuda_path_vs_reference_produced_goldens(method):
 @pytest.mark.parametrize("method", ["adc2", "adc2x", "adc3"])
 def test_cuda_packed_engine_vs_reference_produced_goldens(method):
     check_product(method, doubles_storage="packed")
+
+
+@pytest.mark.parametrize("method,storage", [("adc2", "dense"), ("adc2x", "packed"), ("cvs-adc2", "dense")])
+def test_cuda_lanczos_vs_reference_produced_goldens(method, storage):
+    """run_adc(..., eigensolver="lanczos") on the device: the reference's energies and iteration counts."""
+    from reference_golden_common import check_lanczos
+    check_lanczos(method, storage, iter_slack=2)
