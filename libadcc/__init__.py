@@ -255,7 +255,10 @@ def linear_combination_strict(coefficients, tensors):
     Davidson residual of 1e-9, and the reference's solver - which relies on the structural symmetry
     for the singles block (adcc/solver/explicit_symmetrisation.py:80-98 touches the doubles only) -
     then lets lower-lying states of the other spin kind grow in.  The result is therefore projected
-    onto the maps of its operands (adccb_spin_project), which is what libtensor's storage does."""
+    onto the maps of its operands (adccb_spin_project), which is what libtensor's storage does.
+    Operands without symmetry metadata (results of contractions, e.g. A x) are taken to share the
+    maps: on this dense store a contraction of symmetric tensors is symmetric up to rounding, and a
+    calculation whose vectors are not (spin-flip, kind "any") carries no maps at all."""
     tensors = list(tensors)
     res = _fn.linear_combination_strict(coefficients, tensors)
     sym = next((t.symmetry for t in tensors if _spin_flip_factor(getattr(t, "symmetry", None)) is not None), None)
