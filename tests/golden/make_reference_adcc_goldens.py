@@ -28,6 +28,7 @@ REF = "/root/reference"
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools", "refshim"), REF,
                 os.path.join(REF, "examples", "water")]
 
+OPEN_SHELL_METHODS = ["adc1", "adc2", "adc2x", "adc3"]
 LANCZOS_METHODS = ["adc2", "adc2x", "cvs-adc2"]      # ADC(0) / ADC(1) of this fixture exhaust their Krylov space
 METHODS = ["adc0", "adc1", "adc2", "adc2x", "adc3", "cvs-adc0", "cvs-adc1", "cvs-adc2", "cvs-adc2x", "cvs-adc3"]
 
@@ -121,6 +122,45 @@ def main():
                 out[f"{key}/lanczos/{kind}/n_iter"] = np.array(state.n_iter)
         print(method, out[f"{key}/singlet/energies"], out[f"{key}/singlet/n_iter"], flush=True)
     np.savez_compressed(os.path.join(HERE, "reference_adcc_h2o_sto3g.npz"), **out)
+    open_shell(adcc, guess_zero)
+
+
+def open_shell(adcc, guess_zero):
+    """Second input: the UNRESTRICTED open-shell SCF dict of tests/adc_parity_common.py::open_shell_dict
+    (3 alpha / 2 beta electrons, 6 spatial orbitals, <pq||rs> given directly, no spin-block
+    structure in the integrals) - the reference's unrestricted code paths (no spin-block maps,
+    ragged alpha / beta halves on every axis, kind "any" and "spin_flip" guesses)."""
+    from adc_parity_common import open_shell_dict
+    data = open_shell_dict()
+    out = {"methods": np.array(OPEN_SHELL_METHODS)}
+    for method in OPEN_SHELL_METHODS:
+        ref = adcc.ReferenceState(data)
+        matrix = adcc.AdcMatrix(method, ref)
+        rng = np.random.default_rng(sum(map(ord, method)) + 7)
+        vec = guess_zero(matrix)
+        for blk in vec.blocks:
+            arr = rng.standard_normal(vec[blk].shape)
+            if blk == "pphh":
+                arr = arr - arr.transpose(0, 1, 3, 2)
+                arr = arr - arr.transpose(1, 0, 2, 3)
+            vec[blk].set_from_ndarray(arr)
+            out[f"{method}/vector/{blk}"] = arr
+        sigma = adcc.evaluate(matrix @ vec)
+        diag = matrix.diagonal()
+        for blk in vec.blocks:
+            out[f"{method}/matvec/{blk}"] = sigma[blk].to_ndarray()
+            out[f"{method}/diagonal/{blk}"] = diag[blk].to_ndarray()
+        out[f"{method}/mp2"] = np.array(matrix.ground_state.energy_correction(2))
+        for kind, kw, n in (("any", "n_states", 3), ("spin_flip", "n_spin_flip", 2)):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                state = adcc.run_adc(matrix, **{kw: n}, conv_tol=1e-8, output=None)
+            assert state.converged
+            out[f"{method}/{kind}/energies"] = np.array(state.excitation_energy)
+            out[f"{method}/{kind}/n_iter"] = np.array(state.n_iter)
+        print("open shell", method, out[f"{method}/any/energies"], out[f"{method}/any/n_iter"],
+              out[f"{method}/spin_flip/n_iter"], flush=True)
+    np.savez_compressed(os.path.join(HERE, "reference_adcc_open_shell.npz"), **out)
 
 
 if __name__ == "__main__":

@@ -214,3 +214,46 @@ def check_lanczos(method, doubles_storage="dense", iter_slack=0):
         # the same states as the Jacobi-Davidson solver finds
         np.testing.assert_allclose(st.excitation_energy, g[f"{key}/{kind}/energies"], atol=1e-7, rtol=0)
         assert np.all(st.solver_state.residual_norms < 1e-5)
+
+
+OPEN_SHELL_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_adcc_open_shell.npz")
+OPEN_SHELL_METHODS = ["adc1", "adc2", "adc2x", "adc3"]
+
+
+def check_open_shell(method, which="product", iter_slack=0):
+    """The unrestricted open-shell input (tests/adc_parity_common.py::open_shell_dict) against what
+    the reference's own Python layer computed for it: sigma, diagonal, MP2 energy, kind "any" and
+    "spin_flip" states with the reference's iteration counts."""
+    import warnings
+    from adc_parity_common import open_shell_dict
+    g = np.load(OPEN_SHELL_GOLDEN)
+    data = open_shell_dict()
+    blocks = sorted(k.split("/")[-1] for k in g.files if k.startswith(f"{method}/vector/"))
+    if which == "oracle":
+        import oracle
+        om = oracle.OracleAdcMatrix(method, oracle.OracleRefState(oracle.OracleHf(data)))
+        sig = om.matvec({b: g[f"{method}/vector/{b}"] for b in blocks})
+        for b in blocks:
+            assert rel(sig[b], g[f"{method}/matvec/{b}"]) < 1e-12, (method, b)
+            assert rel(om.diagonal()[b], g[f"{method}/diagonal/{b}"]) < 1e-12, (method, "diagonal", b)
+        assert abs(om.mp.energy_correction(2) - float(g[f"{method}/mp2"])) < 1e-12
+        for kind, n in (("any", 3), ("spin_flip", 2)):
+            st = oracle.run_adc(om, method, n_states=n, kind=kind, conv_tol=1e-8)
+            np.testing.assert_allclose(st.eigenvalues, g[f"{method}/{kind}/energies"], atol=ENERGY_ATOL, rtol=0)
+        return
+    import adcc_b200 as adcc
+    m = adcc.AdcMatrix(method, adcc.ReferenceState(data), doubles_storage="dense")
+    v = adcc.AmplitudeVector(**{b: adcc.Tensor.from_ndarray(m.mospaces, m.axis_spaces[b], g[f"{method}/vector/{b}"])
+                                for b in blocks})
+    sig = m.matvec(v)
+    for b in blocks:
+        assert rel(sig[b].to_ndarray(), g[f"{method}/matvec/{b}"]) < SIGMA_RTOL, (method, b)
+        assert rel(m.diagonal()[b].to_ndarray(), g[f"{method}/diagonal/{b}"]) < SIGMA_RTOL, (method, "diagonal", b)
+    assert abs(m.ground_state.energy_correction(2) - float(g[f"{method}/mp2"])) < 1e-12
+    for kind, kw, n in (("any", "n_states", 3), ("spin_flip", "n_spin_flip", 2)):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            st = adcc.run_adc(m, conv_tol=1e-8, output=None, **{kw: n})
+        assert st.converged
+        np.testing.assert_allclose(st.excitation_energy, g[f"{method}/{kind}/energies"], atol=ENERGY_ATOL, rtol=0)
+        assert abs(st.n_iter - int(g[f"{method}/{kind}/n_iter"])) <= iter_slack, (method, kind, st.n_iter)

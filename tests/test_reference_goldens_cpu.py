@@ -37,6 +37,17 @@ def test_lanczos_vs_reference_produced_goldens(method, storage, monkeypatch):
     check_lanczos(method, storage)
 
 
+@pytest.mark.parametrize("method", ["adc1", "adc2", "adc2x", "adc3"])
+@pytest.mark.parametrize("which", ["oracle", "product"])
+def test_open_shell_vs_reference_produced_goldens(method, which, monkeypatch):
+    """Unrestricted open-shell reference, kinds "any" and "spin_flip" (the reference's cn / hf cases
+    need non-vendored data; this input is generated in tests/adc_parity_common.py)."""
+    from reference_golden_common import check_open_shell
+    if which == "product":
+        cpu_shim.install(monkeypatch)
+    check_open_shell(method, which)
+
+
 def test_libadcc_module_surface():
     """Every name the reference's Python layer looks up in ``libadcc`` (libadcc.pyi) exists; runs in a
     subprocess because importing libadcc switches select_n_* to libtensor's symmetry-unique mode."""

@@ -24,3 +24,10 @@ def test_cuda_lanczos_vs_reference_produced_goldens(method, storage):
     """run_adc(..., eigensolver="lanczos") on the device: the reference's energies and iteration counts."""
     from reference_golden_common import check_lanczos
     check_lanczos(method, storage, iter_slack=2)
+
+
+@pytest.mark.parametrize("method", ["adc2", "adc3"])
+def test_cuda_open_shell_vs_reference_produced_goldens(method):
+    """Unrestricted open-shell input, kinds "any" and "spin_flip", on the device."""
+    from reference_golden_common import check_open_shell
+    check_open_shell(method, iter_slack=2)      # 30 - 46 iterations: device rounding may move the last one
