@@ -123,6 +123,45 @@ def main():
         print(method, out[f"{key}/singlet/energies"], out[f"{key}/singlet/n_iter"], flush=True)
     np.savez_compressed(os.path.join(HERE, "reference_adcc_h2o_sto3g.npz"), **out)
     open_shell(adcc, guess_zero)
+    workflows(adcc, data)
+
+
+def workflows(adcc, data):
+    """Callers around the matvec that BASELINE's configs use: the projected ADC(2)-x matrix of
+    examples/2_core_excitations/water_core_by_projection.py (AdcMatrixProjected, CVS guesses
+    transferred to the full space) and the reference's frozen-core / frozen-virtual subspace cases
+    (adcc/tests/testcases.py: fc, fv, fc-fv, fv-cvs) on the H2O / STO-3G input."""
+    import adcc.projection
+    from adcc.AdcMatrix import AdcMatrixProjected
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        matrix = adcc.AdcMatrix("adc2x", adcc.ReferenceState(data))
+        pmatrix = AdcMatrixProjected(matrix, ["cv", "ccvv", "ocvv"], core_orbitals=1)
+        sp = adcc.run_adc(pmatrix, n_singlets=2, conv_tol=1e-8, n_guesses=2, n_guesses_doubles=0, output=None)
+        sc = adcc.cvs_adc2x(data, n_singlets=2, conv_tol=1e-8, core_orbitals=1, output=None)
+        guesses = adcc.projection.transfer_cvs_to_full(sc, pmatrix)
+        sp2 = adcc.run_adc(pmatrix, n_singlets=2, conv_tol=1e-8, guesses=guesses, output=None)
+    assert sp.converged and sp2.converged and sc.converged
+    out["projected/energies"], out["projected/n_iter"] = np.array(sp.excitation_energy), np.array(sp.n_iter)
+    out["projected_from_cvs/energies"] = np.array(sp2.excitation_energy)
+    out["projected_from_cvs/n_iter"] = np.array(sp2.n_iter)
+    out["projected/diagonal/ph"] = pmatrix.diagonal().ph.to_ndarray()
+    out["projected/diagonal/pphh"] = pmatrix.diagonal().pphh.to_ndarray()
+    for name, method, kw in (("fc", "adc2", dict(frozen_core=1)), ("fv", "adc2", dict(frozen_virtual=1)),
+                             ("fc_fv", "adc2", dict(frozen_core=1, frozen_virtual=1)),
+                             ("fv_cvs", "cvs-adc2", dict(core_orbitals=1, frozen_virtual=1)),
+                             ("fc_adc3", "adc3", dict(frozen_core=1))):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            st = adcc.run_adc(data, method=method, n_singlets=2, conv_tol=1e-8, output=None, **kw)
+        assert st.converged
+        out[f"{name}/energies"], out[f"{name}/n_iter"] = np.array(st.excitation_energy), np.array(st.n_iter)
+        if method != "adc3":
+            out[f"{name}/oscillator_strength"] = np.array(st.oscillator_strength)
+        print("workflow", name, out[f"{name}/energies"], out[f"{name}/n_iter"], flush=True)
+    print("workflow projected", out["projected/energies"], out["projected/n_iter"], out["projected_from_cvs/n_iter"])
+    np.savez_compressed(os.path.join(HERE, "reference_adcc_workflows.npz"), **out)
 
 
 def open_shell(adcc, guess_zero):

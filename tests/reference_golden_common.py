@@ -257,3 +257,45 @@ def check_open_shell(method, which="product", iter_slack=0):
         assert st.converged
         np.testing.assert_allclose(st.excitation_energy, g[f"{method}/{kind}/energies"], atol=ENERGY_ATOL, rtol=0)
         assert abs(st.n_iter - int(g[f"{method}/{kind}/n_iter"])) <= iter_slack, (method, kind, st.n_iter)
+
+
+WORKFLOW_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_adcc_workflows.npz")
+
+
+def check_workflows():
+    """Callers around the matvec on H2O / STO-3G against the reference's own runs: the projected
+    ADC(2)-x matrix of examples/2_core_excitations/water_core_by_projection.py (AdcMatrixProjected,
+    CVS guesses transferred by transfer_cvs_to_full) and the frozen-core / frozen-virtual cases of
+    adcc/tests/testcases.py (fc, fv, fc-fv, fv-cvs)."""
+    import warnings
+    import adcc_b200 as adcc
+    from adcc_b200.projection import transfer_cvs_to_full
+    g = np.load(WORKFLOW_GOLDEN)
+    data = load_h2o_sto3g()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        matrix = adcc.AdcMatrix("adc2x", adcc.ReferenceState(data))
+        pmatrix = adcc.AdcMatrixProjected(matrix, ["cv", "ccvv", "ocvv"], core_orbitals=1)
+        sp = adcc.run_adc(pmatrix, n_singlets=2, conv_tol=1e-8, n_guesses=2, n_guesses_doubles=0, output=None)
+        sc = adcc.cvs_adc2x(data, n_singlets=2, conv_tol=1e-8, core_orbitals=1, output=None)
+        sp2 = adcc.run_adc(pmatrix, n_singlets=2, conv_tol=1e-8, guesses=transfer_cvs_to_full(sc, pmatrix),
+                           output=None)
+    for st, key in ((sp, "projected"), (sp2, "projected_from_cvs")):
+        assert st.converged
+        np.testing.assert_allclose(st.excitation_energy, g[f"{key}/energies"], atol=ENERGY_ATOL, rtol=0)
+        assert st.n_iter == int(g[f"{key}/n_iter"]), (key, st.n_iter)
+    for blk in ("ph", "pphh"):
+        assert rel(pmatrix.diagonal()[blk].to_ndarray(), g[f"projected/diagonal/{blk}"]) < SIGMA_RTOL
+    for name, method, kw in (("fc", "adc2", dict(frozen_core=1)), ("fv", "adc2", dict(frozen_virtual=1)),
+                             ("fc_fv", "adc2", dict(frozen_core=1, frozen_virtual=1)),
+                             ("fv_cvs", "cvs-adc2", dict(core_orbitals=1, frozen_virtual=1)),
+                             ("fc_adc3", "adc3", dict(frozen_core=1))):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            st = adcc.run_adc(data, method=method, n_singlets=2, conv_tol=1e-8, output=None, **kw)
+        assert st.converged
+        np.testing.assert_allclose(st.excitation_energy, g[f"{name}/energies"], atol=ENERGY_ATOL, rtol=0)
+        assert st.n_iter == int(g[f"{name}/n_iter"]), (name, st.n_iter)
+        if f"{name}/oscillator_strength" in g.files:
+            np.testing.assert_allclose(st.oscillator_strength, g[f"{name}/oscillator_strength"],
+                                       rtol=OSC_RTOL, atol=OSC_ATOL)

@@ -48,6 +48,14 @@ def test_open_shell_vs_reference_produced_goldens(method, which, monkeypatch):
     check_open_shell(method, which)
 
 
+def test_workflows_vs_reference_produced_goldens(monkeypatch):
+    """Projected ADC(2)-x matrix (BASELINE configs[3]'s water_core_by_projection.py) and the frozen-space
+    cases, product host path against the reference's own runs."""
+    from reference_golden_common import check_workflows
+    cpu_shim.install(monkeypatch)
+    check_workflows()
+
+
 def test_libadcc_module_surface():
     """Every name the reference's Python layer looks up in ``libadcc`` (libadcc.pyi) exists; runs in a
     subprocess because importing libadcc switches select_n_* to libtensor's symmetry-unique mode."""
