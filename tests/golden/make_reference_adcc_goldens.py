@@ -14,7 +14,9 @@ adcc/tests/generators/dump_adcc.py:192-263 (random trial vector, matvec, diagona
 results) and is compared by tests/test_reference_goldens_*.py with the oracle, the product host
 path and the CUDA path at the tolerances of adcc/tests/AdcMatrix_test.py:213-285 or tighter.
 
-    python tests/golden/make_reference_adcc_goldens.py      # writes reference_adcc_h2o_sto3g.npz
+    python tests/golden/make_reference_adcc_goldens.py      # writes reference_adcc_h2o_sto3g.npz and the
+                                                            # open_shell / workflows / baseline_shapes files
+    python tests/golden/make_reference_adcc_goldens.py baseline_shapes      # one of the latter only
 """
 import os
 import sys
@@ -46,6 +48,13 @@ def main():
     assert adcc.__file__.startswith(REF), adcc.__file__
 
     data = import_data()
+    only = sys.argv[1:]                           # e.g. "baseline_shapes": regenerate one file only
+    if only:
+        parts = {"open_shell": lambda: open_shell(adcc, guess_zero), "workflows": lambda: workflows(adcc, data),
+                 "baseline_shapes": lambda: baseline_shapes(adcc, guess_zero)}
+        for name in only:
+            parts[name]()
+        return
     out = {"methods": np.array(METHODS)}
     for method in METHODS:
         cvs = method.startswith("cvs")
@@ -124,6 +133,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "reference_adcc_h2o_sto3g.npz"), **out)
     open_shell(adcc, guess_zero)
     workflows(adcc, data)
+    baseline_shapes(adcc, guess_zero)
 
 
 def workflows(adcc, data):
@@ -200,6 +210,73 @@ def open_shell(adcc, guess_zero):
         print("open shell", method, out[f"{method}/any/energies"], out[f"{method}/any/n_iter"],
               out[f"{method}/spin_flip/n_iter"], flush=True)
     np.savez_compressed(os.path.join(HERE, "reference_adcc_open_shell.npz"), **out)
+
+
+
+
+BASELINE_SHAPE_CASES = {     # key: (named_case, method, run_adc arguments as in BASELINE.json's configs)
+    "c1": ("h2o_ccpvdz", "adc2", dict(n_singlets=3, conv_tol=1e-6)),
+    "c1_adc3": ("h2o_ccpvdz", "adc3", dict(n_singlets=3, conv_tol=1e-6)),
+    "c2": ("h2o_ccpvtz", "adc2", dict(n_singlets=10)),
+    "c4": ("h2o_ccpvtz_cvs", "cvs-adc2x", dict(n_singlets=7, conv_tol=1e-8)),
+    "c4_ne": ("ne_ccpvtz_cvs", "cvs-adc2x", dict(n_singlets=4, conv_tol=1e-8)),
+    "c3": ("methyloxirane_ccpvdz", "adc3", dict(n_singlets=8)),       # hours of CPU: only with REF_GOLDEN_C3=1
+}
+
+
+def spin_orbital_eri(data):
+    """The SCF dicts of adcc_b200.synthetic carry the spatial (pq|rs) under an extension key; the
+    reference's DataHfProvider wants the full spin-orbital chemists' array (DataHfProvider.py:122-132)."""
+    d = dict(data)
+    g = d.pop("eri_ffff_spatial")
+    n = g.shape[0]
+    E = np.zeros((2 * n,) * 4)
+    for a in (slice(0, n), slice(n, 2 * n)):
+        for b in (slice(0, n), slice(n, 2 * n)):
+            E[a, a, b, b] = g
+    d["eri_ffff"] = E
+    return d
+
+
+def baseline_shapes(adcc, guess_zero):
+    """The reference's own run_adc on the restricted synthetic SCF inputs of the exact BASELINE
+    shapes (adcc_b200.synthetic.named_case: configs[0..3]): energies, oscillator strengths,
+    iteration counts, and sigma of a seeded trial vector (singles complete, 4096 sampled doubles)."""
+    from adcc_b200.synthetic import named_case
+    path = os.path.join(HERE, "reference_adcc_baseline_shapes.npz")
+    out = dict(np.load(path)) if os.path.exists(path) else {}
+    for key, (name, method, kw) in BASELINE_SHAPE_CASES.items():
+        if key == "c3" and os.environ.get("REF_GOLDEN_C3") != "1":
+            continue
+        data, core = named_case(name)
+        ref = adcc.ReferenceState(spin_orbital_eri(data), core_orbitals=core or None)
+        matrix = adcc.AdcMatrix(method, ref)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            state = adcc.run_adc(matrix, output=None, **kw)
+        assert state.converged
+        out[f"{key}/energies"], out[f"{key}/n_iter"] = np.array(state.excitation_energy), np.array(state.n_iter)
+        out[f"{key}/oscillator_strength"] = np.array(state.oscillator_strength)
+        rng = np.random.default_rng(sum(map(ord, key)))
+        vec = guess_zero(matrix)
+        cvs = method.startswith("cvs")
+        for blk in vec.blocks:
+            arr = rng.standard_normal(vec[blk].shape)
+            if blk == "pphh":
+                arr = arr - arr.transpose(0, 1, 3, 2)
+                if not cvs:
+                    arr = arr - arr.transpose(1, 0, 2, 3)
+            vec[blk].set_from_ndarray(arr)
+        sigma = adcc.evaluate(matrix @ vec)
+        out[f"{key}/vector_seed"] = np.array(sum(map(ord, key)))
+        out[f"{key}/matvec/ph"] = sigma.ph.to_ndarray()
+        s2 = sigma.pphh.to_ndarray().reshape(-1)
+        pick = np.random.default_rng(1).choice(s2.size, size=min(4096, s2.size), replace=False)
+        out[f"{key}/matvec/pphh_index"], out[f"{key}/matvec/pphh_value"] = pick, s2[pick]
+        out[f"{key}/matvec/pphh_max"] = np.array(np.max(np.abs(s2)))
+        print("baseline shape", key, method, out[f"{key}/energies"][:3], out[f"{key}/n_iter"], flush=True)
+        del matrix, ref, state, sigma, vec
+    np.savez_compressed(path, **out)
 
 
 if __name__ == "__main__":

@@ -299,3 +299,62 @@ def check_workflows():
         if f"{name}/oscillator_strength" in g.files:
             np.testing.assert_allclose(st.oscillator_strength, g[f"{name}/oscillator_strength"],
                                        rtol=OSC_RTOL, atol=OSC_ATOL)
+
+
+BASELINE_SHAPES_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                      "reference_adcc_baseline_shapes.npz")
+BASELINE_SHAPE_CASES = {     # as in tests/golden/make_reference_adcc_goldens.py
+    "c1": ("h2o_ccpvdz", "adc2", dict(n_singlets=3, conv_tol=1e-6)),
+    "c1_adc3": ("h2o_ccpvdz", "adc3", dict(n_singlets=3, conv_tol=1e-6)),
+    "c2": ("h2o_ccpvtz", "adc2", dict(n_singlets=10)),
+    "c4": ("h2o_ccpvtz_cvs", "cvs-adc2x", dict(n_singlets=7, conv_tol=1e-8)),
+    "c4_ne": ("ne_ccpvtz_cvs", "cvs-adc2x", dict(n_singlets=4, conv_tol=1e-8)),
+    "c3": ("methyloxirane_ccpvdz", "adc3", dict(n_singlets=8)),
+}
+
+
+def check_baseline_shape(key, run=True, doubles_storage="auto"):
+    """The restricted synthetic SCF input of one exact BASELINE shape (configs[0..3]) against the
+    reference's OWN run_adc on it (through the libadcc surface): sigma of a seeded trial vector
+    (singles complete, 4096 sampled doubles) to 1e-11, then - ``run`` - energies within the
+    convergence tolerance, oscillator strengths and the iteration count."""
+    import warnings
+    import pytest
+    import adcc_b200 as adcc
+    from adcc_b200.synthetic import named_case
+    g = np.load(BASELINE_SHAPES_GOLDEN)
+    if f"{key}/energies" not in g.files:
+        pytest.skip(f"no reference-produced golden for {key} (hours of CPU; see the generator)")
+    name, method, kw = BASELINE_SHAPE_CASES[key]
+    data, core = named_case(name)
+    ref = adcc.ReferenceState(data, core_orbitals=core or None)
+    m = adcc.AdcMatrix(method, ref, doubles_storage=doubles_storage)
+    cvs = method.startswith("cvs")
+    rng = np.random.default_rng(int(g[f"{key}/vector_seed"]))
+    blocks = {}
+    for blk in ("ph", "pphh"):                        # the generator's order of draws
+        arr = rng.standard_normal(tuple(m.mospaces.n_orbs(sp) for sp in m.axis_spaces[blk]))
+        if blk == "pphh":
+            arr = arr - arr.transpose(0, 1, 3, 2)
+            if not cvs:
+                arr = arr - arr.transpose(1, 0, 2, 3)
+        t = adcc.Tensor.from_ndarray(m.mospaces, m.axis_spaces[blk], arr)
+        if blk == "pphh" and m.doubles_storage == "packed":
+            from adcc_b200.packed import PackedDoubles
+            from adcc_b200.packed_cvs import CvsPackedDoubles
+            t = (CvsPackedDoubles if cvs else PackedDoubles).from_dense(t)
+        blocks[blk] = t
+    sig = m.matvec(adcc.AmplitudeVector(**blocks))
+    assert rel(sig.ph.to_ndarray(), g[f"{key}/matvec/ph"]) < SIGMA_RTOL, key
+    s2 = sig.pphh.to_ndarray().reshape(-1)[g[f"{key}/matvec/pphh_index"]]
+    assert np.max(np.abs(s2 - g[f"{key}/matvec/pphh_value"])) < SIGMA_RTOL * float(g[f"{key}/matvec/pphh_max"]), key
+    if not run:
+        return
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        st = adcc.run_adc(m, output=None, **kw)
+    tol = kw.get("conv_tol", 1e-6)
+    assert st.converged
+    np.testing.assert_allclose(st.excitation_energy, g[f"{key}/energies"], atol=max(10 * tol ** 2, 1e-8) + tol * 1e-2, rtol=0)
+    np.testing.assert_allclose(st.oscillator_strength, g[f"{key}/oscillator_strength"], rtol=1e-3, atol=1e-4 * tol / 1e-6)
+    assert st.n_iter == int(g[f"{key}/n_iter"]), (key, st.n_iter)

@@ -56,6 +56,15 @@ def test_workflows_vs_reference_produced_goldens(monkeypatch):
     check_workflows()
 
 
+def test_baseline_shape_sigma_vs_reference_run(monkeypatch):
+    """configs[0] shape (10 / 38 spin orbitals): sigma of the host path against the reference's own
+    matvec on the same synthetic input (the solves at these shapes run in the GPU suite: the test-only
+    CPU stand-in kernels are slow there)."""
+    from reference_golden_common import check_baseline_shape
+    cpu_shim.install(monkeypatch)
+    check_baseline_shape("c1", run=False)
+
+
 def test_libadcc_module_surface():
     """Every name the reference's Python layer looks up in ``libadcc`` (libadcc.pyi) exists; runs in a
     subprocess because importing libadcc switches select_n_* to libtensor's symmetry-unique mode."""

@@ -31,3 +31,11 @@ def test_cuda_open_shell_vs_reference_produced_goldens(method):
     """Unrestricted open-shell input, kinds "any" and "spin_flip", on the device."""
     from reference_golden_common import check_open_shell
     check_open_shell(method, iter_slack=2)      # 30 - 46 iterations: device rounding may move the last one
+
+
+@pytest.mark.parametrize("key", ["c1", "c1_adc3", "c2", "c4", "c4_ne", "c3"])
+def test_cuda_baseline_shapes_vs_reference_run(key):
+    """BASELINE configs[0..3] shapes: sigma, converged states, oscillator strengths and the iteration
+    count of the reference's own run_adc on the same synthetic SCF input."""
+    from reference_golden_common import check_baseline_shape
+    check_baseline_shape(key)
