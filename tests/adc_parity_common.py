@@ -269,6 +269,46 @@ def open_shell_dict(n_orb=6, n_alpha=3, n_beta=2, seed=4, scale=0.03):
             "fock_ff": np.diag(orben), "eri_phys_asym_ffff": g}
 
 
+def synthetic_workload_dict(no, nv, seed, scale):
+    """The synthetic workload of BASELINE configs[4] (counter-based <pq||rs>, adcc_b200/synthetic.py) as
+    a plain SCF dict with the complete antisymmetrised array ``eri_phys_asym_ffff`` over all
+    no + nv spin orbitals, for consumers that know nothing about the packed source (the reference's
+    DataHfProvider).  The six defined blocks are completed by <pq||rs> = -<qp||rs> = -<pq||sr> = <rs||pq>;
+    host order of the orbital axis: alpha (occupied, virtual), then beta (adcc/DataHfProvider.py:84-141)."""
+    from adcc_b200.synthetic import synthetic_eri_block, synthetic_orbital_energies
+    nf = no + nv
+    O, V = slice(0, no), slice(no, nf)
+    B = {k: synthetic_eri_block(seed, k, no, nv, scale) for k in ("oooo", "ooov", "oovv", "ovov", "ovvv", "vvvv")}
+    G = np.zeros((nf,) * 4)
+    G[O, O, O, O] = B["oooo"]
+    G[O, O, O, V] = B["ooov"]
+    G[O, O, V, O] = -B["ooov"].transpose(0, 1, 3, 2)
+    G[O, V, O, O] = B["ooov"].transpose(2, 3, 0, 1)
+    G[V, O, O, O] = -B["ooov"].transpose(3, 2, 0, 1)
+    G[O, O, V, V] = B["oovv"]
+    G[V, V, O, O] = B["oovv"].transpose(2, 3, 0, 1)
+    G[O, V, O, V] = B["ovov"]
+    G[O, V, V, O] = -B["ovov"].transpose(0, 1, 3, 2)
+    G[V, O, O, V] = -B["ovov"].transpose(1, 0, 2, 3)
+    G[V, O, V, O] = B["ovov"].transpose(1, 0, 3, 2)
+    G[O, V, V, V] = B["ovvv"]
+    G[V, O, V, V] = -B["ovvv"].transpose(1, 0, 2, 3)
+    G[V, V, O, V] = B["ovvv"].transpose(2, 3, 0, 1)
+    G[V, V, V, O] = -B["ovvv"].transpose(2, 3, 1, 0)
+    G[V, V, V, V] = B["vvvv"]
+    assert np.max(np.abs(G + G.transpose(1, 0, 2, 3))) == 0 and np.max(np.abs(G + G.transpose(0, 1, 3, 2))) == 0
+    assert np.max(np.abs(G - G.transpose(2, 3, 0, 1))) == 0
+    h2i = np.concatenate((np.arange(no // 2), no + np.arange(nv // 2),
+                          no // 2 + np.arange(no // 2), no + nv // 2 + np.arange(nv // 2)))
+    e_o, e_v = synthetic_orbital_energies(no, nv)
+    orben = np.concatenate((e_o[0::2], e_v[0::2], e_o[1::2], e_v[1::2]))     # as adcc_b200.packed.synthetic_reference_state
+    na = nf // 2
+    occ = np.concatenate((np.ones(no // 2), np.zeros(nv // 2), np.ones(no // 2), np.zeros(nv // 2)))
+    return {"restricted": False, "conv_tol": 1e-12, "energy_scf": 0.0, "spin_multiplicity": 1,
+            "orbcoeff_fb": np.vstack([np.eye(na)] * 2), "occupation_f": occ, "orben_f": orben,
+            "fock_ff": np.diag(orben), "eri_phys_asym_ffff": G[np.ix_(h2i, h2i, h2i, h2i)]}
+
+
 def check_open_shell():
     data = open_shell_dict()
     for method in ("adc2", "adc2x", "adc3"):

@@ -51,7 +51,8 @@ def main():
     only = sys.argv[1:]                           # e.g. "baseline_shapes": regenerate one file only
     if only:
         parts = {"open_shell": lambda: open_shell(adcc, guess_zero), "workflows": lambda: workflows(adcc, data),
-                 "baseline_shapes": lambda: baseline_shapes(adcc, guess_zero)}
+                 "baseline_shapes": lambda: baseline_shapes(adcc, guess_zero),
+                 "synthetic_workload": lambda: synthetic_workload(adcc, guess_zero)}
         for name in only:
             parts[name]()
         return
@@ -134,6 +135,7 @@ def main():
     open_shell(adcc, guess_zero)
     workflows(adcc, data)
     baseline_shapes(adcc, guess_zero)
+    synthetic_workload(adcc, guess_zero)
 
 
 def workflows(adcc, data):
@@ -277,6 +279,45 @@ def baseline_shapes(adcc, guess_zero):
         print("baseline shape", key, method, out[f"{key}/energies"][:3], out[f"{key}/n_iter"], flush=True)
         del matrix, ref, state, sigma, vec
     np.savez_compressed(path, **out)
+
+
+SYNTHETIC_CASES = [(6, 10, 5), (8, 20, 11)]        # (nocc, nvirt, seed) of the counter-based workload
+
+
+def synthetic_workload(adcc, guess_zero):
+    """BASELINE configs[4]'s input definition at small sizes: the counter-based <pq||rs> of
+    adcc_b200/synthetic.py written out as a plain SCF dict (tests/adc_parity_common.py::
+    synthetic_workload_dict) and handed to the reference's own ReferenceState / AdcMatrix / run_adc:
+    sigma of a seeded trial vector, the diagonal and three states of ADC(2), ADC(2)-x and ADC(3)."""
+    from adc_parity_common import synthetic_workload_dict
+    out = {"cases": np.array(SYNTHETIC_CASES)}
+    for no, nv, seed in SYNTHETIC_CASES:
+        data = synthetic_workload_dict(no, nv, seed, 0.02)
+        for method in ("adc2", "adc2x", "adc3"):
+            key = f"{no}_{nv}/{method}"
+            ref = adcc.ReferenceState(data)
+            matrix = adcc.AdcMatrix(method, ref)
+            rng = np.random.default_rng(no * 1000 + nv + sum(map(ord, method)))
+            vec = guess_zero(matrix)
+            for blk in vec.blocks:
+                arr = rng.standard_normal(vec[blk].shape)
+                if blk == "pphh":
+                    arr = arr - arr.transpose(0, 1, 3, 2)
+                    arr = arr - arr.transpose(1, 0, 2, 3)
+                vec[blk].set_from_ndarray(arr)
+                out[f"{key}/vector/{blk}"] = arr
+            sigma = adcc.evaluate(matrix @ vec)
+            diag = matrix.diagonal()
+            for blk in vec.blocks:
+                out[f"{key}/matvec/{blk}"] = sigma[blk].to_ndarray()
+                out[f"{key}/diagonal/{blk}"] = diag[blk].to_ndarray()
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                state = adcc.run_adc(matrix, n_states=3, conv_tol=1e-8, output=None)
+            assert state.converged
+            out[f"{key}/energies"], out[f"{key}/n_iter"] = np.array(state.excitation_energy), np.array(state.n_iter)
+            print("synthetic workload", key, out[f"{key}/energies"], out[f"{key}/n_iter"], flush=True)
+    np.savez_compressed(os.path.join(HERE, "reference_adcc_synthetic_workload.npz"), **out)
 
 
 if __name__ == "__main__":

@@ -358,3 +358,41 @@ def check_baseline_shape(key, run=True, doubles_storage="auto"):
     np.testing.assert_allclose(st.excitation_energy, g[f"{key}/energies"], atol=max(10 * tol ** 2, 1e-8) + tol * 1e-2, rtol=0)
     np.testing.assert_allclose(st.oscillator_strength, g[f"{key}/oscillator_strength"], rtol=1e-3, atol=1e-4 * tol / 1e-6)
     assert st.n_iter == int(g[f"{key}/n_iter"]), (key, st.n_iter)
+
+
+SYNTHETIC_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                "reference_adcc_synthetic_workload.npz")
+
+
+def check_synthetic_workload(no, nv, seed, method):
+    """BASELINE configs[4]'s input definition at a small size.  Reference side (golden): the counter-based
+    <pq||rs> written out as a plain SCF dict and run through the reference's own ReferenceState /
+    AdcMatrix / run_adc.  Product side: the device generator + pair-packed store + fused engine that
+    the headline benchmark uses (synthetic_reference_state, doubles_storage="packed").  Sigma and
+    diagonal to 1e-11, three states to 1e-8 with the reference's iteration count."""
+    import warnings
+    import adcc_b200 as adcc
+    from adcc_b200.packed import PackedDoubles, synthetic_reference_state
+    g = np.load(SYNTHETIC_GOLDEN)
+    key = f"{no}_{nv}/{method}"
+    ref = synthetic_reference_state(no, nv, seed=seed, scale=0.02)
+    m = adcc.AdcMatrix(method, ref, doubles_storage="packed")
+    ph = adcc.Tensor.from_ndarray(m.mospaces, m.axis_spaces["ph"], g[f"{key}/vector/ph"])
+    pphh = PackedDoubles.from_dense(adcc.Tensor.from_ndarray(m.mospaces, m.axis_spaces["pphh"],
+                                                             g[f"{key}/vector/pphh"]))
+    sig = m.matvec(adcc.AmplitudeVector(ph=ph, pphh=pphh))
+    for blk in ("ph", "pphh"):
+        assert rel(sig[blk].to_ndarray(), g[f"{key}/matvec/{blk}"]) < SIGMA_RTOL, (key, blk)
+        d, want = m.diagonal()[blk].to_ndarray(), g[f"{key}/diagonal/{blk}"]
+        if blk == "pphh":                              # i == j / a == b entries are not stored
+            mask = np.ones_like(want, dtype=bool)
+            mask[np.arange(no), np.arange(no)] = False
+            mask[:, :, np.arange(nv), np.arange(nv)] = False
+            d, want = d[mask], want[mask]
+        assert rel(d, want) < SIGMA_RTOL, (key, "diagonal", blk)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        st = adcc.run_adc(m, n_states=3, conv_tol=1e-8, output=None)
+    assert st.converged
+    np.testing.assert_allclose(st.excitation_energy, g[f"{key}/energies"], atol=ENERGY_ATOL, rtol=0)
+    assert st.n_iter == int(g[f"{key}/n_iter"]), (key, st.n_iter)

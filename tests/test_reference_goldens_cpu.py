@@ -65,6 +65,16 @@ def test_baseline_shape_sigma_vs_reference_run(monkeypatch):
     check_baseline_shape("c1", run=False)
 
 
+@pytest.mark.parametrize("method", ["adc2", "adc2x", "adc3"])
+@pytest.mark.parametrize("no,nv,seed", [(6, 10, 5), (8, 20, 11)])
+def test_synthetic_workload_vs_reference_run(no, nv, seed, method, monkeypatch):
+    """The headline workload's input definition + packed engine against the reference's own run on the
+    same integrals given as a plain SCF dict."""
+    from reference_golden_common import check_synthetic_workload
+    cpu_shim.install(monkeypatch)
+    check_synthetic_workload(no, nv, seed, method)
+
+
 def test_libadcc_module_surface():
     """Every name the reference's Python layer looks up in ``libadcc`` (libadcc.pyi) exists; runs in a
     subprocess because importing libadcc switches select_n_* to libtensor's symmetry-unique mode."""

@@ -39,3 +39,12 @@ def test_cuda_baseline_shapes_vs_reference_run(key):
     count of the reference's own run_adc on the same synthetic SCF input."""
     from reference_golden_common import check_baseline_shape
     check_baseline_shape(key)
+
+
+@pytest.mark.parametrize("method", ["adc2", "adc2x", "adc3"])
+@pytest.mark.parametrize("no,nv,seed", [(6, 10, 5), (8, 20, 11)])
+def test_cuda_synthetic_workload_vs_reference_run(no, nv, seed, method):
+    """Device generator + pair-packed store + fused engine of the headline benchmark, at small sizes,
+    against the reference's own run on the same integrals."""
+    from reference_golden_common import check_synthetic_workload
+    check_synthetic_workload(no, nv, seed, method)
