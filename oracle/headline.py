@@ -13,7 +13,10 @@ adcc_b200/synthetic.py::synthetic_eri_value (restated in C in oracle/csrc/headli
 all host threads, the index bookkeeping between the pair store and the GEMM operands is OpenMP C.
 
 Parity: pinned by tests/test_oracle_headline_cpu.py against oracle.OracleAdcMatrix (the dense
-restatement that reproduces the reference's known answers) on small shapes, bit-for-tolerance.
+restatement that reproduces the reference's known answers) on small shapes, bit-for-tolerance, and
+directly against the reference's OWN matvec on the same counter-based integrals at nocc/nvirt = 6/10
+and 8/20 (tests/golden/reference_adcc_synthetic_workload.npz,
+tests/test_reference_goldens_cpu.py::test_oracles_on_synthetic_workload_vs_reference_run).
 Nothing under adcc_b200/ imports this module.
 """
 import ctypes

@@ -396,3 +396,33 @@ def check_synthetic_workload(no, nv, seed, method):
     assert st.converged
     np.testing.assert_allclose(st.excitation_energy, g[f"{key}/energies"], atol=ENERGY_ATOL, rtol=0)
     assert st.n_iter == int(g[f"{key}/n_iter"]), (key, st.n_iter)
+
+
+def check_synthetic_workload_oracle(no, nv, seed, method):
+    """The dense oracle on the synthetic input definition (oracle.synthetic.OracleSyntheticRef) and -
+    for ADC(2)-x - the full-size restatement that serves as the CPU arm of bench.py
+    (oracle/headline.py) against the reference's own run on the same integrals.  This closes the chain
+    reference code -> dense oracle -> headline oracle -> whole GPU sigma at nocc=40 / nvirt=400."""
+    import oracle
+    from oracle.synthetic import OracleSyntheticRef
+    g = np.load(SYNTHETIC_GOLDEN)
+    key = f"{no}_{nv}/{method}"
+    om = oracle.OracleAdcMatrix(method, OracleSyntheticRef(no, nv, seed=seed, scale=0.02))
+    v = {b: g[f"{key}/vector/{b}"] for b in ("ph", "pphh")}
+    sig = om.matvec(v)
+    for b in v:
+        assert rel(sig[b], g[f"{key}/matvec/{b}"]) < 1e-12, (key, b)
+        assert rel(om.diagonal()[b], g[f"{key}/diagonal/{b}"]) < 1e-12, (key, "diagonal", b)
+    st = oracle.run_adc(om, method, n_states=3, conv_tol=1e-8)
+    np.testing.assert_allclose(st.eigenvalues, g[f"{key}/energies"], atol=ENERGY_ATOL, rtol=0)
+    assert st.n_iter == int(g[f"{key}/n_iter"])
+    if method == "adc2x":
+        from oracle.headline import OracleHeadline
+        oh = OracleHeadline(no, nv, seed=seed, scale=0.02)
+        po = [(i, j) for j in range(no) for i in range(j)]
+        pv = [(a, b) for b in range(nv) for a in range(b)]
+        u2 = v["pphh"]
+        packed = np.array([[u2[i, j, a, b] for (a, b) in pv] for (i, j) in po])
+        s1, s2 = oh.matvec(v["ph"], packed)
+        want2 = np.array([[g[f"{key}/matvec/pphh"][i, j, a, b] for (a, b) in pv] for (i, j) in po])
+        assert rel(s1, g[f"{key}/matvec/ph"]) < 1e-12 and rel(s2, want2) < 1e-12, key

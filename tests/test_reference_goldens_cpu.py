@@ -75,6 +75,13 @@ def test_synthetic_workload_vs_reference_run(no, nv, seed, method, monkeypatch):
     check_synthetic_workload(no, nv, seed, method)
 
 
+@pytest.mark.parametrize("method", ["adc2", "adc2x", "adc3"])
+@pytest.mark.parametrize("no,nv,seed", [(6, 10, 5), (8, 20, 11)])
+def test_oracles_on_synthetic_workload_vs_reference_run(no, nv, seed, method):
+    from reference_golden_common import check_synthetic_workload_oracle
+    check_synthetic_workload_oracle(no, nv, seed, method)
+
+
 def test_libadcc_module_surface():
     """Every name the reference's Python layer looks up in ``libadcc`` (libadcc.pyi) exists; runs in a
     subprocess because importing libadcc switches select_n_* to libtensor's symmetry-unique mode."""
