@@ -34,7 +34,7 @@ def transition_dm(method, ground_state, amplitude):
     dm = {"v" + C: u1.transpose()}
     if cvs:
         if level >= 2:
-            u2 = amplitude.pphh
+            u2 = _dense_doubles(amplitude)             # packed CVS store: unpack (a, b) pairs first
             t2 = mp.t2(b.oovv)
             p0 = mp.second_order_dm_correction(apply_cvs=True)
             dm["oc"] = (-1.0 * einsum("ja,Ia->jI", p0.ov, u1)
@@ -44,9 +44,7 @@ def transition_dm(method, ground_state, amplitude):
     if level >= 1:
         dm["ov"] = -1.0 * einsum("ijab,jb->ia", mp.t2(b.oovv), u1)
     if level >= 2:
-        u2 = amplitude.pphh
-        if hasattr(u2, "to_dense"):
-            u2 = u2.to_dense()
+        u2 = _dense_doubles(amplitude)
         t2 = mp.t2(b.oovv)
         td2 = mp.td2(b.oovv)
         p0 = mp.mp2_diffdm

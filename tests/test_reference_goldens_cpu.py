@@ -23,7 +23,7 @@ def test_product_host_path_vs_reference_produced_goldens(method, monkeypatch):
     check_product(method)
 
 
-@pytest.mark.parametrize("method", ["adc2", "adc2x", "adc3"])
+@pytest.mark.parametrize("method", ["adc2", "adc2x", "adc3", "cvs-adc2", "cvs-adc2x"])
 def test_packed_host_path_vs_reference_produced_goldens(method, monkeypatch):
     cpu_shim.install(monkeypatch)
     check_product(method, doubles_storage="packed")
