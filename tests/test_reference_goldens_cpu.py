@@ -134,3 +134,12 @@ def test_unmodified_reference_adcc_runs_on_this_backend():
         "print('ok')\n")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-3000:]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/adcc"), reason="reference tree only exists in the build container")
+def test_validation_and_guesses_match_the_reference_live():
+    """tests/live_reference_diff.py: 810 argument-validation cases and 130 guess sets, the product's
+    code against the reference's own, executed side by side."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "live_reference_diff.py")],
+                         capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert out.returncode == 0 and "ok 810 validation cases, 130 guess sets" in out.stdout, out.stderr[-3000:]
