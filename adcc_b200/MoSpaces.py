@@ -156,8 +156,10 @@ class MoSpaces:
         sort_ss = ["o3", "o2", "o1", "v1", "v2"]
         full = sorted(range(nf), key=lambda i: (spin[i], sort_ss.index(sub[i]), orben[i]))
         self.map_index_hf_provider = {"f": list(full)}
-        self._n_alpha = {"f": noa}
-        self._n = {"f": nf}
+        # absent subspaces count zero orbitals (libadcc_src/MoSpaces.cc:190-194, 265-268 initialise every
+        # subspace entry; adcc/workflow.py:262-270 asks for n_orbs_alpha("o3") of a state without frozen core)
+        self._n_alpha = {"f": noa, "o1": 0, "o2": 0, "o3": 0, "v1": 0, "v2": 0}
+        self._n = {"f": nf, "o1": 0, "o2": 0, "o3": 0, "v1": 0, "v2": 0}
         self.subspaces_occupied = [s for s in ("o1", "o2", "o3") if any(x == s for x in sub)]
         self.subspaces_virtual = [s for s in ("v1", "v2") if any(x == s for x in sub)]
         self.subspaces = self.subspaces_occupied + self.subspaces_virtual

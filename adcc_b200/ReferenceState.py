@@ -26,7 +26,8 @@ class ReferenceState:
         self.timer = Timer()
         self.symmetry_check_on_import = symmetry_check_on_import
         self.restricted = hf.restricted
-        self.spin_multiplicity = hf.spin_multiplicity
+        # 0 ("unknown") for unrestricted references, whatever the provider says (libadcc_src/ReferenceState.cc:333-339)
+        self.spin_multiplicity = hf.spin_multiplicity if hf.restricted else 0
         self.conv_tol = hf.conv_tol
         self.energy_scf = hf.energy_scf
         self.backend = hf.backend

@@ -268,10 +268,17 @@ class Tensor:
         if self._storage != getattr(other, "_storage", None):
             raise ValueError("Cannot combine tensors with different storage "
                              f"({type(self).__name__} vs {type(other).__name__})")
+        # same checks, order and wording as libadcc_src/TensorImpl.cc:44-63 (dimension_mismatch -> ValueError)
+        if self._data.dim() != other._data.dim():
+            raise ValueError(f"Dimensionality of this tensor ({self._data.dim()}) does not agree with the "
+                             "dimensionality of the other tensor passed, which has dimensionality "
+                             f"{other._data.dim()}.")
         if self._data.shape != other._data.shape:
-            raise ValueError(f"Shape mismatch: {self.shape} vs {other.shape}")
+            raise ValueError(f"Shape of this tensor ({self.shape}) does not agree with the shape of the other "
+                             f"tensor passed, which has shape {other.shape}.")
         if self.subspaces != other.subspaces:
-            raise ValueError(f"Subspace mismatch: {self.space} vs {other.space}")
+            raise ValueError(f"Axes of this tensor ({self.space}) do not agree with the axes of the other tensor "
+                             f"passed, which has axis labels {other.space}.")
 
     def __pos__(self): return self
     def __neg__(self): return self._like(be.scaled_copy(self._data, -1.0))
