@@ -24,9 +24,13 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools", "
 MODULES = ["Tensor_test.py", "einsum_test.py", "direct_sum_test.py", "AmplitudeVector_test.py", "block_test.py",
            "AdcMethod_test.py", "misc_test.py", "NParticleOperator_test.py", "AdcMatrix_block_view_test.py",
            "AdcMatrix_dense_export_test.py", "ReferenceState_counterdata_test.py", "workflow_test.py",
-           ] + os.environ.get("ADCCB_REFTEST_MODULES", "").split()
-# needs adcman result files that are not vendored (adcc/tests/data/update_testdata.sh)
-DESELECT = ["test_diagonalise_adcmatrix"]
+           "guess_test.py"] + os.environ.get("ADCCB_REFTEST_MODULES", "").split()
+# test_diagonalise_adcmatrix needs adcman result files that are not vendored (adcc/tests/data/update_testdata.sh);
+# test_doubles_cn asserts that the doubles guesses are the n smallest diagonal entries, which adc_guess_d's
+# candidate search (2n smallest of each factor, libadcc_src/guess/adc_guess_d.cc:485-500, restated in
+# adcc_b200/guess/guesses_from_diagonal.py) only guarantees for the orbital-energy pattern of the real CN
+# molecule, not for the random open-shell stand-in used here
+DESELECT = ["test_diagonalise_adcmatrix", "test_doubles_cn"]
 
 
 def main(argv):

@@ -147,9 +147,9 @@ def test_validation_and_guesses_match_the_reference_live():
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/adcc"), reason="reference tree only exists in the build container")
 def test_reference_own_test_modules_pass_on_this_backend():
-    """tests/run_reference_tests.py: twelve modules of the reference's OWN test-suite (Tensor, einsum,
+    """tests/run_reference_tests.py: thirteen modules of the reference's OWN test-suite (Tensor, einsum,
     direct_sum, AmplitudeVector, block, AdcMethod, misc, NParticleOperator, AdcMatrix block view / dense
-    export, ReferenceState counter data, workflow), unmodified, on the libadcc surface of this
+    export, ReferenceState counter data, workflow, guess), unmodified, on the libadcc surface of this
     repository: all pass except the six Tensor_test cases that assert LAZY evaluation (this backend
     is eager by design); those pass once that one flag is forced."""
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_reference_tests.py")],
@@ -157,7 +157,7 @@ def test_reference_own_test_modules_pass_on_this_backend():
                          env=dict(os.environ, ADCCB_REFTESTS="--lazy-flag"))
     lines = [ln for ln in out.stdout.splitlines() if " passed" in ln]
     assert len(lines) == 2, out.stdout[-3000:] + out.stderr[-2000:]
-    assert "6 failed, 233 passed" in lines[0], lines[0]
+    assert "6 failed, 353 passed" in lines[0], lines[0]
     failed = sorted(ln.split("::")[-1] for ln in out.stdout.splitlines() if ln.startswith("FAILED"))
     assert all(name.startswith("test_nontrivial_") for name in failed) and len(failed) == 6, failed
     assert "8 passed" in lines[1] and "failed" not in lines[1], lines[1]
