@@ -161,3 +161,20 @@ def test_reference_own_test_modules_pass_on_this_backend():
     failed = sorted(ln.split("::")[-1] for ln in out.stdout.splitlines() if ln.startswith("FAILED"))
     assert all(name.startswith("test_nontrivial_") for name in failed) and len(failed) == 6, failed
     assert "8 passed" in lines[1] and "failed" not in lines[1], lines[1]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/examples/water"), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("script,expected", [
+    ("sto3g_adc1.py", ["0.4834361", "0.4054416"]), ("sto3g_adc2.py", ["0.4705131", "0.4028848"]),
+    ("sto3g_adc2x.py", ["0.4451118", "0.3855778"]), ("sto3g_adc3.py", ["0.4519707", "0.3924604"]),
+    ("sto3g_cvs_adc2.py", ["20.00454", "19.95733"]), ("sto3g_fc_adc2.py", ["converged"]),
+    ("sto3g_uadc2.py", ["0.4028848", "0.4705131"])])
+def test_reference_example_scripts_run_unmodified(script, expected):
+    """examples/water/sto3g_*.py of the reference, executed as they are (tests/run_reference_example.py):
+    their printed tables carry the known excitation energies (adcc/tests/smoke_test.py:32-58)."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_reference_example.py"), script],
+                         capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert "NOT CONVERGED" not in out.stdout
+    for number in expected:
+        assert number in out.stdout, (script, number, out.stdout[-1500:])
