@@ -1,6 +1,9 @@
 #!/bin/bash
 # A/B of the GEMM pacing hint and of the stream-K tail policy on the packed vvvv shape (one B200):
 # CUDA-event times first (no profiler), then DRAM bytes / L2 hit rate of one launch under ncu.
+# The two environment switches exist only with tools/studies/gemm_pacing/pacing.patch applied to
+# adcc_b200/csrc/dgemm.cu (the study's build); the shipped library has no pacing and always uses the
+# tail rule that won (ragged round alone when it holds half a tile per CTA).
 set -u
 mkdir -p gpurun_out
 SHAPE=${1:-780x79800x79800}
