@@ -251,6 +251,71 @@ class MoIndexTranslation:
     def split_spin(self, index):
         return self.spin_of(index), self.block_index_spatial_of(index), self.inblock_index_of(index)
 
+    def split(self, index):
+        """(block index, in-block index)  (libadcc_src/MoIndexTranslation.cc:218-251)."""
+        return self.block_index_of(index), self.inblock_index_of(index)
+
+    def combine(self, *args):
+        """combine(block_index, inblock_index) or combine(spin_block, block_index_spatial, inblock_index):
+        the inverse of split / split_spin  (MoIndexTranslation.cc:253-335)."""
+        if len(args) == 3:
+            spin_block, spatial, inblock = args
+            if len(spin_block) != self.ndim or len(spatial) != self.ndim:
+                raise ValueError(f"MoIndexTranslation is for subspace ({self.space}), which is of dimension "
+                                 f"{self.ndim}, but passed spin block / spatial block index do not match.")
+            block = []
+            for k, (c, b) in enumerate(zip(spin_block, spatial)):
+                if c not in "ab":
+                    raise ValueError(f"Invalid spin-block identifier '{spin_block}'")
+                n_a = sum(1 for s in self.mospaces.map_block_spin[self.subspaces[k]] if s == "a")
+                block.append(int(b) + (n_a if c == "b" else 0))
+            return self.combine(tuple(block), inblock)
+        block, inblock = args
+        if len(block) != self.ndim or len(inblock) != self.ndim:
+            raise ValueError(f"MoIndexTranslation is for subspace ({self.space}), which is of dimension "
+                             f"{self.ndim}, but passed block / in-block index do not match.")
+        out = []
+        for k, (b, i) in enumerate(zip(block, inblock)):
+            starts = list(self.mospaces.map_block_start[self.subspaces[k]]) + [self.shape[k]]
+            if b >= len(starts) - 1:
+                raise ValueError(f"Block index {tuple(block)} overshoots the number of blocks at dimension {k}.")
+            if starts[b] + i >= starts[b + 1]:
+                raise ValueError(f"In-block index {tuple(inblock)} overshoots the block size at dimension {k}.")
+            out.append(int(starts[b] + i))
+        return tuple(out)
+
+    def full_index_of(self, index):
+        raise NotImplementedError("full_index_of not yet implemented.")      # MoIndexTranslation.cc:161-164
+
+    def map_range_to_hf_provider(self, ranges):
+        """[(subspace ranges, host ranges), ...]: the index box ``ranges`` (one (start, end) per axis) cut
+        into the boxes that map contiguously onto the SCF provider's orbital order
+        (MoIndexTranslation.cc:361-434)."""
+        ranges = [tuple(int(x) for x in r) for r in ranges]
+        if len(ranges) != self.ndim:
+            raise ValueError(f"MoIndexTranslation is for subspace ({self.space}), which is of dimension "
+                             f"{self.ndim}, but passed index range has a dimension of {len(ranges)}.")
+        per_axis = []
+        for k, (start, end) in enumerate(ranges):
+            if start > end:
+                raise ValueError(f"Passed index range at dimension {k}(== [{start},{end})) is invalid: "
+                                 "start larger than end.")
+            if end > self.shape[k]:
+                raise ValueError(f"Passed index range at dimension {k}(== [{start},{end})) overshoots shape "
+                                 f"{self.shape}.")
+            hmap = self.mospaces.map_index_hf_provider[self.subspaces[k]]
+            pieces = []
+            for i in range(start, end):
+                if pieces and hmap[i] == hmap[i - 1] + 1:
+                    pieces[-1][1] = i + 1
+                else:
+                    pieces.append([i, i + 1])
+            per_axis.append([((a, b), (hmap[a], hmap[a] + b - a)) for a, b in pieces])
+        out = [((), ())]
+        for pieces in per_axis:
+            out = [(src + (s,), dst + (d,)) for src, dst in out for s, d in pieces]
+        return [] if any(not p for p in per_axis) else out
+
     def hf_provider_index_of(self, index):
         return tuple(self.mospaces.map_index_hf_provider[self.subspaces[k]][i]
                      for k, i in enumerate(index))

@@ -68,6 +68,19 @@ class Symmetry:
     def has_permutations(self):
         return len(self._perms) > 1
 
+    # libadcc.pyi:541-631 / libadcc_src/Symmetry.hh:109-172
+    @property
+    def has_irreps_allowed(self):
+        return bool(getattr(self, "irreps_allowed", None))
+
+    @property
+    def has_spin_block_maps(self):
+        return bool(self.spin_block_maps)
+
+    @property
+    def has_spin_blocks_forbidden(self):
+        return bool(self.spin_blocks_forbidden)
+
     @property
     def empty(self):
         return not (self.has_permutations or self.spin_block_maps or self.spin_blocks_forbidden)

@@ -80,6 +80,15 @@ class HartreeFockProvider(HartreeFockSolution_i):
     def get_nuclear_multipole(self, order, gauge_origin=(0.0, 0.0, 0.0)):
         raise NotImplementedError("get_nuclear_multipole")
 
+    def transform_gauge_origin_to_xyz(self, gauge_origin):
+        """libadcc.pyi:140: providers that know the molecule translate "origin", "mass_center", ... to
+        coordinates; the base class only knows the coordinate origin."""
+        if isinstance(gauge_origin, str):
+            if gauge_origin == "origin":
+                return (0.0, 0.0, 0.0)
+            raise NotImplementedError(f"gauge origin {gauge_origin!r} is not known to this provider")
+        return tuple(float(x) for x in gauge_origin)
+
 
 # ------------------------------------------------------------------------------ MO spaces
 class MoSpaces:

@@ -63,8 +63,28 @@ def motrans_cases():
         r"|(?<!_THROWS)\(motrans\.(?P<fn>block_index_of|block_index_spatial_of|inblock_index_of|"
         r"spin_of|hf_provider_index_of)\(\{(?P<idx>[^}]*)\}\)\s*==\s*"
         r'(?:vecsize\{(?P<vec>[^}]*)\}|"(?P<spin>\w+)")\)')
-    out, bs, args, cur = [], None, None, None
-    for m in token.finditer(text):
+    # range mappings: ``std::vector<RangeMapping> ref_N{ {from pairs},{to pairs} ... };`` followed by
+    # ``CHECK(motrans.map_range_to_hf_provider({ranges}) == ref_N);``
+    ref_def = re.compile(r"std::vector<RangeMapping>\s*(ref_\d+)\s*\{(.*?)\};", re.S)
+    ref_use = re.compile(r"map_range_to_hf_provider\(\{(.*?)\}\)\s*==\s*(ref_\d+)\)", re.S)
+    events = sorted([(m.start(), "tok", m) for m in token.finditer(text)]
+                    + [(m.start(), "def", m) for m in ref_def.finditer(text)]
+                    + [(m.start(), "use", m) for m in ref_use.finditer(text)], key=lambda e: e[0])
+    out, bs, args, cur, refs = [], None, None, None, {}
+    for _, kind, m in events:
+        if kind == "def":
+            refs[m.group(1)] = numbers(m.group(2))
+            continue
+        if kind == "use":
+            ndim = len(cur["space"]) // 2
+            rng = numbers(m.group(1))
+            flat = refs[m.group(2)]
+            assert len(rng) == 2 * ndim and len(flat) % (4 * ndim) == 0
+            pairs = lambda v: [v[2 * k:2 * k + 2] for k in range(len(v) // 2)]      # noqa: E731
+            maps = [[pairs(flat[o:o + 2 * ndim]), pairs(flat[o + 2 * ndim:o + 4 * ndim])]
+                    for o in range(0, len(flat), 4 * ndim)]
+            cur.setdefault("range_checks", []).append([pairs(rng), maps])
+            continue
         if m.group("bs"):
             bs = int(m.group("bs"))
         elif m.group("c") is not None:

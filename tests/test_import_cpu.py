@@ -91,7 +91,7 @@ def test_mo_index_translation_reference_expectations():
 
     def split(lst):
         return ([i for i in lst if i < nf // 2], [i - nf // 2 for i in lst if i >= nf // 2])
-    n_checks = 0
+    n_checks = n_ranges = 0
     for case in gold["motrans"]:
         mo = MoSpaces(data, core_orbitals=split(case["core_orbitals"]),
                       frozen_core=split(case["frozen_core"]),
@@ -103,4 +103,13 @@ def test_mo_index_translation_reference_expectations():
             got = got if isinstance(got, str) else list(got)
             assert got == expect, (case["space"], case["block_size"], fn, idx)
             n_checks += 1
-    assert n_checks == 84
+            # split / combine invert each other (MoIndexTranslationTest.cc:68-77)
+            assert tr.combine(*tr.split(idx)) == tuple(idx)
+            assert tr.combine(tr.spin_of(idx), tr.block_index_spatial_of(idx), tr.inblock_index_of(idx)) == tuple(idx)
+        for ranges, expect in case.get("range_checks", []):
+            # contiguous boxes of an index range in the SCF provider's order (MoIndexTranslationTest.cc:83-119, 166-189)
+            got = tr.map_range_to_hf_provider(ranges)
+            assert [[[list(p) for p in src], [list(p) for p in dst]] for src, dst in got] == expect, \
+                (case["space"], case["block_size"], ranges)
+            n_ranges += 1
+    assert n_checks == 84 and n_ranges == 12

@@ -99,6 +99,13 @@ def test_libadcc_module_surface():
         "'select_n_min','select_n_absmax','set_mask','set_random','copy','zeros_like','ones_like','empty_like',"
         "'nosym_like','evaluate','is_allowed','describe_symmetry','describe_expression','set_immutable']:\n"
         "    assert hasattr(libadcc.Tensor, m), m\n"
+        "for m in ['split','combine','split_spin','map_range_to_hf_provider','full_index_of','hf_provider_index_of',"
+        "'block_index_of','block_index_spatial_of','inblock_index_of','spin_of']:\n"
+        "    assert hasattr(libadcc.MoIndexTranslation, m), m\n"
+        "for m in ['has_irreps_allowed','has_permutations','has_spin_block_maps','has_spin_blocks_forbidden','empty',"
+        "'clear','describe']:\n"
+        "    assert hasattr(libadcc.Symmetry, m), m\n"
+        "assert hasattr(libadcc.HartreeFockProvider, 'transform_gauge_origin_to_xyz')\n"
         "assert issubclass(libadcc.HartreeFockProvider, libadcc.HartreeFockSolution_i)\n"
         "print('ok')\n")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT,
