@@ -26,7 +26,17 @@ class HartreeFockProvider:
 
     # -- optional
     def fill_eri_phys_asym_ffff(self, slices, out): raise NotImplementedError
-    def has_eri_phys_asym_ffff_inner(self): return False
+    def has_eri_phys_asym_ffff(self): return False        # the hook host back-ends override (libadcc.pyi:136)
+    def has_eri_phys_asym_ffff_inner(self): return bool(self.has_eri_phys_asym_ffff())
+
+    def transform_gauge_origin_to_xyz(self, gauge_origin):
+        """libadcc.pyi:140; back-ends that know the molecule override it."""
+        if isinstance(gauge_origin, str):
+            if gauge_origin == "origin":
+                return (0.0, 0.0, 0.0)
+            raise NotImplementedError(f"gauge origin {gauge_origin!r} is not known to this provider")
+        return tuple(float(x) for x in gauge_origin)
+
     def get_energy_scf(self): return 0.0
     def get_spin_multiplicity(self): return 1 if self.get_restricted() else 0
     def get_backend(self): return "generic"
