@@ -6,7 +6,10 @@ reference package imports libadcc, which switches select_n_* to libtensor's symm
     combination of n_states / n_singlets / n_triplets / n_spin_flip / kind (810 cases, restricted and
     unrestricted reference): same result tuple or same exception type;
   * adcc.guess.guesses_{singlet,triplet,any,spin_flip} vs the product's, singles and doubles blocks,
-    1 ... 8 guesses, ADC(2), ADC(2)-x, CVS-ADC(2)-x: identical vectors.
+    1 ... 8 guesses, ADC(2), ADC(2)-x, CVS-ADC(2)-x: identical vectors;
+  * sigma and diagonal of random vectors, the reference's AdcMatrix vs the product's, for four inputs
+    (H2O / STO-3G, an unrestricted open-shell input, two restricted synthetic inputs), six choices of
+    core / frozen-core / frozen-virtual spaces and all ten methods: equal to 1e-11.
 """
 import itertools
 import os
@@ -84,4 +87,66 @@ for label, dref, dours, kinds in inputs:
                                 assert np.max(np.abs(a[blk].to_ndarray() - b[blk].to_ndarray())) < 1e-12, \
                                     (label, method, kind, block, n, blk)
                     n_guesses += 1
-print(f"ok {n_validation} validation cases, {n_guesses} guess sets")
+
+# ---- sigma / diagonal of random vectors: reference AdcMatrix vs product AdcMatrix ------------------
+from adcc.guess import guess_zero  # noqa: E402
+from adcc_b200.synthetic import restricted_scf_dict  # noqa: E402
+
+
+def with_spin_orbital_eri(data):
+    """adcc_b200.synthetic dicts keep (pq|rs) spatial; the reference's DataHfProvider wants eri_ffff."""
+    d = dict(data)
+    g = d.pop("eri_ffff_spatial")
+    n = g.shape[0]
+    E = np.zeros((2 * n,) * 4)
+    for a in (slice(0, n), slice(n, 2 * n)):
+        for b in (slice(0, n), slice(n, 2 * n)):
+            E[a, a, b, b] = g
+    d["eri_ffff"] = E
+    return d
+
+
+small, mid = restricted_scf_dict(5, 2, seed=21), restricted_scf_dict(7, 3, seed=22)
+sigma_inputs = [("h2o", import_data(), oracle.hfdata.load_h2o_sto3g()), ("open-shell", open_shell_dict(), open_shell_dict()),
+                ("synthetic 5/2", with_spin_orbital_eri(small), small), ("synthetic 7/3", with_spin_orbital_eri(mid), mid)]
+spaces = [dict(), dict(core_orbitals=1), dict(frozen_core=1), dict(frozen_virtual=1),
+          dict(core_orbitals=1, frozen_virtual=1), dict(frozen_core=1, frozen_virtual=2)]
+n_sigma = 0
+for label, dref, dours in sigma_inputs:
+    for kw in spaces:
+        if label == "open-shell" and kw:
+            continue                                   # subspace lists of unequal alpha / beta counts: not probed here
+        if label == "synthetic 5/2" and kw.get("frozen_virtual") == 2 and kw.get("frozen_core"):
+            continue                                   # would leave one active occupied and one virtual pair
+        cvs = "core_orbitals" in kw
+        for method in (("cvs-adc0", "cvs-adc1", "cvs-adc2", "cvs-adc2x", "cvs-adc3") if cvs else
+                       ("adc0", "adc1", "adc2", "adc2x", "adc3")):
+            try:
+                mo = adcc_b200.AdcMatrix(method, adcc_b200.ReferenceState(dours, **kw))
+            except ValueError as e:                   # e.g. no virtual orbital left: the reference must object too
+                try:
+                    adcc.AdcMatrix(method, adcc.ReferenceState(dref, **kw))
+                except ValueError:
+                    continue
+                raise AssertionError((label, kw, method, "only the product raised", str(e)))
+            mr = adcc.AdcMatrix(method, adcc.ReferenceState(dref, **kw))
+            rng = np.random.default_rng(n_sigma + 5)
+            vr = guess_zero(mr)
+            blocks = {}
+            for blk in vr.blocks:
+                arr = rng.standard_normal(vr[blk].shape)
+                if blk == "pphh":
+                    arr = arr - arr.transpose(0, 1, 3, 2)
+                    if not cvs:
+                        arr = arr - arr.transpose(1, 0, 2, 3)
+                vr[blk].set_from_ndarray(arr)
+                blocks[blk] = adcc_b200.Tensor.from_ndarray(mo.mospaces, mo.axis_spaces[blk], arr)
+            sr = adcc.evaluate(mr @ vr)
+            so = mo.matvec(adcc_b200.AmplitudeVector(**blocks))
+            for blk in vr.blocks:
+                a, b = sr[blk].to_ndarray(), so[blk].to_ndarray()
+                assert np.max(np.abs(a - b)) <= 1e-11 * max(np.max(np.abs(a)), 1e-300), (label, kw, method, blk)
+                a, b = mr.diagonal()[blk].to_ndarray(), mo.diagonal()[blk].to_ndarray()
+                assert np.max(np.abs(a - b)) <= 1e-11 * max(np.max(np.abs(a)), 1e-300), (label, kw, method, "diag", blk)
+            n_sigma += 1
+print(f"ok {n_validation} validation cases, {n_guesses} guess sets, {n_sigma} sigma / diagonal comparisons")
