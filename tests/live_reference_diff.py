@@ -111,7 +111,7 @@ sigma_inputs = [("h2o", import_data(), oracle.hfdata.load_h2o_sto3g()), ("open-s
                 ("synthetic 5/2", with_spin_orbital_eri(small), small), ("synthetic 7/3", with_spin_orbital_eri(mid), mid)]
 spaces = [dict(), dict(core_orbitals=1), dict(frozen_core=1), dict(frozen_virtual=1),
           dict(core_orbitals=1, frozen_virtual=1), dict(frozen_core=1, frozen_virtual=2)]
-n_sigma = 0
+n_sigma = n_packed = 0
 for label, dref, dours in sigma_inputs:
     for kw in spaces:
         if label == "open-shell" and kw:
@@ -149,4 +149,17 @@ for label, dref, dours in sigma_inputs:
                 a, b = mr.diagonal()[blk].to_ndarray(), mo.diagonal()[blk].to_ndarray()
                 assert np.max(np.abs(a - b)) <= 1e-11 * max(np.max(np.abs(a)), 1e-300), (label, kw, method, "diag", blk)
             n_sigma += 1
-print(f"ok {n_validation} validation cases, {n_guesses} guess sets, {n_sigma} sigma / diagonal comparisons")
+            # the hand-scheduled engines on the packed stores, same vector
+            if method in ("adc2", "adc2x", "adc3", "cvs-adc2", "cvs-adc2x"):
+                from adcc_b200.packed import PackedDoubles
+                from adcc_b200.packed_cvs import CvsPackedDoubles
+                mp_ = adcc_b200.AdcMatrix(method, adcc_b200.ReferenceState(dours, **kw), doubles_storage="packed")
+                assert mp_.doubles_storage == "packed"
+                pb = dict(blocks)
+                pb["pphh"] = (CvsPackedDoubles if cvs else PackedDoubles).from_dense(blocks["pphh"])
+                sp = mp_.matvec(adcc_b200.AmplitudeVector(**pb))
+                for blk in vr.blocks:
+                    a, b = sr[blk].to_ndarray(), sp[blk].to_ndarray()
+                    assert np.max(np.abs(a - b)) <= 1e-11 * max(np.max(np.abs(a)), 1e-300), (label, kw, method, "packed", blk)
+                n_packed += 1
+print(f"ok {n_validation} validation cases, {n_guesses} guess sets, {n_sigma} sigma / diagonal comparisons, {n_packed} on the packed engines")
