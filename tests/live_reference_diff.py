@@ -9,7 +9,10 @@ reference package imports libadcc, which switches select_n_* to libtensor's symm
     1 ... 8 guesses, ADC(2), ADC(2)-x, CVS-ADC(2)-x: identical vectors;
   * sigma and diagonal of random vectors, the reference's AdcMatrix vs the product's, for four inputs
     (H2O / STO-3G, an unrestricted open-shell input, two restricted synthetic inputs), six choices of
-    core / frozen-core / frozen-virtual spaces and all ten methods: equal to 1e-11.
+    core / frozen-core / frozen-virtual spaces and all ten methods: equal to 1e-11;
+  * run_adc of both packages on the same inputs (singlet / triplet / any / spin_flip, ADC(1) ... ADC(3) and
+    their CVS variants, with and without frozen spaces; 116 runs): energies to 1e-8, identical iteration
+    counts, same exception type where no run is possible.
 """
 import itertools
 import os
@@ -162,4 +165,31 @@ for label, dref, dours in sigma_inputs:
                     a, b = sr[blk].to_ndarray(), sp[blk].to_ndarray()
                     assert np.max(np.abs(a - b)) <= 1e-11 * max(np.max(np.abs(a)), 1e-300), (label, kw, method, "packed", blk)
                 n_packed += 1
-print(f"ok {n_validation} validation cases, {n_guesses} guess sets, {n_sigma} sigma / diagonal comparisons, {n_packed} on the packed engines")
+
+# ---- converged states: reference run_adc vs product run_adc -----------------------------------------
+n_runs = 0
+for label, dref, dours in sigma_inputs:
+    restricted = label != "open-shell"
+    for kw in (dict(), dict(core_orbitals=1), dict(frozen_core=1, frozen_virtual=1)):
+        if not restricted and kw:
+            continue
+        cvs = "core_orbitals" in kw
+        for method in (("cvs-adc1", "cvs-adc2", "cvs-adc2x", "cvs-adc3") if cvs else ("adc1", "adc2", "adc2x", "adc3")):
+            for kind in (("singlet", "triplet", "any") if restricted else ("any", "spin_flip")):
+                key = {"singlet": "n_singlets", "triplet": "n_triplets", "any": "n_states", "spin_flip": "n_spin_flip"}[kind]
+                res = []
+                for mod, d in ((adcc, dref), (adcc_b200, dours)):
+                    try:
+                        st = mod.run_adc(d, method=method, conv_tol=1e-8, output=None, **{key: 2}, **kw)
+                        res.append((bool(st.converged), int(st.n_iter), np.array(st.excitation_energy)))
+                    except Exception as e:           # e.g. fewer guesses than requested: both must agree
+                        res.append(type(e).__name__)
+                a, b = res
+                if isinstance(a, str) or isinstance(b, str):
+                    assert a == b, (label, kw, method, kind, a, b)
+                else:
+                    assert a[0] and b[0], (label, kw, method, kind, "not converged")
+                    assert np.max(np.abs(a[2] - b[2])) < 1e-8, (label, kw, method, kind, a[2], b[2])
+                    assert a[1] == b[1], (label, kw, method, kind, "iterations", a[1], b[1])
+                n_runs += 1
+print(f"ok {n_validation} validation cases, {n_guesses} guess sets, {n_sigma} sigma / diagonal comparisons, {n_packed} on the packed engines, {n_runs} Davidson runs")

@@ -146,11 +146,11 @@ def test_unmodified_reference_adcc_runs_on_this_backend():
 @pytest.mark.skipif(not os.path.isdir("/root/reference/adcc"), reason="reference tree only exists in the build container")
 def test_validation_guesses_and_sigma_match_the_reference_live():
     """tests/live_reference_diff.py: 810 argument-validation cases, 130 guess sets and 85 sigma / diagonal
-    comparisons (four inputs x core / frozen spaces x ten methods; 45 of them also on the packed engines), the product's code against the
+    comparisons (four inputs x core / frozen spaces x ten methods; 45 of them also on the packed engines) and 116 Davidson runs (energies, iteration counts), the product's code against the
     reference's own, executed side by side."""
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "live_reference_diff.py")],
                          capture_output=True, text=True, cwd=ROOT, timeout=900)
-    assert out.returncode == 0 and "ok 810 validation cases, 130 guess sets, 85 sigma / diagonal comparisons, 45 on the packed engines" in out.stdout, out.stderr[-3000:]
+    assert out.returncode == 0 and "ok 810 validation cases, 130 guess sets, 85 sigma / diagonal comparisons, 45 on the packed engines, 116 Davidson runs" in out.stdout, out.stderr[-3000:]
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/adcc"), reason="reference tree only exists in the build container")
