@@ -167,7 +167,7 @@ for label, dref, dours in sigma_inputs:
                 n_packed += 1
 
 # ---- converged states: reference run_adc vs product run_adc -----------------------------------------
-n_runs = 0
+n_runs = n_runs_packed = 0
 for label, dref, dours in sigma_inputs:
     restricted = label != "open-shell"
     for kw in (dict(), dict(core_orbitals=1), dict(frozen_core=1, frozen_virtual=1)):
@@ -191,5 +191,12 @@ for label, dref, dours in sigma_inputs:
                     assert a[0] and b[0], (label, kw, method, kind, "not converged")
                     assert np.max(np.abs(a[2] - b[2])) < 1e-8, (label, kw, method, kind, a[2], b[2])
                     assert a[1] == b[1], (label, kw, method, kind, "iterations", a[1], b[1])
+                    if method in ("adc2", "adc2x", "adc3", "cvs-adc2", "cvs-adc2x"):
+                        mp_ = adcc_b200.AdcMatrix(method, adcc_b200.ReferenceState(dours, **kw), doubles_storage="packed")
+                        sp = adcc_b200.run_adc(mp_, conv_tol=1e-8, output=None, **{key: 2})
+                        assert sp.converged and np.max(np.abs(a[2] - sp.excitation_energy)) < 1e-8, \
+                            (label, kw, method, kind, "packed")
+                        assert sp.n_iter == a[1], (label, kw, method, kind, "packed iterations", sp.n_iter, a[1])
+                        n_runs_packed += 1
                 n_runs += 1
-print(f"ok {n_validation} validation cases, {n_guesses} guess sets, {n_sigma} sigma / diagonal comparisons, {n_packed} on the packed engines, {n_runs} Davidson runs")
+print(f"ok {n_validation} validation cases, {n_guesses} guess sets, {n_sigma} sigma / diagonal comparisons, {n_packed} on the packed engines, {n_runs} Davidson runs, {n_runs_packed} also on the packed engines")
