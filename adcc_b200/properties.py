@@ -65,7 +65,10 @@ def dipole_mo_block(refstate, blk, component):
     prov = refstate.operator_integral_provider
     if prov is None or not hasattr(prov, "electric_dipole"):
         raise NotImplementedError("The SCF data provides no electric dipole integrals")
-    s1, s2 = _SPACE[blk[0]], _SPACE[blk[1]]
+    if len(blk) == 4:                                  # full subspace names, e.g. "o3o3"
+        s1, s2 = blk[:2], blk[2:]
+    else:
+        s1, s2 = _SPACE[blk[0]], _SPACE[blk[1]]
     d_ao = np.asarray(prov.electric_dipole[component])
     c1 = refstate.orbital_coefficients_host(s1)
     c2 = refstate.orbital_coefficients_host(s2)
@@ -194,9 +197,8 @@ def ground_state_dipole_moment(ground_state, level=2, cache=None):
     ref = ground_state.reference_state
     cache = {} if cache is None else cache
     ms = ref.mospaces
-    spaces = ["o"] + (["c"] if ground_state.has_core_occupied_space else [])
     mu = np.array(ref.nuclear_dipole, dtype=float)
-    for sp in spaces:                                   # tr(D_ss): the HF density is the identity there
+    for sp in ms.subspaces_occupied:                    # o1, o2 (core), o3 (frozen): the HF density is the identity there
         for comp in range(3):
             key = (sp + sp, comp)
             if key not in cache:

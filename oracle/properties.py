@@ -125,7 +125,7 @@ _SP = {"o": "o1", "v": "v1", "c": "o2"}
 
 
 def _dipole_block(hf, blk, comp):
-    s1, s2 = _SP[blk[0]], _SP[blk[1]]
+    s1, s2 = (blk[:2], blk[2:]) if len(blk) == 4 else (_SP[blk[0]], _SP[blk[1]])
     c1, c2 = hf.orbital_coefficients(s1), hf.orbital_coefficients(s2)
     same = hf.spin_of_axis(s1)[:, None] == hf.spin_of_axis(s2)[None, :]
     return (c1 @ hf.hf.dipole_ao[comp] @ c2.T) * same
@@ -144,7 +144,9 @@ def ground_state_dipole_moment(matrix, level=2):
     """adcc/GroundState.py:137-146, 178-189."""
     hf, mp = matrix.hf, matrix.mp
     mu = np.array(hf.hf.nuclear_dipole, dtype=float)
-    for sp in ["o"] + (["c"] if mp.has_core_occupied_space else []):
+    for sp in ("o1", "o2", "o3"):                    # active, core and frozen occupied: HF density = identity
+        if hf.n_orbs.get(sp, 0) == 0:
+            continue
         for comp in range(3):
             mu[comp] += float(np.trace(_dipole_block(hf, sp + sp, comp)))
     if level >= 2:

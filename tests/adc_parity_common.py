@@ -365,6 +365,12 @@ def check_frozen_spaces(data, method, core, frozen_core, frozen_virtual, n=2):
     ostate = oracle.run_adc(omatrix, method, n_singlets=n, conv_tol=1e-8)
     assert state.converged and ostate.converged and state.n_iter == ostate.n_iter
     np.testing.assert_allclose(state.excitation_energy, ostate.eigenvalues, atol=ENERGY_ATOL, rtol=0)
+    # properties with inactive orbitals: the frozen occupied orbitals stay part of the ground-state
+    # density (the identity on o3, adcc/GroundState.py:137-146) - state dipole moments need them
+    from oracle.properties import oscillator_strengths, state_dipole_moments
+    of, _ = oscillator_strengths(omatrix, ostate)
+    np.testing.assert_allclose(state.oscillator_strength, of, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(state.state_dipole_moment, state_dipole_moments(omatrix, ostate), rtol=0, atol=1e-6)
 
 
 def check_extra_term(data):

@@ -12,7 +12,8 @@ reference package imports libadcc, which switches select_n_* to libtensor's symm
     core / frozen-core / frozen-virtual spaces and all ten methods: equal to 1e-11;
   * run_adc of both packages on the same inputs (singlet / triplet / any / spin_flip, ADC(1) ... ADC(3) and
     their CVS variants, with and without frozen spaces; 116 runs): energies to 1e-8, identical iteration
-    counts, same exception type where no run is possible.
+    counts, same exception type where no run is possible; oscillator strengths and state dipole moments of
+    the singlet runs (36 sets) to 1e-6.
 """
 import itertools
 import os
@@ -167,7 +168,7 @@ for label, dref, dours in sigma_inputs:
                 n_packed += 1
 
 # ---- converged states: reference run_adc vs product run_adc -----------------------------------------
-n_runs = n_runs_packed = 0
+n_runs = n_runs_packed = n_props = 0
 for label, dref, dours in sigma_inputs:
     restricted = label != "open-shell"
     for kw in (dict(), dict(core_orbitals=1), dict(frozen_core=1, frozen_virtual=1)):
@@ -181,7 +182,7 @@ for label, dref, dours in sigma_inputs:
                 for mod, d in ((adcc, dref), (adcc_b200, dours)):
                     try:
                         st = mod.run_adc(d, method=method, conv_tol=1e-8, output=None, **{key: 2}, **kw)
-                        res.append((bool(st.converged), int(st.n_iter), np.array(st.excitation_energy)))
+                        res.append((bool(st.converged), int(st.n_iter), np.array(st.excitation_energy), st))
                     except Exception as e:           # e.g. fewer guesses than requested: both must agree
                         res.append(type(e).__name__)
                 a, b = res
@@ -191,6 +192,13 @@ for label, dref, dours in sigma_inputs:
                     assert a[0] and b[0], (label, kw, method, kind, "not converged")
                     assert np.max(np.abs(a[2] - b[2])) < 1e-8, (label, kw, method, kind, a[2], b[2])
                     assert a[1] == b[1], (label, kw, method, kind, "iterations", a[1], b[1])
+                    if kind == "singlet":
+                        # the reference's property code vs adcc_b200/properties.py on the same states
+                        fa, fb = np.array(a[3].oscillator_strength), np.array(b[3].oscillator_strength)
+                        assert np.max(np.abs(fa - fb)) < 1e-6 * max(1.0, np.max(np.abs(fa))), (label, kw, method, "f")
+                        da, db = np.array(a[3].state_dipole_moment), np.array(b[3].state_dipole_moment)
+                        assert np.max(np.abs(da - db)) < 1e-6, (label, kw, method, "state dipole moment")
+                        n_props += 1
                     if method in ("adc2", "adc2x", "adc3", "cvs-adc2", "cvs-adc2x"):
                         mp_ = adcc_b200.AdcMatrix(method, adcc_b200.ReferenceState(dours, **kw), doubles_storage="packed")
                         sp = adcc_b200.run_adc(mp_, conv_tol=1e-8, output=None, **{key: 2})
@@ -199,4 +207,4 @@ for label, dref, dours in sigma_inputs:
                         assert sp.n_iter == a[1], (label, kw, method, kind, "packed iterations", sp.n_iter, a[1])
                         n_runs_packed += 1
                 n_runs += 1
-print(f"ok {n_validation} validation cases, {n_guesses} guess sets, {n_sigma} sigma / diagonal comparisons, {n_packed} on the packed engines, {n_runs} Davidson runs, {n_runs_packed} also on the packed engines")
+print(f"ok {n_validation} validation cases, {n_guesses} guess sets, {n_sigma} sigma / diagonal comparisons, {n_packed} on the packed engines, {n_runs} Davidson runs, {n_runs_packed} also on the packed engines, {n_props} property sets")
