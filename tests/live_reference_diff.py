@@ -198,6 +198,10 @@ for label, dref, dours in sigma_inputs:
                         assert np.max(np.abs(fa - fb)) < 1e-6 * max(1.0, np.max(np.abs(fa))), (label, kw, method, "f")
                         da, db = np.array(a[3].state_dipole_moment), np.array(b[3].state_dipole_moment)
                         assert np.max(np.abs(da - db)) < 1e-6, (label, kw, method, "state dipole moment")
+                        if not cvs:                  # transitions between the two excited states
+                            sa = np.array(adcc.State2States(a[3], initial=0).oscillator_strength)
+                            sb = np.array(adcc_b200.State2States(b[3], initial=0).oscillator_strength)
+                            assert np.max(np.abs(sa - sb)) < 1e-6 * max(1.0, np.max(np.abs(sa))), (label, kw, method, "s2s")
                         n_props += 1
                     if method in ("adc2", "adc2x", "adc3", "cvs-adc2", "cvs-adc2x"):
                         mp_ = adcc_b200.AdcMatrix(method, adcc_b200.ReferenceState(dours, **kw), doubles_storage="packed")
