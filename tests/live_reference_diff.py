@@ -13,7 +13,9 @@ reference package imports libadcc, which switches select_n_* to libtensor's symm
   * run_adc of both packages on the same inputs (singlet / triplet / any / spin_flip, ADC(1) ... ADC(3) and
     their CVS variants, with and without frozen spaces; 116 runs): energies to 1e-8, identical iteration
     counts, same exception type where no run is possible; oscillator strengths and state dipole moments of
-    the singlet runs (36 sets) to 1e-6.
+    the singlet runs (36 sets) to 1e-6;
+  * MP2 / MP3 energies, t2, td2, mp2_diffdm (10 ground states), AdcMatrixShifted / AdcMatrixProjected, and
+    the Lanczos solver (12 runs, identical iteration counts).
 """
 import itertools
 import os
@@ -211,4 +213,63 @@ for label, dref, dours in sigma_inputs:
                         assert sp.n_iter == a[1], (label, kw, method, kind, "packed iterations", sp.n_iter, a[1])
                         n_runs_packed += 1
                 n_runs += 1
-print(f"ok {n_validation} validation cases, {n_guesses} guess sets, {n_sigma} sigma / diagonal comparisons, {n_packed} on the packed engines, {n_runs} Davidson runs, {n_runs_packed} also on the packed engines, {n_props} property sets")
+
+# ---- MP ground state quantities, shifted / projected matrices, Lanczos ------------------------------
+def close(a, b, what, tol=1e-11):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    assert a.shape == b.shape and np.max(np.abs(a - b)) <= tol * max(np.max(np.abs(a)), 1e-300), what
+
+
+n_mp = n_wrapped = n_lanczos = 0
+for label, dref, dours in sigma_inputs:
+    restricted = label != "open-shell"
+    for kw in ((dict(), dict(core_orbitals=1), dict(frozen_core=1, frozen_virtual=1)) if restricted else (dict(),)):
+        rr, ro = adcc.ReferenceState(dref, **kw), adcc_b200.ReferenceState(dours, **kw)
+        gr, go = adcc.LazyMp(rr), adcc_b200.LazyMp(ro)
+        close(gr.energy_correction(2), go.energy_correction(2), (label, kw, "MP2"))
+        if "core_orbitals" not in kw:
+            close(gr.energy_correction(3), go.energy_correction(3), (label, kw, "MP3"))
+            close(gr.td2("o1o1v1v1").to_ndarray(), go.td2("o1o1v1v1").to_ndarray(), (label, kw, "td2"))
+        close(gr.t2("o1o1v1v1").to_ndarray(), go.t2("o1o1v1v1").to_ndarray(), (label, kw, "t2"))
+        dr, do = gr.mp2_diffdm, go.mp2_diffdm
+        for blk, name in (("o1o1", "oo"), ("o1v1", "ov"), ("v1v1", "vv")):
+            close(dr[blk].to_ndarray(), do[name].to_ndarray(), (label, kw, "mp2_diffdm", blk))
+        n_mp += 1
+    # shifted and projected matrices on a random vector (adcc/AdcMatrix.py:649-780)
+    from adcc.AdcMatrix import AdcMatrixProjected as RefProjected, AdcMatrixShifted as RefShifted
+    mr, mo = adcc.AdcMatrix("adc2x", adcc.ReferenceState(dref)), adcc_b200.AdcMatrix("adc2x", adcc_b200.ReferenceState(dours))
+    rng = np.random.default_rng(99)
+    vr = guess_zero(mr)
+    blocks = {}
+    for blk in vr.blocks:
+        arr = rng.standard_normal(vr[blk].shape)
+        if blk == "pphh":
+            arr = arr - arr.transpose(0, 1, 3, 2)
+            arr = arr - arr.transpose(1, 0, 2, 3)
+        vr[blk].set_from_ndarray(arr)
+        blocks[blk] = adcc_b200.Tensor.from_ndarray(mo.mospaces, mo.axis_spaces[blk], arr)
+    vo = adcc_b200.AmplitudeVector(**blocks)
+    pairs = [(RefShifted(mr, -0.4), adcc_b200.AdcMatrixShifted(mo, -0.4))]
+    if restricted:
+        pairs.append((RefProjected(mr, ["cv", "ccvv", "ocvv"], core_orbitals=1),
+                      adcc_b200.AdcMatrixProjected(mo, ["cv", "ccvv", "ocvv"], core_orbitals=1)))
+    for wr, wo in pairs:
+        sr, so = adcc.evaluate(wr @ vr), wo.matvec(vo)
+        for blk in vr.blocks:
+            close(sr[blk].to_ndarray(), so[blk].to_ndarray(), (label, type(wo).__name__, blk))
+            close(wr.diagonal()[blk].to_ndarray(), wo.diagonal()[blk].to_ndarray(), (label, type(wo).__name__, "diag", blk))
+        n_wrapped += 1
+    # the second eigensolver
+    if restricted:
+        for method in ("adc2", "adc2x"):
+            for key in ("n_singlets", "n_triplets"):
+                res = []
+                for mod, d in ((adcc, dref), (adcc_b200, dours)):
+                    st = mod.run_adc(d, method=method, conv_tol=1e-7, output=None, eigensolver="lanczos", **{key: 2})
+                    res.append((bool(st.converged), int(st.n_iter), np.array(st.excitation_energy)))
+                a, b = res
+                assert a[0] == b[0] and a[1] == b[1], (label, method, key, "lanczos", a[:2], b[:2])
+                if a[0]:
+                    assert np.max(np.abs(a[2] - b[2])) < 1e-7, (label, method, key, "lanczos energies")
+                n_lanczos += 1
+print(f"ok {n_validation} validation cases, {n_guesses} guess sets, {n_sigma} sigma / diagonal comparisons, {n_packed} on the packed engines, {n_runs} Davidson runs, {n_runs_packed} also on the packed engines, {n_props} property sets, {n_mp} MP ground states, {n_wrapped} shifted / projected matrices, {n_lanczos} Lanczos runs")
