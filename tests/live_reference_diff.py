@@ -220,7 +220,7 @@ def close(a, b, what, tol=1e-11):
     assert a.shape == b.shape and np.max(np.abs(a - b)) <= tol * max(np.max(np.abs(a)), 1e-300), what
 
 
-n_mp = n_wrapped = n_lanczos = 0
+n_mp = n_wrapped = n_lanczos = n_intermediates = 0
 for label, dref, dours in sigma_inputs:
     restricted = label != "open-shell"
     for kw in ((dict(), dict(core_orbitals=1), dict(frozen_core=1, frozen_virtual=1)) if restricted else (dict(),)):
@@ -235,6 +235,12 @@ for label, dref, dours in sigma_inputs:
         for blk, name in (("o1o1", "oo"), ("o1v1", "ov"), ("v1v1", "vv")):
             close(dr[blk].to_ndarray(), do[name].to_ndarray(), (label, kw, "mp2_diffdm", blk))
         n_mp += 1
+    # ADC(2) / ADC(3) intermediates (adcc/adc_pp/matrix.py:933-1094) of both packages
+    ir = adcc.AdcMatrix("adc3", adcc.ReferenceState(dref)).intermediates
+    io = adcc_b200.AdcMatrix("adc3", adcc_b200.ReferenceState(dours), doubles_storage="dense").intermediates
+    for name in ("adc2_i1", "adc2_i2", "adc3_m11", "adc3_pia", "adc3_pib", "t2sq"):
+        close(getattr(ir, name).to_ndarray(), getattr(io, name).to_ndarray(), (label, "intermediate", name))
+        n_intermediates += 1
     # shifted and projected matrices on a random vector (adcc/AdcMatrix.py:649-780)
     from adcc.AdcMatrix import AdcMatrixProjected as RefProjected, AdcMatrixShifted as RefShifted
     mr, mo = adcc.AdcMatrix("adc2x", adcc.ReferenceState(dref)), adcc_b200.AdcMatrix("adc2x", adcc_b200.ReferenceState(dours))
@@ -272,4 +278,4 @@ for label, dref, dours in sigma_inputs:
                 if a[0]:
                     assert np.max(np.abs(a[2] - b[2])) < 1e-7, (label, method, key, "lanczos energies")
                 n_lanczos += 1
-print(f"ok {n_validation} validation cases, {n_guesses} guess sets, {n_sigma} sigma / diagonal comparisons, {n_packed} on the packed engines, {n_runs} Davidson runs, {n_runs_packed} also on the packed engines, {n_props} property sets, {n_mp} MP ground states, {n_wrapped} shifted / projected matrices, {n_lanczos} Lanczos runs")
+print(f"ok {n_validation} validation cases, {n_guesses} guess sets, {n_sigma} sigma / diagonal comparisons, {n_packed} on the packed engines, {n_runs} Davidson runs, {n_runs_packed} also on the packed engines, {n_props} property sets, {n_mp} MP ground states, {n_wrapped} shifted / projected matrices, {n_lanczos} Lanczos runs, {n_intermediates} intermediates")
