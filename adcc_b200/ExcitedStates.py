@@ -123,12 +123,16 @@ class ExcitedStates:
                     for d in self.state_dipole_moment]
             columns.append(_column("state dipole moment", vals, unit="x(au)    y(au)    z(au)    abs(au)"))
         width = sum(c["width"] for c in columns)
-        method = self.method.name
-        if self.property_method != self.method.name:
-            method += f" ({self.property_method})"
+        # "adc2 (isr2)", "cvs-adc2x (cvs-isr2)": the property method is an IsrMethod in the reference and
+        # never compares equal to the AdcMethod, so it is always shown (adcc/ElectronicStates.py:490-492)
+        method = f"{self.method.name} ({self.property_method.replace('adc', 'isr')})"
         info = []
         if self.kind:
-            info.append(self.kind + ",")
+            info.append(self.kind)
+        if self.spin_change is not None and self.spin_change != 0:
+            info.append(f"(\u0394MS={self.spin_change:+2d})")
+        if info:
+            info[-1] += ","
         info.append("converged" if self.converged else "NOT CONVERGED")
         info = " ".join(info)
         header = f"{method}    {info:>{max(width - len(method) - 4, 0)}s}"

@@ -204,6 +204,11 @@ for label, dref, dours in sigma_inputs:
                             sa = np.array(adcc.State2States(a[3], initial=0).oscillator_strength)
                             sb = np.array(adcc_b200.State2States(b[3], initial=0).oscillator_strength)
                             assert np.max(np.abs(sa - sb)) < 1e-6 * max(1.0, np.max(np.abs(sa))), (label, kw, method, "s2s")
+                        # the table users read (adcc/ExcitedStates.py:50-166)
+                        ta = a[3].describe(state_dipole_moments=True, transition_dipole_moments=False)
+                        tb = b[3].describe(state_dipole_moments=True, transition_dipole_moments=False)
+                        ta, tb = ta.replace("-0.0000", " 0.0000"), tb.replace("-0.0000", " 0.0000")   # sign of a 1e-17
+                        assert ta == tb, (label, kw, method, "describe()\n" + ta + "\n" + tb)
                         n_props += 1
                     if method in ("adc2", "adc2x", "adc3", "cvs-adc2", "cvs-adc2x"):
                         mp_ = adcc_b200.AdcMatrix(method, adcc_b200.ReferenceState(dours, **kw), doubles_storage="packed")

@@ -367,7 +367,7 @@ def test_cis_is_adc1_with_zeroth_order_properties(h2o):
     # describe(): the reference's table layout (adcc/ExcitedStates.py:50-166)
     lines = state.describe().splitlines()
     assert len({len(ln) for ln in lines}) == 1                      # a proper frame
-    assert lines[1].startswith("| adc1 (adc0)") and lines[1].rstrip(" |").endswith("singlet, converged")
+    assert lines[1].startswith("| adc1 (isr0)") and lines[1].rstrip(" |").endswith("singlet, converged")
     assert "excitation energy" in lines[3] and "osc str" in lines[3] and "|v1|^2" in lines[3]
     assert "|v2|^2" not in lines[3] and "(au)" in lines[4] and len(lines) == 5 + 3 + 1
     assert "transition dipole moment" in state.describe(transition_dipole_moments=True)
