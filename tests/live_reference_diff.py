@@ -194,6 +194,11 @@ for label, dref, dours in sigma_inputs:
                     assert a[0] and b[0], (label, kw, method, kind, "not converged")
                     assert np.max(np.abs(a[2] - b[2])) < 1e-8, (label, kw, method, kind, a[2], b[2])
                     assert a[1] == b[1], (label, kw, method, kind, "iterations", a[1], b[1])
+                    # the plain table (energies, block norms, header with kind / spin change) of every run
+                    has_dip = restricted
+                    ta = a[3].describe(oscillator_strengths=has_dip).replace("-0.0000", " 0.0000")
+                    tb = b[3].describe(oscillator_strengths=has_dip).replace("-0.0000", " 0.0000")
+                    assert ta == tb, (label, kw, method, kind, "describe()\n" + ta + "\n" + tb)
                     if kind == "singlet":
                         # the reference's property code vs adcc_b200/properties.py on the same states
                         fa, fb = np.array(a[3].oscillator_strength), np.array(b[3].oscillator_strength)
