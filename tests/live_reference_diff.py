@@ -205,6 +205,24 @@ for label, dref, dours in sigma_inputs:
                         assert np.max(np.abs(fa - fb)) < 1e-6 * max(1.0, np.max(np.abs(fa))), (label, kw, method, "f")
                         da, db = np.array(a[3].state_dipole_moment), np.array(b[3].state_dipole_moment)
                         assert np.max(np.abs(da - db)) < 1e-6, (label, kw, method, "state dipole moment")
+                        # density matrices block by block (state densities are quadratic in the vector: no sign;
+                        # transition densities up to the sign of the eigenvector)
+                        full = {"o": "o1", "v": "v1", "c": "o2"}
+                        for n in range(2):
+                            ddr, ddo = a[3].state_diffdm[n], b[3].state_diffdm[n]
+                            for blk, rho in ddo.items():
+                                name = full[blk[0]] + full[blk[1]]
+                                want = ddr[name].to_ndarray() if name in ddr.blocks_nonzero else 0.0 * rho.to_ndarray()
+                                assert np.max(np.abs(rho.to_ndarray() - want)) < 1e-6, (label, kw, method, "diffdm", blk)
+                            tdr, tdo = a[3].transition_dm[n], b[3].transition_dm[n]
+                            big = max(tdo, key=lambda k: float(np.max(np.abs(tdo[k].to_ndarray()))))
+                            ref_big = tdr[full[big[0]] + full[big[1]]].to_ndarray()
+                            k = np.unravel_index(np.argmax(np.abs(ref_big)), ref_big.shape)
+                            sign = 1.0 if tdo[big].to_ndarray()[k] * ref_big[k] >= 0 else -1.0
+                            for blk, rho in tdo.items():
+                                name = full[blk[0]] + full[blk[1]]
+                                want = tdr[name].to_ndarray() if name in tdr.blocks_nonzero else 0.0 * rho.to_ndarray()
+                                assert np.max(np.abs(sign * rho.to_ndarray() - want)) < 1e-6, (label, kw, method, "tdm", blk)
                         if not cvs:                  # transitions between the two excited states
                             sa = np.array(adcc.State2States(a[3], initial=0).oscillator_strength)
                             sb = np.array(adcc_b200.State2States(b[3], initial=0).oscillator_strength)
