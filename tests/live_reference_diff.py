@@ -248,7 +248,7 @@ def close(a, b, what, tol=1e-11):
     assert a.shape == b.shape and np.max(np.abs(a - b)) <= tol * max(np.max(np.abs(a)), 1e-300), what
 
 
-n_mp = n_wrapped = n_lanczos = n_intermediates = 0
+n_mp = n_wrapped = n_lanczos = n_intermediates = n_dense = 0
 for label, dref, dours in sigma_inputs:
     restricted = label != "open-shell"
     for kw in ((dict(), dict(core_orbitals=1), dict(frozen_core=1, frozen_virtual=1)) if restricted else (dict(),)):
@@ -269,6 +269,15 @@ for label, dref, dours in sigma_inputs:
     for name in ("adc2_i1", "adc2_i2", "adc3_m11", "adc3_pia", "adc3_pib", "t2sq"):
         close(getattr(ir, name).to_ndarray(), getattr(io, name).to_ndarray(), (label, "intermediate", name))
         n_intermediates += 1
+    # dense export in the antisymmetrised basis and block views (adcc/AdcMatrix.py:526-646)
+    if label in ("h2o", "synthetic 5/2"):
+        for method, kwx in (("adc1", {}), ("adc2", {}), ("cvs-adc2x", dict(core_orbitals=1))):
+            er = adcc.AdcMatrix(method, adcc.ReferenceState(dref, **kwx))
+            eo = adcc_b200.AdcMatrix(method, adcc_b200.ReferenceState(dours, **kwx))
+            close(er.to_ndarray(), eo.to_ndarray(), (label, method, "to_ndarray"))
+            assert [tuple(b) for b in er.dense_basis()] == [tuple(b) for b in eo.dense_basis()], (label, method, "dense_basis")
+            close(er.block_view("ph_ph").to_ndarray(), eo.block_view("ph_ph").to_ndarray(), (label, method, "block_view"))
+            n_dense += 1
     # shifted and projected matrices on a random vector (adcc/AdcMatrix.py:649-780)
     from adcc.AdcMatrix import AdcMatrixProjected as RefProjected, AdcMatrixShifted as RefShifted
     mr, mo = adcc.AdcMatrix("adc2x", adcc.ReferenceState(dref)), adcc_b200.AdcMatrix("adc2x", adcc_b200.ReferenceState(dours))
@@ -306,4 +315,4 @@ for label, dref, dours in sigma_inputs:
                 if a[0]:
                     assert np.max(np.abs(a[2] - b[2])) < 1e-7, (label, method, key, "lanczos energies")
                 n_lanczos += 1
-print(f"ok {n_validation} validation cases, {n_guesses} guess sets, {n_sigma} sigma / diagonal comparisons, {n_packed} on the packed engines, {n_runs} Davidson runs, {n_runs_packed} also on the packed engines, {n_props} property sets, {n_mp} MP ground states, {n_wrapped} shifted / projected matrices, {n_lanczos} Lanczos runs, {n_intermediates} intermediates")
+print(f"ok {n_validation} validation cases, {n_guesses} guess sets, {n_sigma} sigma / diagonal comparisons, {n_packed} on the packed engines, {n_runs} Davidson runs, {n_runs_packed} also on the packed engines, {n_props} property sets, {n_mp} MP ground states, {n_wrapped} shifted / projected matrices, {n_lanczos} Lanczos runs, {n_intermediates} intermediates, {n_dense} dense exports")

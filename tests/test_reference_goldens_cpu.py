@@ -150,7 +150,7 @@ def test_validation_guesses_and_sigma_match_the_reference_live():
     reference's own, executed side by side."""
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "live_reference_diff.py")],
                          capture_output=True, text=True, cwd=ROOT, timeout=900)
-    assert out.returncode == 0 and "ok 810 validation cases, 130 guess sets, 85 sigma / diagonal comparisons, 45 on the packed engines, 116 Davidson runs, 75 also on the packed engines, 36 property sets, 10 MP ground states, 7 shifted / projected matrices, 12 Lanczos runs, 24 intermediates" in out.stdout, out.stderr[-3000:]
+    assert out.returncode == 0 and "ok 810 validation cases, 130 guess sets, 85 sigma / diagonal comparisons, 45 on the packed engines, 116 Davidson runs, 75 also on the packed engines, 36 property sets, 10 MP ground states, 7 shifted / projected matrices, 12 Lanczos runs, 24 intermediates, 6 dense exports" in out.stdout, out.stderr[-3000:]
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/adcc"), reason="reference tree only exists in the build container")
